@@ -1,0 +1,144 @@
+/* tetris_b200.h — C ABI of the B200-native batched Tetris placement engine (libtetris_b200.so).
+ *
+ * This is the drop-in boundary for ONE hot path of CogWorks/Tetris-AI: for every live game of a
+ * cross-entropy population, enumerate each rotation x column placement of the current piece
+ * (optionally also of the next piece), drop it, clear lines, compute the board features, score
+ * them against the candidate's weight vector in fp64 and commit the argmax move.
+ *
+ * The reference has no FFI of its own — its extension points are Python callables — so each entry
+ * point below names the reference callable(s) whose work it takes over (paths are under
+ * /root/reference/cogworks/):
+ *
+ *   tb200_play_games     simulate()            tetris/simulator.py:152-189  (whole games)
+ *                        move_drop()           tetris/simulator.py:3-13
+ *                        policy_best()         tetris/simulator.py:123-150  (first-of-max tie rule)
+ *                        State.future()        tetris/game.py:166-180  (+ Board.imprint/full/clear :62-87)
+ *                        State.lines_cleared/level/score   tetris/game.py:150-164
+ *                        the test_f / map_f call of cross_entropy()   learning.py:38
+ *   tb200_best_move      one simulate() iteration: pool_stack + move_policy   simulator.py:156-180
+ *   tb200_eval_features  feature.evaluate(state, features)   feature.py:50-55 over tetris/features.py:18-347
+ *   tb200_hashed_pieces  the caller-supplied zoid_gen (simulator.py:152) as a counter-based stream
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative TB200_E_* code otherwise; nothing throws
+ *     across this boundary; tb200_last_error(ctx) returns a message for the last failure;
+ *   - the caller owns every buffer; the library never frees caller memory and keeps no caller
+ *     pointer after a call returns;
+ *   - `mem` says where ALL buffers of a call live: TB200_MEM_HOST (the library stages them through
+ *     its own device buffers and the call is synchronous) or TB200_MEM_DEVICE (pointers are device
+ *     pointers; work is enqueued on `stream`, the call returns without synchronising);
+ *   - a ctx is bound to one device, is not thread-safe, and different ctxs are independent;
+ *   - there is NO CPU fallback: if no CUDA device is usable tb200_create fails with TB200_E_NO_DEVICE.
+ *
+ * Board exchange format (same as the reference's numpy grid, packed): uint16_t rows[20], rows[0]
+ * is the TOP row, bit c of a row is column c.  Piece ids: I,T,L,J,O,Z,S = 0..6 (tetris/game.py:24-34).
+ * Feature ids: 0..44 in tetris/features.py source order (see TB200_FEATURE_NAMES in tetris_b200_features.h).
+ */
+#ifndef TETRIS_B200_H
+#define TETRIS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB200_ROWS 20
+#define TB200_COLS 10
+#define TB200_NUM_FEATURES 45
+#define TB200_MAX_WEIGHTED 48
+
+#define TB200_MEM_HOST   0
+#define TB200_MEM_DEVICE 1
+
+#define TB200_OK             0
+#define TB200_E_NO_DEVICE   -1
+#define TB200_E_BAD_ARG     -2
+#define TB200_E_CUDA        -3
+#define TB200_E_NO_FEATURES -4
+#define TB200_E_ALLOC       -5
+
+typedef struct tb200_ctx tb200_ctx;
+
+/* per-game result record, written once per game (40 bytes) */
+typedef struct {
+    uint32_t pieces;        /* pieces placed (game length)                         simulator.py:180 */
+    uint32_t lines;         /* State.lines_cleared()                               game.py:150-154  */
+    uint32_t hist[4];       /* State.cleared[k], k = 1..4                          game.py:176      */
+    uint64_t score;         /* State.score() with the default points table          game.py:159-164  */
+    uint64_t placements;    /* scored leaves = scorer calls                        simulator.py:129 */
+} tb200_game_result;
+
+typedef struct {
+    uint32_t struct_size;            /* = sizeof(tb200_play_args) */
+    int32_t  mem;                    /* TB200_MEM_HOST / TB200_MEM_DEVICE for every pointer below */
+    void*    stream;                 /* cudaStream_t for TB200_MEM_DEVICE (NULL = legacy default stream) */
+    int32_t  n_candidates;           /* C */
+    int32_t  games_per_candidate;    /* G; game g belongs to candidate g / G */
+    const double*  weights;          /* f64[C][F], F and the order from tb200_set_features (learning.py:32-35) */
+    const uint8_t* pieces;           /* u8[S][T] piece ids, or NULL => counter-based stream (seed, stream id, t) */
+    int32_t  n_sequences;            /* S */
+    uint32_t T;                      /* pieces per sequence = cap on the game length */
+    uint32_t max_moves;              /* stop (not game over) after this many placements; 0 => T */
+    const int32_t* seq_of_game;      /* i32[C*G] sequence / stream id of each game, or NULL => g % G */
+    uint64_t seed;                   /* seed of the counter-based stream */
+    int32_t  lookahead;              /* 1 or 2 (simulate(..., lookahead)) */
+    int32_t  lanes;                  /* lanes per game: 0 = auto, or 8 / 16 / 32 */
+    const uint16_t* init_rows;       /* u16[C*G][20] initial boards, or NULL => empty boards */
+    tb200_game_result* results;      /* [C*G], required */
+    uint8_t*  trace;                 /* u8[C*G][T][4] = {rot,row,col,k} per move, or NULL */
+    double*   score_trace;           /* f64[C*G][T] winning score per move, or NULL */
+    uint16_t* final_rows;            /* u16[C*G][20] final boards, or NULL */
+    double*   fitness;               /* f64[C] = total lines of the candidate's games / G, or NULL */
+} tb200_play_args;
+
+/* timing of the last tb200_play_games call on this ctx (CUDA events on the launching stream) */
+typedef struct {
+    float kernel_ms;                 /* play kernel only (valid after the stream has been synchronised) */
+    float total_ms;                  /* host mode: H2D + kernels + D2H */
+    int32_t lanes;                   /* lanes per game actually used */
+    int32_t grid, block;             /* launch configuration */
+    int32_t kernels_launched;        /* number of kernels of this library launched by the call */
+    uint64_t h2d_bytes, d2h_bytes;   /* host mode: bytes staged each way */
+} tb200_timing;
+
+int  tb200_create(int device, tb200_ctx** out);
+void tb200_destroy(tb200_ctx* ctx);
+const char* tb200_last_error(const tb200_ctx* ctx);
+const char* tb200_version(void);
+
+/* number of SMs / SM clock (kHz) / device name of the ctx's device */
+int tb200_device_info(tb200_ctx* ctx, int32_t* sms, int32_t* clock_khz, char* name, int32_t name_len);
+
+/* weighted features of the linear scorer, in summation order (the key order of the weights
+ * mapping handed to test_f, learning.py:38).  1 <= F <= TB200_MAX_WEIGHTED, ids in 0..44. */
+int tb200_set_features(tb200_ctx* ctx, const int32_t* feature_ids, int32_t F);
+
+/* whole games for a population: C candidates x G games (K2) */
+int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args);
+int tb200_last_timing(tb200_ctx* ctx, tb200_timing* out);
+
+/* one placement decision per board (K1).  boards u16[N][20]; piece/next u8[N] (next[i] = 255 or
+ * next == NULL => no visible second piece); weights f64[N][F] if per_board_weights else f64[1][F].
+ * out_move u8[N][4] = {rot,row,col,k} (row = 255 => no legal move), out_score f64[N] (may be NULL),
+ * out_count u32[N] scored leaves (may be NULL), out_rows u16[N][20] boards after the move (may be NULL). */
+int tb200_best_move(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
+                    const uint16_t* boards, const uint8_t* piece, const uint8_t* next,
+                    const double* weights, int32_t per_board_weights, int32_t lookahead,
+                    uint8_t* out_move, double* out_score, uint32_t* out_count, uint16_t* out_rows);
+
+/* all 45 features of prev.future(piece, rot, <drop row>, col) for N (board, placement) pairs (K3).
+ * out_features f64[N][45] (ints are exact), out_info i32[N][3] = {legal, row, k}, out_rows u16[N][20]
+ * post-clear boards (may be NULL). */
+int tb200_eval_features(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
+                        const uint16_t* prev_boards, const uint8_t* piece, const uint8_t* rot, const uint8_t* col,
+                        double* out_features, int32_t* out_info, uint16_t* out_rows);
+
+/* materialise the counter-based piece stream (K4): out u8[n_streams][T], stream ids first_stream.. */
+int tb200_hashed_pieces(tb200_ctx* ctx, int32_t mem, void* stream, uint64_t seed, uint64_t first_stream,
+                        int32_t n_streams, uint32_t T, uint8_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TETRIS_B200_H */

@@ -1,0 +1,134 @@
+// emu.cpp — host build of the CUDA core (tetris_ai_b200/csrc/tetris_core.cuh) for CPU-side tests.
+//
+// TEST INFRASTRUCTURE ONLY: it lets `pytest -m "not gpu"` run the very same placement / feature /
+// scoring functions the kernels use against the oracles in a container without a GPU.  It is not
+// part of the product library and libtetris_b200.so exports none of it.  The sequential loops here
+// mirror the kernels' search order (slot-major, strict-greater, first-of-max) but not their
+// shuffles or tickets — those are covered by the -m gpu tests.
+#include <stdint.h>
+#include <string.h>
+#include "../../tetris_ai_b200/csrc/tetris_core.cuh"
+
+using namespace tb;
+
+static int pick_mode(const int* ids, int F)
+{
+    static const int w6[6] = {F_LANDING_HEIGHT, F_ERODED_CELLS, F_ROW_TRANS, F_COL_TRANS, F_PITS, F_CUML_WELLS};
+    bool is_w6 = F == 6, is_all = F == NFEAT;
+    for (int i = 0; i < F && is_w6; ++i) is_w6 = ids[i] == w6[i];
+    for (int i = 0; i < F && is_all; ++i) is_all = ids[i] == i;
+    return is_w6 ? MODE_W6 : (is_all ? MODE_ALL45 : MODE_GENERIC);
+}
+
+template <int MODE>
+static void search_one(const uint32_t c[COLS], const Heights& H, const PrevStat& pv, int piece, const uint8_t* ids,
+                       const double* w, int F, uint64_t rmask, uint32_t tag_hi, uint64_t& key, uint32_t& tag, uint64_t& cnt)
+{
+    const Tables& tab = host_tables();
+    for (int s = 0; s < tab.nslots[piece]; ++s) {
+        Placement P;
+        if (place_slot(c, H, tab.slot[piece][s], P)) {
+            Feat f;
+            memset(&f, 0, sizeof f);
+            eval_features<ModeTraits<MODE>::CMASK>(P, pv, rmask, f);
+            const uint64_t k = score_key(score_features<MODE>(f, ids, w, F));
+            const uint32_t tg = tag_hi | (uint32_t)s;
+            if (k > key || (k == key && tg < tag)) { key = k; tag = tg; }
+            ++cnt;
+        }
+    }
+}
+
+template <int MODE>
+static void play(const int* ids_in, int F, const double* w, const uint8_t* pieces, uint32_t T, uint64_t seed, uint64_t stream,
+                 int lookahead, uint32_t max_moves, const uint16_t* init_rows, uint64_t* res8, uint8_t* trace,
+                 double* score_trace, uint16_t* final_rows)
+{
+    const Tables& tab = host_tables();
+    uint8_t ids[64]; uint64_t rmask = 0;
+    for (int i = 0; i < F; ++i) { ids[i] = (uint8_t)ids_in[i]; rmask |= 1ull << ids_in[i]; }
+    uint32_t c[COLS];
+    if (init_rows) rows_to_cols(init_rows, c); else memset(c, 0, sizeof c);
+    Heights H = pack_heights(c); PrevStat pv = prev_stat(c);
+    uint32_t t = 0, lines = 0, hist[4] = {0, 0, 0, 0}; uint64_t score = 0, cnt = 0;
+    if (!max_moves) max_moves = T;
+    auto piece_at = [&](uint32_t tt) { return pieces ? (int)pieces[tt] : hashed_piece(seed, stream, tt); };
+    while (t < T && t < max_moves) {
+        const int p1 = piece_at(t);
+        if (p1 >= 7) break;
+        uint64_t key = 0; uint32_t tag = 0;
+        const int p2 = (lookahead == 2 && t + 1 < T) ? piece_at(t + 1) : 255;
+        if (p2 < 7) {
+            for (int s1 = 0; s1 < tab.nslots[p1]; ++s1) {
+                Placement P1;
+                if (!place_slot(c, H, tab.slot[p1][s1], P1)) continue;
+                const Heights H1 = pack_heights(P1.n); const PrevStat pv1 = prev_stat(P1.n);
+                search_one<MODE>(P1.n, H1, pv1, p2, ids, w, F, rmask, (uint32_t)s1 << 6, key, tag, cnt);
+            }
+        }
+        if (key == 0) {
+            uint64_t k1 = 0; uint32_t t1 = 0;
+            search_one<MODE>(c, H, pv, p1, ids, w, F, rmask, 0u, k1, t1, cnt);
+            key = k1; tag = t1 << 6;
+        }
+        if (key == 0) break;
+        Placement P;
+        place_slot(c, H, tab.slot[p1][tag >> 6], P);
+        memcpy(c, P.n, sizeof c);
+        H = pack_heights(c); pv = prev_stat(c);
+        lines += (uint32_t)P.k; if (P.k) hist[P.k - 1] += 1;
+        static const uint32_t PTS[5] = {0, 40, 100, 300, 1200};
+        score += (uint64_t)PTS[P.k] * (lines / 10 + 1);
+        if (trace) { trace[4 * t] = (uint8_t)P.rot; trace[4 * t + 1] = (uint8_t)(ROWS - P.y - P.ph); trace[4 * t + 2] = (uint8_t)P.c0; trace[4 * t + 3] = (uint8_t)P.k; }
+        if (score_trace) {
+            const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
+            memcpy(&score_trace[t], &b, 8);
+        }
+        ++t;
+    }
+    res8[0] = t; res8[1] = lines; res8[2] = hist[0]; res8[3] = hist[1]; res8[4] = hist[2]; res8[5] = hist[3]; res8[6] = score; res8[7] = cnt;
+    if (final_rows) cols_to_rows(c, final_rows);
+}
+
+extern "C" {
+
+// mode: -1 = as tb200_set_features would choose, 0 = force the generic (run-time feature list) path
+int emu_play_one(const int* ids, int F, const double* w, const uint8_t* pieces, uint32_t T, uint64_t seed, uint64_t stream,
+                 int lookahead, uint32_t max_moves, int mode, const uint16_t* init_rows, uint64_t* res8, uint8_t* trace,
+                 double* score_trace, uint16_t* final_rows)
+{
+    const int m = mode < 0 ? pick_mode(ids, F) : mode;
+    if (m == MODE_W6) play<MODE_W6>(ids, F, w, pieces, T, seed, stream, lookahead, max_moves, init_rows, res8, trace, score_trace, final_rows);
+    else if (m == MODE_ALL45) play<MODE_ALL45>(ids, F, w, pieces, T, seed, stream, lookahead, max_moves, init_rows, res8, trace, score_trace, final_rows);
+    else play<MODE_GENERIC>(ids, F, w, pieces, T, seed, stream, lookahead, max_moves, init_rows, res8, trace, score_trace, final_rows);
+    return m;
+}
+
+// all 45 features of prev.future(piece, rot, <drop row>, col); info = {legal (-1 = no such slot), row, k}
+void emu_eval_placement(const uint16_t* prev_rows, int piece, int rot, int col, double* feats, uint16_t* post_rows, int* info)
+{
+    const Tables& tab = host_tables();
+    uint32_t c[COLS];
+    rows_to_cols(prev_rows, c);
+    const Heights H = pack_heights(c); const PrevStat pv = prev_stat(c);
+    info[0] = -1; info[1] = -1; info[2] = 0;
+    for (int s = 0; s < tab.nslots[piece]; ++s) {
+        const SlotDesc& d = tab.slot[piece][s];
+        if ((int)((d.w[0] >> 4) & 3u) != rot || (int)(d.w[0] & 15u) != col) continue;
+        Placement P;
+        const bool legal = place_slot(c, H, d, P);
+        info[0] = legal ? 1 : 0;
+        if (legal) {
+            info[1] = ROWS - P.y - P.ph; info[2] = P.k;
+            Feat f; memset(&f, 0, sizeof f);
+            eval_features<0>(P, pv, ALL45_MASK, f);
+            for (int j = 0; j < NFEAT; ++j) feats[j] = feat_value(f, j);
+            if (post_rows) cols_to_rows(P.n, post_rows);
+        }
+        return;
+    }
+}
+
+int emu_hashed_piece(uint64_t seed, uint64_t stream, uint64_t t) { return hashed_piece(seed, stream, t); }
+
+}  // extern "C"

@@ -1,0 +1,125 @@
+"""The CUDA core (tetris_core.cuh) compiled for the HOST, checked against the golden fixtures and
+against the plain-C oracle on thousands of seeded games.  Runs without a GPU; the same checks are
+repeated through the real kernels in test_gpu_parity.py (-m gpu)."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import coracle, pyoracle
+import emu_lib
+
+NAMES = list(pyoracle.FEATURE_NAMES)
+W6_NAMES = ["landing_height", "eroded_cells", "row_trans", "col_trans", "pits", "cuml_wells"]
+W6_VALS = [-4.500158825082766, 3.4181268101392694, -3.2178882868487753, -9.348695305445199, -7.899265427351652, -3.3855972247263626]
+
+
+def fval(v):
+    return float.fromhex(v) if isinstance(v, str) else float(v)
+
+
+def same_double(a, b):
+    return a.hex() == b.hex() or (a == 0.0 and b == 0.0)
+
+
+def test_emu_features_all_golden_states(golden_states):
+    n = 0
+    for st in golden_states["states"]:
+        if st["n_legal"] == 0:
+            continue
+        r = emu_lib.eval_placement(st["prev"], st["piece"], st["rot"], st["col"])
+        assert r["legal"] == 1 and r["row"] == st["row"] and r["k"] == st["k"]
+        assert list(r["post"]) == st["post"]
+        for i, (a, b) in enumerate(zip(r["features"], st["features"])):
+            assert same_double(float(a), fval(b)), (NAMES[i], float(a), b, st)
+        n += 1
+    assert n > 7000
+
+
+def test_emu_legality_all_slots(golden_states):
+    """Every (rot, col) slot: legal exactly when move_drop yields it, with the same drop row."""
+    nrot = [2, 4, 4, 4, 1, 2, 2]
+    checked = 0
+    for st in golden_states["states"]:
+        if st.get("legal_slots") is None:
+            continue
+        want = {(r, c): row for r, c, row in st["legal_slots"]}
+        for rot in range(nrot[st["piece"]]):
+            for col in range(10):
+                r = emu_lib.eval_placement(st["prev"], st["piece"], rot, col)
+                if (rot, col) in want:
+                    assert r["legal"] == 1 and r["row"] == want[(rot, col)]
+                else:
+                    assert r["legal"] in (0, -1)
+        checked += 1
+    assert checked > 200
+
+
+def test_emu_golden_games(golden_games):
+    for g in golden_games["games"]:
+        if g.get("tie") == "last":
+            continue
+        fids = [pyoracle.FEATURE_ID[n] for n, _ in g["weights"]]
+        w = [x for _, x in g["weights"]]
+        seq = pyoracle.piece_sequence(g["seed"], g["T"])
+        for mode in (-1, 0):
+            res = emu_lib.play_one(fids, w, seq, lookahead=g["lookahead"], mode=mode)
+            assert res["pieces"] == g["pieces"] and res["lines"] == g["lines"] and res["hist"] == g["hist"]
+            assert res["score"] == g["score"] and res["placements"] == g["scorer_calls"]
+            assert res["trace"].tobytes().hex() == g["trace_hex"]
+            assert list(res["final"]) == g["final_board"]
+
+
+def test_emu_golden_steps(golden_steps):
+    for s in golden_steps["steps"]:
+        fids = [pyoracle.FEATURE_ID[n] for n, _ in s["weights"]]
+        w = [x for _, x in s["weights"]]
+        for key, la in (("l1", 1), ("l2", 2)):
+            want = s[key]
+            if want is None and key == "l2":
+                continue
+            res = emu_lib.play_one(fids, w, [s["piece"], s["next"]], lookahead=la, max_moves=1, init_rows=s["board"])
+            if want is None:
+                assert res["pieces"] == 0
+                continue
+            assert res["pieces"] == 1
+            assert tuple(int(x) for x in res["trace"][0]) == (want["rot"], want["row"], want["col"], want["k"])
+            assert same_double(float(res["scores"][0]), float.fromhex(want["score"]))
+
+
+def _random_weight_sets(rng, n):
+    out = []
+    for i in range(n):
+        kind = i % 4
+        if kind == 0:
+            out.append((W6_NAMES, [rng.gauss(v, 1.0) for v in W6_VALS]))
+        elif kind == 1:
+            out.append((W6_NAMES, [rng.gauss(0, 10.0) for _ in W6_VALS]))
+        elif kind == 2:
+            names = rng.sample(NAMES, rng.randint(1, 12))
+            out.append((names, [rng.gauss(0, 3.0) for _ in names]))
+        else:
+            out.append((NAMES, [W6_VALS[W6_NAMES.index(n)] + rng.gauss(0, 0.3) if n in W6_NAMES else rng.gauss(0, 0.3) for n in NAMES]))
+    return out
+
+
+@pytest.mark.parametrize("lookahead,ngames,T", [(1, 160, 400), (2, 24, 40)])
+def test_emu_vs_coracle_random_games(lookahead, ngames, T):
+    """Seeded random weight vectors (w6-like, wide, random subsets, all 45) x hashed piece streams."""
+    rng = random.Random(100 + lookahead)
+    for gi, (names, w) in enumerate(_random_weight_sets(rng, ngames)):
+        fids = [pyoracle.FEATURE_ID[n] for n in names]
+        seq = [pyoracle.hashed_piece(77, gi, t) for t in range(T)]
+        a = coracle.play_one(fids, w, seq, lookahead)
+        b = emu_lib.play_one(fids, w, seq, lookahead=lookahead)
+        assert (a["pieces"], a["lines"], a["hist"], a["score"], a["placements"]) == \
+               (b["pieces"], b["lines"], b["hist"], b["score"], b["placements"]), (gi, names)
+        assert a["trace"].tobytes() == b["trace"].tobytes(), (gi, names)
+        assert list(a["final"]) == list(b["final"])
+
+
+def test_emu_hashed_piece_twin():
+    rng = random.Random(9)
+    for _ in range(2000):
+        s, g, t = rng.getrandbits(48), rng.getrandbits(30), rng.getrandbits(20)
+        assert emu_lib.lib().emu_hashed_piece(s, g, t) == pyoracle.hashed_piece(s, g, t)

@@ -1,0 +1,232 @@
+"""Parity of the CUDA path (through the C ABI) against the golden fixtures generated from the
+unmodified reference and against the plain-C oracle on seeded inputs.  Bit-exact everywhere:
+chosen placements, rows cleared, game lengths, scores (fp64 bits), all 45 features."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import coracle, pyoracle
+
+pytestmark = pytest.mark.gpu
+
+NAMES = list(pyoracle.FEATURE_NAMES)
+W6_NAMES = ["landing_height", "eroded_cells", "row_trans", "col_trans", "pits", "cuml_wells"]
+W6_VALS = [-4.500158825082766, 3.4181268101392694, -3.2178882868487753, -9.348695305445199, -7.899265427351652, -3.3855972247263626]
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from tetris_ai_b200 import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def fval(v):
+    return float.fromhex(v) if isinstance(v, str) else float(v)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def assert_same_doubles(got, want, what=""):
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    ok = (bits(got) == bits(want)) | ((got == 0.0) & (want == 0.0))
+    assert ok.all(), (what, np.argwhere(~ok)[:5], got[~ok][:5], want[~ok][:5])
+
+
+def test_library_identifies_b200(eng):
+    assert eng.sms > 0 and "NVIDIA" in eng.device_name
+
+
+def test_k3_features_golden_states(eng, golden_states):
+    sts = [s for s in golden_states["states"] if s["n_legal"] > 0]
+    prev = np.array([s["prev"] for s in sts], dtype=np.uint16)
+    r = eng.eval_features(prev, [s["piece"] for s in sts], [s["rot"] for s in sts], [s["col"] for s in sts], want_rows=True)
+    assert (r["legal"] == 1).all()
+    assert (r["row"] == np.array([s["row"] for s in sts])).all()
+    assert (r["k"] == np.array([s["k"] for s in sts])).all()
+    assert (r["rows"] == np.array([s["post"] for s in sts], dtype=np.uint16)).all()
+    want = np.array([[fval(v) for v in s["features"]] for s in sts])
+    assert_same_doubles(r["features"], want, "features")
+
+
+def test_k3_legality_every_slot(eng, golden_states):
+    nrot = [2, 4, 4, 4, 1, 2, 2]
+    boards, piece, rot, col, want = [], [], [], [], []
+    for st in golden_states["states"]:
+        if st.get("legal_slots") is None:
+            continue
+        legal = {(r, c): row for r, c, row in st["legal_slots"]}
+        for ro in range(nrot[st["piece"]]):
+            for co in range(10):
+                boards.append(st["prev"]); piece.append(st["piece"]); rot.append(ro); col.append(co)
+                want.append(legal.get((ro, co), -1))
+    r = eng.eval_features(np.array(boards, dtype=np.uint16), piece, rot, col)
+    want = np.array(want)
+    assert ((r["legal"] == 1) == (want >= 0)).all()
+    assert (r["row"][want >= 0] == want[want >= 0]).all()
+
+
+def test_k3_vs_coracle_random_boards(eng):
+    rng = random.Random(11)
+    boards, piece, rot, col = [], [], [], []
+    nrot = [2, 4, 4, 4, 1, 2, 2]
+    for _ in range(3000):
+        hmax = rng.randint(0, 19)
+        rows = [0] * 20
+        for r in range(20 - hmax, 20):
+            v = rng.getrandbits(10) | rng.getrandbits(10)
+            rows[r] = v if v != 0x3FF else 0x3FE          # no pre-existing full rows
+        p = rng.randrange(7)
+        boards.append(rows); piece.append(p); rot.append(rng.randrange(nrot[p])); col.append(rng.randrange(10))
+    r = eng.eval_features(np.array(boards, dtype=np.uint16), piece, rot, col, want_rows=True)
+    nlegal = 0
+    for i in range(len(boards)):
+        o = coracle.eval_placement(boards[i], piece[i], rot[i], col[i])
+        if o is None:
+            assert r["legal"][i] != 1
+            continue
+        nlegal += 1
+        assert r["legal"][i] == 1 and r["row"][i] == o["row"] and r["k"][i] == o["k"]
+        assert (r["rows"][i] == o["post"]).all()
+        assert_same_doubles(r["features"][i], o["features"], "board %d" % i)
+    assert nlegal > 1000
+
+
+def test_k1_best_move_golden_steps(eng, golden_steps):
+    steps = golden_steps["steps"]
+    groups = {}
+    for s in steps:
+        groups.setdefault(tuple(n for n, _ in s["weights"]), []).append(s)
+    for names, ss in groups.items():
+        eng.set_features(names)
+        boards = np.array([s["board"] for s in ss], dtype=np.uint16)
+        piece = [s["piece"] for s in ss]
+        nxt = [s["next"] for s in ss]
+        w = np.array([[x for _, x in s["weights"]] for s in ss])
+        for key, la in (("l1", 1), ("l2", 2)):
+            r = eng.best_move(boards, piece, nxt if la == 2 else None, w, lookahead=la, want_rows=True)
+            for i, s in enumerate(ss):
+                want = s[key]
+                if want is None:
+                    if key == "l1":
+                        assert r["move"][i][1] == 255 and r["count"][i] == 0
+                    continue
+                assert tuple(int(x) for x in r["move"][i]) == (want["rot"], want["row"], want["col"], want["k"]), (key, i)
+                assert_same_doubles([r["score"][i]], [float.fromhex(want["score"])], "score")
+                if la == 1:
+                    assert r["count"][i] == want["n_legal"]
+                elif want["n_leaves"]:
+                    assert r["count"][i] == want["n_leaves"]
+
+
+@pytest.mark.parametrize("lanes", [32, 16, 8])
+def test_k2_golden_games(eng, golden_games, lanes):
+    for g in golden_games["games"]:
+        if g.get("tie") == "last":
+            continue
+        eng.set_features([n for n, _ in g["weights"]])
+        w = np.array([[x for _, x in g["weights"]]])
+        seq = np.array([pyoracle.piece_sequence(g["seed"], g["T"])], dtype=np.uint8)
+        r = eng.play_games(w, 1, pieces=seq, lookahead=g["lookahead"], lanes=lanes, want_trace=True, want_final=True)
+        res = r["results"][0]
+        assert int(res["pieces"]) == g["pieces"] and int(res["lines"]) == g["lines"]
+        assert [int(x) for x in res["hist"]] == g["hist"]
+        assert int(res["score"]) == g["score"] and int(res["placements"]) == g["scorer_calls"]
+        assert r["trace"][0, :g["pieces"]].tobytes().hex() == g["trace_hex"]
+        assert list(r["final"][0]) == g["final_board"]
+        assert r["fitness"][0] == g["lines"] / 1
+
+
+def _weight_sets(rng, n, names, kind):
+    if kind == "w6":
+        return [[rng.gauss(v, 1.0) for v in W6_VALS] for _ in range(n)]
+    if kind == "wide":
+        return [[rng.gauss(0, 10.0) for _ in names] for _ in range(n)]
+    return [[(W6_VALS[W6_NAMES.index(x)] if x in W6_NAMES else 0.0) + rng.gauss(0, 0.3) for x in names] for _ in range(n)]
+
+
+@pytest.mark.parametrize("lanes", [32, 16, 8])
+@pytest.mark.parametrize("names,kind,lookahead,C,G,T", [
+    (W6_NAMES, "w6", 1, 48, 4, 300),
+    (W6_NAMES, "wide", 1, 96, 4, 300),
+    (NAMES, "all45", 1, 24, 3, 200),
+    (["pits", "max_ht", "d_mean_ht", "mean_pit_depth", "pattern_div", "tetris_progress", "cd_4"], "wide", 1, 40, 3, 200),
+    (W6_NAMES, "w6", 2, 6, 2, 40),
+    (NAMES, "all45", 2, 4, 2, 25),
+])
+def test_k2_vs_coracle(eng, lanes, names, kind, lookahead, C, G, T):
+    rng = random.Random(hash((kind, lookahead, C)) & 0xFFFF)
+    fids = [pyoracle.FEATURE_ID[n] for n in names]
+    w = np.array(_weight_sets(rng, C, names, kind))
+    eng.set_features(names)
+    seed = 4242 + lookahead
+    r = eng.play_games(w, G, T=T, seed=seed, lookahead=lookahead, lanes=lanes, want_trace=True)
+    o = coracle.play_games(fids, w, G, T=T, seed=seed, lookahead=lookahead, threads=16, want_trace=True)
+    res = r["results"]
+    assert (res["pieces"] == o["pieces"]).all()
+    assert (res["lines"] == o["lines"]).all()
+    assert (res["hist"] == o["hist"]).all()
+    assert (res["score"] == o["score"]).all()
+    assert (res["placements"] == o["placements"]).all()
+    for g in range(C * G):
+        n = int(res["pieces"][g])
+        assert (r["trace"][g, :n] == o["trace"][g, :n]).all(), g
+    fit = o["lines"].reshape(C, G).sum(axis=1) / G
+    assert (r["fitness"] == fit).all()
+
+
+def test_k2_ce_generation_golden(eng, golden_ce):
+    """BASELINE config 2: generation 0 of the golden CE run (100 candidates x 10 games, T=1000)."""
+    ce = golden_ce["ce"]
+    rng = random.Random(ce["rng_seed"])
+    F = len(ce["features"])
+    pop = [[rng.gauss(0, ce["stdev"]) for _ in range(F)] for _ in range(ce["width"])]
+    seqs = np.array([pyoracle.piece_sequence(ce["seed0"] + g, ce["T"]) for g in range(ce["games"])], dtype=np.uint8)
+    eng.set_features(ce["features"])
+    r = eng.play_games(np.array(pop), ce["games"], pieces=seqs)
+    want = [float.fromhex(x) for x in ce["generations"][0]["fitness"]]
+    assert list(r["fitness"]) == want
+    assert int(r["results"]["placements"].sum()) == 775946 and int(r["results"]["pieces"].sum()) == 40087
+
+
+def test_k4_hashed_pieces(eng):
+    got = eng.hashed_pieces(seed=99, first_stream=5, n_streams=7, T=300)
+    for s in range(7):
+        assert list(got[s]) == [pyoracle.hashed_piece(99, 5 + s, t) for t in range(300)]
+
+
+def test_k2_many_games_vs_coracle(eng):
+    """20 000 concurrent games, each with its own candidate and its own hashed stream (config 5 shape)."""
+    rng = np.random.default_rng(99)
+    C = 20000
+    w = np.array(W6_VALS)[None, :] + rng.normal(0, 3.0, size=(C, 6))
+    fids = [pyoracle.FEATURE_ID[n] for n in W6_NAMES]
+    eng.set_features(W6_NAMES)
+    seqid = np.arange(C, dtype=np.int32)
+    r = eng.play_games(w, 1, T=150, seed=7, seq_of_game=seqid)
+    o = coracle.play_games(fids, w, 1, T=150, seed=7, seq_of_game=seqid, threads=16)
+    res = r["results"]
+    assert (res["pieces"] == o["pieces"]).all() and (res["lines"] == o["lines"]).all()
+    assert (res["score"] == o["score"]).all() and (res["placements"] == o["placements"]).all()
+
+
+def test_properties_full_size(eng):
+    """Size-independent properties at a size the oracle would not finish quickly:
+    lanes 8 / 16 / 32 give identical results; results do not depend on how games are batched."""
+    rng = np.random.default_rng(5)
+    C, G, T = 2000, 8, 600
+    w = np.array(W6_VALS)[None, :] + rng.normal(0, 2.0, size=(C, 6))
+    eng.set_features(W6_NAMES)
+    base = eng.play_games(w, G, T=T, seed=11, lanes=32)["results"]
+    for lanes in (16, 8):
+        other = eng.play_games(w, G, T=T, seed=11, lanes=lanes)["results"]
+        assert (other == base).all()
+    half = eng.play_games(w[:C // 2], G, T=T, seed=11)["results"]
+    assert (half == base[: C // 2 * G]).all()
+    assert (base["lines"] == (base["hist"] * np.array([1, 2, 3, 4])).sum(axis=1)).all()
+    assert (base["pieces"] <= T).all()

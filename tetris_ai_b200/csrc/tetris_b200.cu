@@ -1,0 +1,741 @@
+// tetris_b200.cu — kernels + C ABI of libtetris_b200.so (sm_100a only).
+//
+//   K2 play_games_kernel<LANES,MODE,LOOKAHEAD>  persistent, one LANES-wide lane group per game,
+//        placements fan out across the lanes, features by popc/clz bit formulas (tetris_core.cuh),
+//        fp64 dot product without FMA, shuffle argmax with the reference's first-of-max tie rule,
+//        dynamic game tickets (atomic counter) to absorb the heavy-tailed game lengths.
+//   K1 = K2 with per-game initial boards, two-piece sequences and max_moves = 1.
+//   K3 eval_features_kernel   one thread per (board, placement): all 45 features.
+//   K4 hashed_pieces_kernel   counter-based piece stream.
+//   fitness_kernel            per-candidate  sum(lines) / G.
+//
+// Reference lines replaced: see include/tetris_b200.h.  There is no CPU path in this file.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <new>
+
+#include "tetris_core.cuh"
+#include "../../include/tetris_b200.h"
+
+namespace tb {
+
+#define FULLMASK 0xffffffffu
+constexpr int BLOCK = 128;
+
+__constant__ Tables c_tables;
+
+struct PlayParams {
+    const double*  weights;
+    const uint8_t* pieces;
+    const int32_t* seq_of_game;
+    const uint16_t* init_rows;
+    tb200_game_result* results;
+    uint8_t*  trace;
+    double*   score_trace;
+    uint16_t* final_rows;
+    uint32_t* ticket;
+    uint64_t  seed;
+    uint64_t  rmask;
+    uint32_t  n_games;
+    uint32_t  T;
+    uint32_t  max_moves;
+    int32_t   G;
+    int32_t   F;
+    int32_t   per_game_weights;      // K1 (one game per board, sequence id = game): weights row = game (1) or row 0 (-1); K2: 0
+    uint8_t   ids[TB200_MAX_WEIGHTED];
+};
+
+// ---- argmax over a LANES-wide group: maximise key, ties -> smallest tag (first in enumeration order)
+template <int LANES>
+TB_D void group_argmax(uint64_t& key, uint32_t& tag)
+{
+#pragma unroll
+    for (int off = LANES / 2; off > 0; off >>= 1) {
+        const uint32_t ohi = __shfl_xor_sync(FULLMASK, (uint32_t)(key >> 32), off);
+        const uint32_t olo = __shfl_xor_sync(FULLMASK, (uint32_t)key, off);
+        const uint32_t otag = __shfl_xor_sync(FULLMASK, tag, off);
+        const uint64_t okey = ((uint64_t)ohi << 32) | olo;
+        if (okey > key || (okey == key && otag < tag)) { key = okey; tag = otag; }
+    }
+}
+
+TB_D SlotDesc load_slot(const Tables& tab, int piece, int s)
+{
+    const uint4* p = reinterpret_cast<const uint4*>(&tab.slot[piece][s]);
+    const uint4 a = p[0], b = p[1];
+    SlotDesc d;
+    d.w[0] = a.x; d.w[1] = a.y; d.w[2] = a.z; d.w[3] = a.w; d.w[4] = b.x; d.w[5] = b.y; d.w[6] = b.z; d.w[7] = b.w;
+    return d;
+}
+
+// layer-1 search: every legal (rot, col) slot of `piece` on board c, scored as a leaf whose
+// previous state is the board itself.  Lanes take slots gl, gl+LANES, ...; strict > keeps the
+// earliest slot inside a lane.
+template <int LANES, int MODE>
+TB_D void search_one(const uint32_t c[COLS], const Heights& H, const PrevStat& pv, int piece, int gl,
+                     const Tables& tab, const uint8_t* ids, const double* w, int F, uint64_t rmask,
+                     uint32_t tag_hi, uint64_t& key, uint32_t& tag, uint32_t& cnt)
+{
+    const int ns = tab.nslots[piece];
+    for (int s = gl; s < ns; s += LANES) {
+        const SlotDesc d = load_slot(tab, piece, s);
+        Placement P;
+        if (place_slot(c, H, d, P)) {
+            Feat f;
+            eval_features<ModeTraits<MODE>::CMASK>(P, pv, rmask, f);
+            const uint64_t k = score_key(score_features<MODE>(f, ids, w, F));
+            if (k > key) { key = k; tag = tag_hi | (uint32_t)s; }
+            ++cnt;
+        }
+    }
+}
+
+template <int LANES, int MODE, int LOOKAHEAD>
+__global__ void __launch_bounds__(BLOCK) play_games_kernel(const PlayParams prm)
+{
+    constexpr int GROUPS = BLOCK / LANES;
+    __shared__ Tables s_tab;
+    __shared__ double s_w[MODE == MODE_W6 ? 1 : GROUPS][MODE == MODE_W6 ? 1 : TB200_MAX_WEIGHTED];
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (LANES - 1);
+    const int grp = threadIdx.x / LANES;
+    const int F = prm.F;
+    const uint32_t T = prm.T;
+
+    // per-game state (identical in every lane of the group)
+    bool active = false, exhausted = false;
+    uint32_t game = 0, t = 0, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+    uint64_t gscore = 0, stream = 0;
+    const uint8_t* seq = nullptr;
+    uint32_t c[COLS];
+    Heights H; PrevStat pv;
+    double wreg[6];
+    int p_cur = 0, p_next = 0;
+
+    auto fetch_piece = [&](uint32_t tt) -> int {
+        if (tt >= T) return 0;
+        return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, stream, tt);
+    };
+
+    for (;;) {
+        // ---- ticket: groups without a game fetch the next one (shuffles stay warp-convergent) ----
+        const bool want = !active && !exhausted;
+        uint32_t g = 0;
+        if (want && gl == 0) g = atomicAdd(prm.ticket, 1u);
+        g = __shfl_sync(FULLMASK, g, 0, LANES);
+        __syncwarp(FULLMASK);                    // previous game's reads of s_w are complete
+        if (want) {
+            if (g < prm.n_games) {
+                game = g; active = true; t = 0; lines = h1 = h2 = h3 = h4 = 0; cnt = 0; gscore = 0;
+                const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[g] : (prm.per_game_weights != 0 ? g : g % (uint32_t)prm.G);
+                stream = sq;
+                seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
+                if (prm.init_rows) {
+                    uint16_t rows[ROWS];
+                    for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)g * ROWS + r];
+                    rows_to_cols(rows, c);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < COLS; ++k) c[k] = 0;
+                }
+                H = pack_heights(c); pv = prev_stat(c);
+                const size_t wrow = prm.per_game_weights > 0 ? (size_t)g : (prm.per_game_weights < 0 ? 0 : (size_t)(g / (uint32_t)prm.G));
+                const double* wsrc = prm.weights + wrow * (size_t)F;
+                if (MODE == MODE_W6) {
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) wreg[i] = __ldg(wsrc + i);
+                } else {
+                    for (int i = gl; i < F; i += LANES) s_w[MODE == MODE_W6 ? 0 : grp][i] = __ldg(wsrc + i);
+                }
+                p_cur = fetch_piece(0); p_next = fetch_piece(1);
+            } else {
+                exhausted = true;
+            }
+        }
+        __syncwarp(FULLMASK);                    // s_w of a freshly started game is visible to its group
+        if (!__any_sync(FULLMASK, active)) break;
+
+        const double* w = MODE == MODE_W6 ? wreg : s_w[MODE == MODE_W6 ? 0 : grp];
+        const int p_after = active ? fetch_piece(t + 2) : 0;      // prefetch: consumed two steps later
+
+        uint64_t key = 0; uint32_t tag = 0;
+        if (LOOKAHEAD == 2) {
+            if (active && t + 1 < T && p_cur < 7 && p_next < 7) {
+                const int ns1 = s_tab.nslots[p_cur];
+                for (int s1 = 0; s1 < ns1; ++s1) {
+                    const SlotDesc d1 = load_slot(s_tab, p_cur, s1);
+                    Placement P1;
+                    if (!place_slot(c, H, d1, P1)) continue;
+                    const Heights H1 = pack_heights(P1.n);
+                    const PrevStat pv1 = prev_stat(P1.n);
+                    search_one<LANES, MODE>(P1.n, H1, pv1, p_next, gl, s_tab, prm.ids, w, F, prm.rmask,
+                                            (uint32_t)s1 << 6, key, tag, cnt);
+                }
+            }
+            group_argmax<LANES>(key, tag);
+        }
+        const bool need_l1 = active && p_cur < 7 && (LOOKAHEAD == 1 || key == 0);
+        if (LOOKAHEAD == 1 || __any_sync(FULLMASK, need_l1)) {
+            uint64_t k1 = 0; uint32_t t1 = 0;
+            if (need_l1) search_one<LANES, MODE>(c, H, pv, p_cur, gl, s_tab, prm.ids, w, F, prm.rmask, 0u, k1, t1, cnt);
+            group_argmax<LANES>(k1, t1);
+            if (need_l1) { key = k1; tag = t1 << 6; }
+        }
+
+        if (active) {
+            bool finish = false;
+            if (key == 0) {
+                finish = true;                                   // no legal placement: game over (simulator.py:187-189)
+            } else {
+                const int s1 = (int)(tag >> 6);
+                const SlotDesc d1 = load_slot(s_tab, p_cur, s1);
+                Placement P;
+                place_slot(c, H, d1, P);
+#pragma unroll
+                for (int k = 0; k < COLS; ++k) c[k] = P.n[k];
+                H = pack_heights(c); pv = prev_stat(c);
+                lines += (uint32_t)P.k;
+                h1 += P.k == 1; h2 += P.k == 2; h3 += P.k == 3; h4 += P.k == 4;
+                const uint32_t pts = P.k == 0 ? 0u : (P.k == 1 ? 40u : (P.k == 2 ? 100u : (P.k == 3 ? 300u : 1200u)));
+                gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);          // game.py:159-164
+                if (gl == 0) {
+                    if (prm.trace) {
+                        const uint32_t row = (uint32_t)(ROWS - P.y - P.ph);
+                        const uint32_t rec = (uint32_t)P.rot | row << 8 | (uint32_t)P.c0 << 16 | (uint32_t)P.k << 24;
+                        reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = rec;
+                    }
+                    if (prm.score_trace) {
+                        const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
+                        prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
+                    }
+                }
+                ++t;
+                p_cur = p_next; p_next = p_after;
+                if (t >= T || t >= prm.max_moves) finish = true;
+            }
+            if (finish) {
+                if (gl == 0) {
+                    tb200_game_result* r = prm.results + game;
+                    r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4;
+                    r->score = gscore;
+                    if (prm.final_rows) {
+                        uint16_t rows[ROWS];
+                        cols_to_rows(c, rows);
+                        for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2];
+                    }
+                }
+                if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&prm.results[game].placements), (unsigned long long)cnt);
+                active = false;
+            }
+        }
+    }
+}
+
+// K3: all 45 features of one placement per thread
+__global__ void eval_features_kernel(int N, const uint16_t* prev_boards, const uint8_t* piece, const uint8_t* rot,
+                                     const uint8_t* col, double* out_features, int32_t* out_info, uint16_t* out_rows)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    uint16_t rows[ROWS];
+    for (int r = 0; r < ROWS; ++r) rows[r] = prev_boards[(size_t)i * ROWS + r];
+    uint32_t c[COLS];
+    rows_to_cols(rows, c);
+    const Heights H = pack_heights(c);
+    const PrevStat pv = prev_stat(c);
+    const int p = piece[i];
+    int legal = 0, row = -1, k = 0;
+    Feat f;
+    Placement P;
+    bool found = false;
+    if (p < 7) {
+        const int ns = c_tables.nslots[p];
+        for (int s = 0; s < ns; ++s) {
+            const SlotDesc d = c_tables.slot[p][s];
+            if ((int)((d.w[0] >> 4) & 3u) == (int)rot[i] && (int)(d.w[0] & 15u) == (int)col[i]) {
+                found = true;
+                if (place_slot(c, H, d, P)) { legal = 1; row = ROWS - P.y - P.ph; k = P.k; }
+                break;
+            }
+        }
+    }
+    if (legal) {
+        eval_features<0>(P, pv, ALL45_MASK, f);
+        for (int j = 0; j < NFEAT; ++j) out_features[(size_t)i * NFEAT + j] = feat_value(f, j);
+        if (out_rows) { cols_to_rows(P.n, rows); for (int r = 0; r < ROWS; ++r) out_rows[(size_t)i * ROWS + r] = rows[r]; }
+    } else {
+        for (int j = 0; j < NFEAT; ++j) out_features[(size_t)i * NFEAT + j] = 0.0;
+        if (out_rows) for (int r = 0; r < ROWS; ++r) out_rows[(size_t)i * ROWS + r] = rows[r];
+    }
+    out_info[(size_t)i * 3 + 0] = found ? legal : -1;
+    out_info[(size_t)i * 3 + 1] = row;
+    out_info[(size_t)i * 3 + 2] = k;
+}
+
+// K4
+__global__ void hashed_pieces_kernel(uint64_t seed, uint64_t first_stream, int n_streams, uint32_t T, uint8_t* out)
+{
+    const size_t total = (size_t)n_streams * T;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint64_t s = i / T, t = i % T;
+        out[i] = (uint8_t)hashed_piece(seed, first_stream + s, t);
+    }
+}
+
+// fitness[c] = sum(lines of its G games) / G   (one exact int sum, one fp64 division)
+__global__ void fitness_kernel(int C, int G, const tb200_game_result* res, double* fitness)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    long long s = 0;
+    for (int g = 0; g < G; ++g) s += res[(size_t)c * G + g].lines;
+    fitness[c] = __ddiv_rn((double)s, (double)G);
+}
+
+// K1 prologue: sequence of board i = {piece[i], next[i] or 255}
+__global__ void pair_pieces_kernel(int N, const uint8_t* piece, const uint8_t* next, uint8_t* seq)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    seq[2 * (size_t)i] = piece[i];
+    seq[2 * (size_t)i + 1] = next ? next[i] : (uint8_t)255;
+}
+
+// K1 epilogue: repack per-game outputs of a max_moves = 1 play into the best_move layout
+__global__ void best_move_pack_kernel(int N, const tb200_game_result* res, const uint32_t* trace, const double* strace,
+                                      uint8_t* out_move, double* out_score, uint32_t* out_count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const bool moved = res[i].pieces > 0;
+    const uint32_t rec = moved ? trace[(size_t)i * 2] : 0x0000ff00u;
+    reinterpret_cast<uint32_t*>(out_move)[i] = rec;
+    if (out_score) out_score[i] = moved ? strace[(size_t)i * 2] : 0.0;
+    if (out_count) out_count[i] = (uint32_t)res[i].placements;
+}
+
+typedef void (*play_fn)(const PlayParams);
+template <int MODE, int LOOKAHEAD>
+static play_fn pick_lanes(int lanes)
+{
+    switch (lanes) {
+    case 8:  return play_games_kernel<8, MODE, LOOKAHEAD>;
+    case 16: return play_games_kernel<16, MODE, LOOKAHEAD>;
+    default: return play_games_kernel<32, MODE, LOOKAHEAD>;
+    }
+}
+static play_fn pick_kernel(int mode, int lookahead, int lanes)
+{
+    if (lookahead == 2) {
+        if (mode == MODE_W6) return pick_lanes<MODE_W6, 2>(lanes);
+        if (mode == MODE_ALL45) return pick_lanes<MODE_ALL45, 2>(lanes);
+        return pick_lanes<MODE_GENERIC, 2>(lanes);
+    }
+    if (mode == MODE_W6) return pick_lanes<MODE_W6, 1>(lanes);
+    if (mode == MODE_ALL45) return pick_lanes<MODE_ALL45, 1>(lanes);
+    return pick_lanes<MODE_GENERIC, 1>(lanes);
+}
+
+}  // namespace tb
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+struct tb200_ctx {
+    int device = 0;
+    int sms = 0;
+    int clock_khz = 0;
+    char name[128] = {0};
+    std::string err;
+    int F = 0;
+    int mode = tb::MODE_GENERIC;
+    uint64_t rmask = 0;
+    uint8_t ids[TB200_MAX_WEIGHTED] = {0};
+    uint32_t* d_ticket = nullptr;
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool timing_valid = false;
+    tb200_timing timing{};
+    // staging arena for TB200_MEM_HOST calls (grown on demand, reused across calls)
+    char* d_arena = nullptr;
+    size_t arena_cap = 0;
+};
+
+static int fail(tb200_ctx* ctx, int code, const std::string& msg)
+{
+    if (ctx) ctx->err = msg;
+    return code;
+}
+#define TB_CUDA(ctx, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(ctx, TB200_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int ensure_arena(tb200_ctx* ctx, size_t bytes)
+{
+    if (bytes <= ctx->arena_cap) return TB200_OK;
+    if (ctx->d_arena) { TB_CUDA(ctx, cudaFree(ctx->d_arena)); ctx->d_arena = nullptr; ctx->arena_cap = 0; }
+    const size_t cap = bytes + bytes / 4 + (1u << 20);
+    TB_CUDA(ctx, cudaMalloc(&ctx->d_arena, cap));
+    ctx->arena_cap = cap;
+    return TB200_OK;
+}
+
+extern "C" {
+
+const char* tb200_version(void) { return "tetris_b200 0.1 (sm_100a)"; }
+
+int tb200_create(int device, tb200_ctx** out)
+{
+    if (!out) return TB200_E_BAD_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return TB200_E_NO_DEVICE;
+    tb200_ctx* ctx = new (std::nothrow) tb200_ctx();
+    if (!ctx) return TB200_E_ALLOC;
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return TB200_E_NO_DEVICE; }
+    ctx->sms = prop.multiProcessorCount;
+    cudaDeviceGetAttribute(&ctx->clock_khz, cudaDevAttrClockRate, device);
+    strncpy(ctx->name, prop.name, sizeof(ctx->name) - 1);
+    static const tb::Tables host_tab = { TB_SLOT_TABLE_INIT, TB_NSLOTS_INIT };
+    cudaError_t e = cudaMemcpyToSymbol(tb::c_tables, &host_tab, sizeof(tb::Tables));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_ticket, sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "tb200_create: %s\n", cudaGetErrorString(e));
+        tb200_destroy(ctx);
+        return TB200_E_CUDA;
+    }
+    *out = ctx;
+    return TB200_OK;
+}
+
+void tb200_destroy(tb200_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->d_ticket) cudaFree(ctx->d_ticket);
+    if (ctx->d_arena) cudaFree(ctx->d_arena);
+    for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* tb200_last_error(const tb200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+int tb200_device_info(tb200_ctx* ctx, int32_t* sms, int32_t* clock_khz, char* name, int32_t name_len)
+{
+    if (!ctx) return TB200_E_BAD_ARG;
+    if (sms) *sms = ctx->sms;
+    if (clock_khz) *clock_khz = ctx->clock_khz;
+    if (name && name_len > 0) { strncpy(name, ctx->name, (size_t)name_len - 1); name[name_len - 1] = 0; }
+    return TB200_OK;
+}
+
+int tb200_set_features(tb200_ctx* ctx, const int32_t* feature_ids, int32_t F)
+{
+    if (!ctx) return TB200_E_BAD_ARG;
+    if (!feature_ids || F < 1 || F > TB200_MAX_WEIGHTED) return fail(ctx, TB200_E_BAD_ARG, "set_features: F must be 1..48");
+    uint64_t mask = 0;
+    for (int i = 0; i < F; ++i) {
+        if (feature_ids[i] < 0 || feature_ids[i] >= TB200_NUM_FEATURES) return fail(ctx, TB200_E_BAD_ARG, "set_features: feature id out of range");
+        ctx->ids[i] = (uint8_t)feature_ids[i];
+        mask |= 1ull << feature_ids[i];
+    }
+    ctx->F = F; ctx->rmask = mask;
+    static const int w6[6] = {tb::F_LANDING_HEIGHT, tb::F_ERODED_CELLS, tb::F_ROW_TRANS, tb::F_COL_TRANS, tb::F_PITS, tb::F_CUML_WELLS};
+    bool is_w6 = F == 6, is_all = F == TB200_NUM_FEATURES;
+    for (int i = 0; i < F && is_w6; ++i) is_w6 = feature_ids[i] == w6[i];
+    for (int i = 0; i < F && is_all; ++i) is_all = feature_ids[i] == i;
+    ctx->mode = is_w6 ? tb::MODE_W6 : (is_all ? tb::MODE_ALL45 : tb::MODE_GENERIC);
+    return TB200_OK;
+}
+
+int tb200_last_timing(tb200_ctx* ctx, tb200_timing* out)
+{
+    if (!ctx || !out) return TB200_E_BAD_ARG;
+    if (!ctx->timing_valid) return fail(ctx, TB200_E_BAD_ARG, "last_timing: no play_games call yet");
+    if (cudaEventSynchronize(ctx->ev[1]) == cudaSuccess) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->timing.kernel_ms = ms;
+    }
+    *out = ctx->timing;
+    return TB200_OK;
+}
+
+// launch K2 (+ optional fitness) on device buffers
+static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st, int per_game_weights, int* launches)
+{
+    const long long n_games_ll = (long long)a.n_candidates * a.games_per_candidate;
+    const uint32_t n_games = (uint32_t)n_games_ll;
+    int lanes = a.lanes;
+    if (lanes != 8 && lanes != 16 && lanes != 32) {
+        // auto: one warp per game while the whole population fits in one resident wave (lowest latency
+        // per piece), narrower groups when there are more games than resident warps (throughput).
+        const long long resident_warps = (long long)ctx->sms * 16;
+        lanes = n_games_ll <= resident_warps ? 32 : (n_games_ll <= 2 * resident_warps ? 16 : 8);
+    }
+    tb::play_fn fn = tb::pick_kernel(ctx->mode, a.lookahead, lanes);
+    int occ = 0;
+    TB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, tb::BLOCK, 0));
+    if (occ < 1) occ = 1;
+    const int groups_per_block = tb::BLOCK / lanes;
+    long long blocks = (n_games_ll + groups_per_block - 1) / groups_per_block;
+    const long long max_blocks = (long long)ctx->sms * occ;
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks < 1) blocks = 1;
+
+    tb::PlayParams p;
+    memset(&p, 0, sizeof p);
+    p.weights = a.weights; p.pieces = a.pieces; p.seq_of_game = a.seq_of_game; p.init_rows = a.init_rows;
+    p.results = a.results; p.trace = a.trace; p.score_trace = a.score_trace; p.final_rows = a.final_rows;
+    p.ticket = ctx->d_ticket; p.seed = a.seed; p.rmask = ctx->rmask; p.n_games = n_games; p.T = a.T;
+    p.max_moves = a.max_moves ? a.max_moves : a.T; p.G = a.games_per_candidate; p.F = ctx->F;
+    p.per_game_weights = per_game_weights;
+    memcpy(p.ids, ctx->ids, sizeof p.ids);
+
+    TB_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(uint32_t), st));
+    TB_CUDA(ctx, cudaMemsetAsync(a.results, 0, sizeof(tb200_game_result) * (size_t)n_games, st));
+    TB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    fn<<<(unsigned)blocks, tb::BLOCK, 0, st>>>(p);
+    TB_CUDA(ctx, cudaGetLastError());
+    TB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    *launches += 1;
+    if (a.fitness) {
+        tb::fitness_kernel<<<(a.n_candidates + 127) / 128, 128, 0, st>>>(a.n_candidates, a.games_per_candidate, a.results, a.fitness);
+        TB_CUDA(ctx, cudaGetLastError());
+        *launches += 1;
+    }
+    ctx->timing.lanes = lanes; ctx->timing.grid = (int)blocks; ctx->timing.block = tb::BLOCK;
+    return TB200_OK;
+}
+
+static int check_play_args(tb200_ctx* ctx, const tb200_play_args* a)
+{
+    if (!a || a->struct_size != sizeof(tb200_play_args)) return fail(ctx, TB200_E_BAD_ARG, "play_games: bad struct_size");
+    if (ctx->F <= 0) return fail(ctx, TB200_E_NO_FEATURES, "play_games: call tb200_set_features first");
+    if (a->n_candidates < 1 || a->games_per_candidate < 1) return fail(ctx, TB200_E_BAD_ARG, "play_games: C and G must be >= 1");
+    if ((long long)a->n_candidates * a->games_per_candidate > 0x7fffffffLL) return fail(ctx, TB200_E_BAD_ARG, "play_games: too many games");
+    if (!a->weights || !a->results) return fail(ctx, TB200_E_BAD_ARG, "play_games: weights and results are required");
+    if (a->T < 1) return fail(ctx, TB200_E_BAD_ARG, "play_games: T must be >= 1");
+    if (a->lookahead != 1 && a->lookahead != 2) return fail(ctx, TB200_E_BAD_ARG, "play_games: lookahead must be 1 or 2");
+    if (a->pieces && a->n_sequences < 1) return fail(ctx, TB200_E_BAD_ARG, "play_games: n_sequences must be >= 1 with explicit pieces");
+    if (a->pieces && !a->seq_of_game && a->n_sequences < a->games_per_candidate) return fail(ctx, TB200_E_BAD_ARG, "play_games: need S >= G without seq_of_game");
+    if (a->mem != TB200_MEM_HOST && a->mem != TB200_MEM_DEVICE) return fail(ctx, TB200_E_BAD_ARG, "play_games: bad mem");
+    return TB200_OK;
+}
+
+int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
+{
+    if (!ctx) return TB200_E_BAD_ARG;
+    int rc = check_play_args(ctx, args);
+    if (rc) return rc;
+    TB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const tb200_play_args& a = *args;
+    const size_t n_games = (size_t)a.n_candidates * a.games_per_candidate;
+    ctx->timing = tb200_timing{};
+    ctx->timing_valid = false;
+    int launches = 0;
+    if (a.mem == TB200_MEM_DEVICE) {
+        rc = launch_play(ctx, a, (cudaStream_t)a.stream, 0, &launches);
+        if (rc) return rc;
+        ctx->timing.kernels_launched = launches;
+        ctx->timing_valid = true;
+        return TB200_OK;
+    }
+    // ---- host buffers: stage through the ctx arena on the ctx's own stream; synchronous ----------
+    cudaStream_t st = ctx->own_stream;
+    const size_t b_w = sizeof(double) * (size_t)a.n_candidates * ctx->F;
+    const size_t b_p = a.pieces ? (size_t)a.n_sequences * a.T : 0;
+    const size_t b_s = a.seq_of_game ? sizeof(int32_t) * n_games : 0;
+    const size_t b_i = a.init_rows ? sizeof(uint16_t) * TB200_ROWS * n_games : 0;
+    const size_t b_r = sizeof(tb200_game_result) * n_games;
+    const size_t b_t = a.trace ? 4 * (size_t)a.T * n_games : 0;
+    const size_t b_st = a.score_trace ? sizeof(double) * (size_t)a.T * n_games : 0;
+    const size_t b_f = a.final_rows ? sizeof(uint16_t) * TB200_ROWS * n_games : 0;
+    const size_t b_fit = a.fitness ? sizeof(double) * (size_t)a.n_candidates : 0;
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off += align_up(b); return o; };
+    const size_t o_w = take(b_w), o_p = take(b_p), o_s = take(b_s), o_i = take(b_i), o_r = take(b_r), o_t = take(b_t),
+                 o_st = take(b_st), o_f = take(b_f), o_fit = take(b_fit);
+    rc = ensure_arena(ctx, off);
+    if (rc) return rc;
+    char* base = ctx->d_arena;
+    tb200_play_args d = a;
+    d.mem = TB200_MEM_DEVICE;
+    d.weights = (const double*)(base + o_w);
+    d.pieces = a.pieces ? (const uint8_t*)(base + o_p) : nullptr;
+    d.seq_of_game = a.seq_of_game ? (const int32_t*)(base + o_s) : nullptr;
+    d.init_rows = a.init_rows ? (const uint16_t*)(base + o_i) : nullptr;
+    d.results = (tb200_game_result*)(base + o_r);
+    d.trace = a.trace ? (uint8_t*)(base + o_t) : nullptr;
+    d.score_trace = a.score_trace ? (double*)(base + o_st) : nullptr;
+    d.final_rows = a.final_rows ? (uint16_t*)(base + o_f) : nullptr;
+    d.fitness = a.fitness ? (double*)(base + o_fit) : nullptr;
+
+    TB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    TB_CUDA(ctx, cudaMemcpyAsync((void*)d.weights, a.weights, b_w, cudaMemcpyHostToDevice, st));
+    if (b_p) TB_CUDA(ctx, cudaMemcpyAsync((void*)d.pieces, a.pieces, b_p, cudaMemcpyHostToDevice, st));
+    if (b_s) TB_CUDA(ctx, cudaMemcpyAsync((void*)d.seq_of_game, a.seq_of_game, b_s, cudaMemcpyHostToDevice, st));
+    if (b_i) TB_CUDA(ctx, cudaMemcpyAsync((void*)d.init_rows, a.init_rows, b_i, cudaMemcpyHostToDevice, st));
+    if (b_t) TB_CUDA(ctx, cudaMemsetAsync(d.trace, 0, b_t, st));
+    if (b_st) TB_CUDA(ctx, cudaMemsetAsync(d.score_trace, 0, b_st, st));
+    rc = launch_play(ctx, d, st, 0, &launches);
+    if (rc) return rc;
+    TB_CUDA(ctx, cudaMemcpyAsync(a.results, d.results, b_r, cudaMemcpyDeviceToHost, st));
+    if (b_t) TB_CUDA(ctx, cudaMemcpyAsync(a.trace, d.trace, b_t, cudaMemcpyDeviceToHost, st));
+    if (b_st) TB_CUDA(ctx, cudaMemcpyAsync(a.score_trace, d.score_trace, b_st, cudaMemcpyDeviceToHost, st));
+    if (b_f) TB_CUDA(ctx, cudaMemcpyAsync(a.final_rows, d.final_rows, b_f, cudaMemcpyDeviceToHost, st));
+    if (b_fit) TB_CUDA(ctx, cudaMemcpyAsync(a.fitness, d.fitness, b_fit, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    TB_CUDA(ctx, cudaStreamSynchronize(st));
+    float ms = 0.f;
+    TB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+    ctx->timing.total_ms = ms;
+    ctx->timing.h2d_bytes = b_w + b_p + b_s + b_i;
+    ctx->timing.d2h_bytes = b_r + b_t + b_st + b_f + b_fit;
+    ctx->timing.kernels_launched = launches;
+    ctx->timing_valid = true;
+    return TB200_OK;
+}
+
+int tb200_best_move(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
+                    const uint16_t* boards, const uint8_t* piece, const uint8_t* next,
+                    const double* weights, int32_t per_board_weights, int32_t lookahead,
+                    uint8_t* out_move, double* out_score, uint32_t* out_count, uint16_t* out_rows)
+{
+    if (!ctx) return TB200_E_BAD_ARG;
+    if (ctx->F <= 0) return fail(ctx, TB200_E_NO_FEATURES, "best_move: call tb200_set_features first");
+    if (N < 1 || !boards || !piece || !weights || !out_move) return fail(ctx, TB200_E_BAD_ARG, "best_move: missing argument");
+    if (lookahead != 1 && lookahead != 2) return fail(ctx, TB200_E_BAD_ARG, "best_move: lookahead must be 1 or 2");
+    if (mem != TB200_MEM_HOST && mem != TB200_MEM_DEVICE) return fail(ctx, TB200_E_BAD_ARG, "best_move: bad mem");
+    TB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool host = mem == TB200_MEM_HOST;
+    cudaStream_t st = host ? ctx->own_stream : (cudaStream_t)stream;
+    const size_t n = (size_t)N;
+    const size_t nw = per_board_weights ? n : 1;
+    // arena: [staged inputs/outputs when host] + internal (pieces[N][2], results, trace[N][2], strace[N][2])
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off += align_up(b); return o; };
+    const size_t o_seq = take(2 * n), o_res = take(sizeof(tb200_game_result) * n), o_tr = take(8 * n), o_str = take(16 * n);
+    const size_t o_b = take(host ? 40 * n : 0), o_p = take(host ? n : 0), o_n = take(host && next ? n : 0),
+                 o_w = take(host ? sizeof(double) * nw * ctx->F : 0), o_mv = take(host ? 4 * n : 0),
+                 o_sc = take(host && out_score ? 8 * n : 0), o_ct = take(host && out_count ? 4 * n : 0),
+                 o_rows = take(host && out_rows ? 40 * n : 0);
+    int rc = ensure_arena(ctx, off);
+    if (rc) return rc;
+    char* base = ctx->d_arena;
+    const uint16_t* d_boards = boards; const uint8_t* d_piece = piece; const uint8_t* d_next = next; const double* d_w = weights;
+    uint8_t* d_mv = out_move; double* d_sc = out_score; uint32_t* d_ct = out_count; uint16_t* d_rows = out_rows;
+    if (host) {
+        d_boards = (const uint16_t*)(base + o_b); d_piece = (const uint8_t*)(base + o_p); d_next = next ? (const uint8_t*)(base + o_n) : nullptr;
+        d_w = (const double*)(base + o_w); d_mv = (uint8_t*)(base + o_mv); d_sc = out_score ? (double*)(base + o_sc) : nullptr;
+        d_ct = out_count ? (uint32_t*)(base + o_ct) : nullptr; d_rows = out_rows ? (uint16_t*)(base + o_rows) : nullptr;
+        TB_CUDA(ctx, cudaMemcpyAsync((void*)d_boards, boards, 40 * n, cudaMemcpyHostToDevice, st));
+        TB_CUDA(ctx, cudaMemcpyAsync((void*)d_piece, piece, n, cudaMemcpyHostToDevice, st));
+        if (next) TB_CUDA(ctx, cudaMemcpyAsync((void*)d_next, next, n, cudaMemcpyHostToDevice, st));
+        TB_CUDA(ctx, cudaMemcpyAsync((void*)d_w, weights, sizeof(double) * nw * ctx->F, cudaMemcpyHostToDevice, st));
+    }
+    // two-piece sequence per board: {piece, next}; T = 2 when a next piece is visible for lookahead 2, else 1.
+    uint8_t* d_seq = (uint8_t*)(base + o_seq);
+    tb::pair_pieces_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, d_piece, d_next, d_seq);
+    TB_CUDA(ctx, cudaGetLastError());
+    tb200_play_args a;
+    memset(&a, 0, sizeof a);
+    a.struct_size = sizeof a; a.mem = TB200_MEM_DEVICE; a.stream = st;
+    a.n_candidates = N; a.games_per_candidate = 1; a.weights = d_w; a.pieces = d_seq; a.n_sequences = N;
+    a.T = 2; a.max_moves = 1; a.lookahead = lookahead; a.lanes = 0; a.init_rows = d_boards;
+    a.results = (tb200_game_result*)(base + o_res); a.trace = (uint8_t*)(base + o_tr); a.score_trace = (double*)(base + o_str);
+    a.final_rows = d_rows;
+    int launches = 1;
+    ctx->timing = tb200_timing{};
+    rc = launch_play(ctx, a, st, per_board_weights ? 1 : -1, &launches);
+    if (rc) return rc;
+    tb::best_move_pack_kernel<<<(N + 127) / 128, 128, 0, st>>>(N, a.results, (const uint32_t*)a.trace, a.score_trace, d_mv, d_sc, d_ct);
+    TB_CUDA(ctx, cudaGetLastError());
+    launches += 1;
+    ctx->timing.kernels_launched = launches;
+    ctx->timing_valid = true;
+    if (host) {
+        TB_CUDA(ctx, cudaMemcpyAsync(out_move, d_mv, 4 * n, cudaMemcpyDeviceToHost, st));
+        if (out_score) TB_CUDA(ctx, cudaMemcpyAsync(out_score, d_sc, 8 * n, cudaMemcpyDeviceToHost, st));
+        if (out_count) TB_CUDA(ctx, cudaMemcpyAsync(out_count, d_ct, 4 * n, cudaMemcpyDeviceToHost, st));
+        if (out_rows) TB_CUDA(ctx, cudaMemcpyAsync(out_rows, d_rows, 40 * n, cudaMemcpyDeviceToHost, st));
+        TB_CUDA(ctx, cudaStreamSynchronize(st));
+    }
+    return TB200_OK;
+}
+
+int tb200_eval_features(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
+                        const uint16_t* prev_boards, const uint8_t* piece, const uint8_t* rot, const uint8_t* col,
+                        double* out_features, int32_t* out_info, uint16_t* out_rows)
+{
+    if (!ctx) return TB200_E_BAD_ARG;
+    if (N < 1 || !prev_boards || !piece || !rot || !col || !out_features || !out_info) return fail(ctx, TB200_E_BAD_ARG, "eval_features: missing argument");
+    if (mem != TB200_MEM_HOST && mem != TB200_MEM_DEVICE) return fail(ctx, TB200_E_BAD_ARG, "eval_features: bad mem");
+    TB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)N;
+    if (mem == TB200_MEM_DEVICE) {
+        tb::eval_features_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, prev_boards, piece, rot, col, out_features, out_info, out_rows);
+        TB_CUDA(ctx, cudaGetLastError());
+        return TB200_OK;
+    }
+    cudaStream_t st = ctx->own_stream;
+    size_t off = 0;
+    auto take = [&](size_t b) { size_t o = off; off += align_up(b); return o; };
+    const size_t o_b = take(40 * n), o_p = take(n), o_r = take(n), o_c = take(n), o_f = take(8 * 45 * n), o_i = take(12 * n), o_rows = take(out_rows ? 40 * n : 0);
+    int rc = ensure_arena(ctx, off);
+    if (rc) return rc;
+    char* base = ctx->d_arena;
+    TB_CUDA(ctx, cudaMemcpyAsync(base + o_b, prev_boards, 40 * n, cudaMemcpyHostToDevice, st));
+    TB_CUDA(ctx, cudaMemcpyAsync(base + o_p, piece, n, cudaMemcpyHostToDevice, st));
+    TB_CUDA(ctx, cudaMemcpyAsync(base + o_r, rot, n, cudaMemcpyHostToDevice, st));
+    TB_CUDA(ctx, cudaMemcpyAsync(base + o_c, col, n, cudaMemcpyHostToDevice, st));
+    tb::eval_features_kernel<<<(N + 127) / 128, 128, 0, st>>>(N, (const uint16_t*)(base + o_b), (const uint8_t*)(base + o_p),
+        (const uint8_t*)(base + o_r), (const uint8_t*)(base + o_c), (double*)(base + o_f), (int32_t*)(base + o_i),
+        out_rows ? (uint16_t*)(base + o_rows) : nullptr);
+    TB_CUDA(ctx, cudaGetLastError());
+    TB_CUDA(ctx, cudaMemcpyAsync(out_features, base + o_f, 8 * 45 * n, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(ctx, cudaMemcpyAsync(out_info, base + o_i, 12 * n, cudaMemcpyDeviceToHost, st));
+    if (out_rows) TB_CUDA(ctx, cudaMemcpyAsync(out_rows, base + o_rows, 40 * n, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(ctx, cudaStreamSynchronize(st));
+    return TB200_OK;
+}
+
+int tb200_hashed_pieces(tb200_ctx* ctx, int32_t mem, void* stream, uint64_t seed, uint64_t first_stream,
+                        int32_t n_streams, uint32_t T, uint8_t* out)
+{
+    if (!ctx) return TB200_E_BAD_ARG;
+    if (n_streams < 1 || T < 1 || !out) return fail(ctx, TB200_E_BAD_ARG, "hashed_pieces: missing argument");
+    TB_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t total = (size_t)n_streams * T;
+    const int grid = (int)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
+    if (mem == TB200_MEM_DEVICE) {
+        tb::hashed_pieces_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seed, first_stream, n_streams, T, out);
+        TB_CUDA(ctx, cudaGetLastError());
+        return TB200_OK;
+    }
+    int rc = ensure_arena(ctx, total);
+    if (rc) return rc;
+    cudaStream_t st = ctx->own_stream;
+    tb::hashed_pieces_kernel<<<grid, 256, 0, st>>>(seed, first_stream, n_streams, T, (uint8_t*)ctx->d_arena);
+    TB_CUDA(ctx, cudaGetLastError());
+    TB_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_arena, total, cudaMemcpyDeviceToHost, st));
+    TB_CUDA(ctx, cudaStreamSynchronize(st));
+    return TB200_OK;
+}
+
+}  // extern "C"

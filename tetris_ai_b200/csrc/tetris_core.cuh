@@ -1,0 +1,512 @@
+// tetris_core.cuh — column-bitmask Tetris placement core (sm_100a), shared by every kernel.
+//
+// What it replaces in the reference (paths under /root/reference/cogworks/):
+//   tetris/simulator.py:3-13    move_drop        -> tb::place_slot (closed-form landing row, legality)
+//   tetris/game.py:62-87,166-180 imprint/full/clear/future -> tb::place_slot (imprint, full-row AND, compress)
+//   tetris/features.py:18-347   the 45 features  -> tb::eval_features (popc / clz bit formulas)
+//   feature.py:50-55 + the canonical linear scorer -> tb::score_features
+//
+// Data layout: a board is 10 column words; bit i of col[k] is the cell of column k at height i
+// above the floor (i = 0 is the reference's row 19, i = 19 its row 0).  Heights are 32 - clz.
+// Everything is __host__ __device__ so that tests/emu can run the identical code on the CPU
+// against the oracles; the product only ever runs it on the GPU.
+#pragma once
+#include <stdint.h>
+#include "tetris_tables.h"
+
+#if defined(__CUDACC__)
+#define TB_HD __host__ __device__ __forceinline__
+#define TB_D  __device__ __forceinline__
+#define TB_CX __host__ __device__ constexpr
+#else
+#define TB_HD inline
+#define TB_CX constexpr
+#endif
+
+namespace tb {
+
+constexpr int ROWS = 20;
+constexpr int COLS = 10;
+constexpr int NFEAT = 45;
+constexpr uint32_t COLMASK = 0xFFFFFu;
+
+// feature ids = source order of tetris/features.py
+enum : int {
+    F_MEAN_HT = 0, F_MAX_HT, F_MIN_HT, F_ALL_HT, F_MAX_HT_DIFF, F_MIN_HT_DIFF, F_CLEARED, F_CUML_CLEARED,
+    F_TETRIS, F_COL_TRANS, F_ROW_TRANS, F_ALL_TRANS, F_WELLS, F_CUML_WELLS, F_DEEP_WELLS, F_MAX_WELL,
+    F_PITS, F_PIT_ROWS, F_LUMPED_PITS, F_PIT_DEPTH, F_MEAN_PIT_DEPTH,
+    F_CD_1, F_CD_2, F_CD_3, F_CD_4, F_CD_5, F_CD_6, F_CD_7, F_CD_8, F_CD_9,
+    F_ALL_DIFFS, F_MAX_DIFFS, F_JAGGEDNESS, F_D_MAX_HT, F_D_ALL_HT, F_D_MEAN_HT, F_D_PITS,
+    F_LANDING_HEIGHT, F_PATTERN_DIV, F_NINE_FILLED, F_TETRIS_PROGRESS, F_FULL_CELLS, F_WEIGHTED_CELLS,
+    F_ERODED_CELLS, F_CUML_ERODED
+};
+TB_CX uint64_t bit(int id) { return 1ull << id; }
+constexpr uint64_t ALL45_MASK = (1ull << NFEAT) - 1;
+// the "w6" set of SURVEY.md §8c, in its summation order
+constexpr uint64_t W6_MASK = bit(F_LANDING_HEIGHT) | bit(F_ERODED_CELLS) | bit(F_ROW_TRANS) | bit(F_COL_TRANS) |
+                             bit(F_PITS) | bit(F_CUML_WELLS);
+
+// ---------------------------------------------------------------------------------------------
+// tables
+// ---------------------------------------------------------------------------------------------
+struct SlotDesc { uint32_t w[8]; };          // layout: tools/gen_tables.py
+struct Tables {
+    SlotDesc slot[7][TB_MAX_SLOTS];
+    int nslots[7];
+};
+#if !defined(__CUDA_ARCH__)
+static const Tables& host_tables()
+{
+    static const Tables t = { TB_SLOT_TABLE_INIT, TB_NSLOTS_INIT };
+    return t;
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// small intrinsics with host twins
+// ---------------------------------------------------------------------------------------------
+TB_HD int popc(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+TB_HD int fls(uint32_t x)                    // 32 - clz(x); 0 for x == 0  (column height)
+{
+#if defined(__CUDA_ARCH__)
+    return 32 - __clz((int)x);
+#else
+    return x ? 32 - __builtin_clz(x) : 0;
+#endif
+}
+TB_HD int ctz(uint32_t x)                    // x != 0
+{
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+TB_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh)      // (hi:lo) >> sh, sh in 0..31
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+TB_HD uint32_t byte_of(uint32_t v, int j)    // j compile-time
+{
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(v, 0, 0x4440 | j);
+#else
+    return (v >> (8 * j)) & 0xFFu;
+#endif
+}
+// fp64 with explicit rounding per operation: never contracted into FMA
+TB_HD double dmul(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b; return r;
+#endif
+}
+TB_HD double dadd(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b; return r;
+#endif
+}
+TB_HD double dsub(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(a, b);
+#else
+    volatile double r = a - b; return r;
+#endif
+}
+TB_HD double ddiv(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __ddiv_rn(a, b);
+#else
+    volatile double r = a / b; return r;
+#endif
+}
+TB_HD double i2d(int x)                      // exact int -> double without the quarter-rate I2F pipe
+{
+#if defined(__CUDA_ARCH__)
+    // 2^52 + 2^31 + x is exactly representable; subtracting the bias is exact.
+    return __dsub_rn(__hiloint2double(0x43300000, (int)((uint32_t)x ^ 0x80000000u)), 4503601774854144.0);
+#else
+    return (double)x;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: counter-based piece stream (bit-identical twins: oracle/pyoracle.py hashed_piece,
+// oracle/coracle.c hashed_piece)
+// ---------------------------------------------------------------------------------------------
+TB_HD int hashed_piece(uint64_t seed, uint64_t stream, uint64_t t)
+{
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + stream * 0xD1B54A32D192ED03ull + t * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return (int)(((x >> 32) * 7ull) >> 32);
+}
+
+// ---------------------------------------------------------------------------------------------
+// board helpers
+// ---------------------------------------------------------------------------------------------
+struct Heights { uint32_t H0, H1, H2; };     // byte k of (H0,H1,H2) = height of column k; bytes 10,11 = 0
+
+TB_HD Heights pack_heights(const uint32_t c[COLS])
+{
+    Heights h;
+    h.H0 = (uint32_t)fls(c[0]) | (uint32_t)fls(c[1]) << 8 | (uint32_t)fls(c[2]) << 16 | (uint32_t)fls(c[3]) << 24;
+    h.H1 = (uint32_t)fls(c[4]) | (uint32_t)fls(c[5]) << 8 | (uint32_t)fls(c[6]) << 16 | (uint32_t)fls(c[7]) << 24;
+    h.H2 = (uint32_t)fls(c[8]) | (uint32_t)fls(c[9]) << 8;
+    return h;
+}
+
+// what the d_* features need from the previous state (features.py:239-257)
+struct PrevStat { int max_ht, all_ht, pits; };
+
+TB_HD PrevStat prev_stat(const uint32_t c[COLS])
+{
+    PrevStat s; s.max_ht = 0; s.all_ht = 0; int cells = 0;
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) { int h = fls(c[k]); s.all_ht += h; s.max_ht = h > s.max_ht ? h : s.max_ht; cells += popc(c[k]); }
+    s.pits = s.all_ht - cells;
+    return s;
+}
+
+// reference row-mask layout (u16[20], row 0 = top, bit c = column c) <-> column words
+TB_HD void rows_to_cols(const uint16_t rows[ROWS], uint32_t c[COLS])
+{
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) c[k] = 0;
+    for (int r = 0; r < ROWS; ++r) {
+        uint32_t v = rows[r];
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) c[k] |= ((v >> k) & 1u) << (ROWS - 1 - r);
+    }
+}
+TB_HD void cols_to_rows(const uint32_t c[COLS], uint16_t rows[ROWS])
+{
+    for (int r = 0; r < ROWS; ++r) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) v |= ((c[k] >> (ROWS - 1 - r)) & 1u) << k;
+        rows[r] = (uint16_t)v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// one placement: drop + imprint + full rows + clear
+// ---------------------------------------------------------------------------------------------
+struct Placement {
+    uint32_t n[COLS];      // post-clear board
+    int y;                 // height of the piece's bottom bbox row above the floor (pre-clear) = landing_height
+    int k;                 // rows cleared
+    int eroded;            // piece cells that sat in cleared rows
+    int rot, c0, ph;
+};
+
+// Returns false when the slot is illegal for this board (move_drop's hover row < 0, simulator.py:8-10).
+TB_HD bool place_slot(const uint32_t c[COLS], const Heights& H, const SlotDesc& d, Placement& p)
+{
+    const uint32_t misc = d.w[0];
+    const uint32_t sel = d.w[7];
+    // 4-byte window of heights starting at column c0
+    const uint32_t pair = sel >> 8;
+    const uint32_t lo = pair == 0 ? H.H0 : (pair == 1 ? H.H1 : H.H2);
+    const uint32_t hi = pair == 0 ? H.H1 : (pair == 1 ? H.H2 : 0u);
+    const uint32_t hw = funnel_r(lo, hi, sel & 31u);
+    // legal iff max_j h[c0+j] + ph <= ROWS
+    const bool legal = ((hw + d.w[2]) & 0x80808080u) == 0u;
+    // landing: y = max_j (h[c0+j] - bottom_j); biased by 32 so that the byte arithmetic stays unsigned
+    const uint32_t v = hw + d.w[1];
+    uint32_t m01 = byte_of(v, 0), b1 = byte_of(v, 1), b2 = byte_of(v, 2), b3 = v >> 24;
+    m01 = m01 > b1 ? m01 : b1; b2 = b2 > b3 ? b2 : b3; m01 = m01 > b2 ? m01 : b2;
+    const int y = (int)m01 - 32;
+    p.y = y; p.c0 = (int)(misc & 15u); p.rot = (int)((misc >> 4) & 3u); p.ph = (int)((misc >> 9) & 7u);
+    // imprint: piece cells never overlap board cells, so OR == ADD == one multiply-add per column
+    const uint32_t one_y = 1u << (y & 31);
+    p.n[0] = byte_of(d.w[4], 0) * one_y + c[0];
+    p.n[1] = byte_of(d.w[4], 1) * one_y + c[1];
+    p.n[2] = byte_of(d.w[4], 2) * one_y + c[2];
+    p.n[3] = (d.w[4] >> 24)     * one_y + c[3];
+    p.n[4] = byte_of(d.w[5], 0) * one_y + c[4];
+    p.n[5] = byte_of(d.w[5], 1) * one_y + c[5];
+    p.n[6] = byte_of(d.w[5], 2) * one_y + c[6];
+    p.n[7] = (d.w[5] >> 24)     * one_y + c[7];
+    p.n[8] = byte_of(d.w[6], 0) * one_y + c[8];
+    p.n[9] = byte_of(d.w[6], 1) * one_y + c[9];
+    // full rows (game.py:77-78)
+    uint32_t f = (p.n[0] & p.n[1] & p.n[2]) & (p.n[3] & p.n[4] & p.n[5]) & (p.n[6] & p.n[7] & p.n[8]) & p.n[9];
+    p.k = 0; p.eroded = 0;
+    if (legal && f != 0u) {
+        p.k = popc(f);
+        // eroded_cells (features.py:335-340): piece cells in the cleared rows, pre-clear coordinates
+        const uint32_t fr = f >> y, rc = misc >> 12;
+        p.eroded = (int)(((fr & 1u) ? (rc & 7u) : 0u) + ((fr & 2u) ? ((rc >> 3) & 7u) : 0u) +
+                         ((fr & 4u) ? ((rc >> 6) & 7u) : 0u) + ((fr & 8u) ? ((rc >> 9) & 7u) : 0u));
+        // clear (game.py:80-87): drop each full row, everything above moves down one
+        do {
+            const uint32_t low = (1u << ctz(f)) - 1u;
+#pragma unroll
+            for (int k = 0; k < COLS; ++k) p.n[k] = (p.n[k] & low) | ((p.n[k] >> 1) & ~low);
+            f = (f & low) | ((f >> 1) & ~low);
+        } while (f != 0u);
+    }
+    return legal;
+}
+
+// ---------------------------------------------------------------------------------------------
+// features (features.py:18-347).  Ints stay ints, the five inexact ones are computed in fp64
+// with exactly the reference's operation order.
+// ---------------------------------------------------------------------------------------------
+struct Feat {
+    int    iv[NFEAT];      // integer-valued features (also holds exact "x.0" ones)
+    double mean_ht, max_ht_diff, min_ht_diff, mean_pit_depth, d_mean_ht;
+};
+
+constexpr uint64_t M_HEIGHTS = bit(F_MEAN_HT) | bit(F_MAX_HT) | bit(F_MIN_HT) | bit(F_ALL_HT) | bit(F_MAX_HT_DIFF) |
+    bit(F_MIN_HT_DIFF) | bit(F_WELLS) | bit(F_CUML_WELLS) | bit(F_DEEP_WELLS) | bit(F_MAX_WELL) | bit(F_PITS) |
+    bit(F_PIT_ROWS) | bit(F_LUMPED_PITS) | bit(F_MEAN_PIT_DEPTH) | (0x1FFull << F_CD_1) | bit(F_ALL_DIFFS) |
+    bit(F_MAX_DIFFS) | bit(F_JAGGEDNESS) | bit(F_D_MAX_HT) | bit(F_D_ALL_HT) | bit(F_D_MEAN_HT) | bit(F_D_PITS) |
+    bit(F_TETRIS_PROGRESS);
+constexpr uint64_t M_WELLS   = bit(F_WELLS) | bit(F_CUML_WELLS) | bit(F_DEEP_WELLS) | bit(F_MAX_WELL);
+constexpr uint64_t M_CELLS   = bit(F_FULL_CELLS) | bit(F_PITS) | bit(F_D_PITS) | bit(F_PIT_DEPTH) | bit(F_MEAN_PIT_DEPTH) |
+    bit(F_WEIGHTED_CELLS);
+constexpr uint64_t M_WEIGHTED = bit(F_WEIGHTED_CELLS) | bit(F_PIT_DEPTH) | bit(F_MEAN_PIT_DEPTH);
+constexpr uint64_t M_PITMASK = bit(F_PIT_ROWS) | bit(F_LUMPED_PITS);
+constexpr uint64_t M_DIFFS   = (0x1FFull << F_CD_1) | bit(F_ALL_DIFFS) | bit(F_MAX_DIFFS) | bit(F_JAGGEDNESS);
+constexpr uint64_t M_NINE    = bit(F_NINE_FILLED) | bit(F_TETRIS_PROGRESS);
+constexpr uint64_t M_MEAN    = bit(F_MEAN_HT) | bit(F_MAX_HT_DIFF) | bit(F_MIN_HT_DIFF) | bit(F_D_MEAN_HT);
+
+// CMASK != 0: compile-time feature set (dead code removed); CMASK == 0: `rmask` decides at run time.
+template <uint64_t CMASK>
+TB_HD void eval_features(const Placement& p, const PrevStat& pv, uint64_t rmask, Feat& f)
+{
+    const uint64_t need = CMASK ? CMASK : rmask;
+    const uint32_t* n = p.n;
+    int h[COLS];
+    int all_ht = 0, max_ht = 0, min_ht = 0;
+    if (need & M_HEIGHTS) {
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) h[k] = fls(n[k]);
+        all_ht = h[0]; max_ht = h[0]; min_ht = h[0];
+#pragma unroll
+        for (int k = 1; k < COLS; ++k) { all_ht += h[k]; max_ht = h[k] > max_ht ? h[k] : max_ht; min_ht = h[k] < min_ht ? h[k] : min_ht; }
+        f.iv[F_MAX_HT] = max_ht; f.iv[F_MIN_HT] = min_ht; f.iv[F_ALL_HT] = all_ht;
+    }
+    if (need & M_MEAN) {
+        f.mean_ht = ddiv(i2d(all_ht), 10.0);                          // features.py:24-26
+        f.max_ht_diff = dsub(i2d(max_ht), f.mean_ht);                 // :48-50
+        f.min_ht_diff = dsub(f.mean_ht, i2d(min_ht));                 // :54-56
+        f.d_mean_ht = dsub(f.mean_ht, ddiv(i2d(pv.all_ht), 10.0));    // :251-253
+    }
+    f.iv[F_CLEARED] = p.k;                                            // :62-77
+    f.iv[F_CUML_CLEARED] = (p.k * (p.k + 1)) >> 1;
+    f.iv[F_TETRIS] = p.k >> 2;
+    if (need & (bit(F_COL_TRANS) | bit(F_ALL_TRANS))) {               // :83-85 (no floor / ceiling)
+        int s = 0;
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) s += popc((n[k] ^ (n[k] >> 1)) & 0x7FFFFu);
+        f.iv[F_COL_TRANS] = s;
+    }
+    if (need & (bit(F_ROW_TRANS) | bit(F_ALL_TRANS))) {               // :89-91 (no walls)
+        int s = 0;
+#pragma unroll
+        for (int k = 0; k + 1 < COLS; ++k) s += popc(n[k] ^ n[k + 1]);
+        f.iv[F_ROW_TRANS] = s;
+    }
+    if (need & bit(F_ALL_TRANS)) f.iv[F_ALL_TRANS] = f.iv[F_COL_TRANS] + f.iv[F_ROW_TRANS];
+    if (need & M_WELLS) {                                             // :106-137, walls count as height ROWS
+        int ws = 0, cw = 0, dw = 0, mw = 0;
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) {
+            const int l = k == 0 ? ROWS : h[k - 1], r = k == COLS - 1 ? ROWS : h[k + 1];
+            int w = (l < r ? l : r) - h[k]; w = w > 0 ? w : 0;
+            ws += w; cw += w * (w + 1); dw += w > 1 ? w : 0; mw = w > mw ? w : mw;
+        }
+        f.iv[F_WELLS] = ws; f.iv[F_CUML_WELLS] = cw >> 1; f.iv[F_DEEP_WELLS] = dw; f.iv[F_MAX_WELL] = mw;
+    }
+    int cells = 0, tri = 0;            // tri = sum_k m_k (m_k - 1) / 2
+    if (need & M_CELLS) {
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) { const int m = popc(n[k]); cells += m; tri += m * (m - 1); }
+        tri >>= 1;
+        f.iv[F_FULL_CELLS] = cells;                                   // :323-325
+        f.iv[F_PITS] = all_ht - cells;                                // :146-160  (empty cells under a column top)
+        f.iv[F_D_PITS] = f.iv[F_PITS] - pv.pits;                      // :257-259
+    }
+    if (need & M_WEIGHTED) {                                          // :329-331  sum over cells of (height index + 1)
+        int p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0;
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) {
+            p0 += popc(n[k] & 0xAAAAAu); p1 += popc(n[k] & 0xCCCCCu); p2 += popc(n[k] & 0x0F0F0u);
+            p3 += popc(n[k] & 0x0FF00u); p4 += popc(n[k] & 0xF0000u);
+        }
+        const int possum = p0 + 2 * p1 + 4 * p2 + 8 * p3 + 16 * p4;
+        f.iv[F_WEIGHTED_CELLS] = possum + cells;
+        // pit_depth (:182-188) = sum over filled cells of the empties below them
+        //                      = sum of height indices of filled cells - sum_k m_k(m_k-1)/2
+        f.iv[F_PIT_DEPTH] = possum - tri;
+    }
+    if (need & bit(F_MEAN_PIT_DEPTH))                                 // :192-194
+        f.mean_pit_depth = f.iv[F_PITS] != 0 ? ddiv(i2d(f.iv[F_PIT_DEPTH]), i2d(f.iv[F_PITS])) : 0.0;
+    if (need & M_PITMASK) {                                           // :164-178
+        uint32_t any = 0; int lumped = 0;
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) {
+            const uint32_t pm = ((1u << h[k]) - 1u) & ~n[k];
+            any |= pm; lumped += popc(pm & ~(pm >> 1));
+        }
+        f.iv[F_PIT_ROWS] = popc(any); f.iv[F_LUMPED_PITS] = lumped;
+    }
+    if (need & M_DIFFS) {                                             // :201-233
+        int mx = h[1] - h[0], jag = 0;
+#pragma unroll
+        for (int k = 1; k < COLS; ++k) {
+            const int d = h[k] - h[k - 1];
+            f.iv[F_CD_1 + k - 1] = d; mx = d > mx ? d : mx; jag += d < 0 ? -d : d;
+        }
+        f.iv[F_ALL_DIFFS] = h[COLS - 1] - h[0]; f.iv[F_MAX_DIFFS] = mx; f.iv[F_JAGGEDNESS] = jag;
+    }
+    f.iv[F_D_MAX_HT] = max_ht - pv.max_ht;                            // :239-247
+    f.iv[F_D_ALL_HT] = all_ht - pv.all_ht;
+    f.iv[F_LANDING_HEIGHT] = p.y;                                     // :265-267 (pre-clear)
+    if (need & bit(F_PATTERN_DIV)) {                                  // :271-273 distinct column-to-column difference vectors
+        uint32_t a[COLS - 1], b[COLS - 1];
+#pragma unroll
+        for (int j = 0; j + 1 < COLS; ++j) { a[j] = n[j + 1] & ~n[j]; b[j] = n[j] & ~n[j + 1]; }
+        int distinct = 0;
+#pragma unroll
+        for (int j = 0; j + 1 < COLS; ++j) {
+            uint32_t dup = 0;
+#pragma unroll
+            for (int i = 0; i < j; ++i) dup |= (uint32_t)(((a[i] ^ a[j]) | (b[i] ^ b[j])) == 0u);
+            distinct += dup ? 0 : 1;
+        }
+        f.iv[F_PATTERN_DIV] = distinct;
+    }
+    if (need & M_NINE) {                                              // :279-319
+        uint32_t one = 0, two = 0;     // rows with >=1 / >=2 empty cells
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) { const uint32_t e = ~n[k]; two |= one & e; one |= e; }
+        const uint32_t nine = one & ~two & COLMASK;
+        f.iv[F_NINE_FILLED] = popc(nine);
+        // tetris_progress: the scan from the top can only end just below the lowest column top, so the
+        // result is the run of nine-filled rows starting at height index min_ht
+        const uint32_t run = ~(nine >> min_ht);
+        f.iv[F_TETRIS_PROGRESS] = ctz(run);
+    }
+    f.iv[F_ERODED_CELLS] = p.eroded;                                  // :335-347
+    f.iv[F_CUML_ERODED] = (p.eroded * (p.eroded + 1)) >> 1;
+}
+
+// value of feature `id` as the double the canonical scorer multiplies (float(f))
+TB_HD double feat_value(const Feat& f, int id)
+{
+    switch (id) {
+    case F_MEAN_HT: return f.mean_ht;
+    case F_MAX_HT_DIFF: return f.max_ht_diff;
+    case F_MIN_HT_DIFF: return f.min_ht_diff;
+    case F_MEAN_PIT_DEPTH: return f.mean_pit_depth;
+    case F_D_MEAN_HT: return f.d_mean_ht;
+    case F_MAX_HT: return i2d(f.iv[F_MAX_HT]);
+    case F_MIN_HT: return i2d(f.iv[F_MIN_HT]);
+    case F_ALL_HT: return i2d(f.iv[F_ALL_HT]);
+    case F_CLEARED: return i2d(f.iv[F_CLEARED]);
+    case F_CUML_CLEARED: return i2d(f.iv[F_CUML_CLEARED]);
+    case F_TETRIS: return i2d(f.iv[F_TETRIS]);
+    case F_COL_TRANS: return i2d(f.iv[F_COL_TRANS]);
+    case F_ROW_TRANS: return i2d(f.iv[F_ROW_TRANS]);
+    case F_ALL_TRANS: return i2d(f.iv[F_ALL_TRANS]);
+    case F_WELLS: return i2d(f.iv[F_WELLS]);
+    case F_CUML_WELLS: return i2d(f.iv[F_CUML_WELLS]);
+    case F_DEEP_WELLS: return i2d(f.iv[F_DEEP_WELLS]);
+    case F_MAX_WELL: return i2d(f.iv[F_MAX_WELL]);
+    case F_PITS: return i2d(f.iv[F_PITS]);
+    case F_PIT_ROWS: return i2d(f.iv[F_PIT_ROWS]);
+    case F_LUMPED_PITS: return i2d(f.iv[F_LUMPED_PITS]);
+    case F_PIT_DEPTH: return i2d(f.iv[F_PIT_DEPTH]);
+    case F_CD_1: return i2d(f.iv[F_CD_1]);
+    case F_CD_2: return i2d(f.iv[F_CD_2]);
+    case F_CD_3: return i2d(f.iv[F_CD_3]);
+    case F_CD_4: return i2d(f.iv[F_CD_4]);
+    case F_CD_5: return i2d(f.iv[F_CD_5]);
+    case F_CD_6: return i2d(f.iv[F_CD_6]);
+    case F_CD_7: return i2d(f.iv[F_CD_7]);
+    case F_CD_8: return i2d(f.iv[F_CD_8]);
+    case F_CD_9: return i2d(f.iv[F_CD_9]);
+    case F_ALL_DIFFS: return i2d(f.iv[F_ALL_DIFFS]);
+    case F_MAX_DIFFS: return i2d(f.iv[F_MAX_DIFFS]);
+    case F_JAGGEDNESS: return i2d(f.iv[F_JAGGEDNESS]);
+    case F_D_MAX_HT: return i2d(f.iv[F_D_MAX_HT]);
+    case F_D_ALL_HT: return i2d(f.iv[F_D_ALL_HT]);
+    case F_D_PITS: return i2d(f.iv[F_D_PITS]);
+    case F_LANDING_HEIGHT: return i2d(f.iv[F_LANDING_HEIGHT]);
+    case F_PATTERN_DIV: return i2d(f.iv[F_PATTERN_DIV]);
+    case F_NINE_FILLED: return i2d(f.iv[F_NINE_FILLED]);
+    case F_TETRIS_PROGRESS: return i2d(f.iv[F_TETRIS_PROGRESS]);
+    case F_FULL_CELLS: return i2d(f.iv[F_FULL_CELLS]);
+    case F_WEIGHTED_CELLS: return i2d(f.iv[F_WEIGHTED_CELLS]);
+    case F_ERODED_CELLS: return i2d(f.iv[F_ERODED_CELLS]);
+    case F_CUML_ERODED: return i2d(f.iv[F_CUML_ERODED]);
+    default: return 0.0;
+    }
+}
+
+// Scoring modes: the feature list and its order are compile-time for the two headline sets.
+enum : int { MODE_GENERIC = 0, MODE_W6 = 1, MODE_ALL45 = 2 };
+template <int MODE> struct ModeTraits;
+template <> struct ModeTraits<MODE_GENERIC> { static constexpr uint64_t CMASK = 0; };
+template <> struct ModeTraits<MODE_W6>      { static constexpr uint64_t CMASK = W6_MASK; };
+template <> struct ModeTraits<MODE_ALL45>   { static constexpr uint64_t CMASK = ALL45_MASK; };
+
+// canonical scorer: acc = 0.0; acc += float(f_i) * w_i in the caller's order,
+// one rounded multiply and one rounded add per feature.
+template <int MODE>
+TB_HD double score_features(const Feat& f, const uint8_t* ids, const double* w, int F)
+{
+    double acc = 0.0;
+    if (MODE == MODE_W6) {
+        acc = dadd(acc, dmul(feat_value(f, F_LANDING_HEIGHT), w[0]));
+        acc = dadd(acc, dmul(feat_value(f, F_ERODED_CELLS), w[1]));
+        acc = dadd(acc, dmul(feat_value(f, F_ROW_TRANS), w[2]));
+        acc = dadd(acc, dmul(feat_value(f, F_COL_TRANS), w[3]));
+        acc = dadd(acc, dmul(feat_value(f, F_PITS), w[4]));
+        acc = dadd(acc, dmul(feat_value(f, F_CUML_WELLS), w[5]));
+    } else if (MODE == MODE_ALL45) {
+#pragma unroll
+        for (int i = 0; i < NFEAT; ++i) acc = dadd(acc, dmul(feat_value(f, i), w[i]));
+    } else {
+        for (int i = 0; i < F; ++i) acc = dadd(acc, dmul(feat_value(f, ids[i]), w[i]));
+    }
+    return acc;
+}
+
+// order-preserving map double -> u64 (a < b  <=>  key(a) < key(b)); -0.0 is canonicalised to +0.0
+// first so that it ties with +0.0 exactly as Python's `<` does (simulator.py:130,134).
+TB_HD uint64_t score_key(double s)
+{
+    s = dadd(s, 0.0);
+#if defined(__CUDA_ARCH__)
+    const uint64_t b = (uint64_t)__double_as_longlong(s);
+#else
+    uint64_t b; __builtin_memcpy(&b, &s, 8);
+#endif
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+}  // namespace tb
