@@ -1,0 +1,116 @@
+"""GPU-backed mirror of cogworks/tetris/simulator.py for the hard-drop path.
+
+  move_drop(state, zoid)                       simulator.py:3    legal (rot,row,col) in rot-major, col-minor order
+  policy_best(scorer, tie_breaker)             simulator.py:123  argmax with the first-of-max tie rule
+  simulate(state, zoid_gen, move_gen, move_policy, lookahead=1)   simulator.py:152  generator of States
+
+The search (enumerate, drop, clear, features, fp64 score, argmax, commit) runs in the K2 kernel;
+this module only adapts the reference's call signatures.  Only the combination the hot path is
+defined for is accepted — move_gen = move_drop and a policy built by policy_best(linear_scorer(...),
+tie_first); anything else raises, because this engine has no CPU fallback.
+"""
+from __future__ import annotations
+
+import collections.abc
+import itertools
+
+import numpy as np
+
+from ..feature import default_engine
+from .features import Feature
+from .game import PIECES, State
+
+CHUNK = 4096          # pieces handed to the device per launch by simulate()
+
+
+def move_drop(state, zoid, engine=None):
+    """Yield every legal hard-drop placement (rot, row, col) of `zoid` on state.board, in the reference's order."""
+    eng = engine or default_engine()
+    slots = [(rot, col) for rot in range(len(zoid)) for col in range(state.board.cols() - zoid[rot].shape[1] + 1)]
+    n = len(slots)
+    r = eng.eval_features(np.tile(state.board.rows16(), (n, 1)), [zoid.id] * n, [s[0] for s in slots], [s[1] for s in slots])
+    for (rot, col), legal, row in zip(slots, r["legal"], r["row"]):
+        if legal == 1:
+            yield (rot, int(row), col)
+
+
+class LinearScorer:
+    """The canonical scorer: acc = 0.0; for f, w in weights.items(): acc += float(f(state)) * w (device fp64, no FMA)."""
+
+    def __init__(self, weights):
+        if not isinstance(weights, collections.abc.Mapping) or not weights:
+            raise TypeError("linear_scorer needs a non-empty Mapping feature -> weight")
+        for f in weights:
+            if not isinstance(f, Feature):
+                raise TypeError("feature %r is not a device feature; the B200 engine has no CPU fallback" % (f,))
+        self.features = list(weights.keys())
+        self.weights = [float(w) for w in weights.values()]
+
+    def __call__(self, state):
+        from ..feature import evaluate
+        acc = 0.0
+        for v in evaluate(state, dict(zip(self.features, self.weights))).values():
+            acc += v
+        return acc
+
+
+def linear_scorer(weights):
+    return LinearScorer(weights)
+
+
+def tie_first(maxes):
+    """Canonical tie-breaker: first element of the max group (lowest rot, then lowest col)."""
+    return maxes[0]
+
+
+class BestPolicy:
+    def __init__(self, scorer, tie_breaker):
+        if not isinstance(scorer, LinearScorer):
+            raise TypeError("policy_best on the B200 engine needs linear_scorer(weights); arbitrary Python scorers "
+                            "would need a CPU path, which this engine does not have")
+        if tie_breaker is not tie_first:
+            raise TypeError("only tie_first (first of the max group in enumeration order) is implemented on the device")
+        self.scorer = scorer
+
+    def __call__(self, futures):
+        raise TypeError("a device policy is consumed by simulate(); it does not score host-side State lists")
+
+
+def policy_best(scorer, tie_breaker=tie_first):
+    return BestPolicy(scorer, tie_breaker)
+
+
+def simulate(state, zoid_gen, move_gen, move_policy, lookahead=1, engine=None):
+    """Generator of successive States, identical to the reference's for the accepted arguments."""
+    if lookahead not in (1, 2):
+        raise ValueError("lookahead must be 1 or 2")
+    if move_gen is not move_drop:
+        raise TypeError("only move_drop is implemented on the device (no CPU fallback)")
+    if not isinstance(move_policy, BestPolicy):
+        raise TypeError("move_policy must come from policy_best(linear_scorer(weights), tie_first)")
+    eng = engine or default_engine()
+    sc = move_policy.scorer
+    zoid_gen = iter(zoid_gen)
+    carry = []
+    while True:
+        chunk = carry + list(itertools.islice(zoid_gen, 0, CHUNK - len(carry)))
+        if not chunk:
+            return
+        more = len(chunk) == CHUNK
+        # with lookahead 2 the last piece of a non-final chunk is only looked at, not placed
+        commit = len(chunk) - 1 if (more and lookahead == 2) else len(chunk)
+        ids = np.array([[z.id for z in chunk]], dtype=np.uint8)
+        eng.set_features(sc.features)
+        r = eng.play_games(np.array([sc.weights]), 1, pieces=ids, lookahead=lookahead, max_moves=commit,
+                           init_rows=[state.board.rows16()], want_trace=True, want_fitness=False)
+        placed = int(r["results"]["pieces"][0])
+        for t in range(placed):
+            rot, row, col, _k = (int(x) for x in r["trace"][0, t])
+            state = state.future(chunk[t], rot, row, col)
+            yield state
+        if placed < commit or not more:
+            return
+        carry = chunk[commit:]
+
+
+__all__ = ["move_drop", "policy_best", "simulate", "linear_scorer", "tie_first", "LinearScorer", "BestPolicy", "PIECES"]
