@@ -1,0 +1,379 @@
+#!/usr/bin/env python3
+"""bench.py — placements evaluated / s (and CE generations / s) of the GPU placement engine.
+
+Contract (see the task statement):  python bench.py --gpus N --steps K --warmup W [--impl reference]
+prints ONE JSON line from rank 0.
+
+Workload (BASELINE.json configs[1]): one cross-entropy generation of 100 candidates x 10 games,
+one-piece placement search, the 6-feature "w6" set, injected sequences random.Random(1000..1009),
+cap T = 1000 pieces.  The population is generation 1 of the canonical CE run (random.Random(42),
+sigma = 10; mean/std after generation 0 from tests/golden/ce.json): 6 680 307 placements in
+294 598 pieces — a mid-training generation in which many games reach the cap.  A step = one pass of
+the hot path over that population = evaluating the whole generation (one K2 launch + the fitness
+reduction).  For N > 1 (weak scaling) every rank evaluates its own 100-candidate shard of a
+100*N-candidate population drawn from the same distribution and the per-candidate fitness is
+all-gathered over NCCL inside the step.
+
+value      : device-timed (CUDA events on the launching stream), inputs resident in HBM.
+e2e        : the same step through the public API (PopulationEvaluator.evaluate -> C ABI with HOST
+             buffers in pinned memory): H2D of weights + pieces and D2H of results + fitness inside
+             the timed region, wall clock.
+roofline   : this path is integer/bitwise work, so the bound is the SM integer-issue rate, not HBM
+             or tensor cores (documented deviation from the "hbm"|"tensor" enum): achieved =
+             placements/s x 220 algorithmic thread-ops per placement against the
+             INT_PEAK measured on this pool's B200 by bin/int_peak (profiles/INT_PEAK_r01.json).
+cpu_baseline: oracle/pyoracle.py (numpy port of the reference's CPU path, kind "port") on all host
+             cores over a bounded sample of the same population.
+--impl reference: the same CPU port timed as its own arm.
+"""
+import argparse
+import json
+import os
+import random
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W6_NAMES = ["landing_height", "eroded_cells", "row_trans", "col_trans", "pits", "cuml_wells"]
+W6_OPS_PER_PLACEMENT = 220.0          # SURVEY.md §8d algorithmic thread-ops per placement, 6-feature set
+CANDIDATES_PER_GPU, GAMES, T_CAP = 100, 10, 1000
+METRIC, UNIT = "placements evaluated/sec (CE generation, 100 candidates x 10 games per GPU)", "placements/s"
+
+
+# ---------------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------------
+def canonical_population(n_total):
+    """Generation-1 population of the canonical CE run, extended to n_total candidates for N > 1."""
+    ce = json.load(open(os.path.join(ROOT, "tests", "golden", "ce.json")))["ce"]
+    rng = random.Random(ce["rng_seed"])
+    for _ in range(ce["width"]):                       # generation 0 draws (consumed, not used)
+        [rng.gauss(0, ce["stdev"]) for _ in range(6)]
+    mean = [float.fromhex(x) for x in ce["generations"][0]["mean"]]
+    std = [float.fromhex(x) for x in ce["generations"][0]["std"]]
+    pop = [[rng.gauss(mean[i], std[i]) for i in range(6)] for _ in range(n_total)]
+    seqs = []
+    for g in range(GAMES):
+        r = random.Random(ce["seed0"] + g)
+        seqs.append([r.randrange(7) for _ in range(T_CAP)])
+    return np.array(pop, dtype=np.float64), np.array(seqs, dtype=np.uint8)
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "BASELINE configs[1]: CE generation, 100 candidates x 10 games per GPU, lookahead 1, w6 features, T=1000, "
+                    "population = generation 1 of the canonical run (Random(42), sigma 10)",
+        "candidates_per_gpu": CANDIDATES_PER_GPU, "games_per_candidate": GAMES, "cap_pieces": T_CAP, "features": W6_NAMES,
+        "lookahead": 1, "parallelism": "candidates sharded per rank; fitness all-gather (NCCL)" if n_gpus > 1 else "single GPU",
+        "l2": "L2 flushed (256 MiB write) between timed steps, outside the per-step event pairs",
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm (oracle port) — also used for cpu_baseline
+# ---------------------------------------------------------------------------------------------
+_CPU_JOB = None
+
+
+def _cpu_one(i):
+    from oracle import coracle, pyoracle
+    fids, w, seqs = _CPU_JOB
+    total = 0
+    for s in seqs:
+        total += pyoracle.play_game(fids, list(w[i]), [int(x) for x in s])["lines"]
+    return total
+
+
+def cpu_port_rate(pop, seqs, n_cand, n_games, cores):
+    """placements/s of oracle/pyoracle.py on `cores` processes over the first n_cand candidates x n_games games."""
+    import multiprocessing as mp
+    from oracle import coracle, pyoracle
+    global _CPU_JOB
+    fids = [pyoracle.FEATURE_ID[n] for n in W6_NAMES]
+    sub = seqs[:n_games]
+    _CPU_JOB = (fids, pop, sub)
+    # placements of the sample are counted with the C oracle (same games, bit-identical by the parity tests)
+    placements = int(coracle.play_games(fids, pop[:n_cand], n_games, pieces=sub, threads=cores)["placements"].sum())
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_cpu_one, range(n_cand), chunksize=1)
+    dt = time.perf_counter() - t0
+    return placements / dt, placements, dt
+
+
+def cpu_c_rate(pop, seqs, cores):
+    from oracle import coracle, pyoracle
+    fids = [pyoracle.FEATURE_ID[n] for n in W6_NAMES]
+    t0 = time.perf_counter()
+    res = coracle.play_games(fids, pop, GAMES, pieces=seqs, threads=cores)
+    dt = time.perf_counter() - t0
+    return int(res["placements"].sum()) / dt, dt
+
+
+def pick_cpu_sample(cores, long=False):
+    # ~18 k placements/s/core for the numpy port.  long (cpu_baseline leg, measured once): 4 candidates per core x
+    # all 10 games ~ 15-20 s; short (one step of the --impl reference arm): 2 candidates per core x 4 games ~ 3-6 s.
+    if long:
+        return min(CANDIDATES_PER_GPU, 4 * cores), GAMES
+    return min(CANDIDATES_PER_GPU, 2 * cores), 4
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    pop, seqs = canonical_population(CANDIDATES_PER_GPU)
+    n_cand, n_games = pick_cpu_sample(cores)
+    rates, times = [], []
+    for i in range(args.warmup + args.steps):
+        rate, placements, dt = cpu_port_rate(pop, seqs, n_cand, n_games, cores)
+        if i >= args.warmup:
+            rates.append(rate)
+            times.append(dt)
+    value = statistics.mean(rates)
+    sample = "first %d candidates x first %d games of the same population (%d placements per step)" % (n_cand, n_games, placements)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32 bitboards + f64 score", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference's CPU path = oracle/pyoracle.py, a numpy restatement of cogworks (pure-Python reference cannot travel to this box); "
+                "fork pool over all host cores, one candidate per task (learning.py:38 granularity)",
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from tetris_ai_b200 import Engine, _lib
+    from tetris_ai_b200.learning import PopulationEvaluator
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    pop_all, seqs = canonical_population(CANDIDATES_PER_GPU * world)
+    pop = pop_all[rank * CANDIDATES_PER_GPU:(rank + 1) * CANDIDATES_PER_GPU]
+    eng = Engine(local)
+    eng.set_features(W6_NAMES)
+    C, G, n_games = CANDIDATES_PER_GPU, GAMES, CANDIDATES_PER_GPU * GAMES
+
+    # ---- device-resident buffers (value) ----
+    d_w = torch.from_numpy(pop).to(dev)
+    d_p = torch.from_numpy(seqs).to(dev)
+    d_res = torch.zeros(n_games * _lib.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    d_fit = torch.zeros(C, dtype=torch.float64, device=dev)
+    d_all = torch.zeros(C * world, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        eng.play_games_device(stream.cuda_stream, C, G, d_w.data_ptr(), d_res.data_ptr(), T_CAP, pieces_ptr=d_p.data_ptr(),
+                              n_sequences=G, fitness_ptr=d_fit.data_ptr(), lanes=args.lanes)
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_fit)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = []
+    sync_all()
+    t_wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.fill_(1)                                    # L2 flush, outside the event pair
+        a.record(stream)
+        step_device()
+        b.record(stream)
+    sync_all()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
+    kernel_ms = eng.last_timing()["kernel_ms"]            # K2 alone, last step
+    lanes_used = eng.last_timing()["lanes"]
+    res = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=_lib.RESULT_DTYPE)
+    placements = int(res["placements"].sum())
+    pieces = int(res["pieces"].sum())
+
+    # ---- e2e: public API, pinned host buffers, copies inside the timed region ----
+    h_w = torch.from_numpy(pop).pin_memory()
+    h_p = torch.from_numpy(seqs).pin_memory()
+    evalr = PopulationEvaluator(eng, W6_NAMES, G, pieces=h_p.numpy(), lanes=args.lanes)
+    for _ in range(3):
+        evalr.evaluate(h_w.numpy())
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fit = evalr.evaluate(h_w.numpy())
+        if world > 1:
+            d_fit.copy_(torch.from_numpy(fit))
+            dist.all_gather_into_tensor(d_all, d_fit)
+            fit_all = d_all.cpu()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    tm = eng.last_timing()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- reduce over ranks: max time, sum placements ----
+    stats = torch.tensor([total_ms, e2e_s, float(placements), float(pieces), kernel_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        total_ms, e2e_s, kernel_ms = float(mx[0]), float(mx[1]), float(mx[4])
+        placements_all, pieces_all = int(sm[2]), int(sm[3])
+    else:
+        placements_all, pieces_all = placements, pieces
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = placements_all * args.steps / (total_ms * 1e-3)
+    e2e_value = placements_all * args.steps / e2e_s
+    peaks_path = os.path.join(ROOT, "profiles", "INT_PEAK_r01.json")
+    int_peak = json.load(open(peaks_path))["int_peak_thread_ops_per_s"] if os.path.exists(peaks_path) else 148 * 128 * 1.965e9
+    # roofline of the dominant kernel (K2 alone, this rank's launch): algorithmic thread-ops / kernel time
+    k_rate = placements / (kernel_ms * 1e-3)
+    achieved = k_rate * W6_OPS_PER_PLACEMENT
+    hbm_peak = 6554.2
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    alg_bytes = C * 6 * 8 + seqs.size + n_games * _lib.RESULT_DTYPE.itemsize + C * 8
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_r01_summary.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 bitboards + f64 score", "data": "synthetic", "config": workload_config(world),
+        "generations_per_s": args.steps / (total_ms * 1e-3),
+        "placements_per_step": placements_all, "pieces_per_step": pieces_all, "lanes_per_game": lanes_used,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tm["h2d_bytes"]), "d2h_bytes_per_step": int(tm["d2h_bytes"]),
+                "ms_per_step": 1e3 * e2e_s / args.steps, "api": "PopulationEvaluator.evaluate -> tb200_play_games (host buffers, pinned)"},
+        "gpu_launches": 2 * args.steps,
+        "roofline": {"bound": "int-issue", "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tops/s (thread integer ops)",
+                     "frac": achieved / int_peak, "traffic": traffic,
+                     "kernel": "play_games_kernel<%d,W6,1>" % lanes_used, "kernel_ms": kernel_ms,
+                     "algorithmic_ops_per_placement": W6_OPS_PER_PLACEMENT,
+                     "peak_source": "measured: bin/int_peak on this pool's B200 (profiles/INT_PEAK_r01.json)",
+                     "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9,
+                             "peak_gbs": hbm_peak, "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak}},
+        "clocks": clocks,
+        "wall_s_timed_region": t_wall,
+    }
+    if not args.no_cpu:
+        cores = os.cpu_count() or 1
+        n_cand, n_games_s = pick_cpu_sample(cores, long=True)
+        rate, pl, dt = cpu_port_rate(pop, seqs, n_cand, n_games_s, cores)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "oracle/pyoracle.py (numpy port of the reference), first %d candidates x first %d games of this population: "
+                                          "%d placements in %.1f s" % (n_cand, n_games_s, pl, dt)}
+        c_rate, c_dt = cpu_c_rate(pop, seqs, cores)
+        line["cpu_baseline_c"] = {"value": c_rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                  "sample": "oracle/coracle.c (plain-C restatement, pthreads), the whole step (%d placements) in %.2f s" % (placements, c_dt)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()
