@@ -90,6 +90,50 @@ static void play(const int* ids_in, int F, const double* w, const uint8_t* piece
     if (final_rows) cols_to_rows(c, final_rows);
 }
 
+// the w32 kernel's fast path for the w6 set (w6_pre / w6_clear / w6_post), lookahead 1
+static void play_w6_fast(const double* w, const uint8_t* pieces, uint32_t T, uint64_t seed, uint64_t stream, uint32_t max_moves,
+                         const uint16_t* init_rows, uint64_t* res8, uint8_t* trace, double* score_trace, uint16_t* final_rows)
+{
+    const Tables& tab = host_tables();
+    uint32_t c[COLS];
+    if (init_rows) rows_to_cols(init_rows, c); else memset(c, 0, sizeof c);
+    GameStat g = game_stat(c);
+    const int cells0 = g.cells;
+    uint32_t t = 0, lines = 0, hist[4] = {0, 0, 0, 0}; uint64_t score = 0, cnt = 0;
+    if (!max_moves) max_moves = T;
+    while (t < T && t < max_moves) {
+        const int p1 = pieces ? (int)pieces[t] : hashed_piece(seed, stream, t);
+        if (p1 >= 7) break;
+        uint64_t key = 0; int best = -1; W6Cand bestc; Heights bestH;
+        memset(&bestc, 0, sizeof bestc); memset(&bestH, 0, sizeof bestH);
+        for (int s = 0; s < tab.nslots[p1]; ++s) {
+            W6Cand a;
+            w6_pre(c, g, tab.slot[p1][s], a);
+            if (a.legal && a.full != 0u) w6_clear(tab.slot[p1][s], a);
+            Heights Hn;
+            const uint64_t k = w6_post(a, w, Hn);
+            cnt += a.legal ? 1 : 0;
+            if (k > key) { key = k; best = s; bestc = a; bestH = Hn; }
+        }
+        if (best < 0) break;
+        memcpy(c, bestc.P.n, sizeof c);
+        g.H = bestH; unpack_heights(g.H, g.gh);
+        const Placement& P = bestc.P;
+        lines += (uint32_t)P.k; if (P.k) hist[P.k - 1] += 1;
+        g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)lines;
+        static const uint32_t PTS[5] = {0, 40, 100, 300, 1200};
+        score += (uint64_t)PTS[P.k] * (lines / 10 + 1);
+        if (trace) { trace[4 * t] = (uint8_t)P.rot; trace[4 * t + 1] = (uint8_t)(ROWS - P.y - P.ph); trace[4 * t + 2] = (uint8_t)P.c0; trace[4 * t + 3] = (uint8_t)P.k; }
+        if (score_trace) {
+            const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
+            memcpy(&score_trace[t], &b, 8);
+        }
+        ++t;
+    }
+    res8[0] = t; res8[1] = lines; res8[2] = hist[0]; res8[3] = hist[1]; res8[4] = hist[2]; res8[5] = hist[3]; res8[6] = score; res8[7] = cnt;
+    if (final_rows) cols_to_rows(c, final_rows);
+}
+
 extern "C" {
 
 // mode: -1 = as tb200_set_features would choose, 0 = force the generic (run-time feature list) path
@@ -98,6 +142,10 @@ int emu_play_one(const int* ids, int F, const double* w, const uint8_t* pieces, 
                  double* score_trace, uint16_t* final_rows)
 {
     const int m = mode < 0 ? pick_mode(ids, F) : mode;
+    if (m == 3) {           // fast w6 path of the one-warp-per-game kernel (caller guarantees the w6 feature list, lookahead 1)
+        play_w6_fast(w, pieces, T, seed, stream, max_moves, init_rows, res8, trace, score_trace, final_rows);
+        return m;
+    }
     if (m == MODE_W6) play<MODE_W6>(ids, F, w, pieces, T, seed, stream, lookahead, max_moves, init_rows, res8, trace, score_trace, final_rows);
     else if (m == MODE_ALL45) play<MODE_ALL45>(ids, F, w, pieces, T, seed, stream, lookahead, max_moves, init_rows, res8, trace, score_trace, final_rows);
     else play<MODE_GENERIC>(ids, F, w, pieces, T, seed, stream, lookahead, max_moves, init_rows, res8, trace, score_trace, final_rows);

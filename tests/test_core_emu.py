@@ -123,3 +123,30 @@ def test_emu_hashed_piece_twin():
     for _ in range(2000):
         s, g, t = rng.getrandbits(48), rng.getrandbits(30), rng.getrandbits(20)
         assert emu_lib.lib().emu_hashed_piece(s, g, t) == pyoracle.hashed_piece(s, g, t)
+
+
+def test_emu_fast_w6_path_vs_coracle(golden_games):
+    """The w32 kernel's arithmetic-heights / incremental-cells fast path for the w6 set (emu mode 3)."""
+    fids = [pyoracle.FEATURE_ID[n] for n in W6_NAMES]
+    for g in golden_games["games"]:
+        if [n for n, _ in g["weights"]] != W6_NAMES or g["lookahead"] != 1 or g.get("tie") == "last":
+            continue
+        seq = pyoracle.piece_sequence(g["seed"], g["T"])
+        res = emu_lib.play_one(fids, [x for _, x in g["weights"]], seq, mode=3)
+        assert res["trace"].tobytes().hex() == g["trace_hex"] and res["score"] == g["score"]
+    rng = random.Random(321)
+    for gi in range(300):
+        w = [rng.gauss(v, 1.5) for v in W6_VALS] if gi % 2 else [rng.gauss(0, 10.0) for _ in W6_VALS]
+        seq = [pyoracle.hashed_piece(5, gi, t) for t in range(500)]
+        a = coracle.play_one(fids, w, seq, 1)
+        b = emu_lib.play_one(fids, w, seq, mode=3)
+        assert (a["pieces"], a["lines"], a["hist"], a["score"], a["placements"]) == (b["pieces"], b["lines"], b["hist"], b["score"], b["placements"]), gi
+        assert a["trace"].tobytes() == b["trace"].tobytes() and list(a["final"]) == list(b["final"])
+    # from a non-empty initial board
+    init = [0] * 16 + [0x0F0, 0x3CF, 0x1FF, 0x3FE]
+    for gi in range(20):
+        w = [rng.gauss(v, 1.0) for v in W6_VALS]
+        seq = [pyoracle.hashed_piece(6, gi, t) for t in range(200)]
+        a = coracle.play_one(fids, w, seq, 1, init_rows=init)
+        b = emu_lib.play_one(fids, w, seq, mode=3, init_rows=init)
+        assert a["trace"].tobytes() == b["trace"].tobytes() and a["score"] == b["score"]

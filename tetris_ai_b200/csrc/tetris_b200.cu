@@ -26,6 +26,12 @@ namespace tb {
 constexpr int BLOCK = 128;
 
 __constant__ Tables c_tables;
+#ifdef TB_PHASES
+__device__ unsigned long long g_phase[8];
+#define PH(i) { const long long now_ = clock64(); ph[i] += now_ - last_; last_ = now_; }
+#else
+#define PH(i)
+#endif
 
 struct PlayParams {
     const double*  weights;
@@ -241,6 +247,370 @@ __global__ void __launch_bounds__(BLOCK) play_games_kernel(const PlayParams prm)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K2w: the latency-optimised variant for lookahead 1 with one full warp per game.  Used when the
+// population fits in one resident wave (BASELINE config 2: 1000 games), where the run time is the
+// serial chain of the longest game, so what matters is the per-piece latency of a single warp:
+//   * slots s and s+32 of a 34-slot piece (T, L, J) are evaluated as two interleaved straight-line
+//     instruction streams in ONE pass instead of two dependent passes,
+//   * argmax by three REDUX (hi word, lo word, tag) instead of a 5-step shuffle butterfly,
+//   * commit by broadcasting the winning lane's candidate board (SHFL) instead of recomputing it,
+//   * the ticket fetch is outside the per-piece loop.
+// ---------------------------------------------------------------------------------------------
+TB_D void warp_argmax32(uint64_t& key, uint32_t& tag)
+{
+    const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+    const uint32_t mhi = __reduce_max_sync(FULLMASK, hi);
+    const uint32_t mlo = __reduce_max_sync(FULLMASK, hi == mhi ? lo : 0u);
+    const bool win = hi == mhi && lo == mlo;
+    tag = __reduce_min_sync(FULLMASK, win ? tag : 0xffffffffu);
+    key = ((uint64_t)mhi << 32) | mlo;
+}
+
+template <int MODE>
+TB_D uint64_t eval_key(const Placement& P, bool legal, const PrevStat& pv, const uint8_t* ids, const double* w, int F, uint64_t rmask)
+{
+    Feat f;
+    eval_features<ModeTraits<MODE>::CMASK>(P, pv, rmask, f);
+    const uint64_t k = score_key(score_features<MODE>(f, ids, w, F));
+    return legal ? k : 0ull;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(BLOCK) play_games_w32_kernel(const PlayParams prm)
+{
+    constexpr int GROUPS = BLOCK / 32;
+    __shared__ Tables s_tab;
+    __shared__ double s_w[MODE == MODE_W6 ? 1 : GROUPS][MODE == MODE_W6 ? 1 : TB200_MAX_WEIGHTED];
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int grp = threadIdx.x >> 5;
+    const int F = prm.F;
+    const uint32_t T = prm.T;
+    double wreg[6];
+    const double* w = MODE == MODE_W6 ? wreg : s_w[MODE == MODE_W6 ? 0 : grp];
+
+    for (;;) {
+        uint32_t game = 0;
+        if (lane == 0) game = atomicAdd(prm.ticket, 1u);
+        game = __shfl_sync(FULLMASK, game, 0);
+        if (game >= prm.n_games) break;
+        const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : (prm.per_game_weights != 0 ? game : game % (uint32_t)prm.G);
+        const uint64_t stream = sq;
+        const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
+        uint32_t c[COLS];
+        if (prm.init_rows) {
+            uint16_t rows[ROWS];
+            for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
+            rows_to_cols(rows, c);
+        } else {
+#pragma unroll
+            for (int k = 0; k < COLS; ++k) c[k] = 0;
+        }
+        Heights H = pack_heights(c);
+        PrevStat pv = prev_stat(c);
+        {
+            const size_t wrow = prm.per_game_weights > 0 ? (size_t)game : (prm.per_game_weights < 0 ? 0 : (size_t)(game / (uint32_t)prm.G));
+            const double* wsrc = prm.weights + wrow * (size_t)F;
+            if (MODE == MODE_W6) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) wreg[i] = __ldg(wsrc + i);
+            } else {
+                __syncwarp(FULLMASK);
+                for (int i = lane; i < F; i += 32) s_w[MODE == MODE_W6 ? 0 : grp][i] = __ldg(wsrc + i);
+                __syncwarp(FULLMASK);
+            }
+        }
+        auto fetch_piece = [&](uint32_t tt) -> int {
+            if (tt >= T) return 7;
+            return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, stream, tt);
+        };
+        uint32_t t = 0, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+        uint64_t gscore = 0;
+        int p_cur = fetch_piece(0), p_next = fetch_piece(1);
+        const uint32_t max_moves = prm.max_moves;
+
+#ifdef TB_PHASES
+        long long ph[8] = {0,0,0,0,0,0,0,0}; long long last_ = clock64();
+#endif
+        while (t < T && t < max_moves && p_cur < 7) {
+            PH(5)
+            const int p_after = fetch_piece(t + 2);
+            const int ns = s_tab.nslots[p_cur];
+            // ---- stream A: slot = lane ----
+            const bool hasA = lane < ns;
+            const SlotDesc dA = load_slot(s_tab, p_cur, hasA ? lane : 0);
+            Placement PA; uint32_t fA;
+            const bool legalA = place_pre(c, H, dA, PA, &fA) && hasA;
+            uint64_t key; uint32_t tag = (uint32_t)lane;
+            PH(0)
+            if (MODE == MODE_W6 && ns > 32) {
+                // ---- stream B: slot = lane + 32 (only lanes 0, 1 of the 34-slot pieces), interleaved with A ----
+                const bool hasB = lane + 32 < ns;
+                const SlotDesc dB = load_slot(s_tab, p_cur, hasB ? lane + 32 : 0);
+                Placement PB; uint32_t fB;
+                const bool legalB = place_pre(c, H, dB, PB, &fB) && hasB;
+                if ((legalA && fA != 0u) || (legalB && fB != 0u)) {
+                    if (legalA && fA != 0u) place_clear(dA, PA, fA);
+                    if (legalB && fB != 0u) place_clear(dB, PB, fB);
+                }
+                const uint64_t kA = eval_key<MODE>(PA, legalA, pv, prm.ids, w, F, prm.rmask);
+                const uint64_t kB = eval_key<MODE>(PB, legalB, pv, prm.ids, w, F, prm.rmask);
+                cnt += (uint32_t)legalA + (uint32_t)legalB;
+                key = kA;
+                if (kB > kA) {                      // strict: the earlier slot keeps ties
+                    key = kB; tag = (uint32_t)lane + 32u;
+#pragma unroll
+                    for (int k = 0; k < COLS; ++k) PA.n[k] = PB.n[k];
+                    PA.y = PB.y; PA.k = PB.k; PA.rot = PB.rot; PA.c0 = PB.c0; PA.ph = PB.ph;
+                }
+            } else {
+                if (legalA && fA != 0u) place_clear(dA, PA, fA);
+                key = eval_key<MODE>(PA, legalA, pv, prm.ids, w, F, prm.rmask);
+                cnt += (uint32_t)legalA;
+                if (MODE != MODE_W6 && ns > 32) {   // big feature sets: second pass after the first (register budget)
+                    const bool hasB = lane + 32 < ns;
+                    const SlotDesc dB = load_slot(s_tab, p_cur, hasB ? lane + 32 : 0);
+                    Placement PB;
+                    const bool legalB = place_slot(c, H, dB, PB) && hasB;
+                    if (__any_sync(FULLMASK, legalB)) {
+                        const uint64_t kB = eval_key<MODE>(PB, legalB, pv, prm.ids, w, F, prm.rmask);
+                        cnt += (uint32_t)legalB;
+                        if (kB > key) {
+                            key = kB; tag = (uint32_t)lane + 32u;
+#pragma unroll
+                            for (int k = 0; k < COLS; ++k) PA.n[k] = PB.n[k];
+                            PA.y = PB.y; PA.k = PB.k; PA.rot = PB.rot; PA.c0 = PB.c0; PA.ph = PB.ph;
+                        }
+                    }
+                }
+            }
+            PH(ns > 32 ? 2 : 1)
+            warp_argmax32(key, tag);
+            PH(3)
+            if (key == 0) break;                    // no legal placement: game over (simulator.py:187-189)
+            // ---- commit: broadcast the winner's candidate board ----
+            const int src = (int)(tag & 31u);
+#pragma unroll
+            for (int k = 0; k < COLS; ++k) c[k] = __shfl_sync(FULLMASK, PA.n[k], src);
+            const uint32_t info = __shfl_sync(FULLMASK, (uint32_t)PA.y | (uint32_t)PA.k << 8 | (uint32_t)PA.rot << 12 | (uint32_t)PA.c0 << 16 | (uint32_t)PA.ph << 24, src);
+            const uint32_t wk = (info >> 8) & 15u;
+            H = pack_heights(c);
+            if (ModeTraits<MODE>::CMASK == 0 || (ModeTraits<MODE>::CMASK & (bit(F_D_MAX_HT) | bit(F_D_ALL_HT) | bit(F_D_MEAN_HT) | bit(F_D_PITS)))) pv = prev_stat(c);
+            lines += wk;
+            h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
+            const uint32_t pts = wk == 0 ? 0u : (wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u)));
+            gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
+            if (lane == 0) {
+                if (prm.trace) {
+                    const uint32_t wy = info & 255u, wph = info >> 24;
+                    const uint32_t row = (uint32_t)ROWS - wy - wph;
+                    reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = ((info >> 12) & 15u) | row << 8 | ((info >> 16) & 255u) << 16 | wk << 24;
+                }
+                if (prm.score_trace) {
+                    const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
+                    prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
+                }
+            }
+            ++t;
+            p_cur = p_next; p_next = p_after;
+            PH(4)
+        }
+#ifdef TB_PHASES
+        if (lane == 0) { for (int i = 0; i < 6; ++i) atomicAdd(&g_phase[i], (unsigned long long)ph[i]); atomicAdd(&g_phase[6], (unsigned long long)t); }
+#endif
+        // ---- game finished (over, cap reached or max_moves) ----
+        cnt = __reduce_add_sync(FULLMASK, cnt);
+        if (lane == 0) {
+            tb200_game_result* r = prm.results + game;
+            r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4;
+            r->score = gscore; r->placements = cnt;
+            if (prm.final_rows) {
+                uint16_t rows[ROWS];
+                cols_to_rows(c, rows);
+                for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2f: one warp per game, lookahead 1, the w6 feature set — the BASELINE config-2 hot kernel.
+// Per piece: [descriptors for this piece were prefetched] -> w6_pre (landing, legality, imprint,
+// arithmetic heights) -> rare clear fix-up -> w6_post (transitions by popc, wells, fp64 score)
+// -> REDUX argmax (+ ballot; the lo-word / tag REDUX only on a tie of the hi word) -> commit by
+// broadcasting the winner's board, packed heights and move (14 SHFL, no clz, no popc).
+// Slots 32 and 33 of the 34-slot pieces run as a second, interleaved instruction stream.
+// ---------------------------------------------------------------------------------------------
+TB_D SlotDesc load_slot12(const Tables& tab, int piece, int s)
+{
+    const uint4* p = reinterpret_cast<const uint4*>(&tab.slot[piece][s]);
+    const uint4 a = p[0], b = p[1], e = p[2];
+    SlotDesc d;
+    d.w[0] = a.x; d.w[1] = a.y; d.w[2] = a.z; d.w[3] = a.w; d.w[4] = b.x; d.w[5] = b.y; d.w[6] = b.z; d.w[7] = b.w;
+    d.w[8] = e.x; d.w[9] = e.y; d.w[10] = e.z; d.w[11] = e.w;
+    return d;
+}
+
+__global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayParams prm)
+{
+    __shared__ Tables s_tab;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t T = prm.T;
+
+    for (;;) {
+        uint32_t game = 0;
+        if (lane == 0) game = atomicAdd(prm.ticket, 1u);
+        game = __shfl_sync(FULLMASK, game, 0);
+        if (game >= prm.n_games) break;
+        const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : (prm.per_game_weights != 0 ? game : game % (uint32_t)prm.G);
+        const uint64_t stream = sq;
+        const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
+        uint32_t c[COLS];
+        if (prm.init_rows) {
+            uint16_t rows[ROWS];
+            for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
+            rows_to_cols(rows, c);
+        } else {
+#pragma unroll
+            for (int k = 0; k < COLS; ++k) c[k] = 0;
+        }
+        GameStat g = game_stat(c);
+        const int cells0 = g.cells;
+        double w[6];
+        {
+            const size_t wrow = prm.per_game_weights > 0 ? (size_t)game : (prm.per_game_weights < 0 ? 0 : (size_t)(game / (uint32_t)prm.G));
+            const double* wsrc = prm.weights + wrow * 6;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) w[i] = __ldg(wsrc + i);
+        }
+        auto fetch_piece = [&](uint32_t tt) -> int {
+            if (tt >= T) return 7;
+            return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, stream, tt);
+        };
+        uint32_t t = 0, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+        uint64_t gscore = 0;
+        const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
+        int p_cur = fetch_piece(0), p_next = fetch_piece(1);
+        // descriptors of the current piece (prefetched one piece ahead, they do not depend on the board)
+        int ns = p_cur < 7 ? s_tab.nslots[p_cur] : 0;
+        SlotDesc dA = load_slot12(s_tab, p_cur < 7 ? p_cur : 0, lane < ns ? lane : 0);
+        SlotDesc dB = load_slot12(s_tab, p_cur < 7 ? p_cur : 0, lane + 32 < ns ? lane + 32 : 0);
+
+#ifdef TB_PHASES
+        long long ph[8] = {0,0,0,0,0,0,0,0}; long long last_ = clock64();
+#endif
+        while (t < stop && p_cur < 7) {
+            PH(5)
+            const int p_after = fetch_piece(t + 2);
+            // prefetch the next piece's descriptors
+            const int pn = p_next < 7 ? p_next : 0;
+            const int ns_next = p_next < 7 ? s_tab.nslots[pn] : 0;
+            const SlotDesc dA_next = load_slot12(s_tab, pn, lane < ns_next ? lane : 0);
+            const SlotDesc dB_next = load_slot12(s_tab, pn, lane + 32 < ns_next ? lane + 32 : 0);
+
+            PH(0)
+            W6Cand A;
+            w6_pre(c, g, dA, A);
+            A.legal = A.legal && lane < ns;
+            uint64_t key; uint32_t tag = (uint32_t)lane;
+            Heights Hn;
+            if (ns > 32) {
+                W6Cand B;
+                w6_pre(c, g, dB, B);
+                B.legal = B.legal && lane + 32 < ns;
+                if ((A.legal && A.full != 0u) || (B.legal && B.full != 0u)) {
+                    if (A.legal && A.full != 0u) w6_clear(dA, A);
+                    if (B.legal && B.full != 0u) w6_clear(dB, B);
+                }
+                Heights HnB;
+                const uint64_t kA = w6_post(A, w, Hn);
+                const uint64_t kB = w6_post(B, w, HnB);
+                cnt += (uint32_t)A.legal + (uint32_t)B.legal;
+                key = kA;
+                if (kB > kA) {                      // strict: the earlier slot keeps ties
+                    key = kB; tag = (uint32_t)lane + 32u; Hn = HnB;
+#pragma unroll
+                    for (int k = 0; k < COLS; ++k) A.P.n[k] = B.P.n[k];
+                    A.P.y = B.P.y; A.P.k = B.P.k; A.P.rot = B.P.rot; A.P.c0 = B.P.c0; A.P.ph = B.P.ph;
+                }
+            } else {
+                if (A.legal && A.full != 0u) w6_clear(dA, A);
+                key = w6_post(A, w, Hn);
+                cnt += (uint32_t)A.legal;
+            }
+            PH(ns > 32 ? 2 : 1)
+            // ---- argmax: hi word by REDUX; the lo word / tag only when two lanes share the hi word ----
+            const uint32_t hi = (uint32_t)(key >> 32);
+            const uint32_t mhi = __reduce_max_sync(FULLMASK, hi);
+            if (mhi == 0u) break;                   // no legal placement: game over (simulator.py:187-189)
+            const uint32_t tie = __ballot_sync(FULLMASK, hi == mhi);
+            int src = __ffs((int)tie) - 1;
+            if (tie & (tie - 1u)) {
+                const uint32_t lo = (uint32_t)key;
+                const uint32_t mlo = __reduce_max_sync(FULLMASK, hi == mhi ? lo : 0u);
+                const uint32_t mtag = __reduce_min_sync(FULLMASK, (hi == mhi && lo == mlo) ? tag : 0xffffffffu);
+                src = (int)(mtag & 31u);
+            }
+            PH(3)
+            // ---- commit: broadcast the winner's candidate board, heights and move ----
+#pragma unroll
+            for (int k = 0; k < COLS; ++k) c[k] = __shfl_sync(FULLMASK, A.P.n[k], src);
+            g.H.H0 = __shfl_sync(FULLMASK, Hn.H0, src);
+            g.H.H1 = __shfl_sync(FULLMASK, Hn.H1, src);
+            g.H.H2 = __shfl_sync(FULLMASK, Hn.H2, src);
+            const uint32_t info = __shfl_sync(FULLMASK, (uint32_t)A.P.y | (uint32_t)A.P.k << 8 | (uint32_t)A.P.rot << 12 | (uint32_t)A.P.c0 << 16 | (uint32_t)A.P.ph << 24, src);
+            unpack_heights(g.H, g.gh);
+            const uint32_t wk = (info >> 8) & 15u;
+            lines += wk;
+            g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)lines;
+            h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
+            const uint32_t pts = wk == 0 ? 0u : (wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u)));
+            gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
+            if (prm.trace && lane == 0) {
+                const uint32_t wy = info & 255u, wph = info >> 24;
+                const uint32_t row = (uint32_t)ROWS - wy - wph;
+                reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = ((info >> 12) & 15u) | row << 8 | ((info >> 16) & 255u) << 16 | wk << 24;
+            }
+            if (prm.score_trace) {
+                const uint32_t khi = __shfl_sync(FULLMASK, (uint32_t)(key >> 32), src), klo = __shfl_sync(FULLMASK, (uint32_t)key, src);
+                const uint64_t kk = ((uint64_t)khi << 32) | klo;
+                const uint64_t b = (kk & 0x8000000000000000ull) ? (kk & 0x7FFFFFFFFFFFFFFFull) : ~kk;
+                if (lane == 0) prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
+            }
+            ++t;
+            p_cur = p_next; p_next = p_after;
+            ns = ns_next; dA = dA_next; dB = dB_next;
+            PH(4)
+        }
+#ifdef TB_PHASES
+        if (lane == 0) { for (int i = 0; i < 6; ++i) atomicAdd(&g_phase[i], (unsigned long long)ph[i]); atomicAdd(&g_phase[6], (unsigned long long)t); }
+#endif
+        cnt = __reduce_add_sync(FULLMASK, cnt);
+        if (lane == 0) {
+            tb200_game_result* r = prm.results + game;
+            r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4;
+            r->score = gscore; r->placements = cnt;
+            if (prm.final_rows) {
+                uint16_t rows[ROWS];
+                cols_to_rows(c, rows);
+                for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2];
+            }
+        }
+    }
+}
+
 // K3: all 45 features of one placement per thread
 __global__ void eval_features_kernel(int N, const uint16_t* prev_boards, const uint8_t* piece, const uint8_t* rot,
                                      const uint8_t* col, double* out_features, int32_t* out_info, uint16_t* out_rows)
@@ -336,6 +706,11 @@ static play_fn pick_lanes(int lanes)
 }
 static play_fn pick_kernel(int mode, int lookahead, int lanes)
 {
+    if (lookahead == 1 && lanes == 32) {
+        if (mode == MODE_W6) return play_games_w6fast_kernel;
+        if (mode == MODE_ALL45) return play_games_w32_kernel<MODE_ALL45>;
+        return play_games_w32_kernel<MODE_GENERIC>;
+    }
     if (lookahead == 2) {
         if (mode == MODE_W6) return pick_lanes<MODE_W6, 2>(lanes);
         if (mode == MODE_ALL45) return pick_lanes<MODE_ALL45, 2>(lanes);
@@ -394,6 +769,16 @@ static int ensure_arena(tb200_ctx* ctx, size_t bytes)
 extern "C" {
 
 const char* tb200_version(void) { return "tetris_b200 0.1 (sm_100a)"; }
+#ifdef TB_PHASES
+int tb200_debug_phases(unsigned long long* out8, int reset)
+{
+    unsigned long long z[8] = {0,0,0,0,0,0,0,0};
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out8, tb::g_phase, sizeof z);
+    if (reset) cudaMemcpyToSymbol(tb::g_phase, z, sizeof z);
+    return 0;
+}
+#endif
 
 int tb200_create(int device, tb200_ctx** out)
 {

@@ -49,7 +49,7 @@ constexpr uint64_t W6_MASK = bit(F_LANDING_HEIGHT) | bit(F_ERODED_CELLS) | bit(F
 // ---------------------------------------------------------------------------------------------
 // tables
 // ---------------------------------------------------------------------------------------------
-struct SlotDesc { uint32_t w[8]; };          // layout: tools/gen_tables.py
+struct SlotDesc { uint32_t w[12]; };         // layout: tools/gen_tables.py
 struct Tables {
     SlotDesc slot[7][TB_MAX_SLOTS];
     int nslots[7];
@@ -219,11 +219,13 @@ struct Placement {
     int rot, c0, ph;
 };
 
-// Returns false when the slot is illegal for this board (move_drop's hover row < 0, simulator.py:8-10).
-TB_HD bool place_slot(const uint32_t c[COLS], const Heights& H, const SlotDesc& d, Placement& p)
+// Straight-line part of a placement: landing row, legality, imprint, full-row mask.  Returns the
+// legality (move_drop's hover row >= 0, simulator.py:8-10); *full receives the mask of full rows
+// (bit i = height index i), still present in p.n.
+TB_HD bool place_pre(const uint32_t c[COLS], const Heights& H, const SlotDesc& d, Placement& p, uint32_t* full)
 {
     const uint32_t misc = d.w[0];
-    const uint32_t sel = d.w[7];
+    const uint32_t sel = d.w[3];
     // 4-byte window of heights starting at column c0
     const uint32_t pair = sel >> 8;
     const uint32_t lo = pair == 0 ? H.H0 : (pair == 1 ? H.H1 : H.H2);
@@ -250,22 +252,33 @@ TB_HD bool place_slot(const uint32_t c[COLS], const Heights& H, const SlotDesc& 
     p.n[8] = byte_of(d.w[6], 0) * one_y + c[8];
     p.n[9] = byte_of(d.w[6], 1) * one_y + c[9];
     // full rows (game.py:77-78)
-    uint32_t f = (p.n[0] & p.n[1] & p.n[2]) & (p.n[3] & p.n[4] & p.n[5]) & (p.n[6] & p.n[7] & p.n[8]) & p.n[9];
+    *full = (p.n[0] & p.n[1] & p.n[2]) & (p.n[3] & p.n[4] & p.n[5]) & (p.n[6] & p.n[7] & p.n[8]) & p.n[9];
     p.k = 0; p.eroded = 0;
-    if (legal && f != 0u) {
-        p.k = popc(f);
-        // eroded_cells (features.py:335-340): piece cells in the cleared rows, pre-clear coordinates
-        const uint32_t fr = f >> y, rc = misc >> 12;
-        p.eroded = (int)(((fr & 1u) ? (rc & 7u) : 0u) + ((fr & 2u) ? ((rc >> 3) & 7u) : 0u) +
-                         ((fr & 4u) ? ((rc >> 6) & 7u) : 0u) + ((fr & 8u) ? ((rc >> 9) & 7u) : 0u));
-        // clear (game.py:80-87): drop each full row, everything above moves down one
-        do {
-            const uint32_t low = (1u << ctz(f)) - 1u;
+    return legal;
+}
+
+// Rare part: remove the full rows `f` (non-zero) from p.n, count them and the eroded piece cells.
+TB_HD void place_clear(const SlotDesc& d, Placement& p, uint32_t f)
+{
+    p.k = popc(f);
+    // eroded_cells (features.py:335-340): piece cells in the cleared rows, pre-clear coordinates
+    const uint32_t fr = f >> p.y, rc = d.w[0] >> 12;
+    p.eroded = (int)(((fr & 1u) ? (rc & 7u) : 0u) + ((fr & 2u) ? ((rc >> 3) & 7u) : 0u) +
+                     ((fr & 4u) ? ((rc >> 6) & 7u) : 0u) + ((fr & 8u) ? ((rc >> 9) & 7u) : 0u));
+    // clear (game.py:80-87): drop each full row, everything above moves down one
+    do {
+        const uint32_t low = (1u << ctz(f)) - 1u;
 #pragma unroll
-            for (int k = 0; k < COLS; ++k) p.n[k] = (p.n[k] & low) | ((p.n[k] >> 1) & ~low);
-            f = (f & low) | ((f >> 1) & ~low);
-        } while (f != 0u);
-    }
+        for (int k = 0; k < COLS; ++k) p.n[k] = (p.n[k] & low) | ((p.n[k] >> 1) & ~low);
+        f = (f & low) | ((f >> 1) & ~low);
+    } while (f != 0u);
+}
+
+TB_HD bool place_slot(const uint32_t c[COLS], const Heights& H, const SlotDesc& d, Placement& p)
+{
+    uint32_t f;
+    const bool legal = place_pre(c, H, d, p, &f);
+    if (legal && f != 0u) place_clear(d, p, f);
     return legal;
 }
 
@@ -507,6 +520,108 @@ TB_HD uint64_t score_key(double s)
     uint64_t b; __builtin_memcpy(&b, &s, 8);
 #endif
     return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast evaluation of the "w6" feature set (landing_height, eroded_cells, row_trans, col_trans,
+// pits, cuml_wells — SURVEY.md §8c).  Same results as eval_features<W6_MASK> + score_features, but
+// organised for a short dependency chain: when the placement clears no row (the common case)
+// the new column heights come from arithmetic on the landing row (no clz), the filled-cell count
+// is the game's count + 4 (no popc), and only the two transition counts need popc.
+// ---------------------------------------------------------------------------------------------
+struct GameStat {
+    int gh[COLS];          // column heights of the game's current board
+    Heights H;             // the same, packed (byte k = height of column k)
+    int cells;             // filled cells on the board
+};
+
+TB_HD void unpack_heights(const Heights& H, int gh[COLS])
+{
+    gh[0] = (int)byte_of(H.H0, 0); gh[1] = (int)byte_of(H.H0, 1); gh[2] = (int)byte_of(H.H0, 2); gh[3] = (int)(H.H0 >> 24);
+    gh[4] = (int)byte_of(H.H1, 0); gh[5] = (int)byte_of(H.H1, 1); gh[6] = (int)byte_of(H.H1, 2); gh[7] = (int)(H.H1 >> 24);
+    gh[8] = (int)byte_of(H.H2, 0); gh[9] = (int)byte_of(H.H2, 1);
+}
+
+TB_HD GameStat game_stat(const uint32_t c[COLS])
+{
+    GameStat g;
+    g.H = pack_heights(c);
+    unpack_heights(g.H, g.gh);
+    g.cells = 0;
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) g.cells += popc(c[k]);
+    return g;
+}
+
+struct W6Cand {            // one candidate placement in flight
+    Placement P;
+    int h[COLS];           // post-move column heights
+    int cells;             // post-move filled cells
+    uint32_t full;         // full-row mask before clearing
+    bool legal;
+};
+
+// straight-line part: landing, legality, imprint, full-row mask, no-clear heights and cell count
+TB_HD void w6_pre(const uint32_t c[COLS], const GameStat& g, const SlotDesc& d, W6Cand& a)
+{
+    a.legal = place_pre(c, g.H, d, a.P, &a.full);
+    const int yb = a.P.y - 32;
+    int t;
+    t = (int)byte_of(d.w[8], 0) + yb;  a.h[0] = t > g.gh[0] ? t : g.gh[0];
+    t = (int)byte_of(d.w[8], 1) + yb;  a.h[1] = t > g.gh[1] ? t : g.gh[1];
+    t = (int)byte_of(d.w[8], 2) + yb;  a.h[2] = t > g.gh[2] ? t : g.gh[2];
+    t = (int)(d.w[8] >> 24) + yb;      a.h[3] = t > g.gh[3] ? t : g.gh[3];
+    t = (int)byte_of(d.w[9], 0) + yb;  a.h[4] = t > g.gh[4] ? t : g.gh[4];
+    t = (int)byte_of(d.w[9], 1) + yb;  a.h[5] = t > g.gh[5] ? t : g.gh[5];
+    t = (int)byte_of(d.w[9], 2) + yb;  a.h[6] = t > g.gh[6] ? t : g.gh[6];
+    t = (int)(d.w[9] >> 24) + yb;      a.h[7] = t > g.gh[7] ? t : g.gh[7];
+    t = (int)byte_of(d.w[10], 0) + yb; a.h[8] = t > g.gh[8] ? t : g.gh[8];
+    t = (int)byte_of(d.w[10], 1) + yb; a.h[9] = t > g.gh[9] ? t : g.gh[9];
+    a.cells = g.cells + 4;
+}
+
+// rare part (call only when a.legal && a.full != 0): clear rows, then heights by clz, cells - 10 per row
+TB_HD void w6_clear(const SlotDesc& d, W6Cand& a)
+{
+    place_clear(d, a.P, a.full);
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) a.h[k] = fls(a.P.n[k]);
+    a.cells -= 10 * a.P.k;
+}
+
+// features + canonical fp64 score; returns the comparison key (0 when the slot is illegal) and the
+// packed post-move heights
+TB_HD uint64_t w6_post(const W6Cand& a, const double* w, Heights& Hn)
+{
+    const uint32_t* n = a.P.n;
+    const int* h = a.h;
+    int all_ht = ((h[0] + h[1]) + (h[2] + h[3])) + ((h[4] + h[5]) + (h[6] + h[7])) + (h[8] + h[9]);
+    const int pits = all_ht - a.cells;                                       // features.py:146-160
+    int cw = 0;                                                              // features.py:106-125
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) {
+        const int l = k == 0 ? ROWS : h[k - 1], r = k == COLS - 1 ? ROWS : h[k + 1];
+        int wl = (l < r ? l : r) - h[k]; wl = wl > 0 ? wl : 0;
+        cw += wl * (wl + 1);
+    }
+    cw >>= 1;
+    int rt = 0, ct = 0;
+#pragma unroll
+    for (int k = 0; k + 1 < COLS; ++k) rt += popc(n[k] ^ n[k + 1]);          // features.py:89-91
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) ct += popc((n[k] ^ (n[k] >> 1)) & 0x7FFFFu);   // features.py:83-85
+    Hn.H0 = (uint32_t)h[0] | (uint32_t)h[1] << 8 | (uint32_t)h[2] << 16 | (uint32_t)h[3] << 24;
+    Hn.H1 = (uint32_t)h[4] | (uint32_t)h[5] << 8 | (uint32_t)h[6] << 16 | (uint32_t)h[7] << 24;
+    Hn.H2 = (uint32_t)h[8] | (uint32_t)h[9] << 8;
+    double acc = 0.0;                                                        // canonical order
+    acc = dadd(acc, dmul(i2d(a.P.y), w[0]));                                 // landing_height
+    acc = dadd(acc, dmul(i2d(a.P.eroded), w[1]));                            // eroded_cells
+    acc = dadd(acc, dmul(i2d(rt), w[2]));                                    // row_trans
+    acc = dadd(acc, dmul(i2d(ct), w[3]));                                    // col_trans
+    acc = dadd(acc, dmul(i2d(pits), w[4]));                                  // pits
+    acc = dadd(acc, dmul(i2d(cw), w[5]));                                    // cuml_wells
+    const uint64_t key = score_key(acc);
+    return a.legal ? key : 0ull;
 }
 
 }  // namespace tb
