@@ -197,3 +197,29 @@ dist.destroy_process_group()
     gen = cross_entropy(["a", "b", "c"], 5.0, 21, 4, random.Random(3), test_f)
     want = [[[float(x).hex() for x in m.values()], [float(x).hex() for x in s.values()]] for m, s in (next(gen) for _ in range(3))]
     assert r0["refits"] == want
+
+
+def test_unmodified_reference_driver_with_evaluator_adapter(golden_ce):
+    """the UNMODIFIED cogworks.learning.cross_entropy drives the batching adapter with the
+    reference's own feature objects as mapping keys (evaluation by the C oracle here; by the GPU in test_gpu_api)."""
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not present on this box")
+    import collections.abc
+    collections.Mapping = collections.abc.Mapping
+    sys.path.insert(0, ref)
+    try:
+        from cogworks import learning as ref_learning
+        from cogworks.tetris import features as ref_features
+    finally:
+        sys.path.remove(ref)
+    from tetris_ai_b200.learning import PopulationEvaluator
+    from oracle import pyoracle
+    ce = golden_ce["ce"]
+    feats = [getattr(ref_features, n) for n in ce["features"]]
+    seqs = np.array([pyoracle.piece_sequence(ce["seed0"] + g, ce["T"]) for g in range(ce["games"])], dtype=np.uint8)
+    ev = PopulationEvaluator(_FakeEngine(), feats, ce["games"], pieces=seqs)
+    gen = ref_learning.cross_entropy(feats, ce["stdev"], ce["width"], ce["keep"], random.Random(ce["rng_seed"]), ev.test_f, map_f=ev.map_f)
+    mean, std = next(gen)
+    assert [float(v).hex() for v in mean.values()] == ce["generations"][0]["mean"]
+    assert [float(v).hex() for v in std.values()] == ce["generations"][0]["std"]
