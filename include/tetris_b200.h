@@ -83,7 +83,7 @@ typedef struct {
     const int32_t* seq_of_game;      /* i32[C*G] sequence / stream id of each game, or NULL => g % G */
     uint64_t seed;                   /* seed of the counter-based stream */
     int32_t  lookahead;              /* 1 or 2 (simulate(..., lookahead)) */
-    int32_t  lanes;                  /* lanes per game: 0 = auto, or 8 / 16 / 32 */
+    int32_t  lanes;                  /* lanes per game: 0 = auto, or 8 / 16 / 32 / 64 (64 = two warps per game; w6 set, lookahead 1 only) */
     const uint16_t* init_rows;       /* u16[C*G][20] initial boards, or NULL => empty boards */
     tb200_game_result* results;      /* [C*G], required */
     uint8_t*  trace;                 /* u8[C*G][T][4] = {rot,row,col,k} per move, or NULL */

@@ -124,7 +124,7 @@ def test_k1_best_move_golden_steps(eng, golden_steps):
                     assert r["count"][i] == want["n_leaves"]
 
 
-@pytest.mark.parametrize("lanes", [32, 16, 8])
+@pytest.mark.parametrize("lanes", [64, 32, 16, 8])
 def test_k2_golden_games(eng, golden_games, lanes):
     for g in golden_games["games"]:
         if g.get("tie") == "last":
@@ -150,7 +150,7 @@ def _weight_sets(rng, n, names, kind):
     return [[(W6_VALS[W6_NAMES.index(x)] if x in W6_NAMES else 0.0) + rng.gauss(0, 0.3) for x in names] for _ in range(n)]
 
 
-@pytest.mark.parametrize("lanes", [32, 16, 8])
+@pytest.mark.parametrize("lanes", [64, 32, 16, 8])
 @pytest.mark.parametrize("names,kind,lookahead,C,G,T", [
     (W6_NAMES, "w6", 1, 48, 4, 300),
     (W6_NAMES, "wide", 1, 96, 4, 300),
@@ -223,7 +223,7 @@ def test_properties_full_size(eng):
     w = np.array(W6_VALS)[None, :] + rng.normal(0, 2.0, size=(C, 6))
     eng.set_features(W6_NAMES)
     base = eng.play_games(w, G, T=T, seed=11, lanes=32)["results"]
-    for lanes in (16, 8):
+    for lanes in (64, 16, 8):
         other = eng.play_games(w, G, T=T, seed=11, lanes=lanes)["results"]
         assert (other == base).all()
     half = eng.play_games(w[:C // 2], G, T=T, seed=11)["results"]

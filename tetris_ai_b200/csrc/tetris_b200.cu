@@ -611,6 +611,317 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayPara
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K2p: TWO warps per game (one 64-thread block per game), lookahead 1, w6 — for populations so
+// small that warp schedulers would otherwise idle (BASELINE config 2: 1000 games on 592
+// schedulers).  Slots are split even / odd between the two warps, so every piece — including the
+// 34-slot T, L, J — is ONE pass of at most 17 lanes per warp.  Each warp finds its best slot
+// (REDUX), its winning lane publishes {key, slot, move, board, heights} to shared memory, one
+// block barrier, then both warps read both records, pick the global winner (higher key, then lower
+// slot = first in enumeration order) and commit it.  Records are double-buffered by piece parity.
+// Pieces are prefetched 32 at a time (one per lane) and handed out by shuffle.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64) play_games_w6pair_kernel(const PlayParams prm)
+{
+    __shared__ Tables s_tab;
+    __shared__ uint4 s_x[2][2][5];
+    __shared__ uint32_t s_game;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += 64) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int slot = 2 * lane + warp;              // lanes 17.. have slot >= 34: never legal
+    const int myslot = slot < TB_MAX_SLOTS ? slot : 0;
+    const uint32_t T = prm.T;
+
+    for (;;) {
+        if (threadIdx.x == 0) s_game = atomicAdd(prm.ticket, 1u);
+        __syncthreads();
+        const uint32_t game = s_game;
+        __syncthreads();
+        if (game >= prm.n_games) break;
+        const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : (prm.per_game_weights != 0 ? game : game % (uint32_t)prm.G);
+        const uint64_t stream = sq;
+        const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
+        uint32_t c[COLS];
+        if (prm.init_rows) {
+            uint16_t rows[ROWS];
+            for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
+            rows_to_cols(rows, c);
+        } else {
+#pragma unroll
+            for (int k = 0; k < COLS; ++k) c[k] = 0;
+        }
+        GameStat g = game_stat(c);
+        const int cells0 = g.cells;
+        double w[6];
+        {
+            const size_t wrow = prm.per_game_weights > 0 ? (size_t)game : (prm.per_game_weights < 0 ? 0 : (size_t)(game / (uint32_t)prm.G));
+            const double* wsrc = prm.weights + wrow * 6;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) w[i] = __ldg(wsrc + i);
+        }
+        // piece window: lane i holds pieces base+i (byte 0) and base+32+i (byte 1)
+        auto load_piece = [&](uint32_t tt) -> uint32_t {
+            if (tt >= T) return 7u;
+            return seq ? (uint32_t)__ldg(seq + tt) : (uint32_t)hashed_piece(prm.seed, stream, tt);
+        };
+        uint32_t base = 0;
+        uint32_t win = load_piece((uint32_t)lane) | load_piece(32u + (uint32_t)lane) << 8;
+        auto piece_at = [&](uint32_t tt) -> int {          // base <= tt < base + 64, uniform tt
+            const uint32_t idx = tt - base;
+            const uint32_t v = __shfl_sync(FULLMASK, win, (int)(idx & 31u));
+            return (int)((v >> ((idx >> 5) * 8u)) & 255u);
+        };
+        uint32_t t = 0, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+        uint64_t gscore = 0;
+        const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
+        int p_cur = piece_at(0), p_next = piece_at(1);
+        SlotDesc d = load_slot12(s_tab, p_cur < 7 ? p_cur : 0, myslot);
+        uint32_t par = 0;
+
+        while (t < stop && p_cur < 7) {
+            // advance the piece window when the look-ahead index leaves it
+            if (t + 2u - base >= 64u) {
+                base += 32u;
+                win = (win >> 8) | load_piece(base + 32u + (uint32_t)lane) << 8;
+            }
+            const int p_after = piece_at(t + 2u);
+            const SlotDesc d_next = load_slot12(s_tab, p_next < 7 ? p_next : 0, myslot);
+
+            W6Cand A;
+            w6_pre(c, g, d, A);
+            A.legal = A.legal && slot < (int)d.w[7];
+            if (A.legal && A.full != 0u) w6_clear(d, A);
+            Heights Hn;
+            const uint64_t key = w6_post(A, w, Hn);
+            cnt += (uint32_t)A.legal;
+            // ---- warp-local argmax ----
+            const uint32_t hi = (uint32_t)(key >> 32);
+            const uint32_t mhi = __reduce_max_sync(FULLMASK, hi);
+            const uint32_t tie = __ballot_sync(FULLMASK, hi == mhi);
+            int src = __ffs((int)tie) - 1;
+            if (mhi != 0u && (tie & (tie - 1u))) {
+                const uint32_t lo = (uint32_t)key;
+                const uint32_t mlo = __reduce_max_sync(FULLMASK, hi == mhi ? lo : 0u);
+                const uint32_t mtag = __reduce_min_sync(FULLMASK, (hi == mhi && lo == mlo) ? (uint32_t)slot : 0xffffffffu);
+                src = (int)(mtag >> 1);
+            }
+            if (lane == src) {
+                uint4* rec = s_x[par][warp];
+                const uint32_t info = (uint32_t)A.P.y | (uint32_t)A.P.k << 8 | (uint32_t)A.P.rot << 12 | (uint32_t)A.P.c0 << 16 | (uint32_t)A.P.ph << 24;
+                rec[0] = make_uint4(hi, (uint32_t)key, (uint32_t)slot, info);
+                rec[1] = make_uint4(A.P.n[0], A.P.n[1], A.P.n[2], A.P.n[3]);
+                rec[2] = make_uint4(A.P.n[4], A.P.n[5], A.P.n[6], A.P.n[7]);
+                rec[3] = make_uint4(A.P.n[8], A.P.n[9], Hn.H0, Hn.H1);
+                rec[4] = make_uint4(Hn.H2, 0u, 0u, 0u);
+            }
+            __syncthreads();
+            // ---- global winner of the two warps: higher key, then lower slot ----
+            const uint4 ra = s_x[par][0][0], rb = s_x[par][1][0];
+            const uint64_t ka = ((uint64_t)ra.x << 32) | ra.y, kb = ((uint64_t)rb.x << 32) | rb.y;
+            if ((ra.x | rb.x) == 0u) break;         // no legal placement in either half: game over (simulator.py:187-189)
+            const int wsel = (kb > ka || (kb == ka && rb.z < ra.z)) ? 1 : 0;
+            const uint4* rec = s_x[par][wsel];
+            const uint4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3], r4 = rec[4];
+            par ^= 1u;
+            c[0] = r1.x; c[1] = r1.y; c[2] = r1.z; c[3] = r1.w; c[4] = r2.x; c[5] = r2.y; c[6] = r2.z; c[7] = r2.w; c[8] = r3.x; c[9] = r3.y;
+            g.H.H0 = r3.z; g.H.H1 = r3.w; g.H.H2 = r4.x;
+            unpack_heights(g.H, g.gh);
+            const uint32_t info = r0.w;
+            const uint32_t wk = (info >> 8) & 15u;
+            if (wk != 0u) {
+                lines += wk;
+                h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
+                const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
+                gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
+            }
+            g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)lines;
+            if (threadIdx.x == 0) {
+                if (prm.trace) {
+                    const uint32_t wy = info & 255u, wph = info >> 24;
+                    const uint32_t row = (uint32_t)ROWS - wy - wph;
+                    reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = ((info >> 12) & 15u) | row << 8 | ((info >> 16) & 255u) << 16 | wk << 24;
+                }
+                if (prm.score_trace) {
+                    const uint64_t kk = wsel ? kb : ka;
+                    const uint64_t b = (kk & 0x8000000000000000ull) ? (kk & 0x7FFFFFFFFFFFFFFFull) : ~kk;
+                    prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
+                }
+            }
+            ++t;
+            p_cur = p_next; p_next = p_after;
+            d = d_next;
+        }
+        cnt = __reduce_add_sync(FULLMASK, cnt);
+        if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&prm.results[game].placements), (unsigned long long)cnt);
+        if (threadIdx.x == 0) {
+            tb200_game_result* r = prm.results + game;
+            r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4;
+            r->score = gscore;
+            if (prm.final_rows) {
+                uint16_t rows[ROWS];
+                cols_to_rows(c, rows);
+                for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2g: the throughput kernel for the w6 set, lookahead 1: LANES (8 or 16) lanes per game, 32/LANES
+// games per warp, for populations larger than one resident wave (BASELINE configs[2] / [4]).
+// Same fast evaluation as K2f (w6_pre / w6_clear / w6_post: no clz, popc only for the transition
+// counts), slots in rounds of LANES with a per-lane running best, shuffle-butterfly argmax inside
+// the group, commit by re-placing the winning slot with w6_pre (its heights come out of the
+// placement arithmetic, so the commit needs no clz either).  Persistent, ticket per group.
+// ---------------------------------------------------------------------------------------------
+template <int LANES>
+__global__ void __launch_bounds__(BLOCK) play_games_w6grp_kernel(const PlayParams prm)
+{
+    __shared__ Tables s_tab;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (LANES - 1);
+    const uint32_t T = prm.T;
+    const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
+
+    bool active = false, exhausted = false;
+    uint32_t game = 0, t = 0, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+    uint64_t gscore = 0, stream = 0;
+    const uint8_t* seq = nullptr;
+    uint32_t c[COLS];
+    GameStat g;
+    int cells0 = 0;
+    double w[6];
+    int p_cur = 7, p_next = 7;
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) { c[k] = 0; g.gh[k] = 0; }
+    g.H.H0 = g.H.H1 = g.H.H2 = 0; g.cells = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) w[i] = 0.0;
+
+    auto fetch_piece = [&](uint32_t tt) -> int {
+        if (tt >= T) return 7;
+        return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, stream, tt);
+    };
+
+    for (;;) {
+        const bool want = !active && !exhausted;
+        uint32_t tk = 0;
+        if (want && gl == 0) tk = atomicAdd(prm.ticket, 1u);
+        tk = __shfl_sync(FULLMASK, tk, 0, LANES);
+        if (want) {
+            if (tk < prm.n_games) {
+                game = tk; active = true; t = 0; lines = h1 = h2 = h3 = h4 = 0; cnt = 0; gscore = 0;
+                const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : (prm.per_game_weights != 0 ? game : game % (uint32_t)prm.G);
+                stream = sq;
+                seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
+                if (prm.init_rows) {
+                    uint16_t rows[ROWS];
+                    for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
+                    rows_to_cols(rows, c);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < COLS; ++k) c[k] = 0;
+                }
+                g = game_stat(c);
+                cells0 = g.cells;
+                const size_t wrow = prm.per_game_weights > 0 ? (size_t)game : (prm.per_game_weights < 0 ? 0 : (size_t)(game / (uint32_t)prm.G));
+                const double* wsrc = prm.weights + wrow * 6;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) w[i] = __ldg(wsrc + i);
+                p_cur = fetch_piece(0); p_next = fetch_piece(1);
+                if (stop == 0 || p_cur >= 7) {            // nothing to play: finish immediately
+                    if (gl == 0) { tb200_game_result* r = prm.results + game; r->pieces = 0; r->lines = 0; r->score = 0; }
+                    active = false;
+                }
+            } else {
+                exhausted = true;
+            }
+        }
+        if (!__any_sync(FULLMASK, active)) break;
+
+        const int p_after = active ? fetch_piece(t + 2) : 7;
+        uint64_t key = 0; uint32_t tag = 0;
+        if (active) {
+            const int pc = p_cur < 7 ? p_cur : 0;
+            const int ns = p_cur < 7 ? s_tab.nslots[pc] : 0;
+            for (int s = gl; s < ns; s += LANES) {
+                const SlotDesc d = load_slot12(s_tab, pc, s);
+                W6Cand A;
+                w6_pre(c, g, d, A);
+                if (A.legal && A.full != 0u) w6_clear(d, A);
+                Heights Hn;
+                const uint64_t k = w6_post(A, w, Hn);
+                cnt += (uint32_t)A.legal;
+                if (k > key) { key = k; tag = (uint32_t)s; }
+            }
+        }
+        group_argmax<LANES>(key, tag);
+        if (active) {
+            bool finish = false;
+            if (key == 0) {
+                finish = true;                            // no legal placement: game over
+            } else {
+                const SlotDesc d = load_slot12(s_tab, p_cur, (int)tag);
+                W6Cand A;
+                w6_pre(c, g, d, A);
+                if (A.full != 0u) w6_clear(d, A);
+#pragma unroll
+                for (int k = 0; k < COLS; ++k) { c[k] = A.P.n[k]; g.gh[k] = A.h[k]; }
+                g.H.H0 = (uint32_t)A.h[0] | (uint32_t)A.h[1] << 8 | (uint32_t)A.h[2] << 16 | (uint32_t)A.h[3] << 24;
+                g.H.H1 = (uint32_t)A.h[4] | (uint32_t)A.h[5] << 8 | (uint32_t)A.h[6] << 16 | (uint32_t)A.h[7] << 24;
+                g.H.H2 = (uint32_t)A.h[8] | (uint32_t)A.h[9] << 8;
+                const uint32_t wk = (uint32_t)A.P.k;
+                if (wk != 0u) {
+                    lines += wk;
+                    h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
+                    const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
+                    gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
+                }
+                g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)lines;
+                if (gl == 0) {
+                    if (prm.trace) {
+                        const uint32_t row = (uint32_t)(ROWS - A.P.y - A.P.ph);
+                        reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = (uint32_t)A.P.rot | row << 8 | (uint32_t)A.P.c0 << 16 | wk << 24;
+                    }
+                    if (prm.score_trace) {
+                        const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
+                        prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
+                    }
+                }
+                ++t;
+                p_cur = p_next; p_next = p_after;
+                if (t >= stop || p_cur >= 7) finish = true;
+            }
+            if (finish) {
+                if (gl == 0) {
+                    tb200_game_result* r = prm.results + game;
+                    r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4;
+                    r->score = gscore;
+                    if (prm.final_rows) {
+                        uint16_t rows[ROWS];
+                        cols_to_rows(c, rows);
+                        for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2];
+                    }
+                }
+                if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&prm.results[game].placements), (unsigned long long)cnt);
+                active = false;
+            }
+        }
+    }
+}
+
 // K3: all 45 features of one placement per thread
 __global__ void eval_features_kernel(int N, const uint16_t* prev_boards, const uint8_t* piece, const uint8_t* rot,
                                      const uint8_t* col, double* out_features, int32_t* out_info, uint16_t* out_rows)
@@ -706,6 +1017,9 @@ static play_fn pick_lanes(int lanes)
 }
 static play_fn pick_kernel(int mode, int lookahead, int lanes)
 {
+    if (lanes == 64) return play_games_w6pair_kernel;      // caller guarantees lookahead 1 and the w6 set
+    if (lookahead == 1 && mode == MODE_W6 && lanes == 16) return play_games_w6grp_kernel<16>;
+    if (lookahead == 1 && mode == MODE_W6 && lanes == 8) return play_games_w6grp_kernel<8>;
     if (lookahead == 1 && lanes == 32) {
         if (mode == MODE_W6) return play_games_w6fast_kernel;
         if (mode == MODE_ALL45) return play_games_w32_kernel<MODE_ALL45>;
@@ -867,17 +1181,22 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
     const long long n_games_ll = (long long)a.n_candidates * a.games_per_candidate;
     const uint32_t n_games = (uint32_t)n_games_ll;
     int lanes = a.lanes;
-    if (lanes != 8 && lanes != 16 && lanes != 32) {
-        // auto: one warp per game while the whole population fits in one resident wave (lowest latency
-        // per piece), narrower groups when there are more games than resident warps (throughput).
+    const bool pair_ok = ctx->mode == tb::MODE_W6 && a.lookahead == 1;
+    if (lanes == 64 && !pair_ok) lanes = 32;
+    if (lanes != 8 && lanes != 16 && lanes != 32 && lanes != 64) {
+        // auto: two warps per game while even that leaves warp schedulers idle (lowest latency per piece),
+        // one warp per game while the whole population fits in one resident wave, narrower groups when
+        // there are more games than resident warps (throughput).
         const long long resident_warps = (long long)ctx->sms * 16;
-        lanes = n_games_ll <= resident_warps ? 32 : (n_games_ll <= 2 * resident_warps ? 16 : 8);
+        if (pair_ok && 2 * n_games_ll <= resident_warps) lanes = 64;
+        else lanes = n_games_ll <= resident_warps ? 32 : (n_games_ll <= 2 * resident_warps ? 16 : 8);
     }
     tb::play_fn fn = tb::pick_kernel(ctx->mode, a.lookahead, lanes);
+    const int block = lanes == 64 ? 64 : tb::BLOCK;
     int occ = 0;
-    TB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, tb::BLOCK, 0));
+    TB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, block, 0));
     if (occ < 1) occ = 1;
-    const int groups_per_block = tb::BLOCK / lanes;
+    const int groups_per_block = lanes == 64 ? 1 : tb::BLOCK / lanes;
     long long blocks = (n_games_ll + groups_per_block - 1) / groups_per_block;
     const long long max_blocks = (long long)ctx->sms * occ;
     if (blocks > max_blocks) blocks = max_blocks;
@@ -895,7 +1214,7 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
     TB_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(uint32_t), st));
     TB_CUDA(ctx, cudaMemsetAsync(a.results, 0, sizeof(tb200_game_result) * (size_t)n_games, st));
     TB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
-    fn<<<(unsigned)blocks, tb::BLOCK, 0, st>>>(p);
+    fn<<<(unsigned)blocks, block, 0, st>>>(p);
     TB_CUDA(ctx, cudaGetLastError());
     TB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     *launches += 1;
@@ -904,7 +1223,7 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
         TB_CUDA(ctx, cudaGetLastError());
         *launches += 1;
     }
-    ctx->timing.lanes = lanes; ctx->timing.grid = (int)blocks; ctx->timing.block = tb::BLOCK;
+    ctx->timing.lanes = lanes; ctx->timing.grid = (int)blocks; ctx->timing.block = block;
     return TB200_OK;
 }
 

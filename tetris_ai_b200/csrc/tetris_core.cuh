@@ -148,6 +148,15 @@ TB_HD double i2d(int x)                      // exact int -> double without the 
 #endif
 }
 
+TB_HD double u2d(int x)                      // exact conversion of a NON-NEGATIVE int (one DADD, no integer op)
+{
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(__hiloint2double(0x43300000, x), 4503599627370496.0);      // (2^52 + x) - 2^52
+#else
+    return (double)x;
+#endif
+}
+
 // ---------------------------------------------------------------------------------------------
 // K4: counter-based piece stream (bit-identical twins: oracle/pyoracle.py hashed_piece,
 // oracle/coracle.c hashed_piece)
@@ -597,29 +606,31 @@ TB_HD uint64_t w6_post(const W6Cand& a, const double* w, Heights& Hn)
     const int* h = a.h;
     int all_ht = ((h[0] + h[1]) + (h[2] + h[3])) + ((h[4] + h[5]) + (h[6] + h[7])) + (h[8] + h[9]);
     const int pits = all_ht - a.cells;                                       // features.py:146-160
-    int cw = 0;                                                              // features.py:106-125
+    int w1 = 0, w2 = 0;                                                      // features.py:106-125: sum w(w+1)/2
 #pragma unroll
     for (int k = 0; k < COLS; ++k) {
         const int l = k == 0 ? ROWS : h[k - 1], r = k == COLS - 1 ? ROWS : h[k + 1];
         int wl = (l < r ? l : r) - h[k]; wl = wl > 0 ? wl : 0;
-        cw += wl * (wl + 1);
+        w1 += wl; w2 += wl * wl;
     }
-    cw >>= 1;
+    const int cw = (w1 + w2) >> 1;
     int rt = 0, ct = 0;
 #pragma unroll
     for (int k = 0; k + 1 < COLS; ++k) rt += popc(n[k] ^ n[k + 1]);          // features.py:89-91
+    // features.py:83-85: bit i of n ^ 2n (i = 1..19) compares heights i-1 and i; the doubling is an integer
+    // multiply-add, which runs on the FMA pipe instead of the (busier) ALU pipe
 #pragma unroll
-    for (int k = 0; k < COLS; ++k) ct += popc((n[k] ^ (n[k] >> 1)) & 0x7FFFFu);   // features.py:83-85
+    for (int k = 0; k < COLS; ++k) ct += popc((n[k] ^ (n[k] * 2u)) & 0xFFFFEu);
     Hn.H0 = (uint32_t)h[0] | (uint32_t)h[1] << 8 | (uint32_t)h[2] << 16 | (uint32_t)h[3] << 24;
     Hn.H1 = (uint32_t)h[4] | (uint32_t)h[5] << 8 | (uint32_t)h[6] << 16 | (uint32_t)h[7] << 24;
     Hn.H2 = (uint32_t)h[8] | (uint32_t)h[9] << 8;
     double acc = 0.0;                                                        // canonical order
-    acc = dadd(acc, dmul(i2d(a.P.y), w[0]));                                 // landing_height
-    acc = dadd(acc, dmul(i2d(a.P.eroded), w[1]));                            // eroded_cells
-    acc = dadd(acc, dmul(i2d(rt), w[2]));                                    // row_trans
-    acc = dadd(acc, dmul(i2d(ct), w[3]));                                    // col_trans
-    acc = dadd(acc, dmul(i2d(pits), w[4]));                                  // pits
-    acc = dadd(acc, dmul(i2d(cw), w[5]));                                    // cuml_wells
+    acc = dadd(acc, dmul(u2d(a.P.y), w[0]));                                 // landing_height (all six are >= 0)
+    acc = dadd(acc, dmul(u2d(a.P.eroded), w[1]));                            // eroded_cells
+    acc = dadd(acc, dmul(u2d(rt), w[2]));                                    // row_trans
+    acc = dadd(acc, dmul(u2d(ct), w[3]));                                    // col_trans
+    acc = dadd(acc, dmul(u2d(pits), w[4]));                                  // pits
+    acc = dadd(acc, dmul(u2d(cw), w[5]));                                    // cuml_wells
     const uint64_t key = score_key(acc);
     return a.legal ? key : 0ull;
 }

@@ -47,14 +47,14 @@ def main():
     pops, seqs = ce_populations()
     rows = []
     for gi, pop in enumerate(pops):
-        for lanes in (32, 16, 8):
+        for lanes in (64, 32, 16, 8):
             ms, out = timeit(eng, 5, weights=pop, games_per_candidate=10, pieces=seqs, lanes=lanes)
             pl = int(out["results"]["placements"].sum())
             rows.append(("ce_gen%d 100x10" % gi, lanes, ms, pl, int(out["results"]["pieces"].sum())))
     rng = np.random.default_rng(1)
     for n in (1024, 8192, 65536, 262144):
         w = np.array(W6_VALS)[None, :] + rng.normal(0, 3.0, size=(n, 6))
-        for lanes in (32, 16, 8):
+        for lanes in ((64, 32, 16, 8) if n <= 8192 else (32, 16, 8)):
             ms, out = timeit(eng, 2, weights=w, games_per_candidate=1, T=400, seed=5, seq_of_game=np.arange(n, dtype=np.int32), lanes=lanes)
             pl = int(out["results"]["placements"].sum())
             rows.append(("sweep %d games T=400" % n, lanes, ms, pl, int(out["results"]["pieces"].sum())))
