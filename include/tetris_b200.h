@@ -76,7 +76,7 @@ typedef struct {
     int32_t  n_candidates;           /* C */
     int32_t  games_per_candidate;    /* G; game g belongs to candidate g / G */
     const double*  weights;          /* f64[C][F], F and the order from tb200_set_features (learning.py:32-35) */
-    const uint8_t* pieces;           /* u8[S][T] piece ids, or NULL => counter-based stream (seed, stream id, t) */
+    const uint8_t* pieces;           /* u8[S][T] piece ids (an id > 6 ends the game there), or NULL => counter-based stream (seed, stream id, t) */
     int32_t  n_sequences;            /* S */
     uint32_t T;                      /* pieces per sequence = cap on the game length */
     uint32_t max_moves;              /* stop (not game over) after this many placements; 0 => T */

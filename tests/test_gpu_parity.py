@@ -230,3 +230,95 @@ def test_properties_full_size(eng):
     assert (half == base[: C // 2 * G]).all()
     assert (base["lines"] == (base["hist"] * np.array([1, 2, 3, 4])).sum(axis=1)).all()
     assert (base["pieces"] <= T).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases: tiny / ragged shapes, immediate game over, max_moves, explicit sequence maps, many tickets
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lanes", [0, 64, 32, 16, 8])
+def test_edge_shapes(eng, lanes):
+    fids = [pyoracle.FEATURE_ID[n] for n in W6_NAMES]
+    eng.set_features(W6_NAMES)
+    # one candidate, one game, one piece
+    r = eng.play_games(np.array([W6_VALS]), 1, pieces=np.array([[3]], dtype=np.uint8), lanes=lanes, want_trace=True)
+    o = coracle.play_one(fids, W6_VALS, [3], 1)
+    assert int(r["results"]["pieces"][0]) == 1 and r["trace"][0, 0].tobytes() == o["trace"][0].tobytes()
+    # ragged: 7 candidates x 3 games (21 games: not a multiple of any group count), explicit sequence map, S > G
+    rng = np.random.default_rng(17)
+    w = np.array(W6_VALS)[None, :] + rng.normal(0, 4.0, size=(7, 6))
+    seqs = rng.integers(0, 7, size=(5, 90)).astype(np.uint8)
+    smap = rng.integers(0, 5, size=21).astype(np.int32)
+    r = eng.play_games(w, 3, pieces=seqs, seq_of_game=smap, lanes=lanes, want_trace=True, want_final=True)
+    for g in range(21):
+        o = coracle.play_one(fids, w[g // 3], seqs[smap[g]], 1)
+        n = o["pieces"]
+        assert int(r["results"]["pieces"][g]) == n and int(r["results"]["score"][g]) == o["score"]
+        assert r["trace"][g, :n].tobytes() == o["trace"].tobytes() and list(r["final"][g]) == list(o["final"])
+
+
+@pytest.mark.parametrize("lanes", [64, 32, 8])
+@pytest.mark.parametrize("lookahead", [1, 2])
+def test_edge_initial_boards_and_max_moves(eng, lanes, lookahead):
+    fids = [pyoracle.FEATURE_ID[n] for n in W6_NAMES]
+    eng.set_features(W6_NAMES)
+    rng = np.random.default_rng(23)
+    boards = []
+    tall = [0x1FF] * 19 + [0x3FE]                 # heights 19..: only a vertical I in the last column or nothing fits
+    tall[0] = 0x0FF
+    boards.append(tall)
+    boards.append([0] * 12 + [0x155, 0x2AA, 0x155, 0x2AA, 0x3FE, 0x1FF, 0x3FD, 0x37F])
+    boards.append([0] * 20)
+    boards = np.array(boards, dtype=np.uint16)
+    seqs = rng.integers(0, 7, size=(3, 40)).astype(np.uint8)
+    w = np.array(W6_VALS)[None, :] + rng.normal(0, 1.0, size=(3, 6))
+    for max_moves in (0, 1, 7):
+        r = eng.play_games(w, 1, pieces=seqs, seq_of_game=np.arange(3, dtype=np.int32), init_rows=boards, lookahead=lookahead,
+                           lanes=lanes, max_moves=max_moves, want_trace=True, want_final=True)
+        for g in range(3):
+            # the oracle has no max_moves: a game stopped after m moves equals the first m moves of the full game
+            o = coracle.play_one(fids, w[g], seqs[g], lookahead, init_rows=boards[g])
+            n = int(r["results"]["pieces"][g])
+            if max_moves == 0:
+                assert n == o["pieces"] and list(r["final"][g]) == list(o["final"]) and int(r["results"]["lines"][g]) == o["lines"]
+            else:
+                assert n == min(max_moves, o["pieces"])
+            if lookahead == 1 or max_moves == 0:
+                assert r["trace"][g, :n].tobytes() == o["trace"][:n].tobytes()
+
+
+def test_edge_many_tickets_and_determinism(eng):
+    """More games than resident groups for the wide kernels (persistent blocks take several tickets); repeated calls agree."""
+    eng.set_features(W6_NAMES)
+    rng = np.random.default_rng(31)
+    C = 6000
+    w = rng.normal(0, 10.0, size=(C, 6))
+    a = eng.play_games(w, 1, T=120, seed=3, seq_of_game=np.arange(C, dtype=np.int32), lanes=64)["results"]
+    b = eng.play_games(w, 1, T=120, seed=3, seq_of_game=np.arange(C, dtype=np.int32), lanes=32)["results"]
+    c = eng.play_games(w, 1, T=120, seed=3, seq_of_game=np.arange(C, dtype=np.int32), lanes=8)["results"]
+    d = eng.play_games(w, 1, T=120, seed=3, seq_of_game=np.arange(C, dtype=np.int32), lanes=64)["results"]
+    assert (a == b).all() and (a == c).all() and (a == d).all()
+    fids = [pyoracle.FEATURE_ID[n] for n in W6_NAMES]
+    o = coracle.play_games(fids, w[:500], 1, T=120, seed=3, seq_of_game=np.arange(500, dtype=np.int32), threads=16)
+    assert (a["pieces"][:500] == o["pieces"]).all() and (a["score"][:500] == o["score"]).all()
+
+
+def test_edge_invalid_piece_ends_game(eng):
+    """A piece id outside 0..6 is treated as the end of the sequence (documented in tetris_b200.h)."""
+    eng.set_features(W6_NAMES)
+    seq = np.array([[1, 2, 9, 3, 4]], dtype=np.uint8)
+    for lanes in (64, 32, 16, 8):
+        r = eng.play_games(np.array([W6_VALS]), 1, pieces=seq, lanes=lanes)
+        assert int(r["results"]["pieces"][0]) == 2
+
+
+def test_k1_large_batch(eng, golden_steps):
+    steps = [s for s in golden_steps["steps"] if s["l1"] is not None and [n for n, _ in s["weights"]] == W6_NAMES]
+    assert len(steps) > 20
+    reps = 3000 // len(steps) + 1
+    ss = (steps * reps)[:3000]
+    eng.set_features(W6_NAMES)
+    r = eng.best_move(np.array([s["board"] for s in ss], dtype=np.uint16), [s["piece"] for s in ss], None,
+                      np.array([[x for _, x in s["weights"]] for s in ss]), lookahead=1)
+    for i, s in enumerate(ss):
+        want = s["l1"]
+        assert tuple(int(x) for x in r["move"][i]) == (want["rot"], want["row"], want["col"], want["k"])
