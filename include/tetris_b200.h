@@ -37,6 +37,7 @@
 #ifndef TETRIS_B200_H
 #define TETRIS_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -83,7 +84,7 @@ typedef struct {
     const int32_t* seq_of_game;      /* i32[C*G] sequence / stream id of each game, or NULL => g % G */
     uint64_t seed;                   /* seed of the counter-based stream */
     int32_t  lookahead;              /* 1 or 2 (simulate(..., lookahead)) */
-    int32_t  lanes;                  /* lanes per game: 0 = auto, or 8 / 16 / 32 / 64 (64 = two warps per game; w6 set, lookahead 1 only) */
+    int32_t  lanes;                  /* lanes per game: 0 = auto, or 8 / 16 / 32; for the w6 set with lookahead 1 also 64 (two warps per game), 4, 2, 1 */
     const uint16_t* init_rows;       /* u16[C*G][20] initial boards, or NULL => empty boards */
     tb200_game_result* results;      /* [C*G], required */
     uint8_t*  trace;                 /* u8[C*G][T][4] = {rot,row,col,k} per move, or NULL */
@@ -101,6 +102,12 @@ typedef struct {
     int32_t kernels_launched;        /* number of kernels of this library launched by the call */
     uint64_t h2d_bytes, d2h_bytes;   /* host mode: bytes staged each way */
 } tb200_timing;
+
+/* page-locked host memory for staging buffers (optional).  A TB200_MEM_HOST play_games call whose buffers are
+ * all pinned and that repeats the previous call's arguments (one CE generation after another) is replayed as a
+ * CUDA graph: one launch instead of a dozen runtime calls.  Set TB200_NO_GRAPHS=1 to disable. */
+int  tb200_alloc_pinned(size_t bytes, void** out);
+void tb200_free_pinned(void* p);
 
 int  tb200_create(int device, tb200_ctx** out);
 void tb200_destroy(tb200_ctx* ctx);

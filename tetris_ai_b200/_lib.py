@@ -44,7 +44,7 @@ class Timing(ctypes.Structure):
 EXPORTS = (
     "tb200_create", "tb200_destroy", "tb200_last_error", "tb200_version", "tb200_device_info",
     "tb200_set_features", "tb200_play_games", "tb200_last_timing", "tb200_best_move",
-    "tb200_eval_features", "tb200_hashed_pieces",
+    "tb200_eval_features", "tb200_hashed_pieces", "tb200_alloc_pinned", "tb200_free_pinned",
 )
 
 _LIB = None
@@ -83,5 +83,9 @@ def load():
     L.tb200_eval_features.restype = ctypes.c_int
     L.tb200_hashed_pieces.argtypes = [vp, i32, vp, u64, u64, i32, u32, vp]
     L.tb200_hashed_pieces.restype = ctypes.c_int
+    L.tb200_alloc_pinned.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]
+    L.tb200_alloc_pinned.restype = ctypes.c_int
+    L.tb200_free_pinned.argtypes = [vp]
+    L.tb200_free_pinned.restype = None
     _LIB = L
     return L

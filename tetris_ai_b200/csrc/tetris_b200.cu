@@ -495,30 +495,43 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayPara
 #pragma unroll
             for (int i = 0; i < 6; ++i) w[i] = __ldg(wsrc + i);
         }
-        auto fetch_piece = [&](uint32_t tt) -> int {
-            if (tt >= T) return 7;
-            return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, stream, tt);
+        // piece window: lane i holds pieces base+i (byte 0) and base+32+i (byte 1); handed out by shuffle
+        auto load_piece = [&](uint32_t tt) -> uint32_t {
+            if (tt >= T) return 7u;
+            return seq ? (uint32_t)__ldg(seq + tt) : (uint32_t)hashed_piece(prm.seed, stream, tt);
+        };
+        uint32_t base = 0;
+        uint32_t win = load_piece((uint32_t)lane) | load_piece(32u + (uint32_t)lane) << 8;
+        auto piece_at = [&](uint32_t tt) -> int {          // base <= tt < base + 64, tt warp-uniform
+            const uint32_t idx = tt - base;
+            const uint32_t v = __shfl_sync(FULLMASK, win, (int)(idx & 31u));
+            return (int)((v >> ((idx >> 5) * 8u)) & 255u);
         };
         uint32_t t = 0, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
         uint64_t gscore = 0;
         const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
-        int p_cur = fetch_piece(0), p_next = fetch_piece(1);
-        // descriptors of the current piece (prefetched one piece ahead, they do not depend on the board)
-        int ns = p_cur < 7 ? s_tab.nslots[p_cur] : 0;
-        SlotDesc dA = load_slot12(s_tab, p_cur < 7 ? p_cur : 0, lane < ns ? lane : 0);
-        SlotDesc dB = load_slot12(s_tab, p_cur < 7 ? p_cur : 0, lane + 32 < ns ? lane + 32 : 0);
+        int p_cur = piece_at(0), p_next = piece_at(1);
+        // descriptors of the current piece (prefetched one piece ahead, they do not depend on the board);
+        // word 7 of every descriptor of a piece (padding slots included) is its slot count
+        const int slotB = lane < 2 ? lane + 32 : 0;
+        SlotDesc dA = load_slot12(s_tab, p_cur < 7 ? p_cur : 0, lane);
+        SlotDesc dB = load_slot12(s_tab, p_cur < 7 ? p_cur : 0, slotB);
 
 #ifdef TB_PHASES
         long long ph[8] = {0,0,0,0,0,0,0,0}; long long last_ = clock64();
 #endif
         while (t < stop && p_cur < 7) {
             PH(5)
-            const int p_after = fetch_piece(t + 2);
+            if (t + 2u - base >= 64u) {              // advance the piece window
+                base += 32u;
+                win = (win >> 8) | load_piece(base + 32u + (uint32_t)lane) << 8;
+            }
+            const int p_after = piece_at(t + 2u);
             // prefetch the next piece's descriptors
             const int pn = p_next < 7 ? p_next : 0;
-            const int ns_next = p_next < 7 ? s_tab.nslots[pn] : 0;
-            const SlotDesc dA_next = load_slot12(s_tab, pn, lane < ns_next ? lane : 0);
-            const SlotDesc dB_next = load_slot12(s_tab, pn, lane + 32 < ns_next ? lane + 32 : 0);
+            const SlotDesc dA_next = load_slot12(s_tab, pn, lane);
+            const SlotDesc dB_next = load_slot12(s_tab, pn, slotB);
+            const int ns = (int)dA.w[7];
 
             PH(0)
             W6Cand A;
@@ -573,11 +586,13 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayPara
             const uint32_t info = __shfl_sync(FULLMASK, (uint32_t)A.P.y | (uint32_t)A.P.k << 8 | (uint32_t)A.P.rot << 12 | (uint32_t)A.P.c0 << 16 | (uint32_t)A.P.ph << 24, src);
             unpack_heights(g.H, g.gh);
             const uint32_t wk = (info >> 8) & 15u;
-            lines += wk;
+            if (wk != 0u) {
+                lines += wk;
+                h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
+                const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
+                gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
+            }
             g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)lines;
-            h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
-            const uint32_t pts = wk == 0 ? 0u : (wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u)));
-            gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
             if (prm.trace && lane == 0) {
                 const uint32_t wy = info & 255u, wph = info >> 24;
                 const uint32_t row = (uint32_t)ROWS - wy - wph;
@@ -591,7 +606,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayPara
             }
             ++t;
             p_cur = p_next; p_next = p_after;
-            ns = ns_next; dA = dA_next; dB = dB_next;
+            dA = dA_next; dB = dB_next;
             PH(4)
         }
 #ifdef TB_PHASES
@@ -1020,6 +1035,9 @@ static play_fn pick_kernel(int mode, int lookahead, int lanes)
     if (lanes == 64) return play_games_w6pair_kernel;      // caller guarantees lookahead 1 and the w6 set
     if (lookahead == 1 && mode == MODE_W6 && lanes == 16) return play_games_w6grp_kernel<16>;
     if (lookahead == 1 && mode == MODE_W6 && lanes == 8) return play_games_w6grp_kernel<8>;
+    if (lookahead == 1 && mode == MODE_W6 && lanes == 4) return play_games_w6grp_kernel<4>;
+    if (lookahead == 1 && mode == MODE_W6 && lanes == 2) return play_games_w6grp_kernel<2>;
+    if (lookahead == 1 && mode == MODE_W6 && lanes == 1) return play_games_w6grp_kernel<1>;
     if (lookahead == 1 && lanes == 32) {
         if (mode == MODE_W6) return play_games_w6fast_kernel;
         if (mode == MODE_ALL45) return play_games_w32_kernel<MODE_ALL45>;
@@ -1058,6 +1076,18 @@ struct tb200_ctx {
     // staging arena for TB200_MEM_HOST calls (grown on demand, reused across calls)
     char* d_arena = nullptr;
     size_t arena_cap = 0;
+    // CUDA-graph cache of the last host-mode play_games call: when the same call (same pinned host buffers,
+    // sizes and options) is repeated — one CE generation after another — the whole H2D / memset / kernels /
+    // D2H sequence is replayed with one cudaGraphLaunch instead of ~12 runtime calls.
+    bool graphs_enabled = true;
+    bool graph_valid = false;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    tb200_play_args graph_args{};
+    int graph_F = 0, graph_mode = 0;
+    uint8_t graph_ids[TB200_MAX_WEIGHTED] = {0};
+    char* graph_arena = nullptr;
+    tb200_timing graph_timing{};
 };
 
 static int fail(tb200_ctx* ctx, int code, const std::string& msg)
@@ -1070,9 +1100,25 @@ static int fail(tb200_ctx* ctx, int code, const std::string& msg)
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
+static void drop_graph(tb200_ctx* ctx)
+{
+    if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+    if (ctx->graph) cudaGraphDestroy(ctx->graph);
+    ctx->graph_exec = nullptr; ctx->graph = nullptr; ctx->graph_valid = false;
+}
+
+static bool is_pinned(const void* p)
+{
+    if (!p) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
 static int ensure_arena(tb200_ctx* ctx, size_t bytes)
 {
     if (bytes <= ctx->arena_cap) return TB200_OK;
+    drop_graph(ctx);
     if (ctx->d_arena) { TB_CUDA(ctx, cudaFree(ctx->d_arena)); ctx->d_arena = nullptr; ctx->arena_cap = 0; }
     const size_t cap = bytes + bytes / 4 + (1u << 20);
     TB_CUDA(ctx, cudaMalloc(&ctx->d_arena, cap));
@@ -1118,14 +1164,24 @@ int tb200_create(int device, tb200_ctx** out)
         tb200_destroy(ctx);
         return TB200_E_CUDA;
     }
+    if (getenv("TB200_NO_GRAPHS")) ctx->graphs_enabled = false;
     *out = ctx;
     return TB200_OK;
 }
+
+int tb200_alloc_pinned(size_t bytes, void** out)
+{
+    if (!out || bytes == 0) return TB200_E_BAD_ARG;
+    return cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess ? TB200_OK : TB200_E_ALLOC;
+}
+
+void tb200_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 
 void tb200_destroy(tb200_ctx* ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    drop_graph(ctx);
     if (ctx->d_ticket) cudaFree(ctx->d_ticket);
     if (ctx->d_arena) cudaFree(ctx->d_arena);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -1183,13 +1239,16 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
     int lanes = a.lanes;
     const bool pair_ok = ctx->mode == tb::MODE_W6 && a.lookahead == 1;
     if (lanes == 64 && !pair_ok) lanes = 32;
-    if (lanes != 8 && lanes != 16 && lanes != 32 && lanes != 64) {
-        // auto: two warps per game while even that leaves warp schedulers idle (lowest latency per piece),
-        // one warp per game while the whole population fits in one resident wave, narrower groups when
-        // there are more games than resident warps (throughput).
-        const long long resident_warps = (long long)ctx->sms * 16;
-        if (pair_ok && 2 * n_games_ll <= resident_warps) lanes = 64;
-        else lanes = n_games_ll <= resident_warps ? 32 : (n_games_ll <= 2 * resident_warps ? 16 : 8);
+    const bool narrow_ok = pair_ok && (lanes == 4 || lanes == 2 || lanes == 1);
+    if (!narrow_ok && lanes != 8 && lanes != 16 && lanes != 32 && lanes != 64) {
+        // auto (measured on B200, tools/lanes_sweep.py): two warps per game only while that still leaves warp
+        // schedulers idle; one warp per game while the population is a few resident waves (lowest latency per
+        // piece); narrower groups — more games per warp, better lane utilisation — as the population grows.
+        const long long per_sm = (n_games_ll + ctx->sms - 1) / ctx->sms;
+        if (pair_ok && per_sm <= 4) lanes = 64;
+        else if (per_sm <= 80) lanes = 32;
+        else if (pair_ok) lanes = per_sm <= 320 ? 8 : (per_sm <= 700 ? 4 : 2);
+        else lanes = per_sm <= 160 ? 16 : 8;
     }
     tb::play_fn fn = tb::pick_kernel(ctx->mode, a.lookahead, lanes);
     const int block = lanes == 64 ? 64 : tb::BLOCK;
@@ -1290,24 +1349,63 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
     d.final_rows = a.final_rows ? (uint16_t*)(base + o_f) : nullptr;
     d.fitness = a.fitness ? (double*)(base + o_fit) : nullptr;
 
-    TB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
-    TB_CUDA(ctx, cudaMemcpyAsync((void*)d.weights, a.weights, b_w, cudaMemcpyHostToDevice, st));
-    if (b_p) TB_CUDA(ctx, cudaMemcpyAsync((void*)d.pieces, a.pieces, b_p, cudaMemcpyHostToDevice, st));
-    if (b_s) TB_CUDA(ctx, cudaMemcpyAsync((void*)d.seq_of_game, a.seq_of_game, b_s, cudaMemcpyHostToDevice, st));
-    if (b_i) TB_CUDA(ctx, cudaMemcpyAsync((void*)d.init_rows, a.init_rows, b_i, cudaMemcpyHostToDevice, st));
-    if (b_t) TB_CUDA(ctx, cudaMemsetAsync(d.trace, 0, b_t, st));
-    if (b_st) TB_CUDA(ctx, cudaMemsetAsync(d.score_trace, 0, b_st, st));
-    rc = launch_play(ctx, d, st, 0, &launches);
-    if (rc) return rc;
-    TB_CUDA(ctx, cudaMemcpyAsync(a.results, d.results, b_r, cudaMemcpyDeviceToHost, st));
-    if (b_t) TB_CUDA(ctx, cudaMemcpyAsync(a.trace, d.trace, b_t, cudaMemcpyDeviceToHost, st));
-    if (b_st) TB_CUDA(ctx, cudaMemcpyAsync(a.score_trace, d.score_trace, b_st, cudaMemcpyDeviceToHost, st));
-    if (b_f) TB_CUDA(ctx, cudaMemcpyAsync(a.final_rows, d.final_rows, b_f, cudaMemcpyDeviceToHost, st));
-    if (b_fit) TB_CUDA(ctx, cudaMemcpyAsync(a.fitness, d.fitness, b_fit, cudaMemcpyDeviceToHost, st));
-    TB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    auto enqueue = [&]() -> int {
+        TB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+        TB_CUDA(ctx, cudaMemcpyAsync((void*)d.weights, a.weights, b_w, cudaMemcpyHostToDevice, st));
+        if (b_p) TB_CUDA(ctx, cudaMemcpyAsync((void*)d.pieces, a.pieces, b_p, cudaMemcpyHostToDevice, st));
+        if (b_s) TB_CUDA(ctx, cudaMemcpyAsync((void*)d.seq_of_game, a.seq_of_game, b_s, cudaMemcpyHostToDevice, st));
+        if (b_i) TB_CUDA(ctx, cudaMemcpyAsync((void*)d.init_rows, a.init_rows, b_i, cudaMemcpyHostToDevice, st));
+        if (b_t) TB_CUDA(ctx, cudaMemsetAsync(d.trace, 0, b_t, st));
+        if (b_st) TB_CUDA(ctx, cudaMemsetAsync(d.score_trace, 0, b_st, st));
+        int rc2 = launch_play(ctx, d, st, 0, &launches);
+        if (rc2) return rc2;
+        TB_CUDA(ctx, cudaMemcpyAsync(a.results, d.results, b_r, cudaMemcpyDeviceToHost, st));
+        if (b_t) TB_CUDA(ctx, cudaMemcpyAsync(a.trace, d.trace, b_t, cudaMemcpyDeviceToHost, st));
+        if (b_st) TB_CUDA(ctx, cudaMemcpyAsync(a.score_trace, d.score_trace, b_st, cudaMemcpyDeviceToHost, st));
+        if (b_f) TB_CUDA(ctx, cudaMemcpyAsync(a.final_rows, d.final_rows, b_f, cudaMemcpyDeviceToHost, st));
+        if (b_fit) TB_CUDA(ctx, cudaMemcpyAsync(a.fitness, d.fitness, b_fit, cudaMemcpyDeviceToHost, st));
+        TB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+        return TB200_OK;
+    };
+    // ---- graph replay: identical call (same pinned buffers, sizes, options, feature list) as last time ----
+    const bool same = ctx->graph_valid && memcmp(&ctx->graph_args, &a, sizeof a) == 0 && ctx->graph_F == ctx->F &&
+                      ctx->graph_mode == ctx->mode && memcmp(ctx->graph_ids, ctx->ids, sizeof ctx->ids) == 0 && ctx->graph_arena == base;
+    bool done = false;
+    if (same) {
+        if (cudaGraphLaunch(ctx->graph_exec, st) == cudaSuccess) { ctx->timing = ctx->graph_timing; launches = ctx->graph_timing.kernels_launched; done = true; }
+        else { cudaGetLastError(); drop_graph(ctx); }
+    } else if (ctx->graphs_enabled && is_pinned(a.weights) && is_pinned(a.pieces) && is_pinned(a.seq_of_game) && is_pinned(a.init_rows) &&
+               is_pinned(a.results) && is_pinned(a.trace) && is_pinned(a.score_trace) && is_pinned(a.final_rows) && is_pinned(a.fitness)) {
+        drop_graph(ctx);
+        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int rc2 = enqueue();
+            cudaGraph_t gr = nullptr;
+            const cudaError_t e1 = cudaStreamEndCapture(st, &gr);
+            if (rc2 == TB200_OK && e1 == cudaSuccess && gr && cudaGraphInstantiate(&ctx->graph_exec, gr, 0) == cudaSuccess) {
+                ctx->graph = gr; ctx->graph_args = a; ctx->graph_F = ctx->F; ctx->graph_mode = ctx->mode;
+                memcpy(ctx->graph_ids, ctx->ids, sizeof ctx->ids); ctx->graph_arena = base;
+                ctx->timing.kernels_launched = launches;
+                ctx->graph_timing = ctx->timing; ctx->graph_valid = true;
+                if (cudaGraphLaunch(ctx->graph_exec, st) == cudaSuccess) done = true;
+                else { cudaGetLastError(); drop_graph(ctx); ctx->graphs_enabled = false; }
+            } else {
+                cudaGetLastError();
+                if (gr) cudaGraphDestroy(gr);
+                ctx->graph_exec = nullptr; ctx->graphs_enabled = false;      // capture not possible here: use the direct path from now on
+                launches = 0;
+            }
+        } else {
+            cudaGetLastError(); ctx->graphs_enabled = false;
+        }
+    }
+    if (!done) {
+        launches = 0;
+        rc = enqueue();
+        if (rc) return rc;
+    }
     TB_CUDA(ctx, cudaStreamSynchronize(st));
     float ms = 0.f;
-    TB_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
+    if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
     ctx->timing.total_ms = ms;
     ctx->timing.h2d_bytes = b_w + b_p + b_s + b_i;
     ctx->timing.d2h_bytes = b_r + b_t + b_st + b_f + b_fit;

@@ -43,6 +43,7 @@ class Engine:
             raise EngineError("tb200_create(device=%d) failed with code %d: no usable CUDA device "
                               "(this engine has no CPU fallback)" % (device, rc))
         self._h = h
+        self._pinned = []
         self.device = int(device)
         self.features = None
         sms, khz = ctypes.c_int32(), ctypes.c_int32()
@@ -54,6 +55,21 @@ class Engine:
         if getattr(self, "_h", None):
             self._L.tb200_destroy(self._h)
             self._h = None
+            for p in self._pinned:
+                self._L.tb200_free_pinned(p)
+            self._pinned = []
+
+    def pinned_empty(self, shape, dtype):
+        """numpy array over page-locked host memory owned by this Engine (freed by close()).  Repeating a play_games call on
+        the same pinned buffers lets the library replay it as a CUDA graph."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = ctypes.c_void_p()
+        if self._L.tb200_alloc_pinned(max(n, 1), ctypes.byref(p)) != 0:
+            raise EngineError("tb200_alloc_pinned(%d) failed" % n)
+        self._pinned.append(p)
+        buf = (ctypes.c_char * max(n, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     def __del__(self):
         try:
@@ -81,7 +97,7 @@ class Engine:
     # ------------------------------------------------------------------ K2 whole games
     def play_games(self, weights, games_per_candidate, pieces=None, T=None, seq_of_game=None, seed=0, lookahead=1,
                    lanes=0, max_moves=0, init_rows=None, want_trace=False, want_scores=False, want_final=False,
-                   want_fitness=True):
+                   want_fitness=True, out_results=None, out_fitness=None):
         """weights f64[C][F] -> dict(results=structured[C*G], fitness=f64[C], trace=..., ...)   (host buffers)."""
         w = np.ascontiguousarray(weights, dtype=np.float64)
         if w.ndim == 1:
@@ -106,11 +122,13 @@ class Engine:
         if init_rows is not None:
             init_rows = np.ascontiguousarray(init_rows, dtype=np.uint16).reshape(n, 20)
         T = int(T)
-        results = np.zeros(n, dtype=_lib.RESULT_DTYPE)
+        results = out_results if out_results is not None else np.zeros(n, dtype=_lib.RESULT_DTYPE)
+        if results.shape != (n,) or results.dtype != _lib.RESULT_DTYPE:
+            raise EngineError("out_results must be a structured array of C*G records")
         trace = np.zeros((n, T, 4), dtype=np.uint8) if want_trace else None
         scores = np.zeros((n, T), dtype=np.float64) if want_scores else None
         final = np.zeros((n, 20), dtype=np.uint16) if want_final else None
-        fitness = np.zeros(C, dtype=np.float64) if want_fitness else None
+        fitness = (out_fitness if out_fitness is not None else np.zeros(C, dtype=np.float64)) if want_fitness else None
         a = _lib.PlayArgs()
         a.struct_size = ctypes.sizeof(_lib.PlayArgs)
         a.mem = _lib.MEM_HOST

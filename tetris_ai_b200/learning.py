@@ -70,6 +70,7 @@ class PopulationEvaluator:
         self.T = int(T if T is not None else self.pieces.shape[1])
         self.seed, self.lookahead, self.lanes = int(seed), int(lookahead), int(lanes)
         self._batch = []
+        self._bufs = None                     # page-locked staging buffers, reused every generation (-> CUDA-graph replay)
         self.last = None                      # raw device results of the last generation
         self.generations = 0
 
@@ -91,8 +92,24 @@ class PopulationEvaluator:
     def evaluate(self, weights):
         """weights f64[C][F] -> fitness f64[C]."""
         self.engine.set_features(self.names)
-        out = self.engine.play_games(weights, self.games, pieces=self.pieces, T=self.T, seed=self.seed,
-                                     lookahead=self.lookahead, lanes=self.lanes)
+        weights = np.asarray(weights, dtype=np.float64)
+        C = weights.shape[0]
+        kw = {}
+        if hasattr(self.engine, "pinned_empty"):
+            if self._bufs is None or self._bufs["C"] != C:
+                from . import _lib
+                pe = self.engine.pinned_empty
+                self._bufs = {"C": C, "w": pe(weights.shape, np.float64), "res": pe((C * self.games,), _lib.RESULT_DTYPE),
+                              "fit": pe((C,), np.float64), "pieces": None}
+                if self.pieces is not None:
+                    self._bufs["pieces"] = pe(self.pieces.shape, np.uint8)
+                    np.copyto(self._bufs["pieces"], self.pieces)
+            np.copyto(self._bufs["w"], weights)
+            weights = self._bufs["w"]
+            kw = {"out_results": self._bufs["res"], "out_fitness": self._bufs["fit"]}
+        pieces = self._bufs["pieces"] if (self._bufs is not None and self._bufs["pieces"] is not None) else self.pieces
+        out = self.engine.play_games(weights, self.games, pieces=pieces, T=self.T, seed=self.seed,
+                                     lookahead=self.lookahead, lanes=self.lanes, **kw)
         self.last = out
         self.generations += 1
         return out["fitness"]
