@@ -10,9 +10,9 @@ cap T = 1000 pieces.  The population is generation 1 of the canonical CE run (ra
 sigma = 10; mean/std after generation 0 from tests/golden/ce.json): 6 680 307 placements in
 294 598 pieces — a mid-training generation in which many games reach the cap.  A step = one pass of
 the hot path over that population = evaluating the whole generation (one K2 launch + the fitness
-reduction).  For N > 1 (weak scaling) every rank evaluates its own 100-candidate shard of a
-100*N-candidate population drawn from the same distribution and the per-candidate fitness is
-all-gathered over NCCL inside the step.
+reduction).  For N > 1 (weak scaling) the population is N replicas of that generation, one
+100-candidate shard per rank (identical work on every rank), and the per-candidate fitness of all
+100*N candidates is all-gathered over NCCL inside the step.
 
 value      : device-timed (CUDA events on the launching stream), inputs resident in HBM.
 e2e        : the same step through the public API (PopulationEvaluator.evaluate -> C ABI with HOST
@@ -71,7 +71,7 @@ def workload_config(n_gpus):
         "workload": "BASELINE configs[1]: CE generation, 100 candidates x 10 games per GPU, lookahead 1, w6 features, T=1000, "
                     "population = generation 1 of the canonical run (Random(42), sigma 10)",
         "candidates_per_gpu": CANDIDATES_PER_GPU, "games_per_candidate": GAMES, "cap_pieces": T_CAP, "features": W6_NAMES,
-        "lookahead": 1, "parallelism": "candidates sharded per rank; fitness all-gather (NCCL)" if n_gpus > 1 else "single GPU",
+        "lookahead": 1, "parallelism": "candidates sharded per rank (population = N replicas of the canonical generation); fitness all-gather (NCCL)" if n_gpus > 1 else "single GPU",
         "l2": "L2 flushed (256 MiB write) between timed steps, outside the per-step event pairs",
     }
 
@@ -220,8 +220,9 @@ def run_gpu_arm(args):
         os.environ["NCCL_DEBUG"] = os.environ.get("TB_NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
-    pop_all, seqs = canonical_population(CANDIDATES_PER_GPU * world)
-    pop = pop_all[rank * CANDIDATES_PER_GPU:(rank + 1) * CANDIDATES_PER_GPU]
+    # weak scaling: the global population is `world` replicas of the canonical 100-candidate generation, one replica
+    # per rank, so that every rank has exactly the same work and the N-GPU figure isolates launch skew + the all-gather
+    pop, seqs = canonical_population(CANDIDATES_PER_GPU)
     eng = Engine(local)
     eng.set_features(W6_NAMES)
     C, G, n_games = CANDIDATES_PER_GPU, GAMES, CANDIDATES_PER_GPU * GAMES
