@@ -30,7 +30,7 @@ static void search_one(const uint32_t c[COLS], const Heights& H, const PrevStat&
         if (place_slot(c, H, tab.slot[piece][s], P)) {
             Feat f;
             memset(&f, 0, sizeof f);
-            eval_features<ModeTraits<MODE>::CMASK>(P, pv, rmask, f);
+            eval_features<ModeTraits<MODE>::CMASK>(P, tab.slot[piece][s], pv, rmask, f);
             const uint64_t k = score_key(score_features<MODE>(f, ids, w, F));
             const uint32_t tg = tag_hi | (uint32_t)s;
             if (k > key || (k == key && tg < tag)) { key = k; tag = tg; }
@@ -62,7 +62,7 @@ static void play(const int* ids_in, int F, const double* w, const uint8_t* piece
             for (int s1 = 0; s1 < tab.nslots[p1]; ++s1) {
                 Placement P1;
                 if (!place_slot(c, H, tab.slot[p1][s1], P1)) continue;
-                const Heights H1 = pack_heights(P1.n); const PrevStat pv1 = prev_stat(P1.n);
+                const PrevStat pv1 = next_stat(pv, P1, tab.slot[p1][s1]); const Heights H1 = pack_gh(pv1.gh);
                 search_one<MODE>(P1.n, H1, pv1, p2, ids, w, F, rmask, (uint32_t)s1 << 6, key, tag, cnt);
             }
         }
@@ -75,7 +75,7 @@ static void play(const int* ids_in, int F, const double* w, const uint8_t* piece
         Placement P;
         place_slot(c, H, tab.slot[p1][tag >> 6], P);
         memcpy(c, P.n, sizeof c);
-        H = pack_heights(c); pv = prev_stat(c);
+        pv = next_stat(pv, P, tab.slot[p1][tag >> 6]); H = pack_gh(pv.gh);
         lines += (uint32_t)P.k; if (P.k) hist[P.k - 1] += 1;
         static const uint32_t PTS[5] = {0, 40, 100, 300, 1200};
         score += (uint64_t)PTS[P.k] * (lines / 10 + 1);
@@ -169,7 +169,7 @@ void emu_eval_placement(const uint16_t* prev_rows, int piece, int rot, int col, 
         if (legal) {
             info[1] = ROWS - P.y - P.ph; info[2] = P.k;
             Feat f; memset(&f, 0, sizeof f);
-            eval_features<0>(P, pv, ALL45_MASK, f);
+            eval_features<0>(P, d, pv, ALL45_MASK, f);
             for (int j = 0; j < NFEAT; ++j) feats[j] = feat_value(f, j);
             if (post_rows) cols_to_rows(P.n, post_rows);
         }

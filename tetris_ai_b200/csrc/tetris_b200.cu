@@ -77,6 +77,16 @@ TB_D SlotDesc load_slot(const Tables& tab, int piece, int s)
     return d;
 }
 
+TB_D SlotDesc load_slot12(const Tables& tab, int piece, int s)
+{
+    const uint4* p = reinterpret_cast<const uint4*>(&tab.slot[piece][s]);
+    const uint4 a = p[0], b = p[1], e = p[2];
+    SlotDesc d;
+    d.w[0] = a.x; d.w[1] = a.y; d.w[2] = a.z; d.w[3] = a.w; d.w[4] = b.x; d.w[5] = b.y; d.w[6] = b.z; d.w[7] = b.w;
+    d.w[8] = e.x; d.w[9] = e.y; d.w[10] = e.z; d.w[11] = e.w;
+    return d;
+}
+
 // layer-1 search: every legal (rot, col) slot of `piece` on board c, scored as a leaf whose
 // previous state is the board itself.  Lanes take slots gl, gl+LANES, ...; strict > keeps the
 // earliest slot inside a lane.
@@ -87,11 +97,11 @@ TB_D void search_one(const uint32_t c[COLS], const Heights& H, const PrevStat& p
 {
     const int ns = tab.nslots[piece];
     for (int s = gl; s < ns; s += LANES) {
-        const SlotDesc d = load_slot(tab, piece, s);
+        const SlotDesc d = load_slot12(tab, piece, s);
         Placement P;
         if (place_slot(c, H, d, P)) {
             Feat f;
-            eval_features<ModeTraits<MODE>::CMASK>(P, pv, rmask, f);
+            eval_features<ModeTraits<MODE>::CMASK>(P, d, pv, rmask, f);
             const uint64_t k = score_key(score_features<MODE>(f, ids, w, F));
             if (k > key) { key = k; tag = tag_hi | (uint32_t)s; }
             ++cnt;
@@ -154,7 +164,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_kernel(const PlayParams prm)
 #pragma unroll
                     for (int k = 0; k < COLS; ++k) c[k] = 0;
                 }
-                H = pack_heights(c); pv = prev_stat(c);
+                pv = prev_stat(c); H = pack_gh(pv.gh);
                 const size_t wrow = prm.per_game_weights > 0 ? (size_t)g : (prm.per_game_weights < 0 ? 0 : (size_t)(g / (uint32_t)prm.G));
                 const double* wsrc = prm.weights + wrow * (size_t)F;
                 if (MODE == MODE_W6) {
@@ -179,11 +189,11 @@ __global__ void __launch_bounds__(BLOCK) play_games_kernel(const PlayParams prm)
             if (active && t + 1 < T && p_cur < 7 && p_next < 7) {
                 const int ns1 = s_tab.nslots[p_cur];
                 for (int s1 = 0; s1 < ns1; ++s1) {
-                    const SlotDesc d1 = load_slot(s_tab, p_cur, s1);
+                    const SlotDesc d1 = load_slot12(s_tab, p_cur, s1);
                     Placement P1;
                     if (!place_slot(c, H, d1, P1)) continue;
-                    const Heights H1 = pack_heights(P1.n);
-                    const PrevStat pv1 = prev_stat(P1.n);
+                    const PrevStat pv1 = next_stat(pv, P1, d1);
+                    const Heights H1 = pack_gh(pv1.gh);
                     search_one<LANES, MODE>(P1.n, H1, pv1, p_next, gl, s_tab, prm.ids, w, F, prm.rmask,
                                             (uint32_t)s1 << 6, key, tag, cnt);
                 }
@@ -204,12 +214,12 @@ __global__ void __launch_bounds__(BLOCK) play_games_kernel(const PlayParams prm)
                 finish = true;                                   // no legal placement: game over (simulator.py:187-189)
             } else {
                 const int s1 = (int)(tag >> 6);
-                const SlotDesc d1 = load_slot(s_tab, p_cur, s1);
+                const SlotDesc d1 = load_slot12(s_tab, p_cur, s1);
                 Placement P;
                 place_slot(c, H, d1, P);
 #pragma unroll
                 for (int k = 0; k < COLS; ++k) c[k] = P.n[k];
-                H = pack_heights(c); pv = prev_stat(c);
+                pv = next_stat(pv, P, d1); H = pack_gh(pv.gh);
                 lines += (uint32_t)P.k;
                 h1 += P.k == 1; h2 += P.k == 2; h3 += P.k == 3; h4 += P.k == 4;
                 const uint32_t pts = P.k == 0 ? 0u : (P.k == 1 ? 40u : (P.k == 2 ? 100u : (P.k == 3 ? 300u : 1200u)));
@@ -268,10 +278,10 @@ TB_D void warp_argmax32(uint64_t& key, uint32_t& tag)
 }
 
 template <int MODE>
-TB_D uint64_t eval_key(const Placement& P, bool legal, const PrevStat& pv, const uint8_t* ids, const double* w, int F, uint64_t rmask)
+TB_D uint64_t eval_key(const Placement& P, const SlotDesc& d, bool legal, const PrevStat& pv, const uint8_t* ids, const double* w, int F, uint64_t rmask)
 {
     Feat f;
-    eval_features<ModeTraits<MODE>::CMASK>(P, pv, rmask, f);
+    eval_features<ModeTraits<MODE>::CMASK>(P, d, pv, rmask, f);
     const uint64_t k = score_key(score_features<MODE>(f, ids, w, F));
     return legal ? k : 0ull;
 }
@@ -312,8 +322,8 @@ __global__ void __launch_bounds__(BLOCK) play_games_w32_kernel(const PlayParams 
 #pragma unroll
             for (int k = 0; k < COLS; ++k) c[k] = 0;
         }
-        Heights H = pack_heights(c);
         PrevStat pv = prev_stat(c);
+        Heights H = pack_gh(pv.gh);
         {
             const size_t wrow = prm.per_game_weights > 0 ? (size_t)game : (prm.per_game_weights < 0 ? 0 : (size_t)(game / (uint32_t)prm.G));
             const double* wsrc = prm.weights + wrow * (size_t)F;
@@ -344,7 +354,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_w32_kernel(const PlayParams 
             const int ns = s_tab.nslots[p_cur];
             // ---- stream A: slot = lane ----
             const bool hasA = lane < ns;
-            const SlotDesc dA = load_slot(s_tab, p_cur, hasA ? lane : 0);
+            const SlotDesc dA = load_slot12(s_tab, p_cur, hasA ? lane : 0);
             Placement PA; uint32_t fA;
             const bool legalA = place_pre(c, H, dA, PA, &fA) && hasA;
             uint64_t key; uint32_t tag = (uint32_t)lane;
@@ -352,15 +362,15 @@ __global__ void __launch_bounds__(BLOCK) play_games_w32_kernel(const PlayParams 
             if (MODE == MODE_W6 && ns > 32) {
                 // ---- stream B: slot = lane + 32 (only lanes 0, 1 of the 34-slot pieces), interleaved with A ----
                 const bool hasB = lane + 32 < ns;
-                const SlotDesc dB = load_slot(s_tab, p_cur, hasB ? lane + 32 : 0);
+                const SlotDesc dB = load_slot12(s_tab, p_cur, hasB ? lane + 32 : 0);
                 Placement PB; uint32_t fB;
                 const bool legalB = place_pre(c, H, dB, PB, &fB) && hasB;
                 if ((legalA && fA != 0u) || (legalB && fB != 0u)) {
                     if (legalA && fA != 0u) place_clear(dA, PA, fA);
                     if (legalB && fB != 0u) place_clear(dB, PB, fB);
                 }
-                const uint64_t kA = eval_key<MODE>(PA, legalA, pv, prm.ids, w, F, prm.rmask);
-                const uint64_t kB = eval_key<MODE>(PB, legalB, pv, prm.ids, w, F, prm.rmask);
+                const uint64_t kA = eval_key<MODE>(PA, dA, legalA, pv, prm.ids, w, F, prm.rmask);
+                const uint64_t kB = eval_key<MODE>(PB, dB, legalB, pv, prm.ids, w, F, prm.rmask);
                 cnt += (uint32_t)legalA + (uint32_t)legalB;
                 key = kA;
                 if (kB > kA) {                      // strict: the earlier slot keeps ties
@@ -371,15 +381,15 @@ __global__ void __launch_bounds__(BLOCK) play_games_w32_kernel(const PlayParams 
                 }
             } else {
                 if (legalA && fA != 0u) place_clear(dA, PA, fA);
-                key = eval_key<MODE>(PA, legalA, pv, prm.ids, w, F, prm.rmask);
+                key = eval_key<MODE>(PA, dA, legalA, pv, prm.ids, w, F, prm.rmask);
                 cnt += (uint32_t)legalA;
                 if (MODE != MODE_W6 && ns > 32) {   // big feature sets: second pass after the first (register budget)
                     const bool hasB = lane + 32 < ns;
-                    const SlotDesc dB = load_slot(s_tab, p_cur, hasB ? lane + 32 : 0);
+                    const SlotDesc dB = load_slot12(s_tab, p_cur, hasB ? lane + 32 : 0);
                     Placement PB;
                     const bool legalB = place_slot(c, H, dB, PB) && hasB;
                     if (__any_sync(FULLMASK, legalB)) {
-                        const uint64_t kB = eval_key<MODE>(PB, legalB, pv, prm.ids, w, F, prm.rmask);
+                        const uint64_t kB = eval_key<MODE>(PB, dB, legalB, pv, prm.ids, w, F, prm.rmask);
                         cnt += (uint32_t)legalB;
                         if (kB > key) {
                             key = kB; tag = (uint32_t)lane + 32u;
@@ -400,8 +410,15 @@ __global__ void __launch_bounds__(BLOCK) play_games_w32_kernel(const PlayParams 
             for (int k = 0; k < COLS; ++k) c[k] = __shfl_sync(FULLMASK, PA.n[k], src);
             const uint32_t info = __shfl_sync(FULLMASK, (uint32_t)PA.y | (uint32_t)PA.k << 8 | (uint32_t)PA.rot << 12 | (uint32_t)PA.c0 << 16 | (uint32_t)PA.ph << 24, src);
             const uint32_t wk = (info >> 8) & 15u;
-            H = pack_heights(c);
-            if (ModeTraits<MODE>::CMASK == 0 || (ModeTraits<MODE>::CMASK & (bit(F_D_MAX_HT) | bit(F_D_ALL_HT) | bit(F_D_MEAN_HT) | bit(F_D_PITS)))) pv = prev_stat(c);
+            {   // statistics of the committed board: arithmetic from the winner's move unless it cleared rows
+                Placement Pw;
+                Pw.y = (int)(info & 255u); Pw.k = (int)wk;
+#pragma unroll
+                for (int k = 0; k < COLS; ++k) Pw.n[k] = c[k];
+                const SlotDesc dw = load_slot12(s_tab, p_cur, (int)tag);
+                pv = next_stat(pv, Pw, dw);
+                H = pack_gh(pv.gh);
+            }
             lines += wk;
             h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
             const uint32_t pts = wk == 0 ? 0u : (wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u)));
@@ -447,15 +464,6 @@ __global__ void __launch_bounds__(BLOCK) play_games_w32_kernel(const PlayParams 
 // broadcasting the winner's board, packed heights and move (14 SHFL, no clz, no popc).
 // Slots 32 and 33 of the 34-slot pieces run as a second, interleaved instruction stream.
 // ---------------------------------------------------------------------------------------------
-TB_D SlotDesc load_slot12(const Tables& tab, int piece, int s)
-{
-    const uint4* p = reinterpret_cast<const uint4*>(&tab.slot[piece][s]);
-    const uint4 a = p[0], b = p[1], e = p[2];
-    SlotDesc d;
-    d.w[0] = a.x; d.w[1] = a.y; d.w[2] = a.z; d.w[3] = a.w; d.w[4] = b.x; d.w[5] = b.y; d.w[6] = b.z; d.w[7] = b.w;
-    d.w[8] = e.x; d.w[9] = e.y; d.w[10] = e.z; d.w[11] = e.w;
-    return d;
-}
 
 __global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayParams prm)
 {
@@ -947,12 +955,13 @@ __global__ void eval_features_kernel(int N, const uint16_t* prev_boards, const u
     for (int r = 0; r < ROWS; ++r) rows[r] = prev_boards[(size_t)i * ROWS + r];
     uint32_t c[COLS];
     rows_to_cols(rows, c);
-    const Heights H = pack_heights(c);
     const PrevStat pv = prev_stat(c);
+    const Heights H = pack_gh(pv.gh);
     const int p = piece[i];
     int legal = 0, row = -1, k = 0;
     Feat f;
     Placement P;
+    SlotDesc dsel;
     bool found = false;
     if (p < 7) {
         const int ns = c_tables.nslots[p];
@@ -960,13 +969,14 @@ __global__ void eval_features_kernel(int N, const uint16_t* prev_boards, const u
             const SlotDesc d = c_tables.slot[p][s];
             if ((int)((d.w[0] >> 4) & 3u) == (int)rot[i] && (int)(d.w[0] & 15u) == (int)col[i]) {
                 found = true;
+                dsel = d;
                 if (place_slot(c, H, d, P)) { legal = 1; row = ROWS - P.y - P.ph; k = P.k; }
                 break;
             }
         }
     }
     if (legal) {
-        eval_features<0>(P, pv, ALL45_MASK, f);
+        eval_features<0>(P, dsel, pv, ALL45_MASK, f);
         for (int j = 0; j < NFEAT; ++j) out_features[(size_t)i * NFEAT + j] = feat_value(f, j);
         if (out_rows) { cols_to_rows(P.n, rows); for (int r = 0; r < ROWS; ++r) out_rows[(size_t)i * ROWS + r] = rows[r]; }
     } else {

@@ -184,16 +184,40 @@ TB_HD Heights pack_heights(const uint32_t c[COLS])
     return h;
 }
 
-// what the d_* features need from the previous state (features.py:239-257)
-struct PrevStat { int max_ht, all_ht, pits; };
+// Cached statistics of a board: what the d_* features need from the previous state
+// (features.py:239-257) plus what lets a placement WITHOUT a line clear be evaluated without
+// clz / popc over the whole board (column heights, filled cells, sum of the height indices of
+// the filled cells).
+struct PrevStat { int max_ht, all_ht, pits, cells, possum; int gh[COLS]; };
+
+TB_HD int possum_of(const uint32_t c[COLS])          // sum over filled cells of their height index
+{
+    int p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0;
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) {
+        p0 += popc(c[k] & 0xAAAAAu); p1 += popc(c[k] & 0xCCCCCu); p2 += popc(c[k] & 0x0F0F0u);
+        p3 += popc(c[k] & 0x0FF00u); p4 += popc(c[k] & 0xF0000u);
+    }
+    return p0 + 2 * p1 + 4 * p2 + 8 * p3 + 16 * p4;
+}
 
 TB_HD PrevStat prev_stat(const uint32_t c[COLS])
 {
-    PrevStat s; s.max_ht = 0; s.all_ht = 0; int cells = 0;
+    PrevStat s; s.max_ht = 0; s.all_ht = 0; s.cells = 0;
 #pragma unroll
-    for (int k = 0; k < COLS; ++k) { int h = fls(c[k]); s.all_ht += h; s.max_ht = h > s.max_ht ? h : s.max_ht; cells += popc(c[k]); }
-    s.pits = s.all_ht - cells;
+    for (int k = 0; k < COLS; ++k) { const int h = fls(c[k]); s.gh[k] = h; s.all_ht += h; s.max_ht = h > s.max_ht ? h : s.max_ht; s.cells += popc(c[k]); }
+    s.pits = s.all_ht - s.cells;
+    s.possum = possum_of(c);
     return s;
+}
+
+TB_HD Heights pack_gh(const int gh[COLS])
+{
+    Heights h;
+    h.H0 = (uint32_t)gh[0] | (uint32_t)gh[1] << 8 | (uint32_t)gh[2] << 16 | (uint32_t)gh[3] << 24;
+    h.H1 = (uint32_t)gh[4] | (uint32_t)gh[5] << 8 | (uint32_t)gh[6] << 16 | (uint32_t)gh[7] << 24;
+    h.H2 = (uint32_t)gh[8] | (uint32_t)gh[9] << 8;
+    return h;
 }
 
 // reference row-mask layout (u16[20], row 0 = top, bit c = column c) <-> column words
@@ -291,6 +315,32 @@ TB_HD bool place_slot(const uint32_t c[COLS], const Heights& H, const SlotDesc& 
     return legal;
 }
 
+// statistics of the board after placement P (made on the board whose statistics are pv)
+TB_HD PrevStat next_stat(const PrevStat& pv, const Placement& P, const SlotDesc& d)
+{
+    if (P.k != 0) return prev_stat(P.n);
+    PrevStat s;
+    const int yb = P.y - 32;
+    int t;
+    t = (int)byte_of(d.w[8], 0) + yb;  s.gh[0] = t > pv.gh[0] ? t : pv.gh[0];
+    t = (int)byte_of(d.w[8], 1) + yb;  s.gh[1] = t > pv.gh[1] ? t : pv.gh[1];
+    t = (int)byte_of(d.w[8], 2) + yb;  s.gh[2] = t > pv.gh[2] ? t : pv.gh[2];
+    t = (int)(d.w[8] >> 24) + yb;      s.gh[3] = t > pv.gh[3] ? t : pv.gh[3];
+    t = (int)byte_of(d.w[9], 0) + yb;  s.gh[4] = t > pv.gh[4] ? t : pv.gh[4];
+    t = (int)byte_of(d.w[9], 1) + yb;  s.gh[5] = t > pv.gh[5] ? t : pv.gh[5];
+    t = (int)byte_of(d.w[9], 2) + yb;  s.gh[6] = t > pv.gh[6] ? t : pv.gh[6];
+    t = (int)(d.w[9] >> 24) + yb;      s.gh[7] = t > pv.gh[7] ? t : pv.gh[7];
+    t = (int)byte_of(d.w[10], 0) + yb; s.gh[8] = t > pv.gh[8] ? t : pv.gh[8];
+    t = (int)byte_of(d.w[10], 1) + yb; s.gh[9] = t > pv.gh[9] ? t : pv.gh[9];
+    s.all_ht = 0; s.max_ht = 0;
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) { s.all_ht += s.gh[k]; s.max_ht = s.gh[k] > s.max_ht ? s.gh[k] : s.max_ht; }
+    s.cells = pv.cells + 4;
+    s.pits = s.all_ht - s.cells;
+    s.possum = pv.possum + 4 * P.y + (int)((d.w[0] >> 24) & 15u);
+    return s;
+}
+
 // ---------------------------------------------------------------------------------------------
 // features (features.py:18-347).  Ints stay ints, the five inexact ones are computed in fp64
 // with exactly the reference's operation order.
@@ -315,16 +365,33 @@ constexpr uint64_t M_NINE    = bit(F_NINE_FILLED) | bit(F_TETRIS_PROGRESS);
 constexpr uint64_t M_MEAN    = bit(F_MEAN_HT) | bit(F_MAX_HT_DIFF) | bit(F_MIN_HT_DIFF) | bit(F_D_MEAN_HT);
 
 // CMASK != 0: compile-time feature set (dead code removed); CMASK == 0: `rmask` decides at run time.
+// `pv` are the cached statistics of the board the piece was placed on and `d` the slot's descriptor:
+// when the move clears no row, heights / cells / height-index sums follow from them by arithmetic.
 template <uint64_t CMASK>
-TB_HD void eval_features(const Placement& p, const PrevStat& pv, uint64_t rmask, Feat& f)
+TB_HD void eval_features(const Placement& p, const SlotDesc& d, const PrevStat& pv, uint64_t rmask, Feat& f)
 {
     const uint64_t need = CMASK ? CMASK : rmask;
     const uint32_t* n = p.n;
     int h[COLS];
     int all_ht = 0, max_ht = 0, min_ht = 0;
     if (need & M_HEIGHTS) {
+        if (p.k == 0) {                 // new top of a covered column = landing row + top of the piece column
+            const int yb = p.y - 32;
+            int t;
+            t = (int)byte_of(d.w[8], 0) + yb;  h[0] = t > pv.gh[0] ? t : pv.gh[0];
+            t = (int)byte_of(d.w[8], 1) + yb;  h[1] = t > pv.gh[1] ? t : pv.gh[1];
+            t = (int)byte_of(d.w[8], 2) + yb;  h[2] = t > pv.gh[2] ? t : pv.gh[2];
+            t = (int)(d.w[8] >> 24) + yb;      h[3] = t > pv.gh[3] ? t : pv.gh[3];
+            t = (int)byte_of(d.w[9], 0) + yb;  h[4] = t > pv.gh[4] ? t : pv.gh[4];
+            t = (int)byte_of(d.w[9], 1) + yb;  h[5] = t > pv.gh[5] ? t : pv.gh[5];
+            t = (int)byte_of(d.w[9], 2) + yb;  h[6] = t > pv.gh[6] ? t : pv.gh[6];
+            t = (int)(d.w[9] >> 24) + yb;      h[7] = t > pv.gh[7] ? t : pv.gh[7];
+            t = (int)byte_of(d.w[10], 0) + yb; h[8] = t > pv.gh[8] ? t : pv.gh[8];
+            t = (int)byte_of(d.w[10], 1) + yb; h[9] = t > pv.gh[9] ? t : pv.gh[9];
+        } else {
 #pragma unroll
-        for (int k = 0; k < COLS; ++k) h[k] = fls(n[k]);
+            for (int k = 0; k < COLS; ++k) h[k] = fls(n[k]);
+        }
         all_ht = h[0]; max_ht = h[0]; min_ht = h[0];
 #pragma unroll
         for (int k = 1; k < COLS; ++k) { all_ht += h[k]; max_ht = h[k] > max_ht ? h[k] : max_ht; min_ht = h[k] < min_ht ? h[k] : min_ht; }
@@ -362,26 +429,25 @@ TB_HD void eval_features(const Placement& p, const PrevStat& pv, uint64_t rmask,
         }
         f.iv[F_WELLS] = ws; f.iv[F_CUML_WELLS] = cw >> 1; f.iv[F_DEEP_WELLS] = dw; f.iv[F_MAX_WELL] = mw;
     }
-    int cells = 0, tri = 0;            // tri = sum_k m_k (m_k - 1) / 2
+    // filled cells: every placement adds 4 cells and every cleared row removes 10 (exact, no popc)
+    const int cells = pv.cells + 4 - 10 * p.k;
     if (need & M_CELLS) {
-#pragma unroll
-        for (int k = 0; k < COLS; ++k) { const int m = popc(n[k]); cells += m; tri += m * (m - 1); }
-        tri >>= 1;
         f.iv[F_FULL_CELLS] = cells;                                   // :323-325
         f.iv[F_PITS] = all_ht - cells;                                // :146-160  (empty cells under a column top)
         f.iv[F_D_PITS] = f.iv[F_PITS] - pv.pits;                      // :257-259
     }
     if (need & M_WEIGHTED) {                                          // :329-331  sum over cells of (height index + 1)
-        int p0 = 0, p1 = 0, p2 = 0, p3 = 0, p4 = 0;
-#pragma unroll
-        for (int k = 0; k < COLS; ++k) {
-            p0 += popc(n[k] & 0xAAAAAu); p1 += popc(n[k] & 0xCCCCCu); p2 += popc(n[k] & 0x0F0F0u);
-            p3 += popc(n[k] & 0x0FF00u); p4 += popc(n[k] & 0xF0000u);
-        }
-        const int possum = p0 + 2 * p1 + 4 * p2 + 8 * p3 + 16 * p4;
+        // sum of height indices: without a clear it grows by the piece's own cells (4 y + a per-orientation constant)
+        const int possum = p.k == 0 ? pv.possum + 4 * p.y + (int)((d.w[0] >> 24) & 15u) : possum_of(n);
         f.iv[F_WEIGHTED_CELLS] = possum + cells;
         // pit_depth (:182-188) = sum over filled cells of the empties below them
-        //                      = sum of height indices of filled cells - sum_k m_k(m_k-1)/2
+        //                      = sum of height indices of filled cells - sum_k m_k(m_k-1)/2, m_k = cells of column k
+        int tri = 0;
+        if (need & (bit(F_PIT_DEPTH) | bit(F_MEAN_PIT_DEPTH))) {
+#pragma unroll
+            for (int k = 0; k < COLS; ++k) { const int m = popc(n[k]); tri += m * (m - 1); }
+            tri >>= 1;
+        }
         f.iv[F_PIT_DEPTH] = possum - tri;
     }
     if (need & bit(F_MEAN_PIT_DEPTH))                                 // :192-194
