@@ -49,6 +49,9 @@ extern "C" {
 #define TB200_NUM_FEATURES 45
 #define TB200_MAX_WEIGHTED 48
 
+#define TB200_MOVES_DROP            0
+#define TB200_MOVES_OVERHANG_SLIDE  1
+
 #define TB200_MEM_HOST   0
 #define TB200_MEM_DEVICE 1
 
@@ -91,6 +94,9 @@ typedef struct {
     double*   score_trace;           /* f64[C*G][T] winning score per move, or NULL */
     uint16_t* final_rows;            /* u16[C*G][20] final boards, or NULL */
     double*   fitness;               /* f64[C] = total lines of the candidate's games / G, or NULL */
+    int32_t   move_set;              /* TB200_MOVES_DROP = move_drop (simulator.py:3-13);
+                                        TB200_MOVES_OVERHANG_SLIDE = move_with_overhang_slide(move_drop) (simulator.py:15-47) */
+    int32_t   reserved;              /* 0 */
 } tb200_play_args;
 
 /* timing of the last tb200_play_games call on this ctx (CUDA events on the launching stream) */

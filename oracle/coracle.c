@@ -97,6 +97,47 @@ static int drop_moves(const board_t* b, int piece, int mv[34][3])
     return n;
 }
 
+#define MAX_MOVES 640
+
+/* simulator.py:15-47 move_with_overhang_slide(move_drop): every hard-drop move, followed by the placements reached
+ * by sliding sideways at the landed row under an overhang (right slides in ascending column order, then left slides
+ * in descending column order), each lowered as far as it goes; a slide direction stops at the first blocked column. */
+static int slide_moves(const board_t* b, int piece, int mv[MAX_MOVES][3])
+{
+    int base[34][3]; int nb = drop_moves(b, piece, base);
+    int n = 0;
+    for (int i = 0; i < nb; ++i) {
+        int rot = base[i][0], row = base[i][1], col = base[i][2];
+        const shape_t* s = &SHAPES[piece][rot];
+        mv[n][0] = rot; mv[n][1] = row; mv[n][2] = col; ++n;
+        if (col + s->w < COLS && row > ROWS - col_height(b, col + s->w)) {            /* :25 */
+            for (int c = col + 1; c <= COLS - s->w; ++c) {                           /* :27 */
+                if (collides(b, s, row, c)) break;
+                int r = row;
+                while (!collides(b, s, r + 1, c)) ++r;
+                mv[n][0] = rot; mv[n][1] = r; mv[n][2] = c; ++n;
+            }
+        }
+        if (col > 0 && row > ROWS - col_height(b, col - 1)) {                        /* :36 */
+            for (int c = col - 1; c >= 0; --c) {                                     /* :38 */
+                if (collides(b, s, row, c)) break;
+                int r = row;
+                while (!collides(b, s, r + 1, c)) ++r;
+                mv[n][0] = rot; mv[n][1] = r; mv[n][2] = c; ++n;
+            }
+        }
+    }
+    return n;
+}
+
+static int gen_moves(const board_t* b, int piece, int move_set, int mv[MAX_MOVES][3])
+{
+    if (move_set == 1) return slide_moves(b, piece, mv);
+    int base[34][3]; int n = drop_moves(b, piece, base);
+    for (int i = 0; i < n; ++i) { mv[i][0] = base[i][0]; mv[i][1] = base[i][1]; mv[i][2] = base[i][2]; }
+    return n;
+}
+
 typedef struct {
     board_t board;          /* post-clear */
     int piece, rot, row, col;
@@ -267,6 +308,17 @@ int co_drop_moves(const uint16_t rows[ROWS], int piece, int* moves)
     return n;
 }
 
+/* move list of move_set (0 = move_drop, 1 = move_with_overhang_slide(move_drop)); moves[i] = {rot,row,col} */
+int co_moves(const uint16_t rows[ROWS], int piece, int move_set, int* moves)
+{
+    init_shapes();
+    board_t b; rows_to_board(rows, &b);
+    static __thread int mv[MAX_MOVES][3];
+    int n = gen_moves(&b, piece, move_set, mv);
+    for (int i = 0; i < n; ++i) { moves[3 * i] = mv[i][0]; moves[3 * i + 1] = mv[i][1]; moves[3 * i + 2] = mv[i][2]; }
+    return n;
+}
+
 /* features of prev.future(piece, rot, <drop row>, col); returns 0 if that slot is illegal, else 1 */
 int co_eval_placement(const uint16_t prev_rows[ROWS], int piece, int rot, int col,
                       double* feats45, uint16_t* post_rows, int* row_out, int* k_out)
@@ -290,18 +342,20 @@ typedef struct { int rot, row, col, k; double score; int n_scored; placed_t st; 
 
 /* One simulate() iteration (simulator.py:156-180) with move_drop and policy_best(linear, first).
  * next_piece < 0 => only one visible piece.  Returns 0 when there is no move (game over). */
-static int choose(const board_t* b, int piece, int next_piece, int lookahead,
+static int choose(const board_t* b, int piece, int next_piece, int lookahead, int move_set,
                   const int* fids, const double* w, int F, choice_t* out)
 {
-    int mv1[34][3]; int n1 = drop_moves(b, piece, mv1);
+    static __thread int mv1[MAX_MOVES][3];
+    int n1 = gen_moves(b, piece, move_set, mv1);
     if (n1 == 0) return 0;
-    static __thread placed_t l1[34];
+    static __thread placed_t l1[MAX_MOVES];
     for (int i = 0; i < n1; ++i) place(b, piece, mv1[i][0], mv1[i][1], mv1[i][2], &l1[i]);
     double f[NFEAT];
     int have = 0; double best = 0.0; int best_i = -1; int scored = 0;
     if (lookahead >= 2 && next_piece >= 0) {
         for (int i = 0; i < n1; ++i) {                       /* layer 2 in enumeration order :162-167 */
-            int mv2[34][3]; int n2 = drop_moves(&l1[i].board, next_piece, mv2);
+            static __thread int mv2[MAX_MOVES][3];
+            int n2 = gen_moves(&l1[i].board, next_piece, move_set, mv2);
             for (int j = 0; j < n2; ++j) {
                 placed_t leaf; place(&l1[i].board, next_piece, mv2[j][0], mv2[j][1], mv2[j][2], &leaf);
                 features45(&l1[i].board, &leaf, f);
@@ -325,12 +379,12 @@ static int choose(const board_t* b, int piece, int next_piece, int lookahead,
 
 /* best move for one board.  out_move = {rot,row,col,k}; returns scored-leaf count (0 = no move) */
 int co_best_move(const uint16_t rows[ROWS], int piece, int next_piece, int lookahead,
-                 const int* fids, const double* w, int F, int* out_move, double* out_score)
+                 const int* fids, const double* w, int F, int* out_move, double* out_score, int move_set)
 {
     init_shapes();
     board_t b; rows_to_board(rows, &b);
     choice_t ch;
-    if (!choose(&b, piece, next_piece, lookahead, fids, w, F, &ch)) return 0;
+    if (!choose(&b, piece, next_piece, lookahead, move_set, fids, w, F, &ch)) return 0;
     out_move[0] = ch.rot; out_move[1] = ch.row; out_move[2] = ch.col; out_move[3] = ch.k;
     if (out_score) *out_score = ch.score;
     return ch.n_scored;
@@ -355,7 +409,7 @@ typedef struct {
 /* One whole game (simulator.py:152-189).  pieces == NULL => hashed stream (seed, stream_id).
  * trace (optional) receives 4 bytes {rot,row,col,k} per move. */
 static void play_game(const int* fids, const double* w, int F, const uint8_t* pieces, uint32_t T,
-                      uint64_t seed, uint64_t stream_id, int lookahead, const uint16_t* init_rows,
+                      uint64_t seed, uint64_t stream_id, int lookahead, int move_set, const uint16_t* init_rows,
                       game_result_t* res, uint8_t* trace, uint16_t* final_rows)
 {
     static const uint32_t POINTS[5] = {0, 40, 100, 300, 1200};         /* game.py:159 */
@@ -366,7 +420,7 @@ static void play_game(const int* fids, const double* w, int F, const uint8_t* pi
         int p  = pieces ? pieces[t] : hashed_piece(seed, stream_id, t);
         int nx = (lookahead >= 2 && t + 1 < T) ? (pieces ? pieces[t + 1] : hashed_piece(seed, stream_id, t + 1)) : -1;
         choice_t ch;
-        if (!choose(&b, p, nx, lookahead, fids, w, F, &ch)) break;
+        if (!choose(&b, p, nx, lookahead, move_set, fids, w, F, &ch)) break;
         b = ch.st.board;
         res->placements += (uint64_t)ch.n_scored;
         res->pieces += 1;
@@ -381,7 +435,7 @@ static void play_game(const int* fids, const double* w, int F, const uint8_t* pi
 typedef struct {
     const int* fids; int F; const double* weights; int C; int G;
     const uint8_t* pieces; int S; uint32_t T; const int32_t* seq_of_game; uint64_t seed; int lookahead;
-    game_result_t* results; uint8_t* trace; volatile int* next; int total;
+    game_result_t* results; uint8_t* trace; volatile int* next; int total; int move_set;
 } job_t;
 
 static void* worker(void* arg)
@@ -393,7 +447,7 @@ static void* worker(void* arg)
         int cand = g / j->G, gi = g % j->G;
         int seq = j->seq_of_game ? j->seq_of_game[g] : gi;
         const uint8_t* ps = j->pieces ? j->pieces + (size_t)seq * j->T : 0;
-        play_game(j->fids, j->weights + (size_t)cand * j->F, j->F, ps, j->T, j->seed, (uint64_t)seq, j->lookahead, 0,
+        play_game(j->fids, j->weights + (size_t)cand * j->F, j->F, ps, j->T, j->seed, (uint64_t)seq, j->lookahead, j->move_set, 0,
                   &j->results[g], j->trace ? j->trace + (size_t)g * j->T * 4 : 0, 0);
     }
     return 0;
@@ -404,7 +458,7 @@ static void* worker(void* arg)
  * threads <= 0 => 1. */
 int co_play_games(const int* fids, int F, const double* weights, int C, int G,
                   const uint8_t* pieces, int S, uint32_t T, const int32_t* seq_of_game, uint64_t seed,
-                  int lookahead, int threads, uint64_t* results, uint8_t* trace)
+                  int lookahead, int threads, uint64_t* results, uint8_t* trace, int move_set)
 {
     init_shapes();
     (void)S;
@@ -412,7 +466,7 @@ int co_play_games(const int* fids, int F, const double* weights, int C, int G,
     game_result_t* tmp = (game_result_t*)calloc((size_t)total, sizeof(game_result_t));
     if (!tmp) return -1;
     volatile int next = 0;
-    job_t j = {fids, F, weights, C, G, pieces, S, T, seq_of_game, seed, lookahead, tmp, trace, &next, total};
+    job_t j = {fids, F, weights, C, G, pieces, S, T, seq_of_game, seed, lookahead, tmp, trace, &next, total, move_set};
     if (threads <= 1) worker(&j);
     else {
         pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);
@@ -432,11 +486,11 @@ int co_play_games(const int* fids, int F, const double* weights, int C, int G,
 
 /* single game with optional initial board / final board (used by the chunked simulate() tests) */
 int co_play_one(const int* fids, int F, const double* w, const uint8_t* pieces, uint32_t T, int lookahead,
-                const uint16_t* init_rows, uint64_t* result8, uint8_t* trace, uint16_t* final_rows)
+                const uint16_t* init_rows, uint64_t* result8, uint8_t* trace, uint16_t* final_rows, int move_set)
 {
     init_shapes();
     game_result_t r;
-    play_game(fids, w, F, pieces, T, 0, 0, lookahead, init_rows, &r, trace, final_rows);
+    play_game(fids, w, F, pieces, T, 0, 0, lookahead, move_set, init_rows, &r, trace, final_rows);
     result8[0] = r.pieces; result8[1] = r.lines; result8[2] = r.hist[0]; result8[3] = r.hist[1];
     result8[4] = r.hist[2]; result8[5] = r.hist[3]; result8[6] = r.score; result8[7] = r.placements;
     return 0;

@@ -36,14 +36,16 @@ def lib():
         L.co_drop_moves.restype = ctypes.c_int
         L.co_eval_placement.argtypes = [u16p, ctypes.c_int, ctypes.c_int, ctypes.c_int, f64p, u16p, i32p, i32p]
         L.co_eval_placement.restype = ctypes.c_int
-        L.co_best_move.argtypes = [u16p, ctypes.c_int, ctypes.c_int, ctypes.c_int, i32p, f64p, ctypes.c_int, i32p, f64p]
+        L.co_moves.argtypes = [u16p, ctypes.c_int, ctypes.c_int, i32p]
+        L.co_moves.restype = ctypes.c_int
+        L.co_best_move.argtypes = [u16p, ctypes.c_int, ctypes.c_int, ctypes.c_int, i32p, f64p, ctypes.c_int, i32p, f64p, ctypes.c_int]
         L.co_best_move.restype = ctypes.c_int
         L.co_hashed_piece.argtypes = [ctypes.c_uint64] * 3
         L.co_hashed_piece.restype = ctypes.c_int
         L.co_play_games.argtypes = [i32p, ctypes.c_int, f64p, ctypes.c_int, ctypes.c_int, u8p, ctypes.c_int,
-                                    ctypes.c_uint32, i32p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, u64p, u8p]
+                                    ctypes.c_uint32, i32p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, u64p, u8p, ctypes.c_int]
         L.co_play_games.restype = ctypes.c_int
-        L.co_play_one.argtypes = [i32p, ctypes.c_int, f64p, u8p, ctypes.c_uint32, ctypes.c_int, u16p, u64p, u8p, u16p]
+        L.co_play_one.argtypes = [i32p, ctypes.c_int, f64p, u8p, ctypes.c_uint32, ctypes.c_int, u16p, u64p, u8p, u16p, ctypes.c_int]
         L.co_play_one.restype = ctypes.c_int
         _LIB = L
     return _LIB
@@ -57,6 +59,17 @@ def drop_moves(rows, piece):
     rows = np.ascontiguousarray(rows, dtype=np.uint16)
     mv = np.zeros((34, 3), dtype=np.int32)
     n = lib().co_drop_moves(_p(rows, ctypes.c_uint16), int(piece), _p(mv, ctypes.c_int32))
+    return [tuple(int(x) for x in mv[i]) for i in range(n)]
+
+
+MOVE_SETS = {"drop": 0, "slide": 1, 0: 0, 1: 1}
+
+
+def moves(rows, piece, move_set="drop"):
+    """move list of move_drop ('drop') or move_with_overhang_slide(move_drop) ('slide')."""
+    rows = np.ascontiguousarray(rows, dtype=np.uint16)
+    mv = np.zeros((640, 3), dtype=np.int32)
+    n = lib().co_moves(_p(rows, ctypes.c_uint16), int(piece), MOVE_SETS[move_set], _p(mv, ctypes.c_int32))
     return [tuple(int(x) for x in mv[i]) for i in range(n)]
 
 
@@ -74,7 +87,7 @@ def eval_placement(prev_rows, piece, rot, col):
     return {"features": f, "post": post, "row": row.value, "k": k.value}
 
 
-def best_move(rows, piece, next_piece, lookahead, fids, weights):
+def best_move(rows, piece, next_piece, lookahead, fids, weights, move_set="drop"):
     """-> None (no move) or dict(rot,row,col,k,score,n_scored)."""
     rows = np.ascontiguousarray(rows, dtype=np.uint16)
     fids = np.ascontiguousarray(fids, dtype=np.int32)
@@ -82,7 +95,8 @@ def best_move(rows, piece, next_piece, lookahead, fids, weights):
     mv = np.zeros(4, dtype=np.int32)
     sc = ctypes.c_double(0.0)
     n = lib().co_best_move(_p(rows, ctypes.c_uint16), int(piece), int(next_piece), int(lookahead),
-                           _p(fids, ctypes.c_int32), _p(w, ctypes.c_double), len(fids), _p(mv, ctypes.c_int32), ctypes.byref(sc))
+                           _p(fids, ctypes.c_int32), _p(w, ctypes.c_double), len(fids), _p(mv, ctypes.c_int32), ctypes.byref(sc),
+                           MOVE_SETS[move_set])
     if n == 0:
         return None
     return {"rot": int(mv[0]), "row": int(mv[1]), "col": int(mv[2]), "k": int(mv[3]), "score": sc.value, "n_scored": n}
@@ -92,7 +106,8 @@ def hashed_piece(seed, game, t):
     return lib().co_hashed_piece(seed, game, t)
 
 
-def play_games(fids, weights, G, pieces=None, T=None, seq_of_game=None, seed=0, lookahead=1, threads=1, want_trace=False):
+def play_games(fids, weights, G, pieces=None, T=None, seq_of_game=None, seed=0, lookahead=1, threads=1, want_trace=False,
+               move_set="drop"):
     """weights f64[C][F]; pieces u8[S][T] or None (hashed stream).  -> dict of u64 arrays [C*G] (+ trace u8[C*G][T][4])."""
     fids = np.ascontiguousarray(fids, dtype=np.int32)
     w = np.ascontiguousarray(weights, dtype=np.float64)
@@ -115,7 +130,7 @@ def play_games(fids, weights, G, pieces=None, T=None, seq_of_game=None, seed=0, 
     trace = np.zeros((C * G, T, 4), dtype=np.uint8) if want_trace else None
     rc = lib().co_play_games(_p(fids, ctypes.c_int32), F, _p(w, ctypes.c_double), C, G, _p(pieces, ctypes.c_uint8), S,
                              int(T), _p(seq_of_game, ctypes.c_int32), int(seed), int(lookahead), int(threads),
-                             _p(res, ctypes.c_uint64), _p(trace, ctypes.c_uint8))
+                             _p(res, ctypes.c_uint64), _p(trace, ctypes.c_uint8), MOVE_SETS[move_set])
     assert rc == 0
     out = {"pieces": res[:, 0], "lines": res[:, 1], "hist": res[:, 2:6], "score": res[:, 6], "placements": res[:, 7]}
     if want_trace:
@@ -123,7 +138,7 @@ def play_games(fids, weights, G, pieces=None, T=None, seq_of_game=None, seed=0, 
     return out
 
 
-def play_one(fids, weights, pieces, lookahead=1, init_rows=None):
+def play_one(fids, weights, pieces, lookahead=1, init_rows=None, move_set="drop"):
     fids = np.ascontiguousarray(fids, dtype=np.int32)
     w = np.ascontiguousarray(weights, dtype=np.float64)
     pieces = np.ascontiguousarray(pieces, dtype=np.uint8)
@@ -133,7 +148,8 @@ def play_one(fids, weights, pieces, lookahead=1, init_rows=None):
     trace = np.zeros((max(T, 1), 4), dtype=np.uint8)
     final = np.zeros(20, dtype=np.uint16)
     lib().co_play_one(_p(fids, ctypes.c_int32), len(fids), _p(w, ctypes.c_double), _p(pieces, ctypes.c_uint8), T, int(lookahead),
-                      _p(init, ctypes.c_uint16), _p(res, ctypes.c_uint64), _p(trace, ctypes.c_uint8), _p(final, ctypes.c_uint16))
+                      _p(init, ctypes.c_uint16), _p(res, ctypes.c_uint64), _p(trace, ctypes.c_uint8), _p(final, ctypes.c_uint16),
+                      MOVE_SETS[move_set])
     n = int(res[0])
     return {"pieces": n, "lines": int(res[1]), "hist": [int(x) for x in res[2:6]], "score": int(res[6]),
             "placements": int(res[7]), "trace": trace[:n].copy(), "final": final}

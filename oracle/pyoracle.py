@@ -179,6 +179,39 @@ def drop_moves(node, piece):
     return out
 
 
+def slide_moves(node, piece):
+    """cogworks/tetris/simulator.py:15-47 move_with_overhang_slide(move_drop): each hard-drop move, then the
+    placements reached by sliding sideways at the landed row under an overhang — right slides in ascending
+    column order (:25-33), then left slides in descending column order (:36-45) — each lowered as far as it
+    goes; a direction stops at the first blocked column."""
+    g = node.grid
+    out = []
+    for rot, row, col in drop_moves(node, piece):
+        out.append((rot, row, col))
+        shape = PIECES[piece][rot]
+        w = shape.shape[1]
+        if col + w < COLS and row > ROWS - g.tops[col + w]:
+            for c in range(col + 1, COLS - w + 1):
+                if g.collides(shape, row, c):
+                    break
+                r = row
+                while not g.collides(shape, r + 1, c):
+                    r += 1
+                out.append((rot, int(r), c))
+        if col > 0 and row > ROWS - g.tops[col - 1]:
+            for c in range(col - 1, -1, -1):
+                if g.collides(shape, row, c):
+                    break
+                r = row
+                while not g.collides(shape, r + 1, c):
+                    r += 1
+                out.append((rot, int(r), c))
+    return out
+
+
+MOVE_GENERATORS = {"drop": drop_moves, "slide": slide_moves}
+
+
 # ---------------------------------------------------------------------------------------------
 # Features.  cogworks/tetris/features.py:18-347; ids = source order (SURVEY.md §8a-F).
 # ---------------------------------------------------------------------------------------------
@@ -395,12 +428,13 @@ def hashed_piece(seed, game, t):
     return ((x >> 32) * 7) >> 32
 
 
-def simulate(node, pieces, fids, weights, lookahead=1, trace=None, prune=True):
+def simulate(node, pieces, fids, weights, lookahead=1, trace=None, prune=True, move_set="drop"):
     """simulator.py:152-189 with move_gen=move_drop and the canonical linear policy.
 
     `pieces` is an iterable of piece ids; returns the final node and the number of pieces placed.
     """
     assert lookahead > 0
+    move_gen = MOVE_GENERATORS[move_set]
     it = iter(pieces)
     key = lambda s: linear_score(s, fids, weights)     # noqa: E731
     placed = 0
@@ -408,7 +442,7 @@ def simulate(node, pieces, fids, weights, lookahead=1, trace=None, prune=True):
         visible = tuple(itertools.islice(it, 0, lookahead))           # :156
         layers = [[node]]
         for p in visible:                                             # :159-167
-            layers.append([prev.child(p, *mv) for prev in layers[-1] for mv in drop_moves(prev, p)])
+            layers.append([prev.child(p, *mv) for prev in layers[-1] for mv in move_gen(prev, p)])
         nxt = None
         while nxt is None and len(layers) > 1:                        # :170-174
             pool = layers.pop()
@@ -429,11 +463,11 @@ def simulate(node, pieces, fids, weights, lookahead=1, trace=None, prune=True):
     return node, placed
 
 
-def play_game(fids, weights, pieces, lookahead=1, want_trace=False):
+def play_game(fids, weights, pieces, lookahead=1, want_trace=False, move_set="drop"):
     """One canonical game from the empty board -> dict(pieces, lines, hist[4], score, trace)."""
     trace = bytearray() if want_trace else None
     root = Node(None, Grid())
-    last, placed = simulate(root, pieces, fids, weights, lookahead, trace, prune=not want_trace)
+    last, placed = simulate(root, pieces, fids, weights, lookahead, trace, prune=not want_trace, move_set=move_set)
     out = {"pieces": placed, "lines": last.lines(), "hist": [last.hist.get(k, 0) for k in (1, 2, 3, 4)]}
     if want_trace:
         out["score"] = game_score(last)

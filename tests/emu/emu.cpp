@@ -20,21 +20,35 @@ static int pick_mode(const int* ids, int F)
     return is_w6 ? MODE_W6 : (is_all ? MODE_ALL45 : MODE_GENERIC);
 }
 
+// candidate bookkeeping: maximise key, ties -> smallest tag (enumeration order); mv = placement to commit
+struct Best { uint64_t key; uint32_t tag; uint32_t mv; };
+
 template <int MODE>
 static void search_one(const uint32_t c[COLS], const Heights& H, const PrevStat& pv, int piece, const uint8_t* ids,
-                       const double* w, int F, uint64_t rmask, uint32_t tag_hi, uint64_t& key, uint32_t& tag, uint64_t& cnt)
+                       const double* w, int F, uint64_t rmask, int move_set, uint32_t tag_hi, uint32_t mv1, bool leaf_is_first,
+                       Best& best, uint64_t& cnt)
 {
     const Tables& tab = host_tables();
+    auto consider = [&](const Placement& P, const SlotDesc& d, uint32_t tg, uint32_t mv) {
+        Feat f;
+        memset(&f, 0, sizeof f);
+        eval_features<ModeTraits<MODE>::CMASK>(P, d, pv, rmask, f);
+        const uint64_t k = score_key(score_features<MODE>(f, ids, w, F));
+        if (k > best.key || (k == best.key && tg < best.tag)) { best.key = k; best.tag = tg; best.mv = leaf_is_first ? mv : mv1; }
+        ++cnt;
+    };
     for (int s = 0; s < tab.nslots[piece]; ++s) {
         Placement P;
-        if (place_slot(c, H, tab.slot[piece][s], P)) {
-            Feat f;
-            memset(&f, 0, sizeof f);
-            eval_features<ModeTraits<MODE>::CMASK>(P, tab.slot[piece][s], pv, rmask, f);
-            const uint64_t k = score_key(score_features<MODE>(f, ids, w, F));
-            const uint32_t tg = tag_hi | (uint32_t)s;
-            if (k > key || (k == key && tg < tag)) { key = k; tag = tg; }
-            ++cnt;
+        if (!place_slot(c, H, tab.slot[piece][s], P)) continue;
+        consider(P, tab.slot[piece][s], tag_hi | (uint32_t)s << 5, (uint32_t)s | (uint32_t)P.y << 8);
+        if (move_set == 1) {
+            for_each_slide(c, H, tab.slot[piece][s], s, P.y, [&](int s2) { return tab.slot[piece][s2]; },
+                [&](const SlotDesc& d2, int s2, int yy, int j) {
+                    Placement P2; uint32_t full;
+                    place_at(c, d2, yy, P2, &full);
+                    if (full != 0u) place_clear(d2, P2, full);
+                    consider(P2, d2, tag_hi | (uint32_t)s << 5 | (uint32_t)j, (uint32_t)s2 | (uint32_t)yy << 8);
+                });
         }
     }
 }
@@ -42,46 +56,61 @@ static void search_one(const uint32_t c[COLS], const Heights& H, const PrevStat&
 template <int MODE>
 static void play(const int* ids_in, int F, const double* w, const uint8_t* pieces, uint32_t T, uint64_t seed, uint64_t stream,
                  int lookahead, uint32_t max_moves, const uint16_t* init_rows, uint64_t* res8, uint8_t* trace,
-                 double* score_trace, uint16_t* final_rows)
+                 double* score_trace, uint16_t* final_rows, int move_set)
 {
     const Tables& tab = host_tables();
     uint8_t ids[64]; uint64_t rmask = 0;
     for (int i = 0; i < F; ++i) { ids[i] = (uint8_t)ids_in[i]; rmask |= 1ull << ids_in[i]; }
     uint32_t c[COLS];
     if (init_rows) rows_to_cols(init_rows, c); else memset(c, 0, sizeof c);
-    Heights H = pack_heights(c); PrevStat pv = prev_stat(c);
+    PrevStat pv = prev_stat(c); Heights H = pack_gh(pv.gh);
     uint32_t t = 0, lines = 0, hist[4] = {0, 0, 0, 0}; uint64_t score = 0, cnt = 0;
     if (!max_moves) max_moves = T;
     auto piece_at = [&](uint32_t tt) { return pieces ? (int)pieces[tt] : hashed_piece(seed, stream, tt); };
     while (t < T && t < max_moves) {
         const int p1 = piece_at(t);
         if (p1 >= 7) break;
-        uint64_t key = 0; uint32_t tag = 0;
+        Best best = {0, 0, 0};
         const int p2 = (lookahead == 2 && t + 1 < T) ? piece_at(t + 1) : 255;
         if (p2 < 7) {
+            // layer 1 in enumeration order (base move, its right slides, its left slides), each expanded by piece 2
+            auto expand = [&](const Placement& P1, const SlotDesc& d1, uint32_t tag1, uint32_t mv1) {
+                const PrevStat pv1 = next_stat(pv, P1, d1); const Heights H1 = pack_gh(pv1.gh);
+                search_one<MODE>(P1.n, H1, pv1, p2, ids, w, F, rmask, move_set, tag1 << 11, mv1, false, best, cnt);
+            };
             for (int s1 = 0; s1 < tab.nslots[p1]; ++s1) {
                 Placement P1;
                 if (!place_slot(c, H, tab.slot[p1][s1], P1)) continue;
-                const PrevStat pv1 = next_stat(pv, P1, tab.slot[p1][s1]); const Heights H1 = pack_gh(pv1.gh);
-                search_one<MODE>(P1.n, H1, pv1, p2, ids, w, F, rmask, (uint32_t)s1 << 6, key, tag, cnt);
+                expand(P1, tab.slot[p1][s1], (uint32_t)s1 << 5, (uint32_t)s1 | (uint32_t)P1.y << 8);
+                if (move_set == 1) {
+                    for_each_slide(c, H, tab.slot[p1][s1], s1, P1.y, [&](int s2) { return tab.slot[p1][s2]; },
+                        [&](const SlotDesc& d2, int s2, int yy, int j) {
+                            Placement P2; uint32_t full;
+                            place_at(c, d2, yy, P2, &full);
+                            if (full != 0u) place_clear(d2, P2, full);
+                            expand(P2, d2, (uint32_t)s1 << 5 | (uint32_t)j, (uint32_t)s2 | (uint32_t)yy << 8);
+                        });
+                }
             }
         }
-        if (key == 0) {
-            uint64_t k1 = 0; uint32_t t1 = 0;
-            search_one<MODE>(c, H, pv, p1, ids, w, F, rmask, 0u, k1, t1, cnt);
-            key = k1; tag = t1 << 6;
+        if (best.key == 0) {
+            Best b1 = {0, 0, 0};
+            search_one<MODE>(c, H, pv, p1, ids, w, F, rmask, move_set, 0u, 0u, true, b1, cnt);
+            best = b1;
         }
-        if (key == 0) break;
-        Placement P;
-        place_slot(c, H, tab.slot[p1][tag >> 6], P);
+        if (best.key == 0) break;
+        const SlotDesc& dw = tab.slot[p1][best.mv & 255u];
+        Placement P; uint32_t full;
+        place_at(c, dw, (int)(best.mv >> 8), P, &full);
+        if (full != 0u) place_clear(dw, P, full);
         memcpy(c, P.n, sizeof c);
-        pv = next_stat(pv, P, tab.slot[p1][tag >> 6]); H = pack_gh(pv.gh);
+        pv = next_stat(pv, P, dw); H = pack_gh(pv.gh);
         lines += (uint32_t)P.k; if (P.k) hist[P.k - 1] += 1;
         static const uint32_t PTS[5] = {0, 40, 100, 300, 1200};
         score += (uint64_t)PTS[P.k] * (lines / 10 + 1);
         if (trace) { trace[4 * t] = (uint8_t)P.rot; trace[4 * t + 1] = (uint8_t)(ROWS - P.y - P.ph); trace[4 * t + 2] = (uint8_t)P.c0; trace[4 * t + 3] = (uint8_t)P.k; }
         if (score_trace) {
-            const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
+            const uint64_t b = (best.key & 0x8000000000000000ull) ? (best.key & 0x7FFFFFFFFFFFFFFFull) : ~best.key;
             memcpy(&score_trace[t], &b, 8);
         }
         ++t;
@@ -139,16 +168,16 @@ extern "C" {
 // mode: -1 = as tb200_set_features would choose, 0 = force the generic (run-time feature list) path
 int emu_play_one(const int* ids, int F, const double* w, const uint8_t* pieces, uint32_t T, uint64_t seed, uint64_t stream,
                  int lookahead, uint32_t max_moves, int mode, const uint16_t* init_rows, uint64_t* res8, uint8_t* trace,
-                 double* score_trace, uint16_t* final_rows)
+                 double* score_trace, uint16_t* final_rows, int move_set)
 {
     const int m = mode < 0 ? pick_mode(ids, F) : mode;
     if (m == 3) {           // fast w6 path of the one-warp-per-game kernel (caller guarantees the w6 feature list, lookahead 1)
         play_w6_fast(w, pieces, T, seed, stream, max_moves, init_rows, res8, trace, score_trace, final_rows);
         return m;
     }
-    if (m == MODE_W6) play<MODE_W6>(ids, F, w, pieces, T, seed, stream, lookahead, max_moves, init_rows, res8, trace, score_trace, final_rows);
-    else if (m == MODE_ALL45) play<MODE_ALL45>(ids, F, w, pieces, T, seed, stream, lookahead, max_moves, init_rows, res8, trace, score_trace, final_rows);
-    else play<MODE_GENERIC>(ids, F, w, pieces, T, seed, stream, lookahead, max_moves, init_rows, res8, trace, score_trace, final_rows);
+    if (m == MODE_W6) play<MODE_W6>(ids, F, w, pieces, T, seed, stream, lookahead, max_moves, init_rows, res8, trace, score_trace, final_rows, move_set);
+    else if (m == MODE_ALL45) play<MODE_ALL45>(ids, F, w, pieces, T, seed, stream, lookahead, max_moves, init_rows, res8, trace, score_trace, final_rows, move_set);
+    else play<MODE_GENERIC>(ids, F, w, pieces, T, seed, stream, lookahead, max_moves, init_rows, res8, trace, score_trace, final_rows, move_set);
     return m;
 }
 
@@ -178,5 +207,26 @@ void emu_eval_placement(const uint16_t* prev_rows, int piece, int rot, int col, 
 }
 
 int emu_hashed_piece(uint64_t seed, uint64_t stream, uint64_t t) { return hashed_piece(seed, stream, t); }
+
+// move list (rot, row, col) of move_set 0 (move_drop) / 1 (move_with_overhang_slide(move_drop)); returns the count
+int emu_moves(const uint16_t* rows, int piece, int move_set, int* out)
+{
+    const Tables& tab = host_tables();
+    uint32_t c[COLS];
+    rows_to_cols(rows, c);
+    const Heights H = pack_heights(c);
+    int n = 0;
+    for (int s = 0; s < tab.nslots[piece]; ++s) {
+        Placement P;
+        if (!place_slot(c, H, tab.slot[piece][s], P)) continue;
+        out[3 * n] = P.rot; out[3 * n + 1] = ROWS - P.y - P.ph; out[3 * n + 2] = P.c0; ++n;
+        if (move_set == 1)
+            for_each_slide(c, H, tab.slot[piece][s], s, P.y, [&](int s2) { return tab.slot[piece][s2]; },
+                [&](const SlotDesc& d2, int, int yy, int) {
+                    out[3 * n] = (int)((d2.w[0] >> 4) & 3u); out[3 * n + 1] = ROWS - yy - (int)((d2.w[0] >> 9) & 7u); out[3 * n + 2] = (int)(d2.w[0] & 15u); ++n;
+                });
+    }
+    return n;
+}
 
 }  // extern "C"

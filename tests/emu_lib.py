@@ -30,7 +30,7 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
 
 
-def play_one(fids, weights, pieces=None, T=None, seed=0, stream=0, lookahead=1, max_moves=0, mode=-1, init_rows=None):
+def play_one(fids, weights, pieces=None, T=None, seed=0, stream=0, lookahead=1, max_moves=0, mode=-1, init_rows=None, move_set=0):
     fids = np.ascontiguousarray(fids, dtype=np.int32)
     w = np.ascontiguousarray(weights, dtype=np.float64)
     if pieces is not None:
@@ -43,7 +43,7 @@ def play_one(fids, weights, pieces=None, T=None, seed=0, stream=0, lookahead=1, 
     final = np.zeros(20, dtype=np.uint16)
     m = lib().emu_play_one(_p(fids), ctypes.c_int(len(fids)), _p(w), _p(pieces), ctypes.c_uint32(T), ctypes.c_uint64(seed),
                            ctypes.c_uint64(stream), ctypes.c_int(lookahead), ctypes.c_uint32(max_moves), ctypes.c_int(mode),
-                           _p(init), _p(res), _p(trace), _p(st), _p(final))
+                           _p(init), _p(res), _p(trace), _p(st), _p(final), ctypes.c_int(move_set))
     n = int(res[0])
     return {"pieces": n, "lines": int(res[1]), "hist": [int(x) for x in res[2:6]], "score": int(res[6]),
             "placements": int(res[7]), "trace": trace[:n].copy(), "scores": st[:n].copy(), "final": final, "mode": m}
@@ -56,3 +56,11 @@ def eval_placement(prev_rows, piece, rot, col):
     info = np.zeros(3, dtype=np.int32)
     lib().emu_eval_placement(_p(prev), ctypes.c_int(piece), ctypes.c_int(rot), ctypes.c_int(col), _p(f), _p(post), _p(info))
     return {"legal": int(info[0]), "row": int(info[1]), "k": int(info[2]), "features": f, "post": post}
+
+
+def moves(rows, piece, move_set=0):
+    rows = np.ascontiguousarray(rows, dtype=np.uint16)
+    out = np.zeros((640, 3), dtype=np.int32)
+    lib().emu_moves.restype = ctypes.c_int
+    n = lib().emu_moves(_p(rows), ctypes.c_int(piece), ctypes.c_int(move_set), _p(out))
+    return [tuple(int(x) for x in out[i]) for i in range(n)]

@@ -105,8 +105,10 @@ def all_features(state):
     return [feat_value(vals[f]) for f in FEATS]
 
 
-def play(named_weights, seed, T, lookahead=1, tie=tie_first, keep_trace=True):
-    """Canonical game: returns summary + byte trace [rot,row,col,k]*."""
+def play(named_weights, seed, T, lookahead=1, tie=tie_first, keep_trace=True, slide=False):
+    """Canonical game: returns summary + byte trace [rot,row,col,k]*.
+    slide=True: move_gen = move_with_overhang_slide(move_drop) (simulator.py:15-47) instead of move_drop."""
+    move_gen = ref_sim.move_with_overhang_slide(ref_sim.move_drop) if slide else ref_sim.move_drop
     weights = weights_by_name(named_weights)
     scorer = make_scorer(weights)
     calls = [0]
@@ -120,7 +122,7 @@ def play(named_weights, seed, T, lookahead=1, tie=tie_first, keep_trace=True):
     trace = bytearray()
     n = 0
     last = state
-    for st in ref_sim.simulate(state, gen, ref_sim.move_drop, ref_sim.policy_best(counting, tie), lookahead):
+    for st in ref_sim.simulate(state, gen, move_gen, ref_sim.policy_best(counting, tie), lookahead):
         d = st.delta
         trace += bytes([d.rot, d.row, d.col, len(d.cleared)])
         n += 1
@@ -133,6 +135,7 @@ def play(named_weights, seed, T, lookahead=1, tie=tie_first, keep_trace=True):
         "scorer_calls": calls[0], "score": int(score),
         "trace_sha16": hashlib.sha256(bytes(trace)).hexdigest()[:16],
         "final_board": board_rows(last.board),
+        "move_gen": "overhang_slide" if slide else "drop",
     }
     if keep_trace:
         out["trace_hex"] = bytes(trace).hex()
@@ -254,6 +257,27 @@ def gen_steps(seed=7, n_games=6, max_pieces=80):
             nxt = best1 if rng.random() < 0.7 else l1[rng.randrange(len(l1))]
             nxt.prev.prev = None
             state = nxt
+    return out
+
+
+def gen_slide_moves(seed=5, n_games=10, max_pieces=60):
+    """Boards with overhangs -> the exact move list of move_with_overhang_slide(move_drop) for every piece."""
+    rng = random.Random(seed)
+    gen_slide = ref_sim.move_with_overhang_slide(ref_sim.move_drop)
+    out = []
+    for g in range(n_games):
+        state = State(None, Board(20, 10))
+        for t in range(max_pieces):
+            zoid = PIECES[rng.randrange(7)]
+            moves = list(gen_slide(state, zoid))
+            if not moves:
+                break
+            base = list(ref_sim.move_drop(state, zoid))
+            if len(moves) > len(base) or rng.random() < 0.1:
+                out.append({"board": board_rows(state.board),
+                            "moves": [[[int(x) for x in m] for m in gen_slide(state, z)] for z in PIECES]})
+            state = state.future(zoid, *moves[rng.randrange(len(moves))])
+            state.prev = None
     return out
 
 
@@ -382,6 +406,22 @@ def main():
         games.append(play(w45b, s, 300))
     games.append(play(w45b, 0, 30, lookahead=2))
     dump("games.json", {"meta": meta, "games": games})
+
+    # §8f rank 2: move_with_overhang_slide(move_drop).  Weight sets that leave overhangs (so that slides happen).
+    t0 = time.time()
+    holes = collections.OrderedDict([("max_ht", -1.0), ("row_trans", -0.2), ("pits", 0.4), ("landing_height", -0.5)])
+    sgames = []
+    for s in (0, 1, 2):
+        sgames.append(play(W6, s, 300, slide=True))
+    for s in (0, 1, 2, 3):
+        sgames.append(play(holes, s, 400, slide=True))
+    sgames.append(play(weak, 1, 5000, slide=True))
+    sgames.append(play(holes, 0, 40, lookahead=2, slide=True))
+    sgames.append(play(W6, 1, 40, lookahead=2, slide=True))
+    sgames.append(play(w45b, 1, 200, slide=True))
+    dump("games_slide.json", {"meta": meta, "games": sgames})
+    print("slide games:", len(sgames), round(time.time() - t0, 1), "s", flush=True)
+    dump("slide_moves.json", {"meta": meta, "boards": gen_slide_moves()})
     print("games:", len(games), round(time.time() - t0, 1), "s", flush=True)
 
     if not args.skip_ce:

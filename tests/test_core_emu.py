@@ -150,3 +150,48 @@ def test_emu_fast_w6_path_vs_coracle(golden_games):
         a = coracle.play_one(fids, w, seq, 1, init_rows=init)
         b = emu_lib.play_one(fids, w, seq, mode=3, init_rows=init)
         assert a["trace"].tobytes() == b["trace"].tobytes() and a["score"] == b["score"]
+
+
+# ------------------------------------------------------------------------------------------------
+# move_with_overhang_slide(move_drop) in the CUDA core (host build)
+# ------------------------------------------------------------------------------------------------
+def test_emu_slide_move_lists():
+    from conftest import load_golden
+    boards = load_golden("slide_moves.json")["boards"]
+    for i, b in enumerate(boards):
+        for p, want in enumerate(b["moves"]):
+            assert [list(m) for m in emu_lib.moves(b["board"], p, 1)] == want, (i, p)
+
+
+def test_emu_slide_games():
+    from conftest import load_golden
+    for g in load_golden("games_slide.json")["games"]:
+        fids = [pyoracle.FEATURE_ID[n] for n, _ in g["weights"]]
+        w = [x for _, x in g["weights"]]
+        seq = pyoracle.piece_sequence(g["seed"], g["T"])
+        for mode in (-1, 0):
+            res = emu_lib.play_one(fids, w, seq, lookahead=g["lookahead"], mode=mode, move_set=1)
+            assert res["pieces"] == g["pieces"] and res["lines"] == g["lines"] and res["score"] == g["score"]
+            assert res["placements"] == g["scorer_calls"] and res["trace"].tobytes().hex() == g["trace_hex"]
+
+
+@pytest.mark.parametrize("lookahead,ngames,T", [(1, 120, 300), (2, 10, 30)])
+def test_emu_slide_vs_coracle_random(lookahead, ngames, T):
+    rng = random.Random(500 + lookahead)
+    slid = 0
+    for gi in range(ngames):
+        if gi % 3 == 0:
+            names, w = W6_NAMES, [rng.gauss(v, 2.0) for v in W6_VALS]
+        elif gi % 3 == 1:
+            names, w = ["max_ht", "row_trans", "pits", "landing_height"], [-1.0, rng.gauss(-0.2, 0.2), rng.gauss(0.4, 0.3), -0.5]
+        else:
+            names = rng.sample(NAMES, rng.randint(2, 10)); w = [rng.gauss(0, 2.0) for _ in names]
+        fids = [pyoracle.FEATURE_ID[n] for n in names]
+        seq = [pyoracle.hashed_piece(88, gi, t) for t in range(T)]
+        a = coracle.play_one(fids, w, seq, lookahead, move_set="slide")
+        b = emu_lib.play_one(fids, w, seq, lookahead=lookahead, move_set=1)
+        assert (a["pieces"], a["lines"], a["hist"], a["score"], a["placements"]) == (b["pieces"], b["lines"], b["hist"], b["score"], b["placements"]), gi
+        assert a["trace"].tobytes() == b["trace"].tobytes(), gi
+        d = coracle.play_one(fids, w, seq, lookahead, move_set="drop")
+        slid += a["trace"].tobytes() != d["trace"].tobytes()
+    assert slid > ngames // 10          # the slide move set really changes games

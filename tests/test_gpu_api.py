@@ -145,3 +145,25 @@ def test_error_reporting(eng):
         eng.play_games(np.zeros((2, 1)), 1, T=10, lookahead=3)
     with pytest.raises(EngineError):
         eng.play_games(np.zeros((2, 3)), 1, T=10)
+
+
+def test_simulate_with_overhang_slide(eng):
+    """Host mirror: simulate(state, zoids, move_with_overhang_slide(move_drop), policy) on the device."""
+    from conftest import load_golden
+    from tetris_ai_b200.tetris import simulator as sim
+    from tetris_ai_b200.tetris.game import Board, State, PIECES
+    for g in load_golden("games_slide.json")["games"]:
+        if g["pieces"] > 120:
+            continue
+        policy = sim.policy_best(sim.linear_scorer(_weights(g["weights"])), sim.tie_first)
+        seq = pyoracle.piece_sequence(g["seed"], g["T"])
+        trace = bytearray()
+        last = State(None, Board(20, 10))
+        for st in sim.simulate(last, iter(PIECES[i] for i in seq), sim.move_with_overhang_slide(sim.move_drop), policy,
+                               lookahead=g["lookahead"], engine=eng):
+            d = st.delta
+            trace += bytes([d.rot, d.row, d.col, len(d.cleared)])
+            last = st
+        assert trace.hex() == g["trace_hex"] and last.score() == g["score"]
+    with pytest.raises(TypeError):
+        sim.move_with_overhang_slide(lambda s, z: [])

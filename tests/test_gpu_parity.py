@@ -322,3 +322,48 @@ def test_k1_large_batch(eng, golden_steps):
     for i, s in enumerate(ss):
         want = s["l1"]
         assert tuple(int(x) for x in r["move"][i]) == (want["rot"], want["row"], want["col"], want["k"])
+
+
+# ------------------------------------------------------------------------------------------------
+# move_with_overhang_slide(move_drop) on the device
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lanes", [32, 16, 8])
+def test_slide_golden_games(eng, lanes):
+    from conftest import load_golden
+    for g in load_golden("games_slide.json")["games"]:
+        eng.set_features([n for n, _ in g["weights"]])
+        w = np.array([[x for _, x in g["weights"]]])
+        seq = np.array([pyoracle.piece_sequence(g["seed"], g["T"])], dtype=np.uint8)
+        r = eng.play_games(w, 1, pieces=seq, lookahead=g["lookahead"], lanes=lanes, want_trace=True, want_final=True, move_set=1)
+        res = r["results"][0]
+        assert int(res["pieces"]) == g["pieces"] and int(res["lines"]) == g["lines"] and [int(x) for x in res["hist"]] == g["hist"]
+        assert int(res["score"]) == g["score"] and int(res["placements"]) == g["scorer_calls"]
+        assert r["trace"][0, :g["pieces"]].tobytes().hex() == g["trace_hex"]
+        assert list(r["final"][0]) == g["final_board"]
+
+
+@pytest.mark.parametrize("lanes", [0, 32, 8])
+@pytest.mark.parametrize("names,kind,lookahead,C,G,T", [
+    (W6_NAMES, "wide", 1, 64, 3, 250),
+    (["max_ht", "row_trans", "pits", "landing_height"], "holes", 1, 64, 3, 250),
+    (NAMES, "all45", 1, 16, 2, 150),
+    (["max_ht", "row_trans", "pits", "landing_height"], "holes", 2, 6, 2, 30),
+])
+def test_slide_vs_coracle(eng, lanes, names, kind, lookahead, C, G, T):
+    rng = random.Random(hash((kind, lookahead, C, "slide")) & 0xFFFF)
+    fids = [pyoracle.FEATURE_ID[n] for n in names]
+    if kind == "holes":
+        w = np.array([[-1.0, rng.gauss(-0.2, 0.2), rng.gauss(0.4, 0.3), -0.5] for _ in range(C)])
+    else:
+        w = np.array(_weight_sets(rng, C, names, kind))
+    eng.set_features(names)
+    r = eng.play_games(w, G, T=T, seed=77, lookahead=lookahead, lanes=lanes, want_trace=True, move_set=1)
+    o = coracle.play_games(fids, w, G, T=T, seed=77, lookahead=lookahead, threads=16, want_trace=True, move_set="slide")
+    d = coracle.play_games(fids, w, G, T=T, seed=77, lookahead=lookahead, threads=16, move_set="drop")
+    res = r["results"]
+    assert (res["pieces"] == o["pieces"]).all() and (res["lines"] == o["lines"]).all() and (res["score"] == o["score"]).all()
+    assert (res["placements"] == o["placements"]).all()
+    for g in range(C * G):
+        n = int(res["pieces"][g])
+        assert (r["trace"][g, :n] == o["trace"][g, :n]).all(), g
+    assert (o["placements"] != d["placements"]).any()          # slides really occurred

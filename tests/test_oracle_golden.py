@@ -181,3 +181,48 @@ def test_coracle_ce_generations(golden_ce):
         assert [float(x).hex() for x in log[-1]] == want["fitness"]
         assert [float(v).hex() for v in mean.values()] == want["mean"]
         assert [float(v).hex() for v in std.values()] == want["std"]
+
+
+# ------------------------------------------------------------------------------------------------
+# move_with_overhang_slide(move_drop)
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="session")
+def golden_slide_games():
+    from conftest import load_golden
+    return load_golden("games_slide.json")
+
+
+@pytest.fixture(scope="session")
+def golden_slide_moves():
+    from conftest import load_golden
+    return load_golden("slide_moves.json")
+
+
+def test_slide_move_lists(golden_slide_moves):
+    """Exact move lists (order included) of the reference's move_with_overhang_slide(move_drop)."""
+    extra = 0
+    for i, b in enumerate(golden_slide_moves["boards"]):
+        for p, want in enumerate(b["moves"]):
+            got = coracle.moves(b["board"], p, "slide")
+            assert [list(m) for m in got] == want, (i, p)
+            extra += len(want) - len(coracle.moves(b["board"], p, "drop"))
+        if i % 10 == 0:
+            node = pyoracle.Node(None, pyoracle.Grid.from_rows(b["board"]))
+            for p, want in enumerate(b["moves"]):
+                assert [list(m) for m in pyoracle.slide_moves(node, p)] == want
+    assert extra > 2000
+
+
+def test_slide_games(golden_slide_games):
+    n_py = 0
+    for g in golden_slide_games["games"]:
+        assert g["move_gen"] == "overhang_slide"
+        fids, w = fids_weights(g["weights"])
+        seq = pyoracle.piece_sequence(g["seed"], g["T"])
+        res = coracle.play_one(fids, w, seq, g["lookahead"], move_set="slide")
+        _check_game(res, g)
+        assert res["placements"] == g["scorer_calls"] and list(res["final"]) == g["final_board"]
+        if g["scorer_calls"] < 1300:
+            _check_game(pyoracle.play_game(fids, w, seq, g["lookahead"], want_trace=True, move_set="slide"), g)
+            n_py += 1
+    assert n_py >= 3

@@ -51,6 +51,7 @@ struct PlayParams {
     int32_t   G;
     int32_t   F;
     int32_t   per_game_weights;      // K1 (one game per board, sequence id = game): weights row = game (1) or row 0 (-1); K2: 0
+    int32_t   move_set;              // 0 = move_drop, 1 = move_with_overhang_slide(move_drop)
     uint8_t   ids[TB200_MAX_WEIGHTED];
 };
 
@@ -65,6 +66,21 @@ TB_D void group_argmax(uint64_t& key, uint32_t& tag)
         const uint32_t otag = __shfl_xor_sync(FULLMASK, tag, off);
         const uint64_t okey = ((uint64_t)ohi << 32) | olo;
         if (okey > key || (okey == key && otag < tag)) { key = okey; tag = otag; }
+    }
+}
+
+// same, carrying the placement to commit (mv = slot | height << 8) along with the winner
+template <int LANES>
+TB_D void group_argmax_mv(uint64_t& key, uint32_t& tag, uint32_t& mv)
+{
+#pragma unroll
+    for (int off = LANES / 2; off > 0; off >>= 1) {
+        const uint32_t ohi = __shfl_xor_sync(FULLMASK, (uint32_t)(key >> 32), off);
+        const uint32_t olo = __shfl_xor_sync(FULLMASK, (uint32_t)key, off);
+        const uint32_t otag = __shfl_xor_sync(FULLMASK, tag, off);
+        const uint32_t omv = __shfl_xor_sync(FULLMASK, mv, off);
+        const uint64_t okey = ((uint64_t)ohi << 32) | olo;
+        if (okey > key || (okey == key && otag < tag)) { key = okey; tag = otag; mv = omv; }
     }
 }
 
@@ -87,29 +103,55 @@ TB_D SlotDesc load_slot12(const Tables& tab, int piece, int s)
     return d;
 }
 
-// layer-1 search: every legal (rot, col) slot of `piece` on board c, scored as a leaf whose
-// previous state is the board itself.  Lanes take slots gl, gl+LANES, ...; strict > keeps the
-// earliest slot inside a lane.
-template <int LANES, int MODE>
+// Moves derived from one legal hard-drop slot: the drop itself (index 0) and, with SLIDE, the overhang slides
+// (simulator.py:15-47) in the reference's order.  list[i] = slot | height << 8 of slide i + 1.
+template <int SLIDE>
+TB_D int collect_slides(const uint32_t c[COLS], const Heights& H, const Tables& tab, int piece, const SlotDesc& d0, int s0, int y0, uint16_t* list)
+{
+    int n = 0;
+    if (SLIDE)
+        for_each_slide(c, H, d0, s0, y0, [&](int s2) { return load_slot12(tab, piece, s2); },
+                       [&](const SlotDesc&, int s2, int yy, int) { list[n++] = (uint16_t)((uint32_t)s2 | (uint32_t)yy << 8); });
+    return n;
+}
+
+// layer search: every move of `piece` on board c (hard drops, plus overhang slides with SLIDE), each scored as a
+// leaf whose previous state is the board itself.  Lanes take slots gl, gl+LANES, ...; inside a lane moves are
+// visited in enumeration order, so a strict > keeps the earliest.  tag = tag_hi | slot << 5 | slide index;
+// mv = the placement to commit if this leaf wins: the leaf's own (leaf_is_first) or the caller's first move mv1.
+template <int LANES, int MODE, int SLIDE>
 TB_D void search_one(const uint32_t c[COLS], const Heights& H, const PrevStat& pv, int piece, int gl,
                      const Tables& tab, const uint8_t* ids, const double* w, int F, uint64_t rmask,
-                     uint32_t tag_hi, uint64_t& key, uint32_t& tag, uint32_t& cnt)
+                     uint32_t tag_hi, uint32_t mv1, bool leaf_is_first, uint64_t& key, uint32_t& tag, uint32_t& mv, uint32_t& cnt)
 {
     const int ns = tab.nslots[piece];
     for (int s = gl; s < ns; s += LANES) {
-        const SlotDesc d = load_slot12(tab, piece, s);
-        Placement P;
-        if (place_slot(c, H, d, P)) {
+        const SlotDesc d0 = load_slot12(tab, piece, s);
+        Placement P0;
+        if (!place_slot(c, H, d0, P0)) continue;
+        uint16_t list[SLIDE ? 18 : 1];
+        const int n = collect_slides<SLIDE>(c, H, tab, piece, d0, s, P0.y, list);
+        for (int i = 0; i <= n; ++i) {
+            const uint32_t m = i == 0 ? ((uint32_t)s | (uint32_t)P0.y << 8) : (uint32_t)list[SLIDE ? i - 1 : 0];
+            Placement P; SlotDesc d;
+            if (SLIDE) {
+                d = load_slot12(tab, piece, (int)(m & 255u));
+                uint32_t full;
+                place_at(c, d, (int)(m >> 8), P, &full);
+                if (full != 0u) place_clear(d, P, full);
+            } else {
+                d = d0; P = P0;
+            }
             Feat f;
             eval_features<ModeTraits<MODE>::CMASK>(P, d, pv, rmask, f);
             const uint64_t k = score_key(score_features<MODE>(f, ids, w, F));
-            if (k > key) { key = k; tag = tag_hi | (uint32_t)s; }
+            if (k > key) { key = k; tag = tag_hi | (uint32_t)s << 5 | (uint32_t)i; mv = leaf_is_first ? m : mv1; }
             ++cnt;
         }
     }
 }
 
-template <int LANES, int MODE, int LOOKAHEAD>
+template <int LANES, int MODE, int LOOKAHEAD, int SLIDE>
 __global__ void __launch_bounds__(BLOCK) play_games_kernel(const PlayParams prm)
 {
     constexpr int GROUPS = BLOCK / LANES;
@@ -184,28 +226,43 @@ __global__ void __launch_bounds__(BLOCK) play_games_kernel(const PlayParams prm)
         const double* w = MODE == MODE_W6 ? wreg : s_w[MODE == MODE_W6 ? 0 : grp];
         const int p_after = active ? fetch_piece(t + 2) : 0;      // prefetch: consumed two steps later
 
-        uint64_t key = 0; uint32_t tag = 0;
+        uint64_t key = 0; uint32_t tag = 0, mv = 0;
         if (LOOKAHEAD == 2) {
             if (active && t + 1 < T && p_cur < 7 && p_next < 7) {
+                // layer 1 (group-uniform): every move of the current piece in enumeration order, expanded by the next piece
                 const int ns1 = s_tab.nslots[p_cur];
                 for (int s1 = 0; s1 < ns1; ++s1) {
-                    const SlotDesc d1 = load_slot12(s_tab, p_cur, s1);
-                    Placement P1;
-                    if (!place_slot(c, H, d1, P1)) continue;
-                    const PrevStat pv1 = next_stat(pv, P1, d1);
-                    const Heights H1 = pack_gh(pv1.gh);
-                    search_one<LANES, MODE>(P1.n, H1, pv1, p_next, gl, s_tab, prm.ids, w, F, prm.rmask,
-                                            (uint32_t)s1 << 6, key, tag, cnt);
+                    const SlotDesc d0 = load_slot12(s_tab, p_cur, s1);
+                    Placement P0;
+                    if (!place_slot(c, H, d0, P0)) continue;
+                    uint16_t list[SLIDE ? 18 : 1];
+                    const int n = collect_slides<SLIDE>(c, H, s_tab, p_cur, d0, s1, P0.y, list);
+                    for (int i = 0; i <= n; ++i) {
+                        const uint32_t m1 = i == 0 ? ((uint32_t)s1 | (uint32_t)P0.y << 8) : (uint32_t)list[SLIDE ? i - 1 : 0];
+                        Placement P1; SlotDesc d1;
+                        if (SLIDE) {
+                            d1 = load_slot12(s_tab, p_cur, (int)(m1 & 255u));
+                            uint32_t full;
+                            place_at(c, d1, (int)(m1 >> 8), P1, &full);
+                            if (full != 0u) place_clear(d1, P1, full);
+                        } else {
+                            d1 = d0; P1 = P0;
+                        }
+                        const PrevStat pv1 = next_stat(pv, P1, d1);
+                        const Heights H1 = pack_gh(pv1.gh);
+                        search_one<LANES, MODE, SLIDE>(P1.n, H1, pv1, p_next, gl, s_tab, prm.ids, w, F, prm.rmask,
+                                                       ((uint32_t)s1 << 5 | (uint32_t)i) << 11, m1, false, key, tag, mv, cnt);
+                    }
                 }
             }
-            group_argmax<LANES>(key, tag);
+            group_argmax_mv<LANES>(key, tag, mv);
         }
         const bool need_l1 = active && p_cur < 7 && (LOOKAHEAD == 1 || key == 0);
         if (LOOKAHEAD == 1 || __any_sync(FULLMASK, need_l1)) {
-            uint64_t k1 = 0; uint32_t t1 = 0;
-            if (need_l1) search_one<LANES, MODE>(c, H, pv, p_cur, gl, s_tab, prm.ids, w, F, prm.rmask, 0u, k1, t1, cnt);
-            group_argmax<LANES>(k1, t1);
-            if (need_l1) { key = k1; tag = t1 << 6; }
+            uint64_t k1 = 0; uint32_t t1 = 0, m1 = 0;
+            if (need_l1) search_one<LANES, MODE, SLIDE>(c, H, pv, p_cur, gl, s_tab, prm.ids, w, F, prm.rmask, 0u, 0u, true, k1, t1, m1, cnt);
+            group_argmax_mv<LANES>(k1, t1, m1);
+            if (need_l1) { key = k1; tag = t1; mv = m1; }
         }
 
         if (active) {
@@ -213,10 +270,13 @@ __global__ void __launch_bounds__(BLOCK) play_games_kernel(const PlayParams prm)
             if (key == 0) {
                 finish = true;                                   // no legal placement: game over (simulator.py:187-189)
             } else {
-                const int s1 = (int)(tag >> 6);
-                const SlotDesc d1 = load_slot12(s_tab, p_cur, s1);
+                const SlotDesc d1 = load_slot12(s_tab, p_cur, (int)(mv & 255u));
                 Placement P;
-                place_slot(c, H, d1, P);
+                {
+                    uint32_t full;
+                    place_at(c, d1, (int)(mv >> 8), P, &full);
+                    if (full != 0u) place_clear(d1, P, full);
+                }
 #pragma unroll
                 for (int k = 0; k < COLS; ++k) c[k] = P.n[k];
                 pv = next_stat(pv, P, d1); H = pack_gh(pv.gh);
@@ -1031,17 +1091,30 @@ __global__ void best_move_pack_kernel(int N, const tb200_game_result* res, const
 }
 
 typedef void (*play_fn)(const PlayParams);
-template <int MODE, int LOOKAHEAD>
+template <int MODE, int LOOKAHEAD, int SLIDE>
 static play_fn pick_lanes(int lanes)
 {
     switch (lanes) {
-    case 8:  return play_games_kernel<8, MODE, LOOKAHEAD>;
-    case 16: return play_games_kernel<16, MODE, LOOKAHEAD>;
-    default: return play_games_kernel<32, MODE, LOOKAHEAD>;
+    case 8:  return play_games_kernel<8, MODE, LOOKAHEAD, SLIDE>;
+    case 16: return play_games_kernel<16, MODE, LOOKAHEAD, SLIDE>;
+    default: return play_games_kernel<32, MODE, LOOKAHEAD, SLIDE>;
     }
 }
-static play_fn pick_kernel(int mode, int lookahead, int lanes)
+template <int SLIDE>
+static play_fn pick_generic(int mode, int lookahead, int lanes)
 {
+    if (lookahead == 2) {
+        if (mode == MODE_W6) return pick_lanes<MODE_W6, 2, SLIDE>(lanes);
+        if (mode == MODE_ALL45) return pick_lanes<MODE_ALL45, 2, SLIDE>(lanes);
+        return pick_lanes<MODE_GENERIC, 2, SLIDE>(lanes);
+    }
+    if (mode == MODE_W6) return pick_lanes<MODE_W6, 1, SLIDE>(lanes);
+    if (mode == MODE_ALL45) return pick_lanes<MODE_ALL45, 1, SLIDE>(lanes);
+    return pick_lanes<MODE_GENERIC, 1, SLIDE>(lanes);
+}
+static play_fn pick_kernel(int mode, int lookahead, int lanes, int move_set)
+{
+    if (move_set == 1) return pick_generic<1>(mode, lookahead, lanes);     // overhang slides: generic kernels only
     if (lanes == 64) return play_games_w6pair_kernel;      // caller guarantees lookahead 1 and the w6 set
     if (lookahead == 1 && mode == MODE_W6 && lanes == 16) return play_games_w6grp_kernel<16>;
     if (lookahead == 1 && mode == MODE_W6 && lanes == 8) return play_games_w6grp_kernel<8>;
@@ -1053,14 +1126,7 @@ static play_fn pick_kernel(int mode, int lookahead, int lanes)
         if (mode == MODE_ALL45) return play_games_w32_kernel<MODE_ALL45>;
         return play_games_w32_kernel<MODE_GENERIC>;
     }
-    if (lookahead == 2) {
-        if (mode == MODE_W6) return pick_lanes<MODE_W6, 2>(lanes);
-        if (mode == MODE_ALL45) return pick_lanes<MODE_ALL45, 2>(lanes);
-        return pick_lanes<MODE_GENERIC, 2>(lanes);
-    }
-    if (mode == MODE_W6) return pick_lanes<MODE_W6, 1>(lanes);
-    if (mode == MODE_ALL45) return pick_lanes<MODE_ALL45, 1>(lanes);
-    return pick_lanes<MODE_GENERIC, 1>(lanes);
+    return pick_generic<0>(mode, lookahead, lanes);
 }
 
 }  // namespace tb
@@ -1247,7 +1313,9 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
     const long long n_games_ll = (long long)a.n_candidates * a.games_per_candidate;
     const uint32_t n_games = (uint32_t)n_games_ll;
     int lanes = a.lanes;
-    const bool pair_ok = ctx->mode == tb::MODE_W6 && a.lookahead == 1;
+    const int move_set = a.move_set;
+    const bool pair_ok = ctx->mode == tb::MODE_W6 && a.lookahead == 1 && move_set == 0;
+    if (move_set == 1 && (lanes == 64 || lanes == 4 || lanes == 2 || lanes == 1)) lanes = lanes == 64 ? 32 : 8;
     if (lanes == 64 && !pair_ok) lanes = 32;
     const bool narrow_ok = pair_ok && (lanes == 4 || lanes == 2 || lanes == 1);
     if (!narrow_ok && lanes != 8 && lanes != 16 && lanes != 32 && lanes != 64) {
@@ -1260,7 +1328,7 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
         else if (pair_ok) lanes = per_sm <= 320 ? 8 : (per_sm <= 700 ? 4 : 2);
         else lanes = per_sm <= 160 ? 16 : 8;
     }
-    tb::play_fn fn = tb::pick_kernel(ctx->mode, a.lookahead, lanes);
+    tb::play_fn fn = tb::pick_kernel(ctx->mode, a.lookahead, lanes, move_set);
     const int block = lanes == 64 ? 64 : tb::BLOCK;
     int occ = 0;
     TB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, block, 0));
@@ -1278,6 +1346,7 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
     p.ticket = ctx->d_ticket; p.seed = a.seed; p.rmask = ctx->rmask; p.n_games = n_games; p.T = a.T;
     p.max_moves = a.max_moves ? a.max_moves : a.T; p.G = a.games_per_candidate; p.F = ctx->F;
     p.per_game_weights = per_game_weights;
+    p.move_set = move_set;
     memcpy(p.ids, ctx->ids, sizeof p.ids);
 
     TB_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(uint32_t), st));
@@ -1308,6 +1377,7 @@ static int check_play_args(tb200_ctx* ctx, const tb200_play_args* a)
     if (a->pieces && a->n_sequences < 1) return fail(ctx, TB200_E_BAD_ARG, "play_games: n_sequences must be >= 1 with explicit pieces");
     if (a->pieces && !a->seq_of_game && a->n_sequences < a->games_per_candidate) return fail(ctx, TB200_E_BAD_ARG, "play_games: need S >= G without seq_of_game");
     if (a->mem != TB200_MEM_HOST && a->mem != TB200_MEM_DEVICE) return fail(ctx, TB200_E_BAD_ARG, "play_games: bad mem");
+    if (a->move_set != TB200_MOVES_DROP && a->move_set != TB200_MOVES_OVERHANG_SLIDE) return fail(ctx, TB200_E_BAD_ARG, "play_games: bad move_set");
     return TB200_OK;
 }
 

@@ -307,6 +307,77 @@ TB_HD void place_clear(const SlotDesc& d, Placement& p, uint32_t f)
     } while (f != 0u);
 }
 
+// ---------------------------------------------------------------------------------------------
+// SURVEY.md §8f rank 2 — move_with_overhang_slide (simulator.py:15-47): placements reached by sliding the
+// piece sideways at its landed row under an overhang.  These are not hard drops, so they need a real
+// collision test against the board columns and an imprint at a given height.
+// ---------------------------------------------------------------------------------------------
+TB_HD int height_at(const Heights& H, int k)                 // k in 0..9 (run-time index into the packed heights)
+{
+    const uint32_t wsel = (uint32_t)k >> 2;
+    const uint32_t word = wsel == 0 ? H.H0 : (wsel == 1 ? H.H1 : H.H2);
+    return (int)((word >> (8u * ((uint32_t)k & 3u))) & 255u);
+}
+
+// does the piece of slot d, with its bbox bottom at height y, lie inside the board and on empty cells?
+TB_HD bool fits_at(const uint32_t c[COLS], const SlotDesc& d, int y)
+{
+    const int ph = (int)((d.w[0] >> 9) & 7u);
+    if (y < 0 || y + ph > ROWS) return false;
+    uint32_t o = 0;
+    o |= (byte_of(d.w[4], 0) << y) & c[0]; o |= (byte_of(d.w[4], 1) << y) & c[1];
+    o |= (byte_of(d.w[4], 2) << y) & c[2]; o |= ((d.w[4] >> 24) << y) & c[3];
+    o |= (byte_of(d.w[5], 0) << y) & c[4]; o |= (byte_of(d.w[5], 1) << y) & c[5];
+    o |= (byte_of(d.w[5], 2) << y) & c[6]; o |= ((d.w[5] >> 24) << y) & c[7];
+    o |= (byte_of(d.w[6], 0) << y) & c[8]; o |= (byte_of(d.w[6], 1) << y) & c[9];
+    return o == 0u;
+}
+
+// imprint the piece of slot d with its bbox bottom at height y (caller guarantees fits_at); *full = full-row mask
+TB_HD void place_at(const uint32_t c[COLS], const SlotDesc& d, int y, Placement& p, uint32_t* full)
+{
+    const uint32_t misc = d.w[0];
+    p.y = y; p.c0 = (int)(misc & 15u); p.rot = (int)((misc >> 4) & 3u); p.ph = (int)((misc >> 9) & 7u);
+    const uint32_t one_y = 1u << (y & 31);
+    p.n[0] = byte_of(d.w[4], 0) * one_y + c[0]; p.n[1] = byte_of(d.w[4], 1) * one_y + c[1];
+    p.n[2] = byte_of(d.w[4], 2) * one_y + c[2]; p.n[3] = (d.w[4] >> 24)     * one_y + c[3];
+    p.n[4] = byte_of(d.w[5], 0) * one_y + c[4]; p.n[5] = byte_of(d.w[5], 1) * one_y + c[5];
+    p.n[6] = byte_of(d.w[5], 2) * one_y + c[6]; p.n[7] = (d.w[5] >> 24)     * one_y + c[7];
+    p.n[8] = byte_of(d.w[6], 0) * one_y + c[8]; p.n[9] = byte_of(d.w[6], 1) * one_y + c[9];
+    *full = (p.n[0] & p.n[1] & p.n[2]) & (p.n[3] & p.n[4] & p.n[5]) & (p.n[6] & p.n[7] & p.n[8]) & p.n[9];
+    p.k = 0; p.eroded = 0;
+}
+
+// Enumerate the slide placements derived from the hard-drop move of slot s0 (descriptor d0, landed at height
+// y0) in the reference's order: right slides by ascending column (:25-33), then left slides by descending
+// column (:36-45); a direction stops at the first column where the piece does not fit at the landed row.
+// fetch(s) returns the descriptor of slot s (slots of one rotation are consecutive, column-minor);
+// emit(d, s, y, j) receives each slide placement with its 1-based index j within this base move.
+template <class Fetch, class Emit>
+TB_HD void for_each_slide(const uint32_t c[COLS], const Heights& H, const SlotDesc& d0, int s0, int y0, Fetch fetch, Emit emit)
+{
+    const int c0 = (int)(d0.w[0] & 15u), w = (int)((d0.w[0] >> 6) & 7u), ph = (int)((d0.w[0] >> 9) & 7u);
+    int j = 1;
+    if (c0 + w < COLS && height_at(H, c0 + w) > y0 + ph) {
+        for (int cc = c0 + 1; cc <= COLS - w; ++cc) {
+            const SlotDesc d = fetch(s0 + (cc - c0));
+            if (!fits_at(c, d, y0)) break;
+            int yy = y0;
+            while (fits_at(c, d, yy - 1)) --yy;
+            emit(d, s0 + (cc - c0), yy, j++);
+        }
+    }
+    if (c0 > 0 && height_at(H, c0 - 1) > y0 + ph) {
+        for (int cc = c0 - 1; cc >= 0; --cc) {
+            const SlotDesc d = fetch(s0 - (c0 - cc));
+            if (!fits_at(c, d, y0)) break;
+            int yy = y0;
+            while (fits_at(c, d, yy - 1)) --yy;
+            emit(d, s0 - (c0 - cc), yy, j++);
+        }
+    }
+}
+
 TB_HD bool place_slot(const uint32_t c[COLS], const Heights& H, const SlotDesc& d, Placement& p)
 {
     uint32_t f;

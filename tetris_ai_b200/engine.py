@@ -97,7 +97,7 @@ class Engine:
     # ------------------------------------------------------------------ K2 whole games
     def play_games(self, weights, games_per_candidate, pieces=None, T=None, seq_of_game=None, seed=0, lookahead=1,
                    lanes=0, max_moves=0, init_rows=None, want_trace=False, want_scores=False, want_final=False,
-                   want_fitness=True, out_results=None, out_fitness=None):
+                   want_fitness=True, out_results=None, out_fitness=None, move_set=0):
         """weights f64[C][F] -> dict(results=structured[C*G], fitness=f64[C], trace=..., ...)   (host buffers)."""
         w = np.ascontiguousarray(weights, dtype=np.float64)
         if w.ndim == 1:
@@ -139,12 +139,13 @@ class Engine:
         a.lookahead, a.lanes, a.init_rows = int(lookahead), int(lanes), _ptr(init_rows)
         a.results, a.trace, a.score_trace = _ptr(results), _ptr(trace), _ptr(scores)
         a.final_rows, a.fitness = _ptr(final), _ptr(fitness)
+        a.move_set = int(move_set)
         self._check(self._L.tb200_play_games(self._h, ctypes.byref(a)))
         return {"results": results, "fitness": fitness, "trace": trace, "scores": scores, "final": final}
 
     def play_games_device(self, stream, n_candidates, games_per_candidate, weights_ptr, results_ptr, T, pieces_ptr=0,
                           n_sequences=0, seq_of_game_ptr=0, seed=0, lookahead=1, lanes=0, max_moves=0, init_rows_ptr=0,
-                          trace_ptr=0, score_trace_ptr=0, final_rows_ptr=0, fitness_ptr=0):
+                          trace_ptr=0, score_trace_ptr=0, final_rows_ptr=0, fitness_ptr=0, move_set=0):
         """All pointers are DEVICE pointers (ints); work is enqueued on `stream` (a cudaStream_t int) and not synchronised."""
         a = _lib.PlayArgs()
         a.struct_size = ctypes.sizeof(_lib.PlayArgs)
@@ -156,6 +157,7 @@ class Engine:
         a.lookahead, a.lanes, a.init_rows = int(lookahead), int(lanes), init_rows_ptr or None
         a.results, a.trace, a.score_trace = results_ptr or None, trace_ptr or None, score_trace_ptr or None
         a.final_rows, a.fitness = final_rows_ptr or None, fitness_ptr or None
+        a.move_set = int(move_set)
         self._check(self._L.tb200_play_games(self._h, ctypes.byref(a)))
 
     def last_timing(self):

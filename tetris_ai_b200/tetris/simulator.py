@@ -34,6 +34,22 @@ def move_drop(state, zoid, engine=None):
             yield (rot, int(row), col)
 
 
+class OverhangSlide:
+    """move_with_overhang_slide(move_drop) (simulator.py:15-47) as a device move set: every hard drop followed by the
+    placements reached by sliding under an overhang at the landed row.  It is consumed by simulate(); enumerating the
+    moves on the host would need a CPU search, which this engine does not have."""
+    move_set = 1
+
+    def __call__(self, state, zoid):
+        raise TypeError("the overhang-slide move set is evaluated on the device; pass it to simulate() as move_gen")
+
+
+def move_with_overhang_slide(move_gen):
+    if move_gen is not move_drop:
+        raise TypeError("only move_with_overhang_slide(move_drop) is implemented on the device (no CPU fallback)")
+    return OverhangSlide()
+
+
 class LinearScorer:
     """The canonical scorer: acc = 0.0; for f, w in weights.items(): acc += float(f(state)) * w (device fp64, no FMA)."""
 
@@ -84,8 +100,12 @@ def simulate(state, zoid_gen, move_gen, move_policy, lookahead=1, engine=None):
     """Generator of successive States, identical to the reference's for the accepted arguments."""
     if lookahead not in (1, 2):
         raise ValueError("lookahead must be 1 or 2")
-    if move_gen is not move_drop:
-        raise TypeError("only move_drop is implemented on the device (no CPU fallback)")
+    if move_gen is move_drop:
+        move_set = 0
+    elif isinstance(move_gen, OverhangSlide):
+        move_set = 1
+    else:
+        raise TypeError("only move_drop and move_with_overhang_slide(move_drop) are implemented on the device (no CPU fallback)")
     if not isinstance(move_policy, BestPolicy):
         raise TypeError("move_policy must come from policy_best(linear_scorer(weights), tie_first)")
     eng = engine or default_engine()
@@ -102,7 +122,7 @@ def simulate(state, zoid_gen, move_gen, move_policy, lookahead=1, engine=None):
         ids = np.array([[z.id for z in chunk]], dtype=np.uint8)
         eng.set_features(sc.features)
         r = eng.play_games(np.array([sc.weights]), 1, pieces=ids, lookahead=lookahead, max_moves=commit,
-                           init_rows=[state.board.rows16()], want_trace=True, want_fitness=False)
+                           init_rows=[state.board.rows16()], want_trace=True, want_fitness=False, move_set=move_set)
         placed = int(r["results"]["pieces"][0])
         for t in range(placed):
             rot, row, col, _k = (int(x) for x in r["trace"][0, t])
@@ -113,4 +133,4 @@ def simulate(state, zoid_gen, move_gen, move_policy, lookahead=1, engine=None):
         carry = chunk[commit:]
 
 
-__all__ = ["move_drop", "policy_best", "simulate", "linear_scorer", "tie_first", "LinearScorer", "BestPolicy", "PIECES"]
+__all__ = ["move_drop", "move_with_overhang_slide", "policy_best", "simulate", "linear_scorer", "tie_first", "LinearScorer", "BestPolicy", "PIECES"]

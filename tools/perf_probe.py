@@ -75,6 +75,18 @@ def main():
     for lanes in (32, 8):
         ms, out = timeit(eng, 1, weights=w6, games_per_candidate=1, T=100, seed=5, seq_of_game=np.arange(2048, dtype=np.int32), lanes=lanes, lookahead=2)
         rows.append(("w6 L2 2048 games T=100", lanes, ms, int(out["results"]["placements"].sum()), int(out["results"]["pieces"].sum())))
+    # overhang-slide move set (generic kernels)
+    hole_names = ["max_ht", "row_trans", "pits", "landing_height"]
+    eng.set_features(hole_names)
+    wh = np.array([-1.0, -0.2, 0.4, -0.5])[None, :] + rng.normal(0, 0.2, size=(8192, 4))
+    for ms in (0, 1):
+        for lanes in (32, 8):
+            ms_t, out = timeit(eng, 2, weights=wh, games_per_candidate=1, T=200, seed=5, seq_of_game=np.arange(8192, dtype=np.int32), lanes=lanes, move_set=ms)
+            rows.append(("holes4 %s 8192 games T=200" % ("slide" if ms else "drop"), lanes, ms_t, int(out["results"]["placements"].sum()), int(out["results"]["pieces"].sum())))
+    eng.set_features(W6_NAMES)
+    for lanes in (32, 8):
+        ms_t, out = timeit(eng, 2, weights=w6, games_per_candidate=1, T=300, seed=5, seq_of_game=np.arange(2048, dtype=np.int32), lanes=lanes, move_set=1)
+        rows.append(("w6 slide 2048 games T=300", lanes, ms_t, int(out["results"]["placements"].sum()), int(out["results"]["pieces"].sum())))
     print("%-32s %5s %10s %12s %10s %14s" % ("workload", "lanes", "kernel_ms", "placements", "pieces", "placements/s"))
     for name, lanes, ms, pl, pc in rows:
         print("%-32s %5d %10.3f %12d %10d %14.4e" % (name, lanes, ms, pl, pc, pl / (ms * 1e-3)))
