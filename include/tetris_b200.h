@@ -51,6 +51,7 @@ extern "C" {
 
 #define TB200_MOVES_DROP            0
 #define TB200_MOVES_OVERHANG_SLIDE  1
+#define TB200_MOVES_PRESSURE        2
 
 #define TB200_MEM_HOST   0
 #define TB200_MEM_DEVICE 1
@@ -94,9 +95,15 @@ typedef struct {
     double*   score_trace;           /* f64[C*G][T] winning score per move, or NULL */
     uint16_t* final_rows;            /* u16[C*G][20] final boards, or NULL */
     double*   fitness;               /* f64[C] = total lines of the candidate's games / G, or NULL */
-    int32_t   move_set;              /* TB200_MOVES_DROP = move_drop (simulator.py:3-13);
-                                        TB200_MOVES_OVERHANG_SLIDE = move_with_overhang_slide(move_drop) (simulator.py:15-47) */
-    int32_t   reserved;              /* 0 */
+    int32_t   move_set;              /* TB200_MOVES_DROP = move_drop (simulator.py:3-13), optionally OR-ed with
+                                        TB200_MOVES_OVERHANG_SLIDE: move_with_overhang_slide(...) (simulator.py:15-47) and / or
+                                        TB200_MOVES_PRESSURE: move_with_pressure(...) as the OUTERMOST wrapper (simulator.py:88-120) */
+    int32_t   pressure_two_but_rot;  /* move_with_pressure(two_but_rot=...) */
+    double    pressure_avg_lat;      /* move_with_pressure(avg_lat=250.9, resp_time=79.8, move_eff=1.23) — no defaults here */
+    double    pressure_resp_time;
+    double    pressure_move_eff;
+    const uint32_t* init_lines;      /* u32[C*G] lines already cleared before the first move (continuing games: the level used
+                                        by score and by the pressure filter; results.lines then reports the running total), or NULL */
 } tb200_play_args;
 
 /* timing of the last tb200_play_games call on this ctx (CUDA events on the launching stream) */

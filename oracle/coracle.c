@@ -130,11 +130,39 @@ static int slide_moves(const board_t* b, int piece, int mv[MAX_MOVES][3])
     return n;
 }
 
-static int gen_moves(const board_t* b, int piece, int move_set, int mv[MAX_MOVES][3])
+/* simulator.py:88-120 move_with_pressure: keep a move iff the time to key it in fits before the piece locks.
+ * press = {avg_lat, resp_time, move_eff, two_but_rot}; level = state.level() of the state the move is generated from. */
+static const int START_COL[7][4] = {{3, 5, 0, 0}, {4, 4, 4, 5}, {4, 4, 4, 5}, {4, 4, 4, 5}, {4, 0, 0, 0}, {4, 5, 0, 0}, {4, 5, 0, 0}};   /* I,T,L,J,O,Z,S :92-100 */
+static int is_time(int piece, int rot, int row, int col, const double* press, int level)
 {
-    if (move_set == 1) return slide_moves(b, piece, mv);
-    int base[34][3]; int n = drop_moves(b, piece, base);
-    for (int i = 0; i < n; ++i) { mv[i][0] = base[i][0]; mv[i][1] = base[i][1]; mv[i][2] = base[i][2]; }
+    static const int BR[15][2] = {{29, 20}, {19, 30}, {16, 50}, {13, 70}, {10, 80}, {9, 100}, {8, 130}, {7, 220}, {6, 300},
+                                  {5, 380}, {4, 470}, {3, 550}, {2, 630}, {1, 720}, {0, 800}};                          /* :110-112 */
+    int d = START_COL[piece][rot] - col; if (d < 0) d = -d;
+    int clicks = d + ((press[3] != 0.0 && rot == 3) ? 1 : rot);                                                        /* :104 */
+    double t = (double)clicks * press[2];                                                                                /* :107, left to right */
+    t = t * press[0];
+    t = press[1] + t;
+    int speed = 800;
+    for (int i = 0; i < 15; ++i) if (BR[i][0] <= level) { speed = BR[i][1]; break; }                                    /* :113-114 */
+    int limit = (ROWS - row) * speed;                                                                                    /* :116 */
+    return t <= (double)limit;
+}
+
+/* move_set bit 0: overhang slides; bit 1: pressure filter applied to whatever the inner generator yields */
+static int gen_moves(const board_t* b, int piece, int move_set, const double* press, int level, int mv[MAX_MOVES][3])
+{
+    int n;
+    if (move_set & 1) n = slide_moves(b, piece, mv);
+    else {
+        int base[34][3]; n = drop_moves(b, piece, base);
+        for (int i = 0; i < n; ++i) { mv[i][0] = base[i][0]; mv[i][1] = base[i][1]; mv[i][2] = base[i][2]; }
+    }
+    if ((move_set & 2) && press) {
+        int m = 0;
+        for (int i = 0; i < n; ++i)
+            if (is_time(piece, mv[i][0], mv[i][1], mv[i][2], press, level)) { mv[m][0] = mv[i][0]; mv[m][1] = mv[i][1]; mv[m][2] = mv[i][2]; ++m; }
+        n = m;
+    }
     return n;
 }
 
@@ -314,7 +342,7 @@ int co_moves(const uint16_t rows[ROWS], int piece, int move_set, int* moves)
     init_shapes();
     board_t b; rows_to_board(rows, &b);
     static __thread int mv[MAX_MOVES][3];
-    int n = gen_moves(&b, piece, move_set, mv);
+    int n = gen_moves(&b, piece, move_set & 1, 0, 0, mv);
     for (int i = 0; i < n; ++i) { moves[3 * i] = mv[i][0]; moves[3 * i + 1] = mv[i][1]; moves[3 * i + 2] = mv[i][2]; }
     return n;
 }
@@ -342,11 +370,11 @@ typedef struct { int rot, row, col, k; double score; int n_scored; placed_t st; 
 
 /* One simulate() iteration (simulator.py:156-180) with move_drop and policy_best(linear, first).
  * next_piece < 0 => only one visible piece.  Returns 0 when there is no move (game over). */
-static int choose(const board_t* b, int piece, int next_piece, int lookahead, int move_set,
+static int choose(const board_t* b, int lines, int piece, int next_piece, int lookahead, int move_set, const double* press,
                   const int* fids, const double* w, int F, choice_t* out)
 {
     static __thread int mv1[MAX_MOVES][3];
-    int n1 = gen_moves(b, piece, move_set, mv1);
+    int n1 = gen_moves(b, piece, move_set, press, lines / 10, mv1);
     if (n1 == 0) return 0;
     static __thread placed_t l1[MAX_MOVES];
     for (int i = 0; i < n1; ++i) place(b, piece, mv1[i][0], mv1[i][1], mv1[i][2], &l1[i]);
@@ -355,7 +383,7 @@ static int choose(const board_t* b, int piece, int next_piece, int lookahead, in
     if (lookahead >= 2 && next_piece >= 0) {
         for (int i = 0; i < n1; ++i) {                       /* layer 2 in enumeration order :162-167 */
             static __thread int mv2[MAX_MOVES][3];
-            int n2 = gen_moves(&l1[i].board, next_piece, move_set, mv2);
+            int n2 = gen_moves(&l1[i].board, next_piece, move_set, press, (lines + l1[i].k) / 10, mv2);
             for (int j = 0; j < n2; ++j) {
                 placed_t leaf; place(&l1[i].board, next_piece, mv2[j][0], mv2[j][1], mv2[j][2], &leaf);
                 features45(&l1[i].board, &leaf, f);
@@ -384,7 +412,7 @@ int co_best_move(const uint16_t rows[ROWS], int piece, int next_piece, int looka
     init_shapes();
     board_t b; rows_to_board(rows, &b);
     choice_t ch;
-    if (!choose(&b, piece, next_piece, lookahead, move_set, fids, w, F, &ch)) return 0;
+    if (!choose(&b, 0, piece, next_piece, lookahead, move_set & 1, 0, fids, w, F, &ch)) return 0;
     out_move[0] = ch.rot; out_move[1] = ch.row; out_move[2] = ch.col; out_move[3] = ch.k;
     if (out_score) *out_score = ch.score;
     return ch.n_scored;
@@ -409,7 +437,7 @@ typedef struct {
 /* One whole game (simulator.py:152-189).  pieces == NULL => hashed stream (seed, stream_id).
  * trace (optional) receives 4 bytes {rot,row,col,k} per move. */
 static void play_game(const int* fids, const double* w, int F, const uint8_t* pieces, uint32_t T,
-                      uint64_t seed, uint64_t stream_id, int lookahead, int move_set, const uint16_t* init_rows,
+                      uint64_t seed, uint64_t stream_id, int lookahead, int move_set, const double* press, const uint16_t* init_rows,
                       game_result_t* res, uint8_t* trace, uint16_t* final_rows)
 {
     static const uint32_t POINTS[5] = {0, 40, 100, 300, 1200};         /* game.py:159 */
@@ -420,7 +448,7 @@ static void play_game(const int* fids, const double* w, int F, const uint8_t* pi
         int p  = pieces ? pieces[t] : hashed_piece(seed, stream_id, t);
         int nx = (lookahead >= 2 && t + 1 < T) ? (pieces ? pieces[t + 1] : hashed_piece(seed, stream_id, t + 1)) : -1;
         choice_t ch;
-        if (!choose(&b, p, nx, lookahead, move_set, fids, w, F, &ch)) break;
+        if (!choose(&b, (int)res->lines, p, nx, lookahead, move_set, press, fids, w, F, &ch)) break;
         b = ch.st.board;
         res->placements += (uint64_t)ch.n_scored;
         res->pieces += 1;
@@ -435,7 +463,7 @@ static void play_game(const int* fids, const double* w, int F, const uint8_t* pi
 typedef struct {
     const int* fids; int F; const double* weights; int C; int G;
     const uint8_t* pieces; int S; uint32_t T; const int32_t* seq_of_game; uint64_t seed; int lookahead;
-    game_result_t* results; uint8_t* trace; volatile int* next; int total; int move_set;
+    game_result_t* results; uint8_t* trace; volatile int* next; int total; int move_set; const double* press;
 } job_t;
 
 static void* worker(void* arg)
@@ -447,7 +475,7 @@ static void* worker(void* arg)
         int cand = g / j->G, gi = g % j->G;
         int seq = j->seq_of_game ? j->seq_of_game[g] : gi;
         const uint8_t* ps = j->pieces ? j->pieces + (size_t)seq * j->T : 0;
-        play_game(j->fids, j->weights + (size_t)cand * j->F, j->F, ps, j->T, j->seed, (uint64_t)seq, j->lookahead, j->move_set, 0,
+        play_game(j->fids, j->weights + (size_t)cand * j->F, j->F, ps, j->T, j->seed, (uint64_t)seq, j->lookahead, j->move_set, j->press, 0,
                   &j->results[g], j->trace ? j->trace + (size_t)g * j->T * 4 : 0, 0);
     }
     return 0;
@@ -458,7 +486,7 @@ static void* worker(void* arg)
  * threads <= 0 => 1. */
 int co_play_games(const int* fids, int F, const double* weights, int C, int G,
                   const uint8_t* pieces, int S, uint32_t T, const int32_t* seq_of_game, uint64_t seed,
-                  int lookahead, int threads, uint64_t* results, uint8_t* trace, int move_set)
+                  int lookahead, int threads, uint64_t* results, uint8_t* trace, int move_set, const double* press)
 {
     init_shapes();
     (void)S;
@@ -466,7 +494,7 @@ int co_play_games(const int* fids, int F, const double* weights, int C, int G,
     game_result_t* tmp = (game_result_t*)calloc((size_t)total, sizeof(game_result_t));
     if (!tmp) return -1;
     volatile int next = 0;
-    job_t j = {fids, F, weights, C, G, pieces, S, T, seq_of_game, seed, lookahead, tmp, trace, &next, total, move_set};
+    job_t j = {fids, F, weights, C, G, pieces, S, T, seq_of_game, seed, lookahead, tmp, trace, &next, total, move_set, press};
     if (threads <= 1) worker(&j);
     else {
         pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)threads);
@@ -486,11 +514,11 @@ int co_play_games(const int* fids, int F, const double* weights, int C, int G,
 
 /* single game with optional initial board / final board (used by the chunked simulate() tests) */
 int co_play_one(const int* fids, int F, const double* w, const uint8_t* pieces, uint32_t T, int lookahead,
-                const uint16_t* init_rows, uint64_t* result8, uint8_t* trace, uint16_t* final_rows, int move_set)
+                const uint16_t* init_rows, uint64_t* result8, uint8_t* trace, uint16_t* final_rows, int move_set, const double* press)
 {
     init_shapes();
     game_result_t r;
-    play_game(fids, w, F, pieces, T, 0, 0, lookahead, move_set, init_rows, &r, trace, final_rows);
+    play_game(fids, w, F, pieces, T, 0, 0, lookahead, move_set, press, init_rows, &r, trace, final_rows);
     result8[0] = r.pieces; result8[1] = r.lines; result8[2] = r.hist[0]; result8[3] = r.hist[1];
     result8[4] = r.hist[2]; result8[5] = r.hist[3]; result8[6] = r.score; result8[7] = r.placements;
     return 0;

@@ -43,9 +43,9 @@ def lib():
         L.co_hashed_piece.argtypes = [ctypes.c_uint64] * 3
         L.co_hashed_piece.restype = ctypes.c_int
         L.co_play_games.argtypes = [i32p, ctypes.c_int, f64p, ctypes.c_int, ctypes.c_int, u8p, ctypes.c_int,
-                                    ctypes.c_uint32, i32p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, u64p, u8p, ctypes.c_int]
+                                    ctypes.c_uint32, i32p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int, u64p, u8p, ctypes.c_int, f64p]
         L.co_play_games.restype = ctypes.c_int
-        L.co_play_one.argtypes = [i32p, ctypes.c_int, f64p, u8p, ctypes.c_uint32, ctypes.c_int, u16p, u64p, u8p, u16p, ctypes.c_int]
+        L.co_play_one.argtypes = [i32p, ctypes.c_int, f64p, u8p, ctypes.c_uint32, ctypes.c_int, u16p, u64p, u8p, u16p, ctypes.c_int, f64p]
         L.co_play_one.restype = ctypes.c_int
         _LIB = L
     return _LIB
@@ -63,6 +63,15 @@ def drop_moves(rows, piece):
 
 
 MOVE_SETS = {"drop": 0, "slide": 1, 0: 0, 1: 1}
+
+
+def _pressure(pressure):
+    """pressure: None or dict(avg_lat, resp_time, move_eff, two_but_rot) with the reference's defaults (simulator.py:88)."""
+    if pressure is None:
+        return 0, None
+    a = np.array([pressure.get("avg_lat", 250.9), pressure.get("resp_time", 79.8), pressure.get("move_eff", 1.23),
+                  1.0 if pressure.get("two_but_rot", False) else 0.0], dtype=np.float64)
+    return 2, a
 
 
 def moves(rows, piece, move_set="drop"):
@@ -107,7 +116,7 @@ def hashed_piece(seed, game, t):
 
 
 def play_games(fids, weights, G, pieces=None, T=None, seq_of_game=None, seed=0, lookahead=1, threads=1, want_trace=False,
-               move_set="drop"):
+               move_set="drop", pressure=None):
     """weights f64[C][F]; pieces u8[S][T] or None (hashed stream).  -> dict of u64 arrays [C*G] (+ trace u8[C*G][T][4])."""
     fids = np.ascontiguousarray(fids, dtype=np.int32)
     w = np.ascontiguousarray(weights, dtype=np.float64)
@@ -130,7 +139,8 @@ def play_games(fids, weights, G, pieces=None, T=None, seq_of_game=None, seed=0, 
     trace = np.zeros((C * G, T, 4), dtype=np.uint8) if want_trace else None
     rc = lib().co_play_games(_p(fids, ctypes.c_int32), F, _p(w, ctypes.c_double), C, G, _p(pieces, ctypes.c_uint8), S,
                              int(T), _p(seq_of_game, ctypes.c_int32), int(seed), int(lookahead), int(threads),
-                             _p(res, ctypes.c_uint64), _p(trace, ctypes.c_uint8), MOVE_SETS[move_set])
+                             _p(res, ctypes.c_uint64), _p(trace, ctypes.c_uint8), MOVE_SETS[move_set] | _pressure(pressure)[0],
+                             _p(_pressure(pressure)[1], ctypes.c_double))
     assert rc == 0
     out = {"pieces": res[:, 0], "lines": res[:, 1], "hist": res[:, 2:6], "score": res[:, 6], "placements": res[:, 7]}
     if want_trace:
@@ -138,7 +148,7 @@ def play_games(fids, weights, G, pieces=None, T=None, seq_of_game=None, seed=0, 
     return out
 
 
-def play_one(fids, weights, pieces, lookahead=1, init_rows=None, move_set="drop"):
+def play_one(fids, weights, pieces, lookahead=1, init_rows=None, move_set="drop", pressure=None):
     fids = np.ascontiguousarray(fids, dtype=np.int32)
     w = np.ascontiguousarray(weights, dtype=np.float64)
     pieces = np.ascontiguousarray(pieces, dtype=np.uint8)
@@ -149,7 +159,7 @@ def play_one(fids, weights, pieces, lookahead=1, init_rows=None, move_set="drop"
     final = np.zeros(20, dtype=np.uint16)
     lib().co_play_one(_p(fids, ctypes.c_int32), len(fids), _p(w, ctypes.c_double), _p(pieces, ctypes.c_uint8), T, int(lookahead),
                       _p(init, ctypes.c_uint16), _p(res, ctypes.c_uint64), _p(trace, ctypes.c_uint8), _p(final, ctypes.c_uint16),
-                      MOVE_SETS[move_set])
+                      MOVE_SETS[move_set] | _pressure(pressure)[0], _p(_pressure(pressure)[1], ctypes.c_double))
     n = int(res[0])
     return {"pieces": n, "lines": int(res[1]), "hist": [int(x) for x in res[2:6]], "score": int(res[6]),
             "placements": int(res[7]), "trace": trace[:n].copy(), "final": final}

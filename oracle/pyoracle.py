@@ -211,6 +211,26 @@ def slide_moves(node, piece):
 
 MOVE_GENERATORS = {"drop": drop_moves, "slide": slide_moves}
 
+_START_COL = {"O": [4], "L": [4, 4, 4, 5], "J": [4, 4, 4, 5], "S": [4, 5], "Z": [4, 5], "T": [4, 4, 4, 5], "I": [3, 5]}
+_BRACKETS = [(29, 20), (19, 30), (16, 50), (13, 70), (10, 80), (9, 100), (8, 130), (7, 220), (6, 300), (5, 380),
+             (4, 470), (3, 550), (2, 630), (1, 720), (0, 800)]
+
+
+def pressure_filter(move_gen, avg_lat=250.9, resp_time=79.8, move_eff=1.23, two_but_rot=False):
+    """cogworks/tetris/simulator.py:88-120 move_with_pressure: keep the moves that can be keyed in before the piece
+    locks at the speed of the CURRENT level (node.level() of the state the moves are generated from)."""
+    def filtered(node, piece):
+        lvl = node.level()
+        speed = next(sp for (lv, sp) in _BRACKETS if lv <= lvl)                      # :113-114
+        out = []
+        for rot, row, col in move_gen(node, piece):
+            clicks = abs(_START_COL[PIECE_NAMES[piece]][rot] - col) + (1 if two_but_rot and rot == 3 else rot)   # :104
+            t = resp_time + (clicks * move_eff * avg_lat)                            # :107
+            if t <= (ROWS - row) * speed:                                            # :116-118
+                out.append((rot, row, col))
+        return out
+    return filtered
+
 
 # ---------------------------------------------------------------------------------------------
 # Features.  cogworks/tetris/features.py:18-347; ids = source order (SURVEY.md §8a-F).
@@ -428,13 +448,15 @@ def hashed_piece(seed, game, t):
     return ((x >> 32) * 7) >> 32
 
 
-def simulate(node, pieces, fids, weights, lookahead=1, trace=None, prune=True, move_set="drop"):
+def simulate(node, pieces, fids, weights, lookahead=1, trace=None, prune=True, move_set="drop", pressure=None):
     """simulator.py:152-189 with move_gen=move_drop and the canonical linear policy.
 
     `pieces` is an iterable of piece ids; returns the final node and the number of pieces placed.
     """
     assert lookahead > 0
     move_gen = MOVE_GENERATORS[move_set]
+    if pressure is not None:
+        move_gen = pressure_filter(move_gen, **pressure)
     it = iter(pieces)
     key = lambda s: linear_score(s, fids, weights)     # noqa: E731
     placed = 0
@@ -463,11 +485,11 @@ def simulate(node, pieces, fids, weights, lookahead=1, trace=None, prune=True, m
     return node, placed
 
 
-def play_game(fids, weights, pieces, lookahead=1, want_trace=False, move_set="drop"):
+def play_game(fids, weights, pieces, lookahead=1, want_trace=False, move_set="drop", pressure=None):
     """One canonical game from the empty board -> dict(pieces, lines, hist[4], score, trace)."""
     trace = bytearray() if want_trace else None
     root = Node(None, Grid())
-    last, placed = simulate(root, pieces, fids, weights, lookahead, trace, prune=not want_trace, move_set=move_set)
+    last, placed = simulate(root, pieces, fids, weights, lookahead, trace, prune=not want_trace, move_set=move_set, pressure=pressure)
     out = {"pieces": placed, "lines": last.lines(), "hist": [last.hist.get(k, 0) for k in (1, 2, 3, 4)]}
     if want_trace:
         out["score"] = game_score(last)

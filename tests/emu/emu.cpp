@@ -25,11 +25,12 @@ struct Best { uint64_t key; uint32_t tag; uint32_t mv; };
 
 template <int MODE>
 static void search_one(const uint32_t c[COLS], const Heights& H, const PrevStat& pv, int piece, const uint8_t* ids,
-                       const double* w, int F, uint64_t rmask, int move_set, uint32_t tag_hi, uint32_t mv1, bool leaf_is_first,
-                       Best& best, uint64_t& cnt)
+                       const double* w, int F, uint64_t rmask, int move_set, const Pressure& pr, int level, uint32_t tag_hi, uint32_t mv1,
+                       bool leaf_is_first, Best& best, uint64_t& cnt)
 {
     const Tables& tab = host_tables();
     auto consider = [&](const Placement& P, const SlotDesc& d, uint32_t tg, uint32_t mv) {
+        if (pr.on && !is_time(d, (int)(mv >> 8), pr, level)) return;
         Feat f;
         memset(&f, 0, sizeof f);
         eval_features<ModeTraits<MODE>::CMASK>(P, d, pv, rmask, f);
@@ -41,7 +42,7 @@ static void search_one(const uint32_t c[COLS], const Heights& H, const PrevStat&
         Placement P;
         if (!place_slot(c, H, tab.slot[piece][s], P)) continue;
         consider(P, tab.slot[piece][s], tag_hi | (uint32_t)s << 5, (uint32_t)s | (uint32_t)P.y << 8);
-        if (move_set == 1) {
+        if (move_set & 1) {
             for_each_slide(c, H, tab.slot[piece][s], s, P.y, [&](int s2) { return tab.slot[piece][s2]; },
                 [&](const SlotDesc& d2, int s2, int yy, int j) {
                     Placement P2; uint32_t full;
@@ -56,9 +57,11 @@ static void search_one(const uint32_t c[COLS], const Heights& H, const PrevStat&
 template <int MODE>
 static void play(const int* ids_in, int F, const double* w, const uint8_t* pieces, uint32_t T, uint64_t seed, uint64_t stream,
                  int lookahead, uint32_t max_moves, const uint16_t* init_rows, uint64_t* res8, uint8_t* trace,
-                 double* score_trace, uint16_t* final_rows, int move_set)
+                 double* score_trace, uint16_t* final_rows, int move_set, const double* press)
 {
     const Tables& tab = host_tables();
+    Pressure pr = {0, 0, 0.0, 0.0, 0.0};
+    if ((move_set & 2) && press) { pr.on = 1; pr.avg_lat = press[0]; pr.resp_time = press[1]; pr.move_eff = press[2]; pr.two_but_rot = press[3] != 0.0; }
     uint8_t ids[64]; uint64_t rmask = 0;
     for (int i = 0; i < F; ++i) { ids[i] = (uint8_t)ids_in[i]; rmask |= 1ull << ids_in[i]; }
     uint32_t c[COLS];
@@ -75,14 +78,15 @@ static void play(const int* ids_in, int F, const double* w, const uint8_t* piece
         if (p2 < 7) {
             // layer 1 in enumeration order (base move, its right slides, its left slides), each expanded by piece 2
             auto expand = [&](const Placement& P1, const SlotDesc& d1, uint32_t tag1, uint32_t mv1) {
+                if (pr.on && !is_time(d1, (int)(mv1 >> 8), pr, (int)(lines / 10))) return;
                 const PrevStat pv1 = next_stat(pv, P1, d1); const Heights H1 = pack_gh(pv1.gh);
-                search_one<MODE>(P1.n, H1, pv1, p2, ids, w, F, rmask, move_set, tag1 << 11, mv1, false, best, cnt);
+                search_one<MODE>(P1.n, H1, pv1, p2, ids, w, F, rmask, move_set, pr, (int)((lines + (uint32_t)P1.k) / 10), tag1 << 11, mv1, false, best, cnt);
             };
             for (int s1 = 0; s1 < tab.nslots[p1]; ++s1) {
                 Placement P1;
                 if (!place_slot(c, H, tab.slot[p1][s1], P1)) continue;
                 expand(P1, tab.slot[p1][s1], (uint32_t)s1 << 5, (uint32_t)s1 | (uint32_t)P1.y << 8);
-                if (move_set == 1) {
+                if (move_set & 1) {
                     for_each_slide(c, H, tab.slot[p1][s1], s1, P1.y, [&](int s2) { return tab.slot[p1][s2]; },
                         [&](const SlotDesc& d2, int s2, int yy, int j) {
                             Placement P2; uint32_t full;
@@ -95,7 +99,7 @@ static void play(const int* ids_in, int F, const double* w, const uint8_t* piece
         }
         if (best.key == 0) {
             Best b1 = {0, 0, 0};
-            search_one<MODE>(c, H, pv, p1, ids, w, F, rmask, move_set, 0u, 0u, true, b1, cnt);
+            search_one<MODE>(c, H, pv, p1, ids, w, F, rmask, move_set, pr, (int)(lines / 10), 0u, 0u, true, b1, cnt);
             best = b1;
         }
         if (best.key == 0) break;
@@ -168,16 +172,16 @@ extern "C" {
 // mode: -1 = as tb200_set_features would choose, 0 = force the generic (run-time feature list) path
 int emu_play_one(const int* ids, int F, const double* w, const uint8_t* pieces, uint32_t T, uint64_t seed, uint64_t stream,
                  int lookahead, uint32_t max_moves, int mode, const uint16_t* init_rows, uint64_t* res8, uint8_t* trace,
-                 double* score_trace, uint16_t* final_rows, int move_set)
+                 double* score_trace, uint16_t* final_rows, int move_set, const double* press)
 {
     const int m = mode < 0 ? pick_mode(ids, F) : mode;
     if (m == 3) {           // fast w6 path of the one-warp-per-game kernel (caller guarantees the w6 feature list, lookahead 1)
         play_w6_fast(w, pieces, T, seed, stream, max_moves, init_rows, res8, trace, score_trace, final_rows);
         return m;
     }
-    if (m == MODE_W6) play<MODE_W6>(ids, F, w, pieces, T, seed, stream, lookahead, max_moves, init_rows, res8, trace, score_trace, final_rows, move_set);
-    else if (m == MODE_ALL45) play<MODE_ALL45>(ids, F, w, pieces, T, seed, stream, lookahead, max_moves, init_rows, res8, trace, score_trace, final_rows, move_set);
-    else play<MODE_GENERIC>(ids, F, w, pieces, T, seed, stream, lookahead, max_moves, init_rows, res8, trace, score_trace, final_rows, move_set);
+    if (m == MODE_W6) play<MODE_W6>(ids, F, w, pieces, T, seed, stream, lookahead, max_moves, init_rows, res8, trace, score_trace, final_rows, move_set, press);
+    else if (m == MODE_ALL45) play<MODE_ALL45>(ids, F, w, pieces, T, seed, stream, lookahead, max_moves, init_rows, res8, trace, score_trace, final_rows, move_set, press);
+    else play<MODE_GENERIC>(ids, F, w, pieces, T, seed, stream, lookahead, max_moves, init_rows, res8, trace, score_trace, final_rows, move_set, press);
     return m;
 }
 

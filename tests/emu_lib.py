@@ -30,7 +30,7 @@ def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
 
 
-def play_one(fids, weights, pieces=None, T=None, seed=0, stream=0, lookahead=1, max_moves=0, mode=-1, init_rows=None, move_set=0):
+def play_one(fids, weights, pieces=None, T=None, seed=0, stream=0, lookahead=1, max_moves=0, mode=-1, init_rows=None, move_set=0, pressure=None):
     fids = np.ascontiguousarray(fids, dtype=np.int32)
     w = np.ascontiguousarray(weights, dtype=np.float64)
     if pieces is not None:
@@ -41,9 +41,14 @@ def play_one(fids, weights, pieces=None, T=None, seed=0, stream=0, lookahead=1, 
     trace = np.zeros((max(T, 1), 4), dtype=np.uint8)
     st = np.zeros(max(T, 1), dtype=np.float64)
     final = np.zeros(20, dtype=np.uint16)
+    press = None
+    if pressure is not None:
+        press = np.array([pressure.get("avg_lat", 250.9), pressure.get("resp_time", 79.8), pressure.get("move_eff", 1.23),
+                          1.0 if pressure.get("two_but_rot", False) else 0.0], dtype=np.float64)
+        move_set |= 2
     m = lib().emu_play_one(_p(fids), ctypes.c_int(len(fids)), _p(w), _p(pieces), ctypes.c_uint32(T), ctypes.c_uint64(seed),
                            ctypes.c_uint64(stream), ctypes.c_int(lookahead), ctypes.c_uint32(max_moves), ctypes.c_int(mode),
-                           _p(init), _p(res), _p(trace), _p(st), _p(final), ctypes.c_int(move_set))
+                           _p(init), _p(res), _p(trace), _p(st), _p(final), ctypes.c_int(move_set), _p(press))
     n = int(res[0])
     return {"pieces": n, "lines": int(res[1]), "hist": [int(x) for x in res[2:6]], "score": int(res[6]),
             "placements": int(res[7]), "trace": trace[:n].copy(), "scores": st[:n].copy(), "final": final, "mode": m}

@@ -105,10 +105,13 @@ def all_features(state):
     return [feat_value(vals[f]) for f in FEATS]
 
 
-def play(named_weights, seed, T, lookahead=1, tie=tie_first, keep_trace=True, slide=False):
+def play(named_weights, seed, T, lookahead=1, tie=tie_first, keep_trace=True, slide=False, pressure=None):
     """Canonical game: returns summary + byte trace [rot,row,col,k]*.
-    slide=True: move_gen = move_with_overhang_slide(move_drop) (simulator.py:15-47) instead of move_drop."""
+    slide=True: move_gen = move_with_overhang_slide(move_drop) (simulator.py:15-47) instead of move_drop.
+    pressure=dict(...): wrap the generator in move_with_pressure(gen, **pressure) (simulator.py:88-120)."""
     move_gen = ref_sim.move_with_overhang_slide(ref_sim.move_drop) if slide else ref_sim.move_drop
+    if pressure is not None:
+        move_gen = ref_sim.move_with_pressure(move_gen, **pressure)
     weights = weights_by_name(named_weights)
     scorer = make_scorer(weights)
     calls = [0]
@@ -136,6 +139,7 @@ def play(named_weights, seed, T, lookahead=1, tie=tie_first, keep_trace=True, sl
         "trace_sha16": hashlib.sha256(bytes(trace)).hexdigest()[:16],
         "final_board": board_rows(last.board),
         "move_gen": "overhang_slide" if slide else "drop",
+        "pressure": pressure,
     }
     if keep_trace:
         out["trace_hex"] = bytes(trace).hex()
@@ -422,6 +426,20 @@ def main():
     dump("games_slide.json", {"meta": meta, "games": sgames})
     print("slide games:", len(sgames), round(time.time() - t0, 1), "s", flush=True)
     dump("slide_moves.json", {"meta": meta, "boards": gen_slide_moves()})
+
+    # §8f rank 3: move_with_pressure (human time-pressure filter, level-dependent)
+    t0 = time.time()
+    pgames = []
+    for s in (0, 1):
+        pgames.append(play(W6, s, 1500, pressure={}))                     # default parameters; ends when the level gets too fast
+    pgames.append(play(W6, 2, 1500, pressure={"two_but_rot": True}))
+    pgames.append(play(W6, 3, 1500, pressure={"avg_lat": 180.0, "resp_time": 60.5, "move_eff": 1.1}))
+    pgames.append(play(W6, 4, 1500, slide=True, pressure={}))
+    pgames.append(play(holes, 0, 400, slide=True, pressure={"two_but_rot": True}))
+    pgames.append(play(W6, 0, 60, lookahead=2, pressure={}))
+    pgames.append(play(w45b, 0, 400, pressure={"avg_lat": 300.0}))
+    dump("games_pressure.json", {"meta": meta, "games": pgames})
+    print("pressure games:", len(pgames), round(time.time() - t0, 1), "s", flush=True)
     print("games:", len(games), round(time.time() - t0, 1), "s", flush=True)
 
     if not args.skip_ce:

@@ -195,3 +195,35 @@ def test_emu_slide_vs_coracle_random(lookahead, ngames, T):
         d = coracle.play_one(fids, w, seq, lookahead, move_set="drop")
         slid += a["trace"].tobytes() != d["trace"].tobytes()
     assert slid > ngames // 10          # the slide move set really changes games
+
+
+# ------------------------------------------------------------------------------------------------
+# move_with_pressure in the CUDA core (host build)
+# ------------------------------------------------------------------------------------------------
+def test_emu_pressure_games():
+    from conftest import load_golden
+    for g in load_golden("games_pressure.json")["games"]:
+        fids = [pyoracle.FEATURE_ID[n] for n, _ in g["weights"]]
+        w = [x for _, x in g["weights"]]
+        seq = pyoracle.piece_sequence(g["seed"], g["T"])
+        ms = 1 if g["move_gen"] == "overhang_slide" else 0
+        res = emu_lib.play_one(fids, w, seq, lookahead=g["lookahead"], move_set=ms, pressure=g["pressure"])
+        assert res["pieces"] == g["pieces"] and res["lines"] == g["lines"] and res["score"] == g["score"]
+        assert res["placements"] == g["scorer_calls"] and res["trace"].tobytes().hex() == g["trace_hex"]
+
+
+def test_emu_pressure_vs_coracle_random():
+    rng = random.Random(901)
+    fids = [pyoracle.FEATURE_ID[n] for n in W6_NAMES]
+    for gi in range(60):
+        w = [rng.gauss(v, 1.0) for v in W6_VALS]
+        pr = {"avg_lat": rng.uniform(120, 320), "resp_time": rng.uniform(40, 120), "move_eff": rng.uniform(1.0, 1.5), "two_but_rot": bool(gi & 1)}
+        seq = [pyoracle.hashed_piece(91, gi, t) for t in range(600)]
+        ms = gi % 2
+        la = 2 if gi % 10 == 0 else 1
+        if la == 2:
+            seq = seq[:40]
+        a = coracle.play_one(fids, w, seq, la, move_set=ms, pressure=pr)
+        b = emu_lib.play_one(fids, w, seq, lookahead=la, move_set=ms, pressure=pr)
+        assert (a["pieces"], a["lines"], a["score"], a["placements"]) == (b["pieces"], b["lines"], b["score"], b["placements"]), gi
+        assert a["trace"].tobytes() == b["trace"].tobytes(), gi

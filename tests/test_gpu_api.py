@@ -167,3 +167,26 @@ def test_simulate_with_overhang_slide(eng):
         assert trace.hex() == g["trace_hex"] and last.score() == g["score"]
     with pytest.raises(TypeError):
         sim.move_with_overhang_slide(lambda s, z: [])
+
+
+@pytest.mark.parametrize("chunk", [4096, 23])
+def test_simulate_with_pressure_chunked(eng, chunk, monkeypatch):
+    """move_with_pressure depends on the level, i.e. on the lines cleared so far: chunked simulate() must carry them."""
+    from conftest import load_golden
+    from tetris_ai_b200.tetris import simulator as sim
+    from tetris_ai_b200.tetris.game import Board, State, PIECES
+    monkeypatch.setattr(sim, "CHUNK", chunk)
+    for g in load_golden("games_pressure.json")["games"]:
+        if g["scorer_calls"] > 6100:
+            continue
+        inner = sim.move_with_overhang_slide(sim.move_drop) if g["move_gen"] == "overhang_slide" else sim.move_drop
+        gen = sim.move_with_pressure(inner, **g["pressure"])
+        policy = sim.policy_best(sim.linear_scorer(_weights(g["weights"])), sim.tie_first)
+        seq = pyoracle.piece_sequence(g["seed"], g["T"])
+        trace = bytearray()
+        last = State(None, Board(20, 10))
+        for st in sim.simulate(last, iter(PIECES[i] for i in seq), gen, policy, lookahead=g["lookahead"], engine=eng):
+            d = st.delta
+            trace += bytes([d.rot, d.row, d.col, len(d.cleared)])
+            last = st
+        assert trace.hex() == g["trace_hex"] and last.score() == g["score"], (g["seed"], chunk)

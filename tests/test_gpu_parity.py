@@ -367,3 +367,42 @@ def test_slide_vs_coracle(eng, lanes, names, kind, lookahead, C, G, T):
         n = int(res["pieces"][g])
         assert (r["trace"][g, :n] == o["trace"][g, :n]).all(), g
     assert (o["placements"] != d["placements"]).any()          # slides really occurred
+
+
+# ------------------------------------------------------------------------------------------------
+# move_with_pressure on the device
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lanes", [32, 8])
+def test_pressure_golden_games(eng, lanes):
+    from conftest import load_golden
+    for g in load_golden("games_pressure.json")["games"]:
+        eng.set_features([n for n, _ in g["weights"]])
+        w = np.array([[x for _, x in g["weights"]]])
+        seq = np.array([pyoracle.piece_sequence(g["seed"], g["T"])], dtype=np.uint8)
+        ms = 1 if g["move_gen"] == "overhang_slide" else 0
+        r = eng.play_games(w, 1, pieces=seq, lookahead=g["lookahead"], lanes=lanes, want_trace=True, want_final=True,
+                           move_set=ms, pressure=g["pressure"])
+        res = r["results"][0]
+        assert int(res["pieces"]) == g["pieces"] and int(res["lines"]) == g["lines"] and [int(x) for x in res["hist"]] == g["hist"]
+        assert int(res["score"]) == g["score"] and int(res["placements"]) == g["scorer_calls"]
+        assert r["trace"][0, :g["pieces"]].tobytes().hex() == g["trace_hex"]
+        assert list(r["final"][0]) == g["final_board"]
+
+
+@pytest.mark.parametrize("lookahead,C,G,T,ms", [(1, 96, 3, 500, 0), (1, 64, 3, 400, 1), (2, 6, 2, 40, 1)])
+def test_pressure_vs_coracle(eng, lookahead, C, G, T, ms):
+    rng = random.Random(4000 + lookahead + ms)
+    fids = [pyoracle.FEATURE_ID[n] for n in W6_NAMES]
+    w = np.array(_weight_sets(rng, C, W6_NAMES, "w6"))
+    pr = {"avg_lat": 210.0, "resp_time": 70.0, "move_eff": 1.3, "two_but_rot": True}
+    eng.set_features(W6_NAMES)
+    r = eng.play_games(w, G, T=T, seed=12, lookahead=lookahead, want_trace=True, move_set=ms, pressure=pr)
+    o = coracle.play_games(fids, w, G, T=T, seed=12, lookahead=lookahead, threads=16, want_trace=True, move_set=ms, pressure=pr)
+    res = r["results"]
+    assert (res["pieces"] == o["pieces"]).all() and (res["lines"] == o["lines"]).all() and (res["score"] == o["score"]).all()
+    assert (res["placements"] == o["placements"]).all()
+    for g in range(C * G):
+        n = int(res["pieces"][g])
+        assert (r["trace"][g, :n] == o["trace"][g, :n]).all(), g
+    if lookahead == 1:
+        assert (res["pieces"] < T).any()                    # the pressure filter ended some games

@@ -226,3 +226,22 @@ def test_slide_games(golden_slide_games):
             _check_game(pyoracle.play_game(fids, w, seq, g["lookahead"], want_trace=True, move_set="slide"), g)
             n_py += 1
     assert n_py >= 3
+
+
+# ------------------------------------------------------------------------------------------------
+# move_with_pressure(move_drop | move_with_overhang_slide(move_drop))
+# ------------------------------------------------------------------------------------------------
+def test_pressure_games():
+    from conftest import load_golden
+    n_py = 0
+    for g in load_golden("games_pressure.json")["games"]:
+        fids, w = fids_weights(g["weights"])
+        seq = pyoracle.piece_sequence(g["seed"], g["T"])
+        ms = "slide" if g["move_gen"] == "overhang_slide" else "drop"
+        res = coracle.play_one(fids, w, seq, g["lookahead"], move_set=ms, pressure=g["pressure"])
+        _check_game(res, g)
+        assert res["placements"] == g["scorer_calls"] and list(res["final"]) == g["final_board"]
+        if g["scorer_calls"] < 4000:
+            _check_game(pyoracle.play_game(fids, w, seq, g["lookahead"], want_trace=True, move_set=ms, pressure=g["pressure"]), g)
+            n_py += 1
+    assert n_py >= 2

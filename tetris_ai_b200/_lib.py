@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtetris_b200.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
-MOVES_DROP, MOVES_OVERHANG_SLIDE = 0, 1
+MOVES_DROP, MOVES_OVERHANG_SLIDE, MOVES_PRESSURE = 0, 1, 2
 NUM_FEATURES = 45
 MAX_WEIGHTED = 48
 
@@ -31,7 +31,9 @@ class PlayArgs(ctypes.Structure):
         ("seed", ctypes.c_uint64), ("lookahead", ctypes.c_int32), ("lanes", ctypes.c_int32),
         ("init_rows", ctypes.c_void_p), ("results", ctypes.c_void_p), ("trace", ctypes.c_void_p),
         ("score_trace", ctypes.c_void_p), ("final_rows", ctypes.c_void_p), ("fitness", ctypes.c_void_p),
-        ("move_set", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("move_set", ctypes.c_int32), ("pressure_two_but_rot", ctypes.c_int32),
+        ("pressure_avg_lat", ctypes.c_double), ("pressure_resp_time", ctypes.c_double), ("pressure_move_eff", ctypes.c_double),
+        ("init_lines", ctypes.c_void_p),
     ]
 
 

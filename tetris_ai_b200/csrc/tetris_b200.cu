@@ -38,6 +38,7 @@ struct PlayParams {
     const uint8_t* pieces;
     const int32_t* seq_of_game;
     const uint16_t* init_rows;
+    const uint32_t* init_lines;      // lines already cleared before the first move (level for score / pressure), or null
     tb200_game_result* results;
     uint8_t*  trace;
     double*   score_trace;
@@ -51,7 +52,8 @@ struct PlayParams {
     int32_t   G;
     int32_t   F;
     int32_t   per_game_weights;      // K1 (one game per board, sequence id = game): weights row = game (1) or row 0 (-1); K2: 0
-    int32_t   move_set;              // 0 = move_drop, 1 = move_with_overhang_slide(move_drop)
+    int32_t   move_set;              // bit 0: overhang slides, bit 1: pressure filter (extended generic kernels only)
+    Pressure  press;                 // move_with_pressure parameters (press.on mirrors bit 1)
     uint8_t   ids[TB200_MAX_WEIGHTED];
 };
 
@@ -106,10 +108,10 @@ TB_D SlotDesc load_slot12(const Tables& tab, int piece, int s)
 // Moves derived from one legal hard-drop slot: the drop itself (index 0) and, with SLIDE, the overhang slides
 // (simulator.py:15-47) in the reference's order.  list[i] = slot | height << 8 of slide i + 1.
 template <int SLIDE>
-TB_D int collect_slides(const uint32_t c[COLS], const Heights& H, const Tables& tab, int piece, const SlotDesc& d0, int s0, int y0, uint16_t* list)
+TB_D int collect_slides(const uint32_t c[COLS], const Heights& H, const Tables& tab, int piece, const SlotDesc& d0, int s0, int y0, bool slide_on, uint16_t* list)
 {
     int n = 0;
-    if (SLIDE)
+    if (SLIDE && slide_on)
         for_each_slide(c, H, d0, s0, y0, [&](int s2) { return load_slot12(tab, piece, s2); },
                        [&](const SlotDesc&, int s2, int yy, int) { list[n++] = (uint16_t)((uint32_t)s2 | (uint32_t)yy << 8); });
     return n;
@@ -122,6 +124,7 @@ TB_D int collect_slides(const uint32_t c[COLS], const Heights& H, const Tables& 
 template <int LANES, int MODE, int SLIDE>
 TB_D void search_one(const uint32_t c[COLS], const Heights& H, const PrevStat& pv, int piece, int gl,
                      const Tables& tab, const uint8_t* ids, const double* w, int F, uint64_t rmask,
+                     bool slide_on, const Pressure& pr, int level,
                      uint32_t tag_hi, uint32_t mv1, bool leaf_is_first, uint64_t& key, uint32_t& tag, uint32_t& mv, uint32_t& cnt)
 {
     const int ns = tab.nslots[piece];
@@ -130,12 +133,13 @@ TB_D void search_one(const uint32_t c[COLS], const Heights& H, const PrevStat& p
         Placement P0;
         if (!place_slot(c, H, d0, P0)) continue;
         uint16_t list[SLIDE ? 18 : 1];
-        const int n = collect_slides<SLIDE>(c, H, tab, piece, d0, s, P0.y, list);
+        const int n = collect_slides<SLIDE>(c, H, tab, piece, d0, s, P0.y, slide_on, list);
         for (int i = 0; i <= n; ++i) {
             const uint32_t m = i == 0 ? ((uint32_t)s | (uint32_t)P0.y << 8) : (uint32_t)list[SLIDE ? i - 1 : 0];
             Placement P; SlotDesc d;
             if (SLIDE) {
                 d = load_slot12(tab, piece, (int)(m & 255u));
+                if (pr.on && !is_time(d, (int)(m >> 8), pr, level)) continue;      // move_with_pressure filter
                 uint32_t full;
                 place_at(c, d, (int)(m >> 8), P, &full);
                 if (full != 0u) place_clear(d, P, full);
@@ -194,7 +198,8 @@ __global__ void __launch_bounds__(BLOCK) play_games_kernel(const PlayParams prm)
         __syncwarp(FULLMASK);                    // previous game's reads of s_w are complete
         if (want) {
             if (g < prm.n_games) {
-                game = g; active = true; t = 0; lines = h1 = h2 = h3 = h4 = 0; cnt = 0; gscore = 0;
+                game = g; active = true; t = 0; h1 = h2 = h3 = h4 = 0; cnt = 0; gscore = 0;
+                lines = prm.init_lines ? prm.init_lines[g] : 0u;
                 const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[g] : (prm.per_game_weights != 0 ? g : g % (uint32_t)prm.G);
                 stream = sq;
                 seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
@@ -227,6 +232,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_kernel(const PlayParams prm)
         const int p_after = active ? fetch_piece(t + 2) : 0;      // prefetch: consumed two steps later
 
         uint64_t key = 0; uint32_t tag = 0, mv = 0;
+        const bool slide_on = (prm.move_set & 1) != 0;
         if (LOOKAHEAD == 2) {
             if (active && t + 1 < T && p_cur < 7 && p_next < 7) {
                 // layer 1 (group-uniform): every move of the current piece in enumeration order, expanded by the next piece
@@ -236,12 +242,13 @@ __global__ void __launch_bounds__(BLOCK) play_games_kernel(const PlayParams prm)
                     Placement P0;
                     if (!place_slot(c, H, d0, P0)) continue;
                     uint16_t list[SLIDE ? 18 : 1];
-                    const int n = collect_slides<SLIDE>(c, H, s_tab, p_cur, d0, s1, P0.y, list);
+                    const int n = collect_slides<SLIDE>(c, H, s_tab, p_cur, d0, s1, P0.y, slide_on, list);
                     for (int i = 0; i <= n; ++i) {
                         const uint32_t m1 = i == 0 ? ((uint32_t)s1 | (uint32_t)P0.y << 8) : (uint32_t)list[SLIDE ? i - 1 : 0];
                         Placement P1; SlotDesc d1;
                         if (SLIDE) {
                             d1 = load_slot12(s_tab, p_cur, (int)(m1 & 255u));
+                            if (prm.press.on && !is_time(d1, (int)(m1 >> 8), prm.press, (int)(lines / 10u))) continue;
                             uint32_t full;
                             place_at(c, d1, (int)(m1 >> 8), P1, &full);
                             if (full != 0u) place_clear(d1, P1, full);
@@ -251,6 +258,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_kernel(const PlayParams prm)
                         const PrevStat pv1 = next_stat(pv, P1, d1);
                         const Heights H1 = pack_gh(pv1.gh);
                         search_one<LANES, MODE, SLIDE>(P1.n, H1, pv1, p_next, gl, s_tab, prm.ids, w, F, prm.rmask,
+                                                       slide_on, prm.press, (int)((lines + (uint32_t)P1.k) / 10u),
                                                        ((uint32_t)s1 << 5 | (uint32_t)i) << 11, m1, false, key, tag, mv, cnt);
                     }
                 }
@@ -260,7 +268,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_kernel(const PlayParams prm)
         const bool need_l1 = active && p_cur < 7 && (LOOKAHEAD == 1 || key == 0);
         if (LOOKAHEAD == 1 || __any_sync(FULLMASK, need_l1)) {
             uint64_t k1 = 0; uint32_t t1 = 0, m1 = 0;
-            if (need_l1) search_one<LANES, MODE, SLIDE>(c, H, pv, p_cur, gl, s_tab, prm.ids, w, F, prm.rmask, 0u, 0u, true, k1, t1, m1, cnt);
+            if (need_l1) search_one<LANES, MODE, SLIDE>(c, H, pv, p_cur, gl, s_tab, prm.ids, w, F, prm.rmask, slide_on, prm.press, (int)(lines / 10u), 0u, 0u, true, k1, t1, m1, cnt);
             group_argmax_mv<LANES>(k1, t1, m1);
             if (need_l1) { key = k1; tag = t1; mv = m1; }
         }
@@ -400,7 +408,8 @@ __global__ void __launch_bounds__(BLOCK) play_games_w32_kernel(const PlayParams 
             if (tt >= T) return 7;
             return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, stream, tt);
         };
-        uint32_t t = 0, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+        uint32_t t = 0, lines = prm.init_lines ? prm.init_lines[game] : 0u, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+        const uint32_t lines0 = lines;
         uint64_t gscore = 0;
         int p_cur = fetch_piece(0), p_next = fetch_piece(1);
         const uint32_t max_moves = prm.max_moves;
@@ -575,7 +584,8 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayPara
             const uint32_t v = __shfl_sync(FULLMASK, win, (int)(idx & 31u));
             return (int)((v >> ((idx >> 5) * 8u)) & 255u);
         };
-        uint32_t t = 0, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+        uint32_t t = 0, lines = prm.init_lines ? prm.init_lines[game] : 0u, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+        const uint32_t lines0 = lines;
         uint64_t gscore = 0;
         const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
         int p_cur = piece_at(0), p_next = piece_at(1);
@@ -660,7 +670,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayPara
                 const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
                 gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
             }
-            g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)lines;
+            g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)(lines - lines0);
             if (prm.trace && lane == 0) {
                 const uint32_t wy = info & 255u, wph = info >> 24;
                 const uint32_t row = (uint32_t)ROWS - wy - wph;
@@ -760,7 +770,8 @@ __global__ void __launch_bounds__(64) play_games_w6pair_kernel(const PlayParams 
             const uint32_t v = __shfl_sync(FULLMASK, win, (int)(idx & 31u));
             return (int)((v >> ((idx >> 5) * 8u)) & 255u);
         };
-        uint32_t t = 0, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+        uint32_t t = 0, lines = prm.init_lines ? prm.init_lines[game] : 0u, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+        const uint32_t lines0 = lines;
         uint64_t gscore = 0;
         const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
         int p_cur = piece_at(0), p_next = piece_at(1);
@@ -823,7 +834,7 @@ __global__ void __launch_bounds__(64) play_games_w6pair_kernel(const PlayParams 
                 const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
                 gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
             }
-            g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)lines;
+            g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)(lines - lines0);
             if (threadIdx.x == 0) {
                 if (prm.trace) {
                     const uint32_t wy = info & 255u, wph = info >> 24;
@@ -879,7 +890,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6grp_kernel(const PlayParam
     const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
 
     bool active = false, exhausted = false;
-    uint32_t game = 0, t = 0, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+    uint32_t game = 0, t = 0, lines = 0, lines0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
     uint64_t gscore = 0, stream = 0;
     const uint8_t* seq = nullptr;
     uint32_t c[COLS];
@@ -905,7 +916,8 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6grp_kernel(const PlayParam
         tk = __shfl_sync(FULLMASK, tk, 0, LANES);
         if (want) {
             if (tk < prm.n_games) {
-                game = tk; active = true; t = 0; lines = h1 = h2 = h3 = h4 = 0; cnt = 0; gscore = 0;
+                game = tk; active = true; t = 0; h1 = h2 = h3 = h4 = 0; cnt = 0; gscore = 0;
+                lines = prm.init_lines ? prm.init_lines[tk] : 0u; lines0 = lines;
                 const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : (prm.per_game_weights != 0 ? game : game % (uint32_t)prm.G);
                 stream = sq;
                 seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
@@ -972,7 +984,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6grp_kernel(const PlayParam
                     const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
                     gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
                 }
-                g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)lines;
+                g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)(lines - lines0);
                 if (gl == 0) {
                     if (prm.trace) {
                         const uint32_t row = (uint32_t)(ROWS - A.P.y - A.P.ph);
@@ -1114,7 +1126,7 @@ static play_fn pick_generic(int mode, int lookahead, int lanes)
 }
 static play_fn pick_kernel(int mode, int lookahead, int lanes, int move_set)
 {
-    if (move_set == 1) return pick_generic<1>(mode, lookahead, lanes);     // overhang slides: generic kernels only
+    if (move_set != 0) return pick_generic<1>(mode, lookahead, lanes);     // overhang slides / pressure: extended generic kernels
     if (lanes == 64) return play_games_w6pair_kernel;      // caller guarantees lookahead 1 and the w6 set
     if (lookahead == 1 && mode == MODE_W6 && lanes == 16) return play_games_w6grp_kernel<16>;
     if (lookahead == 1 && mode == MODE_W6 && lanes == 8) return play_games_w6grp_kernel<8>;
@@ -1315,7 +1327,7 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
     int lanes = a.lanes;
     const int move_set = a.move_set;
     const bool pair_ok = ctx->mode == tb::MODE_W6 && a.lookahead == 1 && move_set == 0;
-    if (move_set == 1 && (lanes == 64 || lanes == 4 || lanes == 2 || lanes == 1)) lanes = lanes == 64 ? 32 : 8;
+    if (move_set != 0 && (lanes == 64 || lanes == 4 || lanes == 2 || lanes == 1)) lanes = lanes == 64 ? 32 : 8;
     if (lanes == 64 && !pair_ok) lanes = 32;
     const bool narrow_ok = pair_ok && (lanes == 4 || lanes == 2 || lanes == 1);
     if (!narrow_ok && lanes != 8 && lanes != 16 && lanes != 32 && lanes != 64) {
@@ -1341,12 +1353,15 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
 
     tb::PlayParams p;
     memset(&p, 0, sizeof p);
-    p.weights = a.weights; p.pieces = a.pieces; p.seq_of_game = a.seq_of_game; p.init_rows = a.init_rows;
+    p.weights = a.weights; p.pieces = a.pieces; p.seq_of_game = a.seq_of_game; p.init_rows = a.init_rows; p.init_lines = a.init_lines;
     p.results = a.results; p.trace = a.trace; p.score_trace = a.score_trace; p.final_rows = a.final_rows;
     p.ticket = ctx->d_ticket; p.seed = a.seed; p.rmask = ctx->rmask; p.n_games = n_games; p.T = a.T;
     p.max_moves = a.max_moves ? a.max_moves : a.T; p.G = a.games_per_candidate; p.F = ctx->F;
     p.per_game_weights = per_game_weights;
     p.move_set = move_set;
+    p.press.on = (move_set & TB200_MOVES_PRESSURE) ? 1 : 0;
+    p.press.two_but_rot = a.pressure_two_but_rot ? 1 : 0;
+    p.press.avg_lat = a.pressure_avg_lat; p.press.resp_time = a.pressure_resp_time; p.press.move_eff = a.pressure_move_eff;
     memcpy(p.ids, ctx->ids, sizeof p.ids);
 
     TB_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(uint32_t), st));
@@ -1377,7 +1392,7 @@ static int check_play_args(tb200_ctx* ctx, const tb200_play_args* a)
     if (a->pieces && a->n_sequences < 1) return fail(ctx, TB200_E_BAD_ARG, "play_games: n_sequences must be >= 1 with explicit pieces");
     if (a->pieces && !a->seq_of_game && a->n_sequences < a->games_per_candidate) return fail(ctx, TB200_E_BAD_ARG, "play_games: need S >= G without seq_of_game");
     if (a->mem != TB200_MEM_HOST && a->mem != TB200_MEM_DEVICE) return fail(ctx, TB200_E_BAD_ARG, "play_games: bad mem");
-    if (a->move_set != TB200_MOVES_DROP && a->move_set != TB200_MOVES_OVERHANG_SLIDE) return fail(ctx, TB200_E_BAD_ARG, "play_games: bad move_set");
+    if (a->move_set < 0 || a->move_set > (TB200_MOVES_OVERHANG_SLIDE | TB200_MOVES_PRESSURE)) return fail(ctx, TB200_E_BAD_ARG, "play_games: bad move_set");
     return TB200_OK;
 }
 
@@ -1405,6 +1420,7 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
     const size_t b_p = a.pieces ? (size_t)a.n_sequences * a.T : 0;
     const size_t b_s = a.seq_of_game ? sizeof(int32_t) * n_games : 0;
     const size_t b_i = a.init_rows ? sizeof(uint16_t) * TB200_ROWS * n_games : 0;
+    const size_t b_il = a.init_lines ? sizeof(uint32_t) * n_games : 0;
     const size_t b_r = sizeof(tb200_game_result) * n_games;
     const size_t b_t = a.trace ? 4 * (size_t)a.T * n_games : 0;
     const size_t b_st = a.score_trace ? sizeof(double) * (size_t)a.T * n_games : 0;
@@ -1413,7 +1429,7 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off += align_up(b); return o; };
     const size_t o_w = take(b_w), o_p = take(b_p), o_s = take(b_s), o_i = take(b_i), o_r = take(b_r), o_t = take(b_t),
-                 o_st = take(b_st), o_f = take(b_f), o_fit = take(b_fit);
+                 o_st = take(b_st), o_f = take(b_f), o_fit = take(b_fit), o_il = take(b_il);
     rc = ensure_arena(ctx, off);
     if (rc) return rc;
     char* base = ctx->d_arena;
@@ -1423,6 +1439,7 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
     d.pieces = a.pieces ? (const uint8_t*)(base + o_p) : nullptr;
     d.seq_of_game = a.seq_of_game ? (const int32_t*)(base + o_s) : nullptr;
     d.init_rows = a.init_rows ? (const uint16_t*)(base + o_i) : nullptr;
+    d.init_lines = a.init_lines ? (const uint32_t*)(base + o_il) : nullptr;
     d.results = (tb200_game_result*)(base + o_r);
     d.trace = a.trace ? (uint8_t*)(base + o_t) : nullptr;
     d.score_trace = a.score_trace ? (double*)(base + o_st) : nullptr;
@@ -1435,6 +1452,7 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
         if (b_p) TB_CUDA(ctx, cudaMemcpyAsync((void*)d.pieces, a.pieces, b_p, cudaMemcpyHostToDevice, st));
         if (b_s) TB_CUDA(ctx, cudaMemcpyAsync((void*)d.seq_of_game, a.seq_of_game, b_s, cudaMemcpyHostToDevice, st));
         if (b_i) TB_CUDA(ctx, cudaMemcpyAsync((void*)d.init_rows, a.init_rows, b_i, cudaMemcpyHostToDevice, st));
+        if (b_il) TB_CUDA(ctx, cudaMemcpyAsync((void*)d.init_lines, a.init_lines, b_il, cudaMemcpyHostToDevice, st));
         if (b_t) TB_CUDA(ctx, cudaMemsetAsync(d.trace, 0, b_t, st));
         if (b_st) TB_CUDA(ctx, cudaMemsetAsync(d.score_trace, 0, b_st, st));
         int rc2 = launch_play(ctx, d, st, 0, &launches);
@@ -1454,7 +1472,7 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
     if (same) {
         if (cudaGraphLaunch(ctx->graph_exec, st) == cudaSuccess) { ctx->timing = ctx->graph_timing; launches = ctx->graph_timing.kernels_launched; done = true; }
         else { cudaGetLastError(); drop_graph(ctx); }
-    } else if (ctx->graphs_enabled && is_pinned(a.weights) && is_pinned(a.pieces) && is_pinned(a.seq_of_game) && is_pinned(a.init_rows) &&
+    } else if (ctx->graphs_enabled && is_pinned(a.weights) && is_pinned(a.pieces) && is_pinned(a.seq_of_game) && is_pinned(a.init_rows) && is_pinned(a.init_lines) &&
                is_pinned(a.results) && is_pinned(a.trace) && is_pinned(a.score_trace) && is_pinned(a.final_rows) && is_pinned(a.fitness)) {
         drop_graph(ctx);
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -1487,7 +1505,7 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
     ctx->timing.total_ms = ms;
-    ctx->timing.h2d_bytes = b_w + b_p + b_s + b_i;
+    ctx->timing.h2d_bytes = b_w + b_p + b_s + b_i + b_il;
     ctx->timing.d2h_bytes = b_r + b_t + b_st + b_f + b_fit;
     ctx->timing.kernels_launched = launches;
     ctx->timing_valid = true;

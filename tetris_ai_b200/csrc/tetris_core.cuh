@@ -378,6 +378,29 @@ TB_HD void for_each_slide(const uint32_t c[COLS], const Heights& H, const SlotDe
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// SURVEY.md §8f rank 3 — move_with_pressure (simulator.py:88-120): a move survives iff the time to key it in
+// (response time + key presses x efficiency x latency) fits before the piece locks at the current level's speed.
+// ---------------------------------------------------------------------------------------------
+struct Pressure { int on; int two_but_rot; double avg_lat, resp_time, move_eff; };
+
+TB_HD int speed_of_level(int level)                           // the descending bracket table of simulator.py:110-114
+{
+    return level >= 29 ? 20 : level >= 19 ? 30 : level >= 16 ? 50 : level >= 13 ? 70 : level >= 10 ? 80 :
+           level == 9 ? 100 : level == 8 ? 130 : level == 7 ? 220 : level == 6 ? 300 : level == 5 ? 380 :
+           level == 4 ? 470 : level == 3 ? 550 : level == 2 ? 630 : level == 1 ? 720 : 800;
+}
+
+// d = descriptor of the placement's slot, y = height of its bbox bottom, level = level of the state it is generated from
+TB_HD bool is_time(const SlotDesc& d, int y, const Pressure& pr, int level)
+{
+    const int rot = (int)((d.w[0] >> 4) & 3u), ph = (int)((d.w[0] >> 9) & 7u);
+    const int clicks = (int)d.w[11] - ((pr.two_but_rot && rot == 3) ? 2 : 0);            // rot 3 costs 1 press instead of 3
+    const double t = dadd(pr.resp_time, dmul(dmul(i2d(clicks), pr.move_eff), pr.avg_lat));   // :107, left to right
+    const int limit = (y + ph) * speed_of_level(level);                                  // (rows - row) * speed, :116
+    return t <= i2d(limit);
+}
+
 TB_HD bool place_slot(const uint32_t c[COLS], const Heights& H, const SlotDesc& d, Placement& p)
 {
     uint32_t f;

@@ -21,6 +21,17 @@ def _ptr(a):
     return a.ctypes.data if a is not None else None
 
 
+def _set_pressure(a, pressure):
+    """pressure: None or a dict with any of avg_lat / resp_time / move_eff / two_but_rot (reference defaults, simulator.py:88)."""
+    if pressure is None:
+        return
+    a.move_set |= _lib.MOVES_PRESSURE
+    a.pressure_avg_lat = float(pressure.get("avg_lat", 250.9))
+    a.pressure_resp_time = float(pressure.get("resp_time", 79.8))
+    a.pressure_move_eff = float(pressure.get("move_eff", 1.23))
+    a.pressure_two_but_rot = 1 if pressure.get("two_but_rot", False) else 0
+
+
 def feature_ids(features):
     """Accepts ids, names, or feature objects carrying __name__ (the reference's protocol, feature.py:23)."""
     out = []
@@ -97,7 +108,7 @@ class Engine:
     # ------------------------------------------------------------------ K2 whole games
     def play_games(self, weights, games_per_candidate, pieces=None, T=None, seq_of_game=None, seed=0, lookahead=1,
                    lanes=0, max_moves=0, init_rows=None, want_trace=False, want_scores=False, want_final=False,
-                   want_fitness=True, out_results=None, out_fitness=None, move_set=0):
+                   want_fitness=True, out_results=None, out_fitness=None, move_set=0, pressure=None, init_lines=None):
         """weights f64[C][F] -> dict(results=structured[C*G], fitness=f64[C], trace=..., ...)   (host buffers)."""
         w = np.ascontiguousarray(weights, dtype=np.float64)
         if w.ndim == 1:
@@ -140,6 +151,10 @@ class Engine:
         a.results, a.trace, a.score_trace = _ptr(results), _ptr(trace), _ptr(scores)
         a.final_rows, a.fitness = _ptr(final), _ptr(fitness)
         a.move_set = int(move_set)
+        _set_pressure(a, pressure)
+        if init_lines is not None:
+            init_lines = np.ascontiguousarray(np.broadcast_to(np.asarray(init_lines, dtype=np.uint32), (n,)), dtype=np.uint32)
+            a.init_lines = _ptr(init_lines)
         self._check(self._L.tb200_play_games(self._h, ctypes.byref(a)))
         return {"results": results, "fitness": fitness, "trace": trace, "scores": scores, "final": final}
 

@@ -50,6 +50,28 @@ def move_with_overhang_slide(move_gen):
     return OverhangSlide()
 
 
+class Pressure:
+    """move_with_pressure(move_gen, avg_lat, resp_time, move_eff, two_but_rot) (simulator.py:88-120) as a device move set:
+    the level-dependent time-pressure filter, applied to the moves of move_drop or of move_with_overhang_slide(move_drop)."""
+
+    def __init__(self, inner_move_set, avg_lat, resp_time, move_eff, two_but_rot):
+        self.move_set = inner_move_set
+        self.params = {"avg_lat": avg_lat, "resp_time": resp_time, "move_eff": move_eff, "two_but_rot": two_but_rot}
+
+    def __call__(self, state, zoid):
+        raise TypeError("the pressure move set is evaluated on the device; pass it to simulate() as move_gen")
+
+
+def move_with_pressure(move_gen, avg_lat=250.9, resp_time=79.8, move_eff=1.23, two_but_rot=False):
+    if move_gen is move_drop:
+        inner = 0
+    elif isinstance(move_gen, OverhangSlide):
+        inner = 1
+    else:
+        raise TypeError("move_with_pressure is implemented on the device around move_drop or move_with_overhang_slide(move_drop) only")
+    return Pressure(inner, avg_lat, resp_time, move_eff, two_but_rot)
+
+
 class LinearScorer:
     """The canonical scorer: acc = 0.0; for f, w in weights.items(): acc += float(f(state)) * w (device fp64, no FMA)."""
 
@@ -100,10 +122,13 @@ def simulate(state, zoid_gen, move_gen, move_policy, lookahead=1, engine=None):
     """Generator of successive States, identical to the reference's for the accepted arguments."""
     if lookahead not in (1, 2):
         raise ValueError("lookahead must be 1 or 2")
+    pressure = None
     if move_gen is move_drop:
         move_set = 0
     elif isinstance(move_gen, OverhangSlide):
         move_set = 1
+    elif isinstance(move_gen, Pressure):
+        move_set, pressure = move_gen.move_set, move_gen.params
     else:
         raise TypeError("only move_drop and move_with_overhang_slide(move_drop) are implemented on the device (no CPU fallback)")
     if not isinstance(move_policy, BestPolicy):
@@ -122,7 +147,8 @@ def simulate(state, zoid_gen, move_gen, move_policy, lookahead=1, engine=None):
         ids = np.array([[z.id for z in chunk]], dtype=np.uint8)
         eng.set_features(sc.features)
         r = eng.play_games(np.array([sc.weights]), 1, pieces=ids, lookahead=lookahead, max_moves=commit,
-                           init_rows=[state.board.rows16()], want_trace=True, want_fitness=False, move_set=move_set)
+                           init_rows=[state.board.rows16()], want_trace=True, want_fitness=False, move_set=move_set, pressure=pressure,
+                           init_lines=state.lines_cleared())
         placed = int(r["results"]["pieces"][0])
         for t in range(placed):
             rot, row, col, _k = (int(x) for x in r["trace"][0, t])
@@ -133,4 +159,4 @@ def simulate(state, zoid_gen, move_gen, move_policy, lookahead=1, engine=None):
         carry = chunk[commit:]
 
 
-__all__ = ["move_drop", "move_with_overhang_slide", "policy_best", "simulate", "linear_scorer", "tie_first", "LinearScorer", "BestPolicy", "PIECES"]
+__all__ = ["move_drop", "move_with_overhang_slide", "move_with_pressure", "policy_best", "simulate", "linear_scorer", "tie_first", "LinearScorer", "BestPolicy", "PIECES"]
