@@ -154,6 +154,13 @@ int tb200_eval_features(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
                         const uint16_t* prev_boards, const uint8_t* piece, const uint8_t* rot, const uint8_t* col,
                         double* out_features, int32_t* out_info, uint16_t* out_rows);
 
+/* same, for placements at an explicit row (row u8[N] = row of the piece's top bbox row, 255 => hard drop): the piece
+ * only has to fit there — State.future(zoid, rot, row, col) (game.py:166) does not check support either — which
+ * covers the states produced by the overhang-slide move set.  row may be NULL (= tb200_eval_features). */
+int tb200_eval_features_at(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
+                           const uint16_t* prev_boards, const uint8_t* piece, const uint8_t* rot, const uint8_t* col, const uint8_t* row,
+                           double* out_features, int32_t* out_info, uint16_t* out_rows);
+
 /* materialise the counter-based piece stream (K4): out u8[n_streams][T], stream ids first_stream.. */
 int tb200_hashed_pieces(tb200_ctx* ctx, int32_t mem, void* stream, uint64_t seed, uint64_t first_stream,
                         int32_t n_streams, uint32_t T, uint8_t* out);

@@ -190,3 +190,30 @@ def test_simulate_with_pressure_chunked(eng, chunk, monkeypatch):
             trace += bytes([d.rot, d.row, d.col, len(d.cleared)])
             last = st
         assert trace.hex() == g["trace_hex"] and last.score() == g["score"], (g["seed"], chunk)
+
+
+def test_evaluate_on_slide_states(eng):
+    """feature.evaluate on states produced by overhang slides (explicit-row K3 path) equals the C oracle's features."""
+    from conftest import load_golden
+    from tetris_ai_b200 import feature
+    from tetris_ai_b200.tetris import features as F
+    from tetris_ai_b200.tetris.game import Board, State, PIECES
+    feats = [getattr(F, n) for n in pyoracle.FEATURE_NAMES]
+    checked = 0
+    for b in load_golden("slide_moves.json")["boards"][:40]:
+        for p, moves in enumerate(b["moves"]):
+            base = set(coracle.moves(b["board"], p, "drop"))
+            for rot, row, col in moves:
+                if (rot, row, col) in base:
+                    continue
+                root = State(None, Board(masks=b["board"]))
+                node = root.future(PIECES[p], rot, row, col)
+                vals = feature.evaluate(node, feats, engine=eng)
+                onode = pyoracle.Node(None, pyoracle.Grid.from_rows(b["board"])).child(p, rot, row, col)
+                want = pyoracle.all_features(onode)
+                for f, wv in zip(feats, want):
+                    assert float(vals[f]) == float(wv), (f, vals[f], wv)
+                checked += 1
+                if checked >= 60:
+                    return
+    assert checked > 10

@@ -48,7 +48,7 @@ class Timing(ctypes.Structure):
 EXPORTS = (
     "tb200_create", "tb200_destroy", "tb200_last_error", "tb200_version", "tb200_device_info",
     "tb200_set_features", "tb200_play_games", "tb200_last_timing", "tb200_best_move",
-    "tb200_eval_features", "tb200_hashed_pieces", "tb200_alloc_pinned", "tb200_free_pinned",
+    "tb200_eval_features", "tb200_eval_features_at", "tb200_hashed_pieces", "tb200_alloc_pinned", "tb200_free_pinned",
 )
 
 _LIB = None
@@ -85,6 +85,8 @@ def load():
     L.tb200_best_move.restype = ctypes.c_int
     L.tb200_eval_features.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp]
     L.tb200_eval_features.restype = ctypes.c_int
+    L.tb200_eval_features_at.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.tb200_eval_features_at.restype = ctypes.c_int
     L.tb200_hashed_pieces.argtypes = [vp, i32, vp, u64, u64, i32, u32, vp]
     L.tb200_hashed_pieces.restype = ctypes.c_int
     L.tb200_alloc_pinned.argtypes = [ctypes.c_size_t, ctypes.POINTER(vp)]

@@ -1018,8 +1018,10 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6grp_kernel(const PlayParam
 }
 
 // K3: all 45 features of one placement per thread
+// at_row (optional): row of the piece's top bbox row; 255 / null => hard drop.  With an explicit row the placement only
+// has to fit (State.future does not check support either), which covers the overhang-slide placements.
 __global__ void eval_features_kernel(int N, const uint16_t* prev_boards, const uint8_t* piece, const uint8_t* rot,
-                                     const uint8_t* col, double* out_features, int32_t* out_info, uint16_t* out_rows)
+                                     const uint8_t* col, const uint8_t* at_row, double* out_features, int32_t* out_info, uint16_t* out_rows)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
@@ -1042,7 +1044,15 @@ __global__ void eval_features_kernel(int N, const uint16_t* prev_boards, const u
             if ((int)((d.w[0] >> 4) & 3u) == (int)rot[i] && (int)(d.w[0] & 15u) == (int)col[i]) {
                 found = true;
                 dsel = d;
-                if (place_slot(c, H, d, P)) { legal = 1; row = ROWS - P.y - P.ph; k = P.k; }
+                if (at_row && at_row[i] != 255) {
+                    const int ph = (int)((d.w[0] >> 9) & 7u), y = ROWS - (int)at_row[i] - ph;
+                    if (fits_at(c, d, y)) {
+                        uint32_t full;
+                        place_at(c, d, y, P, &full);
+                        if (full != 0u) place_clear(d, P, full);
+                        legal = 1; row = (int)at_row[i]; k = P.k;
+                    }
+                } else if (place_slot(c, H, d, P)) { legal = 1; row = ROWS - P.y - P.ph; k = P.k; }
                 break;
             }
         }
@@ -1579,9 +1589,9 @@ int tb200_best_move(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
     return TB200_OK;
 }
 
-int tb200_eval_features(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
-                        const uint16_t* prev_boards, const uint8_t* piece, const uint8_t* rot, const uint8_t* col,
-                        double* out_features, int32_t* out_info, uint16_t* out_rows)
+int tb200_eval_features_at(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
+                           const uint16_t* prev_boards, const uint8_t* piece, const uint8_t* rot, const uint8_t* col, const uint8_t* row,
+                           double* out_features, int32_t* out_info, uint16_t* out_rows)
 {
     if (!ctx) return TB200_E_BAD_ARG;
     if (N < 1 || !prev_boards || !piece || !rot || !col || !out_features || !out_info) return fail(ctx, TB200_E_BAD_ARG, "eval_features: missing argument");
@@ -1589,14 +1599,15 @@ int tb200_eval_features(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
     TB_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t n = (size_t)N;
     if (mem == TB200_MEM_DEVICE) {
-        tb::eval_features_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, prev_boards, piece, rot, col, out_features, out_info, out_rows);
+        tb::eval_features_kernel<<<(N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, prev_boards, piece, rot, col, row, out_features, out_info, out_rows);
         TB_CUDA(ctx, cudaGetLastError());
         return TB200_OK;
     }
     cudaStream_t st = ctx->own_stream;
     size_t off = 0;
     auto take = [&](size_t b) { size_t o = off; off += align_up(b); return o; };
-    const size_t o_b = take(40 * n), o_p = take(n), o_r = take(n), o_c = take(n), o_f = take(8 * 45 * n), o_i = take(12 * n), o_rows = take(out_rows ? 40 * n : 0);
+    const size_t o_b = take(40 * n), o_p = take(n), o_r = take(n), o_c = take(n), o_f = take(8 * 45 * n), o_i = take(12 * n), o_rows = take(out_rows ? 40 * n : 0),
+                 o_ar = take(row ? n : 0);
     int rc = ensure_arena(ctx, off);
     if (rc) return rc;
     char* base = ctx->d_arena;
@@ -1604,8 +1615,9 @@ int tb200_eval_features(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
     TB_CUDA(ctx, cudaMemcpyAsync(base + o_p, piece, n, cudaMemcpyHostToDevice, st));
     TB_CUDA(ctx, cudaMemcpyAsync(base + o_r, rot, n, cudaMemcpyHostToDevice, st));
     TB_CUDA(ctx, cudaMemcpyAsync(base + o_c, col, n, cudaMemcpyHostToDevice, st));
+    if (row) TB_CUDA(ctx, cudaMemcpyAsync(base + o_ar, row, n, cudaMemcpyHostToDevice, st));
     tb::eval_features_kernel<<<(N + 127) / 128, 128, 0, st>>>(N, (const uint16_t*)(base + o_b), (const uint8_t*)(base + o_p),
-        (const uint8_t*)(base + o_r), (const uint8_t*)(base + o_c), (double*)(base + o_f), (int32_t*)(base + o_i),
+        (const uint8_t*)(base + o_r), (const uint8_t*)(base + o_c), row ? (const uint8_t*)(base + o_ar) : nullptr, (double*)(base + o_f), (int32_t*)(base + o_i),
         out_rows ? (uint16_t*)(base + o_rows) : nullptr);
     TB_CUDA(ctx, cudaGetLastError());
     TB_CUDA(ctx, cudaMemcpyAsync(out_features, base + o_f, 8 * 45 * n, cudaMemcpyDeviceToHost, st));
@@ -1613,6 +1625,13 @@ int tb200_eval_features(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
     if (out_rows) TB_CUDA(ctx, cudaMemcpyAsync(out_rows, base + o_rows, 40 * n, cudaMemcpyDeviceToHost, st));
     TB_CUDA(ctx, cudaStreamSynchronize(st));
     return TB200_OK;
+}
+
+int tb200_eval_features(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
+                        const uint16_t* prev_boards, const uint8_t* piece, const uint8_t* rot, const uint8_t* col,
+                        double* out_features, int32_t* out_info, uint16_t* out_rows)
+{
+    return tb200_eval_features_at(ctx, mem, stream, N, prev_boards, piece, rot, col, nullptr, out_features, out_info, out_rows);
 }
 
 int tb200_hashed_pieces(tb200_ctx* ctx, int32_t mem, void* stream, uint64_t seed, uint64_t first_stream,

@@ -199,17 +199,18 @@ class Engine:
         return {"move": move, "score": score, "count": count, "rows": rows}
 
     # ------------------------------------------------------------------ K3 features of placements
-    def eval_features(self, prev_boards, piece, rot, col, want_rows=False):
+    def eval_features(self, prev_boards, piece, rot, col, want_rows=False, row=None):
         prev = np.ascontiguousarray(prev_boards, dtype=np.uint16).reshape(-1, 20)
         N = prev.shape[0]
         piece = np.ascontiguousarray(piece, dtype=np.uint8).reshape(N)
         rot = np.ascontiguousarray(rot, dtype=np.uint8).reshape(N)
         col = np.ascontiguousarray(col, dtype=np.uint8).reshape(N)
+        at_row = np.ascontiguousarray(row, dtype=np.uint8).reshape(N) if row is not None else None
         feats = np.zeros((N, _lib.NUM_FEATURES), dtype=np.float64)
         info = np.zeros((N, 3), dtype=np.int32)
         rows = np.zeros((N, 20), dtype=np.uint16) if want_rows else None
-        self._check(self._L.tb200_eval_features(self._h, _lib.MEM_HOST, None, N, _ptr(prev), _ptr(piece), _ptr(rot), _ptr(col),
-                                                _ptr(feats), _ptr(info), _ptr(rows)))
+        self._check(self._L.tb200_eval_features_at(self._h, _lib.MEM_HOST, None, N, _ptr(prev), _ptr(piece), _ptr(rot), _ptr(col),
+                                                   _ptr(at_row), _ptr(feats), _ptr(info), _ptr(rows)))
         return {"features": feats, "legal": info[:, 0], "row": info[:, 1], "k": info[:, 2], "rows": rows}
 
     # ------------------------------------------------------------------ K4 piece stream

@@ -76,9 +76,9 @@ def device_features(state, engine=None):
         raise ValueError("device features need a state with a previous state and a delta (a placed piece)")
     eng = engine or default_engine()
     d = state.delta
-    r = eng.eval_features([state.prev.board.rows16()], [d.zoid.id], [d.rot], [d.col])
-    if int(r["legal"][0]) != 1 or int(r["row"][0]) != int(d.row):
-        raise ValueError("state.delta is not a hard-drop placement of its previous state")
+    r = eng.eval_features([state.prev.board.rows16()], [d.zoid.id], [d.rot], [d.col], row=[d.row])
+    if int(r["legal"][0]) != 1:
+        raise ValueError("state.delta does not fit on its previous state's board")
     return r["features"][0]
 
 
