@@ -217,3 +217,38 @@ def test_evaluate_on_slide_states(eng):
                 if checked >= 60:
                     return
     assert checked > 10
+
+
+def test_cross_entropy_six_generations_vs_c_oracle(eng):
+    """A longer CE run (later generations: most games reach the cap): GPU evaluation vs the plain-C oracle evaluation must give
+    bit-identical means / standard deviations generation after generation (one mismatched placement anywhere would diverge)."""
+    from tetris_ai_b200.learning import PopulationEvaluator, cross_entropy
+    from tetris_ai_b200.tetris import features as F
+    names = ["landing_height", "eroded_cells", "row_trans", "col_trans", "pits", "cuml_wells"]
+    feats = [getattr(F, n) for n in names]
+    fids = [pyoracle.FEATURE_ID[n] for n in names]
+    G, T, width, keep = 6, 500, 60, 8
+    seqs = np.array([pyoracle.piece_sequence(2000 + g, T) for g in range(G)], dtype=np.uint8)
+    ev = PopulationEvaluator(eng, feats, G, pieces=seqs)
+    gpu = cross_entropy(feats, 10.0, width, keep, random.Random(7), ev.test_f, map_f=ev.map_f)
+
+    batch = []
+
+    def test_f(wd):
+        batch.append(list(wd.values()))
+
+    def map_f(fn, it):
+        idx = list(it)
+        batch.clear()
+        for i in idx:
+            fn(i)
+        res = coracle.play_games(fids, np.array(batch), G, pieces=seqs, threads=16)
+        fit = res["lines"].reshape(len(idx), G).sum(axis=1) / G
+        return [(float(fit[i]), i) for i in idx]
+
+    cpu = cross_entropy(feats, 10.0, width, keep, random.Random(7), test_f, map_f=map_f)
+    for g in range(6):
+        (m1, s1), (m2, s2) = next(gpu), next(cpu)
+        assert [float(v).hex() for v in m1.values()] == [float(v).hex() for v in m2.values()], g
+        assert [float(v).hex() for v in s1.values()] == [float(v).hex() for v in s2.values()], g
+    assert float(np.max(ev.last["fitness"])) > 50.0           # the population has learned to clear lines

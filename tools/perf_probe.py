@@ -58,6 +58,15 @@ def main():
             ms, out = timeit(eng, 2, weights=w, games_per_candidate=1, T=400, seed=5, seq_of_game=np.arange(n, dtype=np.int32), lanes=lanes)
             pl = int(out["results"]["placements"].sum())
             rows.append(("sweep %d games T=400" % n, lanes, ms, pl, int(out["results"]["pieces"].sum())))
+    # BASELINE configs[2] shard: 10 000 candidates x 30 games over 8 GPUs = 1 250 x 30 per GPU (w6, T = 1000, generation-1-like population)
+    import json as _json
+    ce = _json.load(open(os.path.join(ROOT, "tests", "golden", "ce.json")))["ce"]
+    mean = np.array([float.fromhex(x) for x in ce["generations"][0]["mean"]]); std = np.array([float.fromhex(x) for x in ce["generations"][0]["std"]])
+    w3 = mean[None, :] + std[None, :] * rng.normal(0, 1.0, size=(1250, 6))
+    seqs30 = np.array([[random.Random(1000 + g).randrange(7) for _ in range(1000)] for g in range(30)], dtype=np.uint8)
+    for lanes in (0, 32, 8, 4):
+        ms, out = timeit(eng, 2, weights=w3, games_per_candidate=30, pieces=seqs30, lanes=lanes)
+        rows.append(("config3 shard 1250x30 T=1000", eng.last_timing()["lanes"], ms, int(out["results"]["placements"].sum()), int(out["results"]["pieces"].sum())))
     # all-45 and lookahead-2
     eng.set_features(list(range(45)))
     w = rng.normal(0, 0.3, size=(4096, 45))
