@@ -52,6 +52,8 @@ extern "C" {
 #define TB200_MOVES_DROP            0
 #define TB200_MOVES_OVERHANG_SLIDE  1
 #define TB200_MOVES_PRESSURE        2
+#define TB200_MOVES_WIGGLE          4      /* move_wiggle: flood fill from the top of every column (simulator.py:81-85); lookahead 1 */
+#define TB200_MOVES_WIGGLE_DROP     8      /* move_with_wiggle(move_drop) (simulator.py:49-77); lookahead 1 */
 
 #define TB200_MEM_HOST   0
 #define TB200_MEM_DEVICE 1
@@ -96,7 +98,8 @@ typedef struct {
     uint16_t* final_rows;            /* u16[C*G][20] final boards, or NULL */
     double*   fitness;               /* f64[C] = total lines of the candidate's games / G, or NULL */
     int32_t   move_set;              /* TB200_MOVES_DROP = move_drop (simulator.py:3-13), optionally OR-ed with
-                                        TB200_MOVES_OVERHANG_SLIDE: move_with_overhang_slide(...) (simulator.py:15-47) and / or
+                                        TB200_MOVES_OVERHANG_SLIDE: move_with_overhang_slide(...) (simulator.py:15-47), or with
+                                        TB200_MOVES_WIGGLE / TB200_MOVES_WIGGLE_DROP (simulator.py:49-85), and / or
                                         TB200_MOVES_PRESSURE: move_with_pressure(...) as the OUTERMOST wrapper (simulator.py:88-120) */
     int32_t   pressure_two_but_rot;  /* move_with_pressure(two_but_rot=...) */
     double    pressure_avg_lat;      /* move_with_pressure(avg_lat=250.9, resp_time=79.8, move_eff=1.23) — no defaults here */

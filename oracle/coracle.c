@@ -130,6 +130,41 @@ static int slide_moves(const board_t* b, int piece, int mv[MAX_MOVES][3])
     return n;
 }
 
+/* simulator.py:49-85 move_with_wiggle / move_wiggle: depth-first flood fill of the positions the piece can reach by moving
+ * down, left and right (in that order) from each start; a position where the piece cannot move down is a move.  `seen` is
+ * shared by all starts of one piece, so the ORDER of the move list is the order of the recursion. */
+typedef struct { uint8_t seen[4][ROWS + 2][COLS + 2]; int (*mv)[3]; int n; const board_t* b; int piece; } wiggle_t;
+
+static void wiggle_rec(wiggle_t* wg, int rot, int row, int col)
+{
+    if (wg->seen[rot][row][col]) return;                                  /* :52 */
+    wg->seen[rot][row][col] = 1;
+    const shape_t* s = &SHAPES[wg->piece][rot];
+    if (collides(wg->b, s, row, col)) return;                             /* :54 */
+    if (collides(wg->b, s, row + 1, col)) {                               /* :55-57 resting: a move */
+        wg->mv[wg->n][0] = rot; wg->mv[wg->n][1] = row; wg->mv[wg->n][2] = col; ++wg->n;
+    } else {
+        wiggle_rec(wg, rot, row + 1, col);                                /* :58-60 */
+    }
+    if (col > 0) wiggle_rec(wg, rot, row, col - 1);                       /* :63-64 */
+    if (col + s->w <= COLS) wiggle_rec(wg, rot, row, col + 1);            /* :65-66 */
+}
+
+/* from_top != 0: move_wiggle (starts (rot, 0, col) for every rot, col); else move_with_wiggle(move_drop) */
+static int wiggle_moves(const board_t* b, int piece, int from_top, int mv[MAX_MOVES][3])
+{
+    wiggle_t wg; memset(&wg, 0, sizeof wg);
+    wg.mv = mv; wg.b = b; wg.piece = piece;
+    if (from_top) {
+        for (int rot = 0; rot < NROT[piece]; ++rot)
+            for (int col = 0; col <= COLS - SHAPES[piece][rot].w; ++col) wiggle_rec(&wg, rot, 0, col);
+    } else {
+        int base[34][3]; int nb = drop_moves(b, piece, base);
+        for (int i = 0; i < nb; ++i) wiggle_rec(&wg, base[i][0], base[i][1], base[i][2]);
+    }
+    return wg.n;
+}
+
 /* simulator.py:88-120 move_with_pressure: keep a move iff the time to key it in fits before the piece locks.
  * press = {avg_lat, resp_time, move_eff, two_but_rot}; level = state.level() of the state the move is generated from. */
 static const int START_COL[7][4] = {{3, 5, 0, 0}, {4, 4, 4, 5}, {4, 4, 4, 5}, {4, 4, 4, 5}, {4, 0, 0, 0}, {4, 5, 0, 0}, {4, 5, 0, 0}};   /* I,T,L,J,O,Z,S :92-100 */
@@ -148,11 +183,14 @@ static int is_time(int piece, int rot, int row, int col, const double* press, in
     return t <= (double)limit;
 }
 
-/* move_set bit 0: overhang slides; bit 1: pressure filter applied to whatever the inner generator yields */
+/* move_set bit 0: overhang slides; bit 2: move_wiggle; bit 3: move_with_wiggle(move_drop); bit 1: pressure filter applied to
+ * whatever the inner generator yields */
 static int gen_moves(const board_t* b, int piece, int move_set, const double* press, int level, int mv[MAX_MOVES][3])
 {
     int n;
-    if (move_set & 1) n = slide_moves(b, piece, mv);
+    if (move_set & 4) n = wiggle_moves(b, piece, 1, mv);
+    else if (move_set & 8) n = wiggle_moves(b, piece, 0, mv);
+    else if (move_set & 1) n = slide_moves(b, piece, mv);
     else {
         int base[34][3]; n = drop_moves(b, piece, base);
         for (int i = 0; i < n; ++i) { mv[i][0] = base[i][0]; mv[i][1] = base[i][1]; mv[i][2] = base[i][2]; }
@@ -342,7 +380,7 @@ int co_moves(const uint16_t rows[ROWS], int piece, int move_set, int* moves)
     init_shapes();
     board_t b; rows_to_board(rows, &b);
     static __thread int mv[MAX_MOVES][3];
-    int n = gen_moves(&b, piece, move_set & 1, 0, 0, mv);
+    int n = gen_moves(&b, piece, move_set & 13, 0, 0, mv);
     for (int i = 0; i < n; ++i) { moves[3 * i] = mv[i][0]; moves[3 * i + 1] = mv[i][1]; moves[3 * i + 2] = mv[i][2]; }
     return n;
 }

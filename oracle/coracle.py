@@ -62,7 +62,7 @@ def drop_moves(rows, piece):
     return [tuple(int(x) for x in mv[i]) for i in range(n)]
 
 
-MOVE_SETS = {"drop": 0, "slide": 1, 0: 0, 1: 1}
+MOVE_SETS = {"drop": 0, "slide": 1, "wiggle_top": 4, "wiggle_drop": 8, 0: 0, 1: 1, 4: 4, 8: 8}
 
 
 def _pressure(pressure):

@@ -209,7 +209,45 @@ def slide_moves(node, piece):
     return out
 
 
-MOVE_GENERATORS = {"drop": drop_moves, "slide": slide_moves}
+def _wiggle(node, piece, starts):
+    """cogworks/tetris/simulator.py:49-77 move_with_wiggle: depth-first flood fill (down, then left, then right) from each
+    start with a `seen` set shared by all starts; a position that cannot move down is a move; the list order is the
+    recursion order."""
+    import sys
+    sys.setrecursionlimit(max(sys.getrecursionlimit(), 5000))
+    g = node.grid
+    seen = set()
+    out = []
+
+    def rec(rot, row, col):
+        if (rot, row, col) in seen:
+            return
+        seen.add((rot, row, col))
+        shape = PIECES[piece][rot]
+        if g.collides(shape, row, col):
+            return
+        if g.collides(shape, row + 1, col):
+            out.append((rot, row, col))
+        else:
+            rec(rot, row + 1, col)
+        if col > 0:
+            rec(rot, row, col - 1)
+        if col + shape.shape[1] <= COLS:
+            rec(rot, row, col + 1)
+    for rot, row, col in starts:
+        rec(rot, row, col)
+    return out
+
+
+def wiggle_moves_top(node, piece):        # simulator.py:81-85 move_wiggle
+    return _wiggle(node, piece, [(rot, 0, col) for rot, shape in enumerate(PIECES[piece]) for col in range(COLS - shape.shape[1] + 1)])
+
+
+def wiggle_moves_drop(node, piece):       # move_with_wiggle(move_drop)
+    return _wiggle(node, piece, drop_moves(node, piece))
+
+
+MOVE_GENERATORS = {"drop": drop_moves, "slide": slide_moves, "wiggle_top": wiggle_moves_top, "wiggle_drop": wiggle_moves_drop}
 
 _START_COL = {"O": [4], "L": [4, 4, 4, 5], "J": [4, 4, 4, 5], "S": [4, 5], "Z": [4, 5], "T": [4, 4, 4, 5], "I": [3, 5]}
 _BRACKETS = [(29, 20), (19, 30), (16, 50), (13, 70), (10, 80), (9, 100), (8, 130), (7, 220), (6, 300), (5, 380),

@@ -20,6 +20,30 @@ static int pick_mode(const int* ids, int F)
     return is_w6 ? MODE_W6 : (is_all ? MODE_ALL45 : MODE_GENERIC);
 }
 
+// move list of move_wiggle (from_top) / move_with_wiggle(move_drop): entries = slot | y << 8 in the reference's order
+static int wiggle_list(const uint32_t c[COLS], const Heights& H, int piece, bool from_top, uint16_t* out, int cap)
+{
+    const Tables& tab = host_tables();
+    int n = 0, s0 = 0;
+    while (s0 < tab.nslots[piece]) {
+        const int rot = (int)((tab.slot[piece][s0].w[0] >> 4) & 3u), w = (int)((tab.slot[piece][s0].w[0] >> 6) & 7u), ph = (int)((tab.slot[piece][s0].w[0] >> 9) & 7u);
+        const int ncol = COLS - w + 1;
+        uint32_t fm[COLS + 1]; uint16_t starts[COLS]; int ns = 0;
+        for (int i = 0; i <= COLS; ++i) fm[i] = 0;
+        for (int col = 0; col < ncol; ++col) {
+            fm[col] = free_mask(c, tab.slot[piece][s0 + col]);
+            if (from_top) starts[ns++] = (uint16_t)((ROWS - ph) | col << 8);
+            else { Placement P; if (place_slot(c, H, tab.slot[piece][s0 + col], P)) starts[ns++] = (uint16_t)(P.y | col << 8); }
+        }
+        uint16_t stack[256]; uint32_t seen[COLS + 1]; uint16_t lst[256];
+        const int m = wiggle_rot(fm, w, starts, ns, stack, seen, lst, 256);
+        for (int i = 0; i < m && n < cap; ++i) out[n++] = (uint16_t)((uint32_t)(s0 + (lst[i] >> 8)) | (uint32_t)(lst[i] & 31u) << 8);
+        (void)rot;
+        s0 += ncol;
+    }
+    return n;
+}
+
 // candidate bookkeeping: maximise key, ties -> smallest tag (enumeration order); mv = placement to commit
 struct Best { uint64_t key; uint32_t tag; uint32_t mv; };
 
@@ -38,6 +62,18 @@ static void search_one(const uint32_t c[COLS], const Heights& H, const PrevStat&
         if (k > best.key || (k == best.key && tg < best.tag)) { best.key = k; best.tag = tg; best.mv = leaf_is_first ? mv : mv1; }
         ++cnt;
     };
+    if (move_set & 12) {                 // wiggle move sets: the list order is the tag order
+        uint16_t lst[640];
+        const int m = wiggle_list(c, H, piece, (move_set & 4) != 0, lst, 640);
+        for (int i = 0; i < m; ++i) {
+            const SlotDesc& d2 = tab.slot[piece][lst[i] & 255u];
+            Placement P2; uint32_t full;
+            place_at(c, d2, (int)(lst[i] >> 8), P2, &full);
+            if (full != 0u) place_clear(d2, P2, full);
+            consider(P2, d2, tag_hi | (uint32_t)i, (uint32_t)lst[i]);
+        }
+        return;
+    }
     for (int s = 0; s < tab.nslots[piece]; ++s) {
         Placement P;
         if (!place_slot(c, H, tab.slot[piece][s], P)) continue;
@@ -220,6 +256,15 @@ int emu_moves(const uint16_t* rows, int piece, int move_set, int* out)
     rows_to_cols(rows, c);
     const Heights H = pack_heights(c);
     int n = 0;
+    if (move_set & 12) {
+        uint16_t lst[640];
+        const int m = wiggle_list(c, H, piece, (move_set & 4) != 0, lst, 640);
+        for (int i = 0; i < m; ++i) {
+            const SlotDesc& d2 = tab.slot[piece][lst[i] & 255u];
+            out[3 * n] = (int)((d2.w[0] >> 4) & 3u); out[3 * n + 1] = ROWS - (int)(lst[i] >> 8) - (int)((d2.w[0] >> 9) & 7u); out[3 * n + 2] = (int)(d2.w[0] & 15u); ++n;
+        }
+        return n;
+    }
     for (int s = 0; s < tab.nslots[piece]; ++s) {
         Placement P;
         if (!place_slot(c, H, tab.slot[piece][s], P)) continue;

@@ -105,11 +105,15 @@ def all_features(state):
     return [feat_value(vals[f]) for f in FEATS]
 
 
-def play(named_weights, seed, T, lookahead=1, tie=tie_first, keep_trace=True, slide=False, pressure=None):
+def play(named_weights, seed, T, lookahead=1, tie=tie_first, keep_trace=True, slide=False, pressure=None, wiggle=None):
     """Canonical game: returns summary + byte trace [rot,row,col,k]*.
     slide=True: move_gen = move_with_overhang_slide(move_drop) (simulator.py:15-47) instead of move_drop.
     pressure=dict(...): wrap the generator in move_with_pressure(gen, **pressure) (simulator.py:88-120)."""
     move_gen = ref_sim.move_with_overhang_slide(ref_sim.move_drop) if slide else ref_sim.move_drop
+    if wiggle == "top":                         # move_wiggle: flood fill from the top of every column (simulator.py:81-85)
+        move_gen = ref_sim.move_wiggle
+    elif wiggle == "drop":                      # move_with_wiggle(move_drop) (simulator.py:49-77)
+        move_gen = ref_sim.move_with_wiggle(ref_sim.move_drop)
     if pressure is not None:
         move_gen = ref_sim.move_with_pressure(move_gen, **pressure)
     weights = weights_by_name(named_weights)
@@ -138,7 +142,7 @@ def play(named_weights, seed, T, lookahead=1, tie=tie_first, keep_trace=True, sl
         "scorer_calls": calls[0], "score": int(score),
         "trace_sha16": hashlib.sha256(bytes(trace)).hexdigest()[:16],
         "final_board": board_rows(last.board),
-        "move_gen": "overhang_slide" if slide else "drop",
+        "move_gen": ("wiggle_" + wiggle) if wiggle else ("overhang_slide" if slide else "drop"),
         "pressure": pressure,
     }
     if keep_trace:
@@ -285,6 +289,27 @@ def gen_slide_moves(seed=5, n_games=10, max_pieces=60):
     return out
 
 
+def gen_wiggle_moves(seed=6, n_games=6, max_pieces=50):
+    """Boards (with overhangs / tucks) -> exact move lists of move_wiggle and move_with_wiggle(move_drop) for every piece."""
+    rng = random.Random(seed)
+    drop_w = ref_sim.move_with_wiggle(ref_sim.move_drop)
+    out = []
+    for g in range(n_games):
+        state = State(None, Board(20, 10))
+        for t in range(max_pieces):
+            zoid = PIECES[rng.randrange(7)]
+            moves = list(ref_sim.move_wiggle(state, zoid))
+            if not moves:
+                break
+            if t % 4 == 0 or len(moves) > len(list(ref_sim.move_drop(state, zoid))):
+                out.append({"board": board_rows(state.board),
+                            "top": [[[int(x) for x in m] for m in ref_sim.move_wiggle(state, z)] for z in PIECES],
+                            "drop": [[[int(x) for x in m] for m in drop_w(state, z)] for z in PIECES]})
+            state = state.future(zoid, *moves[rng.randrange(len(moves))])
+            state.prev = None
+    return out
+
+
 # ----------------------------------------------------------------------------- CE fixture
 _CE_FN = None
 
@@ -425,7 +450,7 @@ def main():
     sgames.append(play(w45b, 1, 200, slide=True))
     dump("games_slide.json", {"meta": meta, "games": sgames})
     print("slide games:", len(sgames), round(time.time() - t0, 1), "s", flush=True)
-    dump("slide_moves.json", {"meta": meta, "boards": gen_slide_moves()})
+    dump("slide_moves.json.gz", {"meta": meta, "boards": gen_slide_moves()})
 
     # §8f rank 3: move_with_pressure (human time-pressure filter, level-dependent)
     t0 = time.time()
@@ -439,6 +464,21 @@ def main():
     pgames.append(play(W6, 0, 60, lookahead=2, pressure={}))
     pgames.append(play(w45b, 0, 400, pressure={"avg_lat": 300.0}))
     dump("games_pressure.json", {"meta": meta, "games": pgames})
+
+    # §8f rank 4: move_wiggle / move_with_wiggle(move_drop) (DFS flood fill; the move ORDER is the recursion order)
+    t0 = time.time()
+    wgames = []
+    for s in (0, 1):
+        wgames.append(play(W6, s, 120, wiggle="top"))
+    for s in (0, 1, 2):
+        wgames.append(play(holes, s, 300, wiggle="top"))
+    wgames.append(play(holes, 3, 300, wiggle="drop"))
+    wgames.append(play(W6, 2, 120, wiggle="drop"))
+    wgames.append(play(ties, 0, 200, wiggle="top"))
+    wgames.append(play(W6, 3, 150, wiggle="top", pressure={}))
+    dump("games_wiggle.json", {"meta": meta, "games": wgames})
+    print("wiggle games:", len(wgames), round(time.time() - t0, 1), "s", flush=True)
+    dump("wiggle_moves.json.gz", {"meta": meta, "boards": gen_wiggle_moves()})
     print("pressure games:", len(pgames), round(time.time() - t0, 1), "s", flush=True)
     print("games:", len(games), round(time.time() - t0, 1), "s", flush=True)
 

@@ -157,7 +157,7 @@ def test_emu_fast_w6_path_vs_coracle(golden_games):
 # ------------------------------------------------------------------------------------------------
 def test_emu_slide_move_lists():
     from conftest import load_golden
-    boards = load_golden("slide_moves.json")["boards"]
+    boards = load_golden("slide_moves.json.gz")["boards"]
     for i, b in enumerate(boards):
         for p, want in enumerate(b["moves"]):
             assert [list(m) for m in emu_lib.moves(b["board"], p, 1)] == want, (i, p)
@@ -225,5 +225,44 @@ def test_emu_pressure_vs_coracle_random():
             seq = seq[:40]
         a = coracle.play_one(fids, w, seq, la, move_set=ms, pressure=pr)
         b = emu_lib.play_one(fids, w, seq, lookahead=la, move_set=ms, pressure=pr)
+        assert (a["pieces"], a["lines"], a["score"], a["placements"]) == (b["pieces"], b["lines"], b["score"], b["placements"]), gi
+        assert a["trace"].tobytes() == b["trace"].tobytes(), gi
+
+
+# ------------------------------------------------------------------------------------------------
+# move_wiggle / move_with_wiggle(move_drop) in the CUDA core (host build)
+# ------------------------------------------------------------------------------------------------
+def test_emu_wiggle_move_lists():
+    from conftest import load_golden
+    for i, b in enumerate(load_golden("wiggle_moves.json.gz")["boards"]):
+        for p in range(7):
+            assert [list(m) for m in emu_lib.moves(b["board"], p, 4)] == b["top"][p], (i, p)
+            assert [list(m) for m in emu_lib.moves(b["board"], p, 8)] == b["drop"][p], (i, p)
+
+
+def test_emu_wiggle_games():
+    from conftest import load_golden
+    for g in load_golden("games_wiggle.json")["games"]:
+        fids = [pyoracle.FEATURE_ID[n] for n, _ in g["weights"]]
+        w = [x for _, x in g["weights"]]
+        seq = pyoracle.piece_sequence(g["seed"], g["T"])
+        ms = 4 if g["move_gen"] == "wiggle_top" else 8
+        res = emu_lib.play_one(fids, w, seq, lookahead=g["lookahead"], move_set=ms, pressure=g["pressure"])
+        assert res["pieces"] == g["pieces"] and res["lines"] == g["lines"] and res["score"] == g["score"]
+        assert res["placements"] == g["scorer_calls"] and res["trace"].tobytes().hex() == g["trace_hex"]
+
+
+def test_emu_wiggle_vs_coracle_random():
+    rng = random.Random(77)
+    for gi in range(40):
+        if gi % 2:
+            names, w = ["max_ht", "row_trans", "pits", "landing_height"], [-1.0, rng.gauss(-0.2, 0.2), rng.gauss(0.4, 0.3), -0.5]
+        else:
+            names, w = W6_NAMES, [rng.gauss(v, 2.0) for v in W6_VALS]
+        fids = [pyoracle.FEATURE_ID[n] for n in names]
+        seq = [pyoracle.hashed_piece(55, gi, t) for t in range(200)]
+        ms = ("wiggle_top", 4) if gi % 4 < 2 else ("wiggle_drop", 8)
+        a = coracle.play_one(fids, w, seq, 1, move_set=ms[0])
+        b = emu_lib.play_one(fids, w, seq, move_set=ms[1])
         assert (a["pieces"], a["lines"], a["score"], a["placements"]) == (b["pieces"], b["lines"], b["score"], b["placements"]), gi
         assert a["trace"].tobytes() == b["trace"].tobytes(), gi

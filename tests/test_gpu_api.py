@@ -200,7 +200,7 @@ def test_evaluate_on_slide_states(eng):
     from tetris_ai_b200.tetris.game import Board, State, PIECES
     feats = [getattr(F, n) for n in pyoracle.FEATURE_NAMES]
     checked = 0
-    for b in load_golden("slide_moves.json")["boards"][:40]:
+    for b in load_golden("slide_moves.json.gz")["boards"][:40]:
         for p, moves in enumerate(b["moves"]):
             base = set(coracle.moves(b["board"], p, "drop"))
             for rot, row, col in moves:
@@ -252,3 +252,22 @@ def test_cross_entropy_six_generations_vs_c_oracle(eng):
         assert [float(v).hex() for v in m1.values()] == [float(v).hex() for v in m2.values()], g
         assert [float(v).hex() for v in s1.values()] == [float(v).hex() for v in s2.values()], g
     assert float(np.max(ev.last["fitness"])) > 50.0           # the population has learned to clear lines
+
+
+def test_simulate_with_wiggle(eng):
+    from conftest import load_golden
+    from tetris_ai_b200.tetris import simulator as sim
+    from tetris_ai_b200.tetris.game import Board, State, PIECES
+    for g in load_golden("games_wiggle.json")["games"][:5]:
+        gen = sim.move_wiggle if g["move_gen"] == "wiggle_top" else sim.move_with_wiggle(sim.move_drop)
+        if g["pressure"] is not None:
+            gen = sim.move_with_pressure(gen, **g["pressure"])
+        policy = sim.policy_best(sim.linear_scorer(_weights(g["weights"])), sim.tie_first)
+        seq = pyoracle.piece_sequence(g["seed"], g["T"])
+        trace = bytearray()
+        last = State(None, Board(20, 10))
+        for st in sim.simulate(last, iter(PIECES[i] for i in seq), gen, policy, engine=eng):
+            d = st.delta
+            trace += bytes([d.rot, d.row, d.col, len(d.cleared)])
+            last = st
+        assert trace.hex() == g["trace_hex"] and last.score() == g["score"]

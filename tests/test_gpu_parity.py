@@ -406,3 +406,53 @@ def test_pressure_vs_coracle(eng, lookahead, C, G, T, ms):
         assert (r["trace"][g, :n] == o["trace"][g, :n]).all(), g
     if lookahead == 1:
         assert (res["pieces"] < T).any()                    # the pressure filter ended some games
+
+
+# ------------------------------------------------------------------------------------------------
+# move_wiggle / move_with_wiggle(move_drop) on the device
+# ------------------------------------------------------------------------------------------------
+def test_wiggle_golden_games(eng):
+    from conftest import load_golden
+    for g in load_golden("games_wiggle.json")["games"]:
+        eng.set_features([n for n, _ in g["weights"]])
+        w = np.array([[x for _, x in g["weights"]]])
+        seq = np.array([pyoracle.piece_sequence(g["seed"], g["T"])], dtype=np.uint8)
+        ms = 4 if g["move_gen"] == "wiggle_top" else 8
+        r = eng.play_games(w, 1, pieces=seq, want_trace=True, want_final=True, move_set=ms, pressure=g["pressure"])
+        res = r["results"][0]
+        assert int(res["pieces"]) == g["pieces"] and int(res["lines"]) == g["lines"] and [int(x) for x in res["hist"]] == g["hist"]
+        assert int(res["score"]) == g["score"] and int(res["placements"]) == g["scorer_calls"]
+        assert r["trace"][0, :g["pieces"]].tobytes().hex() == g["trace_hex"]
+        assert list(r["final"][0]) == g["final_board"]
+
+
+@pytest.mark.parametrize("names,kind,ms,C,G,T", [
+    (W6_NAMES, "wide", "wiggle_top", 64, 3, 200),
+    (["max_ht", "row_trans", "pits", "landing_height"], "holes", "wiggle_top", 64, 3, 200),
+    (["max_ht", "row_trans", "pits", "landing_height"], "holes", "wiggle_drop", 64, 3, 200),
+    (NAMES, "all45", "wiggle_drop", 16, 2, 120),
+])
+def test_wiggle_vs_coracle(eng, names, kind, ms, C, G, T):
+    rng = random.Random(hash((kind, ms, C)) & 0xFFFF)
+    fids = [pyoracle.FEATURE_ID[n] for n in names]
+    if kind == "holes":
+        w = np.array([[-1.0, rng.gauss(-0.2, 0.2), rng.gauss(0.4, 0.3), -0.5] for _ in range(C)])
+    else:
+        w = np.array(_weight_sets(rng, C, names, kind))
+    eng.set_features(names)
+    bit = 4 if ms == "wiggle_top" else 8
+    r = eng.play_games(w, G, T=T, seed=21, want_trace=True, move_set=bit)
+    o = coracle.play_games(fids, w, G, T=T, seed=21, threads=16, want_trace=True, move_set=ms)
+    res = r["results"]
+    assert (res["pieces"] == o["pieces"]).all() and (res["lines"] == o["lines"]).all() and (res["score"] == o["score"]).all()
+    assert (res["placements"] == o["placements"]).all()
+    for g in range(C * G):
+        n = int(res["pieces"][g])
+        assert (r["trace"][g, :n] == o["trace"][g, :n]).all(), g
+
+
+def test_wiggle_rejects_lookahead2(eng):
+    from tetris_ai_b200 import EngineError
+    eng.set_features(W6_NAMES)
+    with pytest.raises(EngineError):
+        eng.play_games(np.array([W6_VALS]), 1, T=10, lookahead=2, move_set=4)

@@ -195,7 +195,7 @@ def golden_slide_games():
 @pytest.fixture(scope="session")
 def golden_slide_moves():
     from conftest import load_golden
-    return load_golden("slide_moves.json")
+    return load_golden("slide_moves.json.gz")
 
 
 def test_slide_move_lists(golden_slide_moves):
@@ -243,5 +243,40 @@ def test_pressure_games():
         assert res["placements"] == g["scorer_calls"] and list(res["final"]) == g["final_board"]
         if g["scorer_calls"] < 4000:
             _check_game(pyoracle.play_game(fids, w, seq, g["lookahead"], want_trace=True, move_set=ms, pressure=g["pressure"]), g)
+            n_py += 1
+    assert n_py >= 2
+
+
+# ------------------------------------------------------------------------------------------------
+# move_wiggle / move_with_wiggle(move_drop)
+# ------------------------------------------------------------------------------------------------
+def test_wiggle_move_lists():
+    from conftest import load_golden
+    boards = load_golden("wiggle_moves.json.gz")["boards"]
+    more = 0
+    for i, b in enumerate(boards):
+        for p in range(7):
+            assert [list(m) for m in coracle.moves(b["board"], p, "wiggle_top")] == b["top"][p], (i, p)
+            assert [list(m) for m in coracle.moves(b["board"], p, "wiggle_drop")] == b["drop"][p], (i, p)
+            more += len(b["top"][p]) - len(coracle.moves(b["board"], p, "drop"))
+        if i % 8 == 0:
+            node = pyoracle.Node(None, pyoracle.Grid.from_rows(b["board"]))
+            for p in range(7):
+                assert [list(m) for m in pyoracle.wiggle_moves_top(node, p)] == b["top"][p]
+                assert [list(m) for m in pyoracle.wiggle_moves_drop(node, p)] == b["drop"][p]
+    assert more > 100
+
+
+def test_wiggle_games():
+    from conftest import load_golden
+    n_py = 0
+    for g in load_golden("games_wiggle.json")["games"]:
+        fids, w = fids_weights(g["weights"])
+        seq = pyoracle.piece_sequence(g["seed"], g["T"])
+        res = coracle.play_one(fids, w, seq, g["lookahead"], move_set=g["move_gen"], pressure=g["pressure"])
+        _check_game(res, g)
+        assert res["placements"] == g["scorer_calls"] and list(res["final"]) == g["final_board"]
+        if g["scorer_calls"] < 1500:
+            _check_game(pyoracle.play_game(fids, w, seq, g["lookahead"], want_trace=True, move_set=g["move_gen"], pressure=g["pressure"]), g)
             n_py += 1
     assert n_py >= 2

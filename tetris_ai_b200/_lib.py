@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtetris_b200.so")
 
 MEM_HOST, MEM_DEVICE = 0, 1
-MOVES_DROP, MOVES_OVERHANG_SLIDE, MOVES_PRESSURE = 0, 1, 2
+MOVES_DROP, MOVES_OVERHANG_SLIDE, MOVES_PRESSURE, MOVES_WIGGLE, MOVES_WIGGLE_DROP = 0, 1, 2, 4, 8
 NUM_FEATURES = 45
 MAX_WEIGHTED = 48
 

@@ -1017,6 +1017,177 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6grp_kernel(const PlayParam
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K2x: the wiggle move sets (simulator.py:49-85), one warp per game, lookahead 1.
+// Per piece: every lane computes the free map of its (rotation, column) slot and its hard-drop landing; lanes
+// 0..3 then each run the reference's depth-first flood fill for one rotation (explicit stack in shared memory,
+// same visiting order as the recursion, so the move list comes out in the reference's order); finally the moves
+// are spread over the 32 lanes, scored like any other placement (tag = position in the list = tie order), REDUX
+// argmax, commit by re-placing the winner.  The DFS is inherently serial (about 10x the cost of a hard-drop search).
+// ---------------------------------------------------------------------------------------------
+struct WiggleShared {
+    uint32_t fm[4][12];        // free map per rotation and column (bit y)
+    uint32_t seen[4][12];
+    uint16_t stack[4][256];
+    uint16_t list[4][128];     // moves of each rotation in visiting order: y | col << 8
+    uint8_t  starty[4][12];    // hard-drop landing height per rotation and column, 255 = illegal
+    int cnt[4], base[4], wph[4];
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(BLOCK) play_games_wiggle_kernel(const PlayParams prm)
+{
+    constexpr int GROUPS = BLOCK / 32;
+    __shared__ Tables s_tab;
+    __shared__ WiggleShared s_wg[GROUPS];
+    __shared__ double s_w[GROUPS][TB200_MAX_WEIGHTED];
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int grp = threadIdx.x >> 5;
+    WiggleShared& wg = s_wg[grp];
+    const int F = prm.F;
+    const uint32_t T = prm.T;
+    const bool from_top = (prm.move_set & 4) != 0;
+    const double* w = s_w[grp];
+
+    for (;;) {
+        uint32_t game = 0;
+        if (lane == 0) game = atomicAdd(prm.ticket, 1u);
+        game = __shfl_sync(FULLMASK, game, 0);
+        if (game >= prm.n_games) break;
+        const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : (prm.per_game_weights != 0 ? game : game % (uint32_t)prm.G);
+        const uint64_t stream = sq;
+        const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
+        uint32_t c[COLS];
+        if (prm.init_rows) {
+            uint16_t rows[ROWS];
+            for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
+            rows_to_cols(rows, c);
+        } else {
+#pragma unroll
+            for (int k = 0; k < COLS; ++k) c[k] = 0;
+        }
+        PrevStat pv = prev_stat(c);
+        Heights H = pack_gh(pv.gh);
+        {
+            const size_t wrow = prm.per_game_weights > 0 ? (size_t)game : (prm.per_game_weights < 0 ? 0 : (size_t)(game / (uint32_t)prm.G));
+            const double* wsrc = prm.weights + wrow * (size_t)F;
+            __syncwarp(FULLMASK);
+            for (int i = lane; i < F; i += 32) s_w[grp][i] = __ldg(wsrc + i);
+            __syncwarp(FULLMASK);
+        }
+        auto fetch_piece = [&](uint32_t tt) -> int {
+            if (tt >= T) return 7;
+            return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, stream, tt);
+        };
+        uint32_t t = 0, lines = prm.init_lines ? prm.init_lines[game] : 0u, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+        uint64_t gscore = 0;
+        const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
+        int p_cur = fetch_piece(0), p_next = fetch_piece(1);
+
+        while (t < stop && p_cur < 7) {
+            const int p_after = fetch_piece(t + 2);
+            const int ns = s_tab.nslots[p_cur];
+            const int nrot = (int)((s_tab.slot[p_cur][ns - 1].w[0] >> 4) & 3u) + 1;
+            // ---- free maps and hard-drop landings of every slot ----
+            for (int i = lane; i < 48; i += 32) { wg.fm[i / 12][i % 12] = 0u; wg.starty[i / 12][i % 12] = 255; }
+            __syncwarp(FULLMASK);
+            for (int s = lane; s < ns; s += 32) {
+                const SlotDesc d = load_slot12(s_tab, p_cur, s);
+                const int rot = (int)((d.w[0] >> 4) & 3u), c0 = (int)(d.w[0] & 15u);
+                wg.fm[rot][c0] = free_mask(c, d);
+                Placement P; uint32_t full;
+                if (place_pre(c, H, d, P, &full)) wg.starty[rot][c0] = (uint8_t)P.y;
+                if (c0 == 0) { wg.base[rot] = s; wg.wph[rot] = (int)((d.w[0] >> 6) & 7u) | (int)((d.w[0] >> 9) & 7u) << 8; }
+            }
+            __syncwarp(FULLMASK);
+            // ---- one flood fill per rotation (lanes 0..nrot-1), in the reference's visiting order ----
+            if (lane < nrot) {
+                const int wd = wg.wph[lane] & 255, ph = wg.wph[lane] >> 8;
+                uint16_t starts[COLS]; int nst = 0;
+                for (int col = 0; col <= COLS - wd; ++col) {
+                    if (from_top) starts[nst++] = (uint16_t)((uint32_t)(ROWS - ph) | (uint32_t)col << 8);
+                    else if (wg.starty[lane][col] != 255) starts[nst++] = (uint16_t)((uint32_t)wg.starty[lane][col] | (uint32_t)col << 8);
+                }
+                wg.cnt[lane] = wiggle_rot(wg.fm[lane], wd, starts, nst, wg.stack[lane], wg.seen[lane], wg.list[lane], 128);
+            }
+            __syncwarp(FULLMASK);
+            const int n0 = wg.cnt[0], n1 = n0 + (nrot > 1 ? wg.cnt[1] : 0), n2 = n1 + (nrot > 2 ? wg.cnt[2] : 0), n3 = n2 + (nrot > 3 ? wg.cnt[3] : 0);
+            auto move_at = [&](int idx, int& slot, int& y) {
+                const int r = idx < n0 ? 0 : (idx < n1 ? 1 : (idx < n2 ? 2 : 3));
+                const int i = idx - (r == 0 ? 0 : (r == 1 ? n0 : (r == 2 ? n1 : n2)));
+                const uint32_t e = wg.list[r][i];
+                y = (int)(e & 31u); slot = wg.base[r] + (int)(e >> 8);
+            };
+            // ---- score every move; tag = position in the list ----
+            uint64_t key = 0; uint32_t tag = 0;
+            const int level = (int)(lines / 10u);
+            for (int idx = lane; idx < n3; idx += 32) {
+                int slot, y;
+                move_at(idx, slot, y);
+                const SlotDesc d = load_slot12(s_tab, p_cur, slot);
+                if (prm.press.on && !is_time(d, y, prm.press, level)) continue;
+                Placement P; uint32_t full;
+                place_at(c, d, y, P, &full);
+                if (full != 0u) place_clear(d, P, full);
+                Feat f;
+                eval_features<ModeTraits<MODE>::CMASK>(P, d, pv, prm.rmask, f);
+                const uint64_t k = score_key(score_features<MODE>(f, prm.ids, w, F));
+                if (k > key) { key = k; tag = (uint32_t)idx; }
+                ++cnt;
+            }
+            warp_argmax32(key, tag);
+            if (key == 0) break;
+            // ---- commit ----
+            int slot, y;
+            move_at((int)tag, slot, y);
+            const SlotDesc d = load_slot12(s_tab, p_cur, slot);
+            Placement P; uint32_t full;
+            place_at(c, d, y, P, &full);
+            if (full != 0u) place_clear(d, P, full);
+#pragma unroll
+            for (int k = 0; k < COLS; ++k) c[k] = P.n[k];
+            pv = next_stat(pv, P, d); H = pack_gh(pv.gh);
+            const uint32_t wk = (uint32_t)P.k;
+            if (wk != 0u) {
+                lines += wk;
+                h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
+                const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
+                gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
+            }
+            if (lane == 0) {
+                if (prm.trace) {
+                    const uint32_t row = (uint32_t)(ROWS - P.y - P.ph);
+                    reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = (uint32_t)P.rot | row << 8 | (uint32_t)P.c0 << 16 | wk << 24;
+                }
+                if (prm.score_trace) {
+                    const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
+                    prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
+                }
+            }
+            ++t;
+            p_cur = p_next; p_next = p_after;
+            __syncwarp(FULLMASK);
+        }
+        cnt = __reduce_add_sync(FULLMASK, cnt);
+        if (lane == 0) {
+            tb200_game_result* r = prm.results + game;
+            r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4;
+            r->score = gscore; r->placements = cnt;
+            if (prm.final_rows) {
+                uint16_t rows[ROWS];
+                cols_to_rows(c, rows);
+                for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2];
+            }
+        }
+    }
+}
+
 // K3: all 45 features of one placement per thread
 // at_row (optional): row of the piece's top bbox row; 255 / null => hard drop.  With an explicit row the placement only
 // has to fit (State.future does not check support either), which covers the overhang-slide placements.
@@ -1136,6 +1307,11 @@ static play_fn pick_generic(int mode, int lookahead, int lanes)
 }
 static play_fn pick_kernel(int mode, int lookahead, int lanes, int move_set)
 {
+    if (move_set & (TB200_MOVES_WIGGLE | TB200_MOVES_WIGGLE_DROP)) {      // caller guarantees lookahead 1
+        if (mode == MODE_W6) return play_games_wiggle_kernel<MODE_W6>;
+        if (mode == MODE_ALL45) return play_games_wiggle_kernel<MODE_ALL45>;
+        return play_games_wiggle_kernel<MODE_GENERIC>;
+    }
     if (move_set != 0) return pick_generic<1>(mode, lookahead, lanes);     // overhang slides / pressure: extended generic kernels
     if (lanes == 64) return play_games_w6pair_kernel;      // caller guarantees lookahead 1 and the w6 set
     if (lookahead == 1 && mode == MODE_W6 && lanes == 16) return play_games_w6grp_kernel<16>;
@@ -1338,6 +1514,7 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
     const int move_set = a.move_set;
     const bool pair_ok = ctx->mode == tb::MODE_W6 && a.lookahead == 1 && move_set == 0;
     if (move_set != 0 && (lanes == 64 || lanes == 4 || lanes == 2 || lanes == 1)) lanes = lanes == 64 ? 32 : 8;
+    if (move_set & (TB200_MOVES_WIGGLE | TB200_MOVES_WIGGLE_DROP)) lanes = 32;
     if (lanes == 64 && !pair_ok) lanes = 32;
     const bool narrow_ok = pair_ok && (lanes == 4 || lanes == 2 || lanes == 1);
     if (!narrow_ok && lanes != 8 && lanes != 16 && lanes != 32 && lanes != 64) {
@@ -1402,7 +1579,13 @@ static int check_play_args(tb200_ctx* ctx, const tb200_play_args* a)
     if (a->pieces && a->n_sequences < 1) return fail(ctx, TB200_E_BAD_ARG, "play_games: n_sequences must be >= 1 with explicit pieces");
     if (a->pieces && !a->seq_of_game && a->n_sequences < a->games_per_candidate) return fail(ctx, TB200_E_BAD_ARG, "play_games: need S >= G without seq_of_game");
     if (a->mem != TB200_MEM_HOST && a->mem != TB200_MEM_DEVICE) return fail(ctx, TB200_E_BAD_ARG, "play_games: bad mem");
-    if (a->move_set < 0 || a->move_set > (TB200_MOVES_OVERHANG_SLIDE | TB200_MOVES_PRESSURE)) return fail(ctx, TB200_E_BAD_ARG, "play_games: bad move_set");
+    {
+        const int ms = a->move_set, inner = ms & ~TB200_MOVES_PRESSURE;
+        if (ms < 0 || (inner != 0 && inner != TB200_MOVES_OVERHANG_SLIDE && inner != TB200_MOVES_WIGGLE && inner != TB200_MOVES_WIGGLE_DROP))
+            return fail(ctx, TB200_E_BAD_ARG, "play_games: bad move_set");
+        if ((ms & (TB200_MOVES_WIGGLE | TB200_MOVES_WIGGLE_DROP)) && a->lookahead != 1)
+            return fail(ctx, TB200_E_BAD_ARG, "play_games: the wiggle move sets are implemented for lookahead 1 only");
+    }
     return TB200_OK;
 }
 

@@ -401,6 +401,58 @@ TB_HD bool is_time(const SlotDesc& d, int y, const Pressure& pr, int level)
     return t <= i2d(limit);
 }
 
+// ---------------------------------------------------------------------------------------------
+// SURVEY.md §8f rank 4 — move_with_wiggle / move_wiggle (simulator.py:49-85): depth-first flood fill of the
+// positions a piece can reach by moving down, left, right (in that order); positions where it cannot move
+// down are the moves, and the ORDER of the list (= the tie-break order) is the order of the recursion.
+// ---------------------------------------------------------------------------------------------
+// Free map of one slot (rotation, column): bit y = the piece fits with its bbox bottom at height y.
+TB_HD uint32_t free_mask(const uint32_t c[COLS], const SlotDesc& d)
+{
+    const int ph = (int)((d.w[0] >> 9) & 7u);
+    uint32_t blocked = 0;
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) {
+        const uint32_t q = (d.w[4 + (k >> 2)] >> (8 * (k & 3))) & 255u;       // piece cells in board column k (bit b = bbox row b)
+        blocked |= ((q & 1u) ? c[k] : 0u) | ((q & 2u) ? c[k] >> 1 : 0u) | ((q & 4u) ? c[k] >> 2 : 0u) | ((q & 8u) ? c[k] >> 3 : 0u);
+    }
+    return ~blocked & ((2u << (ROWS - ph)) - 1u);                             // y in 0 .. ROWS - ph
+}
+
+// The reference's recursion for ONE rotation, with an explicit stack.  fm[col] = free map of (rot, col) for col in
+// 0..COLS-w and 0 beyond; starts[i] = y | col << 8 in the order the reference visits them; out[i] = y | col << 8 of the
+// i-th move.  stack needs 256 entries, seen COLS+1 words (zeroed here).  Returns the number of moves (<= cap).
+TB_HD int wiggle_rot(const uint32_t* fm, int w, const uint16_t* starts, int nstarts, uint16_t* stack, uint32_t* seen, uint16_t* out, int cap)
+{
+    for (int i = 0; i <= COLS; ++i) seen[i] = 0u;
+    int n = 0;
+    for (int si = 0; si < nstarts; ++si) {
+        int sp = 0;
+        stack[sp++] = (uint16_t)(starts[si] & 0x0FFFu);                       // frame = y (5 bits) | col << 8 (4 bits) | stage << 12
+        while (sp > 0) {
+            const uint32_t fr = stack[sp - 1];
+            const int y = (int)(fr & 31u), col = (int)((fr >> 8) & 15u), stage = (int)(fr >> 12);
+            if (stage == 0) {
+                if ((seen[col] >> y) & 1u) { --sp; continue; }                    // :52
+                seen[col] |= 1u << y;
+                if (!((fm[col] >> y) & 1u)) { --sp; continue; }                   // :54 overlaps here
+                stack[sp - 1] = (uint16_t)(fr | 0x1000u);
+                if (y > 0 && ((fm[col] >> (y - 1)) & 1u)) stack[sp++] = (uint16_t)((uint32_t)(y - 1) | (uint32_t)col << 8);   // :58-60 keep falling
+                else if (n < cap) out[n++] = (uint16_t)((uint32_t)y | (uint32_t)col << 8);                                      // :55-57 resting: a move
+            } else if (stage == 1) {
+                stack[sp - 1] = (uint16_t)((fr & 0x0FFFu) | 0x2000u);
+                if (col > 0) stack[sp++] = (uint16_t)((uint32_t)y | (uint32_t)(col - 1) << 8);          // :63-64
+            } else if (stage == 2) {
+                stack[sp - 1] = (uint16_t)((fr & 0x0FFFu) | 0x3000u);
+                if (col + w <= COLS) stack[sp++] = (uint16_t)((uint32_t)y | (uint32_t)(col + 1) << 8);   // :65-66
+            } else {
+                --sp;
+            }
+        }
+    }
+    return n;
+}
+
 TB_HD bool place_slot(const uint32_t c[COLS], const Heights& H, const SlotDesc& d, Placement& p)
 {
     uint32_t f;

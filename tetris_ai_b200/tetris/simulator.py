@@ -50,6 +50,26 @@ def move_with_overhang_slide(move_gen):
     return OverhangSlide()
 
 
+class Wiggle:
+    """move_with_wiggle(move_drop) / move_wiggle (simulator.py:49-85) as device move sets: every position the piece can
+    reach by moving down, left and right, in the order of the reference's recursion.  Lookahead 1 only."""
+
+    def __init__(self, move_set):
+        self.move_set = move_set
+
+    def __call__(self, state, zoid):
+        raise TypeError("the wiggle move sets are evaluated on the device; pass them to simulate() as move_gen")
+
+
+def move_with_wiggle(move_gen):
+    if move_gen is not move_drop:
+        raise TypeError("only move_with_wiggle(move_drop) and move_wiggle are implemented on the device (no CPU fallback)")
+    return Wiggle(8)
+
+
+move_wiggle = Wiggle(4)
+
+
 class Pressure:
     """move_with_pressure(move_gen, avg_lat, resp_time, move_eff, two_but_rot) (simulator.py:88-120) as a device move set:
     the level-dependent time-pressure filter, applied to the moves of move_drop or of move_with_overhang_slide(move_drop)."""
@@ -65,10 +85,11 @@ class Pressure:
 def move_with_pressure(move_gen, avg_lat=250.9, resp_time=79.8, move_eff=1.23, two_but_rot=False):
     if move_gen is move_drop:
         inner = 0
-    elif isinstance(move_gen, OverhangSlide):
-        inner = 1
+    elif isinstance(move_gen, (OverhangSlide, Wiggle)):
+        inner = move_gen.move_set
     else:
-        raise TypeError("move_with_pressure is implemented on the device around move_drop or move_with_overhang_slide(move_drop) only")
+        raise TypeError("move_with_pressure is implemented on the device around move_drop, move_with_overhang_slide(move_drop), "
+                        "move_with_wiggle(move_drop) and move_wiggle only")
     return Pressure(inner, avg_lat, resp_time, move_eff, two_but_rot)
 
 
@@ -125,8 +146,8 @@ def simulate(state, zoid_gen, move_gen, move_policy, lookahead=1, engine=None):
     pressure = None
     if move_gen is move_drop:
         move_set = 0
-    elif isinstance(move_gen, OverhangSlide):
-        move_set = 1
+    elif isinstance(move_gen, (OverhangSlide, Wiggle)):
+        move_set = move_gen.move_set
     elif isinstance(move_gen, Pressure):
         move_set, pressure = move_gen.move_set, move_gen.params
     else:
@@ -159,4 +180,4 @@ def simulate(state, zoid_gen, move_gen, move_policy, lookahead=1, engine=None):
         carry = chunk[commit:]
 
 
-__all__ = ["move_drop", "move_with_overhang_slide", "move_with_pressure", "policy_best", "simulate", "linear_scorer", "tie_first", "LinearScorer", "BestPolicy", "PIECES"]
+__all__ = ["move_drop", "move_with_overhang_slide", "move_with_pressure", "move_with_wiggle", "move_wiggle", "policy_best", "simulate", "linear_scorer", "tie_first", "LinearScorer", "BestPolicy", "PIECES"]

@@ -96,6 +96,10 @@ def main():
     for lanes in (32, 8):
         ms_t, out = timeit(eng, 2, weights=w6, games_per_candidate=1, T=300, seed=5, seq_of_game=np.arange(2048, dtype=np.int32), lanes=lanes, move_set=1)
         rows.append(("w6 slide 2048 games T=300", lanes, ms_t, int(out["results"]["placements"].sum()), int(out["results"]["pieces"].sum())))
+    # wiggle move sets (one warp per game, serial flood fill per rotation)
+    for ms, nm in ((4, "wiggle_top"), (8, "wiggle_drop")):
+        ms_t, out = timeit(eng, 2, weights=w6, games_per_candidate=1, T=300, seed=5, seq_of_game=np.arange(2048, dtype=np.int32), move_set=ms)
+        rows.append(("w6 %s 2048 games T=300" % nm, 32, ms_t, int(out["results"]["placements"].sum()), int(out["results"]["pieces"].sum())))
     print("%-32s %5s %10s %12s %10s %14s" % ("workload", "lanes", "kernel_ms", "placements", "pieces", "placements/s"))
     for name, lanes, ms, pl, pc in rows:
         print("%-32s %5d %10.3f %12d %10d %14.4e" % (name, lanes, ms, pl, pc, pl / (ms * 1e-3)))
