@@ -111,7 +111,7 @@ typedef struct {
 
 /* timing of the last tb200_play_games call on this ctx (CUDA events on the launching stream) */
 typedef struct {
-    float kernel_ms;                 /* play kernel only (valid after the stream has been synchronised) */
+    float kernel_ms;                 /* play kernel only (valid after the stream has been synchronised; 0 for a CUDA-graph replay) */
     float total_ms;                  /* host mode: H2D + kernels + D2H */
     int32_t lanes;                   /* lanes per game actually used */
     int32_t grid, block;             /* launch configuration */

@@ -271,3 +271,23 @@ def test_simulate_with_wiggle(eng):
             trace += bytes([d.rot, d.row, d.col, len(d.cleared)])
             last = st
         assert trace.hex() == g["trace_hex"] and last.score() == g["score"]
+
+
+def test_graph_replay_then_direct_calls(eng):
+    """A CUDA-graph replay (repeated evaluator call on pinned buffers) followed by ordinary calls: no stale CUDA error,
+    timings stay sane, results identical to the direct path."""
+    from tetris_ai_b200.learning import PopulationEvaluator
+    names = ["landing_height", "eroded_cells", "row_trans", "col_trans", "pits", "cuml_wells"]
+    rng = np.random.default_rng(8)
+    ev = PopulationEvaluator(eng, names, 4, T=120, seed=3)
+    w = rng.normal(0, 5, size=(50, 6))
+    fits = [ev.evaluate(w).copy() for _ in range(3)]            # capture, replay, replay
+    assert (fits[0] == fits[1]).all() and (fits[1] == fits[2]).all()
+    t = eng.last_timing()
+    assert t["total_ms"] > 0.0
+    w2 = rng.normal(0, 5, size=(50, 6))
+    f2 = ev.evaluate(w2).copy()                                  # replay with new weights in the same pinned buffer
+    eng.set_features(names)
+    direct = eng.play_games(w2, 4, T=120, seed=3)                # pageable buffers: direct path right after a replay
+    assert (direct["fitness"] == f2).all()
+    assert eng.last_timing()["kernel_ms"] > 0.0

@@ -1346,6 +1346,7 @@ struct tb200_ctx {
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool timing_valid = false;
+    bool kernel_events_valid = true;     // false after a graph replay: ev[0] / ev[1] were not recorded by it
     tb200_timing timing{};
     // staging arena for TB200_MEM_HOST calls (grown on demand, reused across calls)
     char* d_arena = nullptr;
@@ -1497,16 +1498,18 @@ int tb200_last_timing(tb200_ctx* ctx, tb200_timing* out)
 {
     if (!ctx || !out) return TB200_E_BAD_ARG;
     if (!ctx->timing_valid) return fail(ctx, TB200_E_BAD_ARG, "last_timing: no play_games call yet");
-    if (cudaEventSynchronize(ctx->ev[1]) == cudaSuccess) {
+    ctx->timing.kernel_ms = 0.f;
+    if (ctx->kernel_events_valid) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->timing.kernel_ms = ms;
+        if (cudaEventSynchronize(ctx->ev[1]) == cudaSuccess && cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->timing.kernel_ms = ms;
+        else cudaGetLastError();         // never leave a stale error behind for the next launch check
     }
     *out = ctx->timing;
     return TB200_OK;
 }
 
 // launch K2 (+ optional fitness) on device buffers
-static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st, int per_game_weights, int* launches)
+static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st, int per_game_weights, int* launches, bool record_events = true)
 {
     const long long n_games_ll = (long long)a.n_candidates * a.games_per_candidate;
     const uint32_t n_games = (uint32_t)n_games_ll;
@@ -1553,10 +1556,10 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
 
     TB_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(uint32_t), st));
     TB_CUDA(ctx, cudaMemsetAsync(a.results, 0, sizeof(tb200_game_result) * (size_t)n_games, st));
-    TB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     fn<<<(unsigned)blocks, block, 0, st>>>(p);
     TB_CUDA(ctx, cudaGetLastError());
-    TB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     *launches += 1;
     if (a.fitness) {
         tb::fitness_kernel<<<(a.n_candidates + 127) / 128, 128, 0, st>>>(a.n_candidates, a.games_per_candidate, a.results, a.fitness);
@@ -1605,6 +1608,7 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
         if (rc) return rc;
         ctx->timing.kernels_launched = launches;
         ctx->timing_valid = true;
+        ctx->kernel_events_valid = true;
         return TB200_OK;
     }
     // ---- host buffers: stage through the ctx arena on the ctx's own stream; synchronous ----------
@@ -1639,8 +1643,9 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
     d.final_rows = a.final_rows ? (uint16_t*)(base + o_f) : nullptr;
     d.fitness = a.fitness ? (double*)(base + o_fit) : nullptr;
 
-    auto enqueue = [&]() -> int {
-        TB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    // timing events are recorded outside a captured graph (event nodes of a graph cannot be used for elapsed time),
+    // so a graph replay reports total_ms only
+    auto enqueue = [&](bool events) -> int {
         TB_CUDA(ctx, cudaMemcpyAsync((void*)d.weights, a.weights, b_w, cudaMemcpyHostToDevice, st));
         if (b_p) TB_CUDA(ctx, cudaMemcpyAsync((void*)d.pieces, a.pieces, b_p, cudaMemcpyHostToDevice, st));
         if (b_s) TB_CUDA(ctx, cudaMemcpyAsync((void*)d.seq_of_game, a.seq_of_game, b_s, cudaMemcpyHostToDevice, st));
@@ -1648,28 +1653,29 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
         if (b_il) TB_CUDA(ctx, cudaMemcpyAsync((void*)d.init_lines, a.init_lines, b_il, cudaMemcpyHostToDevice, st));
         if (b_t) TB_CUDA(ctx, cudaMemsetAsync(d.trace, 0, b_t, st));
         if (b_st) TB_CUDA(ctx, cudaMemsetAsync(d.score_trace, 0, b_st, st));
-        int rc2 = launch_play(ctx, d, st, 0, &launches);
+        int rc2 = launch_play(ctx, d, st, 0, &launches, events);
         if (rc2) return rc2;
         TB_CUDA(ctx, cudaMemcpyAsync(a.results, d.results, b_r, cudaMemcpyDeviceToHost, st));
         if (b_t) TB_CUDA(ctx, cudaMemcpyAsync(a.trace, d.trace, b_t, cudaMemcpyDeviceToHost, st));
         if (b_st) TB_CUDA(ctx, cudaMemcpyAsync(a.score_trace, d.score_trace, b_st, cudaMemcpyDeviceToHost, st));
         if (b_f) TB_CUDA(ctx, cudaMemcpyAsync(a.final_rows, d.final_rows, b_f, cudaMemcpyDeviceToHost, st));
         if (b_fit) TB_CUDA(ctx, cudaMemcpyAsync(a.fitness, d.fitness, b_fit, cudaMemcpyDeviceToHost, st));
-        TB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
         return TB200_OK;
     };
+    bool kernel_events = true;
+    TB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     // ---- graph replay: identical call (same pinned buffers, sizes, options, feature list) as last time ----
     const bool same = ctx->graph_valid && memcmp(&ctx->graph_args, &a, sizeof a) == 0 && ctx->graph_F == ctx->F &&
                       ctx->graph_mode == ctx->mode && memcmp(ctx->graph_ids, ctx->ids, sizeof ctx->ids) == 0 && ctx->graph_arena == base;
     bool done = false;
     if (same) {
-        if (cudaGraphLaunch(ctx->graph_exec, st) == cudaSuccess) { ctx->timing = ctx->graph_timing; launches = ctx->graph_timing.kernels_launched; done = true; }
+        if (cudaGraphLaunch(ctx->graph_exec, st) == cudaSuccess) { ctx->timing = ctx->graph_timing; launches = ctx->graph_timing.kernels_launched; done = true; kernel_events = false; }
         else { cudaGetLastError(); drop_graph(ctx); }
     } else if (ctx->graphs_enabled && is_pinned(a.weights) && is_pinned(a.pieces) && is_pinned(a.seq_of_game) && is_pinned(a.init_rows) && is_pinned(a.init_lines) &&
                is_pinned(a.results) && is_pinned(a.trace) && is_pinned(a.score_trace) && is_pinned(a.final_rows) && is_pinned(a.fitness)) {
         drop_graph(ctx);
         if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-            const int rc2 = enqueue();
+            const int rc2 = enqueue(false);
             cudaGraph_t gr = nullptr;
             const cudaError_t e1 = cudaStreamEndCapture(st, &gr);
             if (rc2 == TB200_OK && e1 == cudaSuccess && gr && cudaGraphInstantiate(&ctx->graph_exec, gr, 0) == cudaSuccess) {
@@ -1677,7 +1683,7 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
                 memcpy(ctx->graph_ids, ctx->ids, sizeof ctx->ids); ctx->graph_arena = base;
                 ctx->timing.kernels_launched = launches;
                 ctx->graph_timing = ctx->timing; ctx->graph_valid = true;
-                if (cudaGraphLaunch(ctx->graph_exec, st) == cudaSuccess) done = true;
+                if (cudaGraphLaunch(ctx->graph_exec, st) == cudaSuccess) { done = true; kernel_events = false; }
                 else { cudaGetLastError(); drop_graph(ctx); ctx->graphs_enabled = false; }
             } else {
                 cudaGetLastError();
@@ -1691,10 +1697,12 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
     }
     if (!done) {
         launches = 0;
-        rc = enqueue();
+        rc = enqueue(true);
         if (rc) return rc;
     }
+    TB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     TB_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->kernel_events_valid = kernel_events;
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
     ctx->timing.total_ms = ms;
