@@ -456,3 +456,18 @@ def test_wiggle_rejects_lookahead2(eng):
     eng.set_features(W6_NAMES)
     with pytest.raises(EngineError):
         eng.play_games(np.array([W6_VALS]), 1, T=10, lookahead=2, move_set=4)
+
+
+@pytest.mark.parametrize("lanes", [64, 32, 8, 2])
+def test_long_games_vs_coracle(eng, lanes):
+    """Games of 20 000 pieces (thousands of lines: level / score arithmetic, many piece-window refills)."""
+    fids = [pyoracle.FEATURE_ID[n] for n in W6_NAMES]
+    eng.set_features(W6_NAMES)
+    w = np.tile(np.array(W6_VALS), (8, 1)) + np.random.default_rng(2).normal(0, 0.3, size=(8, 6))
+    seqid = np.arange(8, dtype=np.int32)
+    r = eng.play_games(w, 1, T=20000, seed=1234, seq_of_game=seqid, lanes=lanes, want_final=True)
+    o = coracle.play_games(fids, w, 1, T=20000, seed=1234, seq_of_game=seqid, threads=8)
+    res = r["results"]
+    assert (res["pieces"] == o["pieces"]).all() and (res["lines"] == o["lines"]).all() and (res["hist"] == o["hist"]).all()
+    assert (res["score"] == o["score"]).all() and (res["placements"] == o["placements"]).all()
+    assert int(res["pieces"].max()) == 20000 and int(res["lines"].max()) > 7000
