@@ -1,10 +1,16 @@
 // tetris_b200.cu — kernels + C ABI of libtetris_b200.so (sm_100a only).
 //
-//   K2 play_games_kernel<LANES,MODE,LOOKAHEAD>  persistent, one LANES-wide lane group per game,
-//        placements fan out across the lanes, features by popc/clz bit formulas (tetris_core.cuh),
-//        fp64 dot product without FMA, shuffle argmax with the reference's first-of-max tie rule,
-//        dynamic game tickets (atomic counter) to absorb the heavy-tailed game lengths.
-//   K1 = K2 with per-game initial boards, two-piece sequences and max_moves = 1.
+//   K2  play_games_kernel<LANES,MODE,LOOKAHEAD,EXT>  persistent, one LANES-wide lane group per game (8 / 16 / 32), lookahead
+//        1 or 2, any feature list; placements fan out across the lanes, features by popc/clz bit formulas
+//        (tetris_core.cuh), fp64 dot product without FMA, shuffle argmax with the reference's first-of-max tie rule,
+//        dynamic game tickets (atomic counter) for the heavy-tailed game lengths.  EXT = 1 adds the overhang-slide
+//        move set and the pressure filter.
+//   K2f play_games_w6fast_kernel        one warp per game, lookahead 1, the w6 feature set: the latency path (config 2).
+//   K2p play_games_w6pair_kernel        two warps per game (tiny populations).
+//   K2g play_games_w6grp_kernel<LANES>  16 / 8 / 4 / 2 / 1 lanes per game: the throughput path (configs 3, 5).
+//   K2w play_games_w32_kernel<MODE>     one warp per game, lookahead 1, all-45 / generic feature lists.
+//   K2x play_games_wiggle_kernel<MODE>  the wiggle move sets (8f rank 4): reference-order flood fill + scoring.
+//   K1 = K2* with per-game initial boards, two-piece sequences and max_moves = 1 (tb200_best_move).
 //   K3 eval_features_kernel   one thread per (board, placement): all 45 features.
 //   K4 hashed_pieces_kernel   counter-based piece stream.
 //   fitness_kernel            per-candidate  sum(lines) / G.
@@ -84,15 +90,6 @@ TB_D void group_argmax_mv(uint64_t& key, uint32_t& tag, uint32_t& mv)
         const uint64_t okey = ((uint64_t)ohi << 32) | olo;
         if (okey > key || (okey == key && otag < tag)) { key = okey; tag = otag; mv = omv; }
     }
-}
-
-TB_D SlotDesc load_slot(const Tables& tab, int piece, int s)
-{
-    const uint4* p = reinterpret_cast<const uint4*>(&tab.slot[piece][s]);
-    const uint4 a = p[0], b = p[1];
-    SlotDesc d;
-    d.w[0] = a.x; d.w[1] = a.y; d.w[2] = a.z; d.w[3] = a.w; d.w[4] = b.x; d.w[5] = b.y; d.w[6] = b.z; d.w[7] = b.w;
-    return d;
 }
 
 TB_D SlotDesc load_slot12(const Tables& tab, int piece, int s)
