@@ -52,8 +52,8 @@ extern "C" {
 #define TB200_MOVES_DROP            0
 #define TB200_MOVES_OVERHANG_SLIDE  1
 #define TB200_MOVES_PRESSURE        2
-#define TB200_MOVES_WIGGLE          4      /* move_wiggle: flood fill from the top of every column (simulator.py:81-85); lookahead 1 */
-#define TB200_MOVES_WIGGLE_DROP     8      /* move_with_wiggle(move_drop) (simulator.py:49-77); lookahead 1 */
+#define TB200_MOVES_WIGGLE          4      /* move_wiggle: flood fill from the top of every column (simulator.py:81-85) */
+#define TB200_MOVES_WIGGLE_DROP     8      /* move_with_wiggle(move_drop) (simulator.py:49-77) */
 
 #define TB200_MEM_HOST   0
 #define TB200_MEM_DEVICE 1

@@ -118,6 +118,17 @@ static void play(const int* ids_in, int F, const double* w, const uint8_t* piece
                 const PrevStat pv1 = next_stat(pv, P1, d1); const Heights H1 = pack_gh(pv1.gh);
                 search_one<MODE>(P1.n, H1, pv1, p2, ids, w, F, rmask, move_set, pr, (int)((lines + (uint32_t)P1.k) / 10), tag1 << 11, mv1, false, best, cnt);
             };
+            if (move_set & 12) {             // wiggle move sets: layer 1 = the flood-fill list, in its order
+                uint16_t lst[640];
+                const int m = wiggle_list(c, H, p1, (move_set & 4) != 0, lst, 640);
+                for (int i = 0; i < m; ++i) {
+                    const SlotDesc& d2 = tab.slot[p1][lst[i] & 255u];
+                    Placement P2; uint32_t full;
+                    place_at(c, d2, (int)(lst[i] >> 8), P2, &full);
+                    if (full != 0u) place_clear(d2, P2, full);
+                    expand(P2, d2, (uint32_t)i, (uint32_t)lst[i]);
+                }
+            } else
             for (int s1 = 0; s1 < tab.nslots[p1]; ++s1) {
                 Placement P1;
                 if (!place_slot(c, H, tab.slot[p1][s1], P1)) continue;

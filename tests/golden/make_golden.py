@@ -476,6 +476,9 @@ def main():
     wgames.append(play(W6, 2, 120, wiggle="drop"))
     wgames.append(play(ties, 0, 200, wiggle="top"))
     wgames.append(play(W6, 3, 150, wiggle="top", pressure={}))
+    wgames.append(play(holes, 0, 25, lookahead=2, wiggle="top"))
+    wgames.append(play(W6, 1, 20, lookahead=2, wiggle="drop"))
+    wgames.append(play(holes, 2, 25, lookahead=2, wiggle="top", pressure={"two_but_rot": True}))
     dump("games_wiggle.json", {"meta": meta, "games": wgames})
     print("wiggle games:", len(wgames), round(time.time() - t0, 1), "s", flush=True)
     dump("wiggle_moves.json.gz", {"meta": meta, "boards": gen_wiggle_moves()})

@@ -258,7 +258,7 @@ def test_simulate_with_wiggle(eng):
     from conftest import load_golden
     from tetris_ai_b200.tetris import simulator as sim
     from tetris_ai_b200.tetris.game import Board, State, PIECES
-    for g in load_golden("games_wiggle.json")["games"][:5]:
+    for g in load_golden("games_wiggle.json")["games"][-7:]:
         gen = sim.move_wiggle if g["move_gen"] == "wiggle_top" else sim.move_with_wiggle(sim.move_drop)
         if g["pressure"] is not None:
             gen = sim.move_with_pressure(gen, **g["pressure"])
@@ -266,7 +266,7 @@ def test_simulate_with_wiggle(eng):
         seq = pyoracle.piece_sequence(g["seed"], g["T"])
         trace = bytearray()
         last = State(None, Board(20, 10))
-        for st in sim.simulate(last, iter(PIECES[i] for i in seq), gen, policy, engine=eng):
+        for st in sim.simulate(last, iter(PIECES[i] for i in seq), gen, policy, lookahead=g["lookahead"], engine=eng):
             d = st.delta
             trace += bytes([d.rot, d.row, d.col, len(d.cleared)])
             last = st

@@ -1031,12 +1031,77 @@ struct WiggleShared {
     int cnt[4], base[4], wph[4];
 };
 
+// Move list of `piece` on board c (warp-cooperative): free maps + hard-drop landings by all lanes, one flood fill per
+// rotation by lanes 0..nrot-1.  off[r] = number of moves of rotations < r; returns the total.
+TB_D int wiggle_collect(WiggleShared& wg, const Tables& tab, const uint32_t c[COLS], const Heights& H, int piece, bool from_top, int lane, int off[5])
+{
+    const int ns = tab.nslots[piece];
+    const int nrot = (int)((tab.slot[piece][ns - 1].w[0] >> 4) & 3u) + 1;
+    __syncwarp(FULLMASK);
+    for (int i = lane; i < 48; i += 32) { wg.fm[i / 12][i % 12] = 0u; wg.starty[i / 12][i % 12] = 255; }
+    __syncwarp(FULLMASK);
+    for (int s = lane; s < ns; s += 32) {
+        const SlotDesc d = load_slot12(tab, piece, s);
+        const int rot = (int)((d.w[0] >> 4) & 3u), c0 = (int)(d.w[0] & 15u);
+        wg.fm[rot][c0] = free_mask(c, d);
+        Placement P; uint32_t full;
+        if (place_pre(c, H, d, P, &full)) wg.starty[rot][c0] = (uint8_t)P.y;
+        if (c0 == 0) { wg.base[rot] = s; wg.wph[rot] = (int)((d.w[0] >> 6) & 7u) | (int)((d.w[0] >> 9) & 7u) << 8; }
+    }
+    __syncwarp(FULLMASK);
+    if (lane < nrot) {
+        const int wd = wg.wph[lane] & 255, ph = wg.wph[lane] >> 8;
+        uint16_t starts[COLS]; int nst = 0;
+        for (int col = 0; col <= COLS - wd; ++col) {
+            if (from_top) starts[nst++] = (uint16_t)((uint32_t)(ROWS - ph) | (uint32_t)col << 8);
+            else if (wg.starty[lane][col] != 255) starts[nst++] = (uint16_t)((uint32_t)wg.starty[lane][col] | (uint32_t)col << 8);
+        }
+        wg.cnt[lane] = wiggle_rot(wg.fm[lane], wd, starts, nst, wg.stack[lane], wg.seen[lane], wg.list[lane], 128);
+    }
+    __syncwarp(FULLMASK);
+    off[0] = 0;
+    off[1] = wg.cnt[0];
+    off[2] = off[1] + (nrot > 1 ? wg.cnt[1] : 0);
+    off[3] = off[2] + (nrot > 2 ? wg.cnt[2] : 0);
+    off[4] = off[3] + (nrot > 3 ? wg.cnt[3] : 0);
+    return off[4];
+}
+
+TB_D void wiggle_move_at(const WiggleShared& wg, const int off[5], int idx, int& slot, int& y)
+{
+    const int r = idx < off[1] ? 0 : (idx < off[2] ? 1 : (idx < off[3] ? 2 : 3));
+    const uint32_t e = wg.list[r][idx - off[r]];
+    y = (int)(e & 31u); slot = wg.base[r] + (int)(e >> 8);
+}
+
+// score every move of the list as a leaf on board c (previous-state statistics pv); tag = tag_hi | position in the list
 template <int MODE>
+TB_D void wiggle_score(const WiggleShared& wg, const int off[5], const Tables& tab, const uint32_t c[COLS], const PrevStat& pv, int piece,
+                       const Pressure& pr, int level, const uint8_t* ids, const double* w, int F, uint64_t rmask, uint32_t tag_hi, int lane,
+                       uint64_t& key, uint32_t& tag, uint32_t& cnt)
+{
+    for (int idx = lane; idx < off[4]; idx += 32) {
+        int slot, y;
+        wiggle_move_at(wg, off, idx, slot, y);
+        const SlotDesc d = load_slot12(tab, piece, slot);
+        if (pr.on && !is_time(d, y, pr, level)) continue;
+        Placement P; uint32_t full;
+        place_at(c, d, y, P, &full);
+        if (full != 0u) place_clear(d, P, full);
+        Feat f;
+        eval_features<ModeTraits<MODE>::CMASK>(P, d, pv, rmask, f);
+        const uint64_t k = score_key(score_features<MODE>(f, ids, w, F));
+        if (k > key) { key = k; tag = tag_hi | (uint32_t)idx; }
+        ++cnt;
+    }
+}
+
+template <int MODE, int LOOKAHEAD>
 __global__ void __launch_bounds__(BLOCK) play_games_wiggle_kernel(const PlayParams prm)
 {
     constexpr int GROUPS = BLOCK / 32;
     __shared__ Tables s_tab;
-    __shared__ WiggleShared s_wg[GROUPS];
+    __shared__ WiggleShared s_wg[GROUPS][LOOKAHEAD];
     __shared__ double s_w[GROUPS][TB200_MAX_WEIGHTED];
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
@@ -1046,7 +1111,8 @@ __global__ void __launch_bounds__(BLOCK) play_games_wiggle_kernel(const PlayPara
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int grp = threadIdx.x >> 5;
-    WiggleShared& wg = s_wg[grp];
+    WiggleShared& wg1 = s_wg[grp][0];
+    WiggleShared& wg2 = s_wg[grp][LOOKAHEAD - 1];
     const int F = prm.F;
     const uint32_t T = prm.T;
     const bool from_top = (prm.move_set & 4) != 0;
@@ -1089,60 +1155,40 @@ __global__ void __launch_bounds__(BLOCK) play_games_wiggle_kernel(const PlayPara
 
         while (t < stop && p_cur < 7) {
             const int p_after = fetch_piece(t + 2);
-            const int ns = s_tab.nslots[p_cur];
-            const int nrot = (int)((s_tab.slot[p_cur][ns - 1].w[0] >> 4) & 3u) + 1;
-            // ---- free maps and hard-drop landings of every slot ----
-            for (int i = lane; i < 48; i += 32) { wg.fm[i / 12][i % 12] = 0u; wg.starty[i / 12][i % 12] = 255; }
-            __syncwarp(FULLMASK);
-            for (int s = lane; s < ns; s += 32) {
-                const SlotDesc d = load_slot12(s_tab, p_cur, s);
-                const int rot = (int)((d.w[0] >> 4) & 3u), c0 = (int)(d.w[0] & 15u);
-                wg.fm[rot][c0] = free_mask(c, d);
-                Placement P; uint32_t full;
-                if (place_pre(c, H, d, P, &full)) wg.starty[rot][c0] = (uint8_t)P.y;
-                if (c0 == 0) { wg.base[rot] = s; wg.wph[rot] = (int)((d.w[0] >> 6) & 7u) | (int)((d.w[0] >> 9) & 7u) << 8; }
-            }
-            __syncwarp(FULLMASK);
-            // ---- one flood fill per rotation (lanes 0..nrot-1), in the reference's visiting order ----
-            if (lane < nrot) {
-                const int wd = wg.wph[lane] & 255, ph = wg.wph[lane] >> 8;
-                uint16_t starts[COLS]; int nst = 0;
-                for (int col = 0; col <= COLS - wd; ++col) {
-                    if (from_top) starts[nst++] = (uint16_t)((uint32_t)(ROWS - ph) | (uint32_t)col << 8);
-                    else if (wg.starty[lane][col] != 255) starts[nst++] = (uint16_t)((uint32_t)wg.starty[lane][col] | (uint32_t)col << 8);
-                }
-                wg.cnt[lane] = wiggle_rot(wg.fm[lane], wd, starts, nst, wg.stack[lane], wg.seen[lane], wg.list[lane], 128);
-            }
-            __syncwarp(FULLMASK);
-            const int n0 = wg.cnt[0], n1 = n0 + (nrot > 1 ? wg.cnt[1] : 0), n2 = n1 + (nrot > 2 ? wg.cnt[2] : 0), n3 = n2 + (nrot > 3 ? wg.cnt[3] : 0);
-            auto move_at = [&](int idx, int& slot, int& y) {
-                const int r = idx < n0 ? 0 : (idx < n1 ? 1 : (idx < n2 ? 2 : 3));
-                const int i = idx - (r == 0 ? 0 : (r == 1 ? n0 : (r == 2 ? n1 : n2)));
-                const uint32_t e = wg.list[r][i];
-                y = (int)(e & 31u); slot = wg.base[r] + (int)(e >> 8);
-            };
-            // ---- score every move; tag = position in the list ----
-            uint64_t key = 0; uint32_t tag = 0;
+            int off1[5];
+            wiggle_collect(wg1, s_tab, c, H, p_cur, from_top, lane, off1);
             const int level = (int)(lines / 10u);
-            for (int idx = lane; idx < n3; idx += 32) {
-                int slot, y;
-                move_at(idx, slot, y);
-                const SlotDesc d = load_slot12(s_tab, p_cur, slot);
-                if (prm.press.on && !is_time(d, y, prm.press, level)) continue;
-                Placement P; uint32_t full;
-                place_at(c, d, y, P, &full);
-                if (full != 0u) place_clear(d, P, full);
-                Feat f;
-                eval_features<ModeTraits<MODE>::CMASK>(P, d, pv, prm.rmask, f);
-                const uint64_t k = score_key(score_features<MODE>(f, prm.ids, w, F));
-                if (k > key) { key = k; tag = (uint32_t)idx; }
-                ++cnt;
+            uint64_t key = 0; uint32_t tag = 0;
+            bool leaf_is_first = true;
+            if (LOOKAHEAD == 2 && t + 1 < T && p_next < 7) {
+                // layer 2: every first move in list order (warp-uniform), expanded by the flood fill of the next piece
+                for (int i1 = 0; i1 < off1[4]; ++i1) {
+                    int slot1, y1;
+                    wiggle_move_at(wg1, off1, i1, slot1, y1);
+                    const SlotDesc d1 = load_slot12(s_tab, p_cur, slot1);
+                    if (prm.press.on && !is_time(d1, y1, prm.press, level)) continue;
+                    Placement P1; uint32_t full;
+                    place_at(c, d1, y1, P1, &full);
+                    if (full != 0u) place_clear(d1, P1, full);
+                    const PrevStat pv1 = next_stat(pv, P1, d1);
+                    const Heights H1 = pack_gh(pv1.gh);
+                    int off2[5];
+                    wiggle_collect(wg2, s_tab, P1.n, H1, p_next, from_top, lane, off2);
+                    wiggle_score<MODE>(wg2, off2, s_tab, P1.n, pv1, p_next, prm.press, (int)((lines + (uint32_t)P1.k) / 10u), prm.ids, w, F, prm.rmask,
+                                       (uint32_t)i1 << 11, lane, key, tag, cnt);
+                }
+                warp_argmax32(key, tag);
+                if (key != 0) leaf_is_first = false;
             }
-            warp_argmax32(key, tag);
+            if (leaf_is_first) {
+                key = 0; tag = 0;
+                wiggle_score<MODE>(wg1, off1, s_tab, c, pv, p_cur, prm.press, level, prm.ids, w, F, prm.rmask, 0u, lane, key, tag, cnt);
+                warp_argmax32(key, tag);
+            }
             if (key == 0) break;
-            // ---- commit ----
+            // ---- commit the (first) move of the winner ----
             int slot, y;
-            move_at((int)tag, slot, y);
+            wiggle_move_at(wg1, off1, (int)(leaf_is_first ? tag : (tag >> 11)), slot, y);
             const SlotDesc d = load_slot12(s_tab, p_cur, slot);
             Placement P; uint32_t full;
             place_at(c, d, y, P, &full);
@@ -1169,7 +1215,6 @@ __global__ void __launch_bounds__(BLOCK) play_games_wiggle_kernel(const PlayPara
             }
             ++t;
             p_cur = p_next; p_next = p_after;
-            __syncwarp(FULLMASK);
         }
         cnt = __reduce_add_sync(FULLMASK, cnt);
         if (lane == 0) {
@@ -1304,10 +1349,15 @@ static play_fn pick_generic(int mode, int lookahead, int lanes)
 }
 static play_fn pick_kernel(int mode, int lookahead, int lanes, int move_set)
 {
-    if (move_set & (TB200_MOVES_WIGGLE | TB200_MOVES_WIGGLE_DROP)) {      // caller guarantees lookahead 1
-        if (mode == MODE_W6) return play_games_wiggle_kernel<MODE_W6>;
-        if (mode == MODE_ALL45) return play_games_wiggle_kernel<MODE_ALL45>;
-        return play_games_wiggle_kernel<MODE_GENERIC>;
+    if (move_set & (TB200_MOVES_WIGGLE | TB200_MOVES_WIGGLE_DROP)) {
+        if (lookahead == 2) {
+            if (mode == MODE_W6) return play_games_wiggle_kernel<MODE_W6, 2>;
+            if (mode == MODE_ALL45) return play_games_wiggle_kernel<MODE_ALL45, 2>;
+            return play_games_wiggle_kernel<MODE_GENERIC, 2>;
+        }
+        if (mode == MODE_W6) return play_games_wiggle_kernel<MODE_W6, 1>;
+        if (mode == MODE_ALL45) return play_games_wiggle_kernel<MODE_ALL45, 1>;
+        return play_games_wiggle_kernel<MODE_GENERIC, 1>;
     }
     if (move_set != 0) return pick_generic<1>(mode, lookahead, lanes);     // overhang slides / pressure: extended generic kernels
     if (lanes == 64) return play_games_w6pair_kernel;      // caller guarantees lookahead 1 and the w6 set
@@ -1583,8 +1633,6 @@ static int check_play_args(tb200_ctx* ctx, const tb200_play_args* a)
         const int ms = a->move_set, inner = ms & ~TB200_MOVES_PRESSURE;
         if (ms < 0 || (inner != 0 && inner != TB200_MOVES_OVERHANG_SLIDE && inner != TB200_MOVES_WIGGLE && inner != TB200_MOVES_WIGGLE_DROP))
             return fail(ctx, TB200_E_BAD_ARG, "play_games: bad move_set");
-        if ((ms & (TB200_MOVES_WIGGLE | TB200_MOVES_WIGGLE_DROP)) && a->lookahead != 1)
-            return fail(ctx, TB200_E_BAD_ARG, "play_games: the wiggle move sets are implemented for lookahead 1 only");
     }
     return TB200_OK;
 }

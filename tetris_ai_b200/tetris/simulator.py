@@ -52,7 +52,7 @@ def move_with_overhang_slide(move_gen):
 
 class Wiggle:
     """move_with_wiggle(move_drop) / move_wiggle (simulator.py:49-85) as device move sets: every position the piece can
-    reach by moving down, left and right, in the order of the reference's recursion.  Lookahead 1 only."""
+    reach by moving down, left and right, in the order of the reference's recursion."""
 
     def __init__(self, move_set):
         self.move_set = move_set
