@@ -421,10 +421,12 @@ TB_HD uint32_t free_mask(const uint32_t c[COLS], const SlotDesc& d)
 
 // The reference's recursion for ONE rotation, with an explicit stack.  fm[col] = free map of (rot, col) for col in
 // 0..COLS-w and 0 beyond; starts[i] = y | col << 8 in the order the reference visits them; out[i] = y | col << 8 of the
-// i-th move.  stack needs 256 entries, seen COLS+1 words (zeroed here).  Returns the number of moves (<= cap).
+// i-th move.  stack needs 256 entries, seen COLS+1 words (scratch).  Returns the number of moves (<= cap).
 TB_HD int wiggle_rot(const uint32_t* fm, int w, const uint16_t* starts, int nstarts, uint16_t* stack, uint32_t* seen, uint16_t* out, int cap)
 {
-    for (int i = 0; i <= COLS; ++i) seen[i] = 0u;
+    // seen[col] holds the cells that are free AND not yet visited (a blocked cell returns at once whether or not it was
+    // seen before, so only free cells need the visited bit)
+    for (int i = 0; i <= COLS; ++i) seen[i] = fm[i];
     int n = 0;
     for (int si = 0; si < nstarts; ++si) {
         int sp = 0;
@@ -433,20 +435,18 @@ TB_HD int wiggle_rot(const uint32_t* fm, int w, const uint16_t* starts, int nsta
             const uint32_t fr = stack[sp - 1];
             const int y = (int)(fr & 31u), col = (int)((fr >> 8) & 15u), stage = (int)(fr >> 12);
             if (stage == 0) {
-                if ((seen[col] >> y) & 1u) { --sp; continue; }                    // :52
-                seen[col] |= 1u << y;
-                if (!((fm[col] >> y) & 1u)) { --sp; continue; }                   // :54 overlaps here
+                if (!((seen[col] >> y) & 1u)) { --sp; continue; }                 // :52 seen before, or :54 overlaps here
+                seen[col] &= ~(1u << y);
                 stack[sp - 1] = (uint16_t)(fr | 0x1000u);
                 if (y > 0 && ((fm[col] >> (y - 1)) & 1u)) stack[sp++] = (uint16_t)((uint32_t)(y - 1) | (uint32_t)col << 8);   // :58-60 keep falling
                 else if (n < cap) out[n++] = (uint16_t)((uint32_t)y | (uint32_t)col << 8);                                      // :55-57 resting: a move
             } else if (stage == 1) {
                 stack[sp - 1] = (uint16_t)((fr & 0x0FFFu) | 0x2000u);
                 if (col > 0) stack[sp++] = (uint16_t)((uint32_t)y | (uint32_t)(col - 1) << 8);          // :63-64
-            } else if (stage == 2) {
-                stack[sp - 1] = (uint16_t)((fr & 0x0FFFu) | 0x3000u);
-                if (col + w <= COLS) stack[sp++] = (uint16_t)((uint32_t)y | (uint32_t)(col + 1) << 8);   // :65-66
             } else {
-                --sp;
+                // :65-66 the right neighbour is the last thing this frame does: replace the frame instead of pushing
+                if (col + w <= COLS) stack[sp - 1] = (uint16_t)((uint32_t)y | (uint32_t)(col + 1) << 8);
+                else --sp;
             }
         }
     }
