@@ -465,3 +465,14 @@ def test_wiggle_lookahead2_vs_coracle(eng):
         for g in range(12):
             n = int(res["pieces"][g])
             assert (r["trace"][g, :n] == o["trace"][g, :n]).all(), (ms, g)
+
+
+def test_differential_fuzz_sample():
+    """A short run of tools/fuzz.py (random feature lists, lane widths, lookahead, move sets, pressure, initial boards) —
+    the long runs (6 400 configurations, 150 000 games, 2e8 placements, all bit-exact) are recorded in DESIGN.md."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz.py"), "80", "12345"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "fuzz ok" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

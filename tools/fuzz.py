@@ -1,0 +1,91 @@
+#!/usr/bin/env python3
+"""Differential fuzzing of the CUDA path against the plain-C oracle: random feature lists / weights / lane widths /
+lookahead / move sets / pressure parameters / initial boards / sequence lengths; every output field and every move is
+compared.  usage: fuzz.py [iterations] [seed]"""
+import os, sys, random, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tetris_ai_b200 import Engine
+from oracle import coracle, pyoracle
+
+NAMES = list(pyoracle.FEATURE_NAMES)
+W6 = ["landing_height", "eroded_cells", "row_trans", "col_trans", "pits", "cuml_wells"]
+W6V = [-4.500158825082766, 3.4181268101392694, -3.2178882868487753, -9.348695305445199, -7.899265427351652, -3.3855972247263626]
+
+
+def random_board(rng):
+    hmax = rng.choice([0, 0, 3, 8, 14, 18, 19])
+    rows = [0] * 20
+    dens = rng.choice([0.5, 0.75, 0.9])
+    for r in range(20 - hmax, 20):
+        v = 0
+        for c in range(10):
+            if rng.random() < dens:
+                v |= 1 << c
+        rows[r] = v if v != 0x3FF else v & ~(1 << rng.randrange(10))
+    return rows
+
+
+def main():
+    iters = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+    rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+    eng = Engine(0)
+    t0 = time.time()
+    stats = {"games": 0, "pieces": 0, "placements": 0}
+    for it in range(iters):
+        kind = rng.randrange(5)
+        if kind == 0:
+            names = W6
+        elif kind == 1:
+            names = NAMES
+        else:
+            names = rng.sample(NAMES, rng.randint(1, 14))
+        ms_name = rng.choice(["drop", "drop", "drop", "slide", "wiggle_top", "wiggle_drop"])
+        la = 2 if rng.random() < 0.25 else 1
+        pressure = None
+        if rng.random() < 0.3:
+            pressure = {"avg_lat": rng.uniform(100, 350), "resp_time": rng.uniform(30, 130), "move_eff": rng.uniform(0.9, 1.6), "two_but_rot": rng.random() < 0.5}
+        lanes = rng.choice([0, 64, 32, 16, 8, 4, 2, 1])
+        C, G = rng.randint(1, 24), rng.randint(1, 3)
+        T = rng.randint(1, 30) if (la == 2 or ms_name.startswith("wiggle")) else rng.randint(1, 220)
+        if la == 2 and ms_name.startswith("wiggle"):
+            T = rng.randint(1, 10); C = min(C, 4)
+        if names is W6 and rng.random() < 0.6:
+            w = np.array([[rng.gauss(v, 2.0) for v in W6V] for _ in range(C)])
+        elif rng.random() < 0.2:
+            w = np.array([[float(rng.randint(-2, 2)) for _ in names] for _ in range(C)])      # many ties
+        else:
+            w = np.array([[rng.gauss(0, 3.0) for _ in names] for _ in range(C)])
+        n = C * G
+        use_pieces = rng.random() < 0.5
+        pieces = np.array([[rng.randrange(7) for _ in range(T)] for _ in range(G)], dtype=np.uint8) if use_pieces else None
+        init = None
+        if rng.random() < 0.4:
+            init = np.array([random_board(rng) for _ in range(n)], dtype=np.uint16)
+        fids = [pyoracle.FEATURE_ID[x] for x in names]
+        bit = {"drop": 0, "slide": 1, "wiggle_top": 4, "wiggle_drop": 8}[ms_name]
+        seed = rng.getrandbits(40)
+        eng.set_features(names)
+        r = eng.play_games(w, G, pieces=pieces, T=T, seed=seed, lookahead=la, lanes=lanes, init_rows=init, want_trace=True, want_final=True,
+                           move_set=bit, pressure=pressure)
+        res = r["results"]
+        for g in range(n):
+            seq = pieces[g % G] if use_pieces else [pyoracle.hashed_piece(seed, g % G, t) for t in range(T)]
+            o = coracle.play_one(fids, w[g // G], seq, la, init_rows=None if init is None else init[g], move_set=ms_name, pressure=pressure)
+            k = o["pieces"]
+            ok = (int(res["pieces"][g]) == k and int(res["lines"][g]) == o["lines"] and [int(x) for x in res["hist"][g]] == o["hist"]
+                  and int(res["score"][g]) == o["score"] and int(res["placements"][g]) == o["placements"]
+                  and r["trace"][g, :k].tobytes() == o["trace"].tobytes() and list(r["final"][g]) == list(o["final"]))
+            if not ok:
+                print("MISMATCH iteration", it, "game", g, dict(names=names, ms=ms_name, la=la, pressure=pressure, lanes=lanes, C=C, G=G, T=T, seed=seed,
+                                                              use_pieces=use_pieces, init=init is not None))
+                print(" gpu:", res[g], r["trace"][g, :k + 1].tolist()[:12])
+                print(" cpu:", o["pieces"], o["lines"], o["hist"], o["score"], o["placements"], o["trace"].tolist()[:12])
+                sys.exit(1)
+            stats["games"] += 1; stats["pieces"] += k; stats["placements"] += o["placements"]
+    print("fuzz ok: %d iterations, %d games, %d pieces, %d placements, %.1f s" % (iters, stats["games"], stats["pieces"], stats["placements"], time.time() - t0))
+
+
+if __name__ == "__main__":
+    main()
