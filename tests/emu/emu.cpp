@@ -44,6 +44,43 @@ static int wiggle_list(const uint32_t c[COLS], const Heights& H, int piece, bool
     return n;
 }
 
+// self-check of wiggle_rot's stop set: for `trials` random subsets of each rotation's move list the early-out search must
+// return the first listed move of the subset.  Returns the number of failures.
+extern "C" int emu_wiggle_stop_check(const uint16_t* rows, int piece, int from_top, uint32_t rng, int trials)
+{
+    const Tables& tab = host_tables();
+    uint32_t c[COLS];
+    rows_to_cols(rows, c);
+    const Heights H = pack_heights(c);
+    int bad = 0, s0 = 0;
+    while (s0 < tab.nslots[piece]) {
+        const int w = (int)((tab.slot[piece][s0].w[0] >> 6) & 7u), ph = (int)((tab.slot[piece][s0].w[0] >> 9) & 7u);
+        const int ncol = COLS - w + 1;
+        uint32_t fm[COLS + 1]; uint16_t starts[COLS]; int ns = 0;
+        for (int i = 0; i <= COLS; ++i) fm[i] = 0;
+        for (int col = 0; col < ncol; ++col) {
+            fm[col] = free_mask(c, tab.slot[piece][s0 + col]);
+            if (from_top) starts[ns++] = (uint16_t)((ROWS - ph) | col << 8);
+            else { Placement P; if (place_slot(c, H, tab.slot[piece][s0 + col], P)) starts[ns++] = (uint16_t)(P.y | col << 8); }
+        }
+        uint16_t stack[256]; uint32_t seen[COLS + 1]; uint16_t lst[256], one[256];
+        const int m = wiggle_rot(fm, w, starts, ns, stack, seen, lst, 256);
+        for (int tr = 0; tr < trials && m > 0; ++tr) {
+            uint32_t stop[COLS + 1];
+            for (int i = 0; i <= COLS; ++i) stop[i] = 0;
+            int first = -1;
+            for (int i = 0; i < m; ++i) {
+                rng = rng * 1664525u + 1013904223u;
+                if ((rng >> 29) == 0u || (first < 0 && i == m - 1)) { stop[lst[i] >> 8] |= 1u << (lst[i] & 31u); if (first < 0) first = i; }
+            }
+            const int r = wiggle_rot(fm, w, starts, ns, stack, seen, one, 256, stop);
+            if (r != 1 || one[0] != lst[first]) ++bad;
+        }
+        s0 += ncol;
+    }
+    return bad;
+}
+
 // candidate bookkeeping: maximise key, ties -> smallest tag (enumeration order); mv = placement to commit
 struct Best { uint64_t key; uint32_t tag; uint32_t mv; };
 
@@ -258,6 +295,33 @@ void emu_eval_placement(const uint16_t* prev_rows, int piece, int rot, int col, 
 }
 
 int emu_hashed_piece(uint64_t seed, uint64_t stream, uint64_t t) { return hashed_piece(seed, stream, t); }
+
+// the wiggle move SET (bit-parallel flood fill, no order): (rot, row, col) triples in slot order
+int emu_wiggle_set(const uint16_t* rows, int piece, int from_top, int* out)
+{
+    const Tables& tab = host_tables();
+    uint32_t c[COLS];
+    rows_to_cols(rows, c);
+    const Heights H = pack_heights(c);
+    int n = 0, s0 = 0;
+    while (s0 < tab.nslots[piece]) {
+        const int rot = (int)((tab.slot[piece][s0].w[0] >> 4) & 3u), w = (int)((tab.slot[piece][s0].w[0] >> 6) & 7u), ph = (int)((tab.slot[piece][s0].w[0] >> 9) & 7u);
+        const int ncol = COLS - w + 1;
+        uint32_t fm[COLS + 1], reach[COLS + 1]; uint16_t starts[COLS]; int ns = 0;
+        for (int i = 0; i <= COLS; ++i) fm[i] = 0;
+        for (int col = 0; col < ncol; ++col) {
+            fm[col] = free_mask(c, tab.slot[piece][s0 + col]);
+            if (from_top) starts[ns++] = (uint16_t)((ROWS - ph) | col << 8);
+            else { Placement P; if (place_slot(c, H, tab.slot[piece][s0 + col], P)) starts[ns++] = (uint16_t)(P.y | col << 8); }
+        }
+        wiggle_reach(fm, w, starts, ns, reach);
+        for (int col = 0; col < ncol; ++col)
+            for (int y = 0; y < ROWS; ++y)
+                if ((reach[col] >> y) & 1u) { out[3 * n] = rot; out[3 * n + 1] = ROWS - y - ph; out[3 * n + 2] = col; ++n; }
+        s0 += ncol;
+    }
+    return n;
+}
 
 // move list (rot, row, col) of move_set 0 (move_drop) / 1 (move_with_overhang_slide(move_drop)); returns the count
 int emu_moves(const uint16_t* rows, int piece, int move_set, int* out)

@@ -69,3 +69,17 @@ def moves(rows, piece, move_set=0):
     lib().emu_moves.restype = ctypes.c_int
     n = lib().emu_moves(_p(rows), ctypes.c_int(piece), ctypes.c_int(move_set), _p(out))
     return [tuple(int(x) for x in out[i]) for i in range(n)]
+
+
+def wiggle_set(rows, piece, from_top=True):
+    rows = np.ascontiguousarray(rows, dtype=np.uint16)
+    out = np.zeros((640, 3), dtype=np.int32)
+    lib().emu_wiggle_set.restype = ctypes.c_int
+    n = lib().emu_wiggle_set(_p(rows), ctypes.c_int(piece), ctypes.c_int(1 if from_top else 0), _p(out))
+    return sorted(tuple(int(x) for x in out[i]) for i in range(n))
+
+
+def wiggle_stop_check(rows, piece, from_top, seed, trials=8):
+    rows = np.ascontiguousarray(rows, dtype=np.uint16)
+    lib().emu_wiggle_stop_check.restype = ctypes.c_int
+    return lib().emu_wiggle_stop_check(_p(rows), ctypes.c_int(piece), ctypes.c_int(1 if from_top else 0), ctypes.c_uint32(seed), ctypes.c_int(trials))

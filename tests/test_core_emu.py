@@ -266,3 +266,26 @@ def test_emu_wiggle_vs_coracle_random():
         b = emu_lib.play_one(fids, w, seq, move_set=ms[1])
         assert (a["pieces"], a["lines"], a["score"], a["placements"]) == (b["pieces"], b["lines"], b["score"], b["placements"]), gi
         assert a["trace"].tobytes() == b["trace"].tobytes(), gi
+
+
+def test_emu_wiggle_set_equals_list_as_set():
+    """The bit-parallel flood fill (wiggle_reach) yields exactly the moves of the reference's recursion, as a set."""
+    from conftest import load_golden
+    import random as _r
+    for i, b in enumerate(load_golden("wiggle_moves.json.gz")["boards"]):
+        for p in range(7):
+            assert emu_lib.wiggle_set(b["board"], p, True) == sorted(tuple(m) for m in b["top"][p]), (i, p)
+            assert emu_lib.wiggle_set(b["board"], p, False) == sorted(tuple(m) for m in b["drop"][p]), (i, p)
+    rng = _r.Random(4)
+    for _ in range(300):                       # random (unreachable, cave-rich) boards against the C oracle's recursion
+        hmax = rng.randint(0, 19)
+        rows = [0] * 20
+        for r in range(20 - hmax, 20):
+            v = rng.getrandbits(10) & rng.getrandbits(10) | (rng.getrandbits(10) if rng.random() < 0.5 else 0)
+            rows[r] = v if v != 0x3FF else 0x3FE
+        p = rng.randrange(7)
+        assert emu_lib.wiggle_set(rows, p, True) == sorted(coracle.moves(rows, p, "wiggle_top"))
+        assert emu_lib.wiggle_set(rows, p, False) == sorted(coracle.moves(rows, p, "wiggle_drop"))
+        # the tie break: the early-out search returns the first listed move of any subset
+        assert emu_lib.wiggle_stop_check(rows, p, True, rng.getrandbits(32)) == 0
+        assert emu_lib.wiggle_stop_check(rows, p, False, rng.getrandbits(32)) == 0

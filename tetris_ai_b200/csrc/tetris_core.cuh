@@ -421,8 +421,10 @@ TB_HD uint32_t free_mask(const uint32_t c[COLS], const SlotDesc& d)
 
 // The reference's recursion for ONE rotation, with an explicit stack.  fm[col] = free map of (rot, col) for col in
 // 0..COLS-w and 0 beyond; starts[i] = y | col << 8 in the order the reference visits them; out[i] = y | col << 8 of the
-// i-th move.  stack needs 256 entries, seen COLS+1 words (scratch).  Returns the number of moves (<= cap).
-TB_HD int wiggle_rot(const uint32_t* fm, int w, const uint16_t* starts, int nstarts, uint16_t* stack, uint32_t* seen, uint16_t* out, int cap)
+// i-th move.  stack needs 256 entries, seen COLS+1 words (scratch).  Returns the number of moves (<= cap).  With a stop
+// set (stop[col] bit y) the search ends at the first visited move that belongs to it: out[0] = that move, returns 1.
+TB_HD int wiggle_rot(const uint32_t* fm, int w, const uint16_t* starts, int nstarts, uint16_t* stack, uint32_t* seen, uint16_t* out, int cap,
+                      const uint32_t* stop = nullptr)
 {
     // seen[col] holds the cells that are free AND not yet visited (a blocked cell returns at once whether or not it was
     // seen before, so only free cells need the visited bit)
@@ -439,7 +441,13 @@ TB_HD int wiggle_rot(const uint32_t* fm, int w, const uint16_t* starts, int nsta
                 seen[col] &= ~(1u << y);
                 stack[sp - 1] = (uint16_t)(fr | 0x1000u);
                 if (y > 0 && ((fm[col] >> (y - 1)) & 1u)) stack[sp++] = (uint16_t)((uint32_t)(y - 1) | (uint32_t)col << 8);   // :58-60 keep falling
-                else if (n < cap) out[n++] = (uint16_t)((uint32_t)y | (uint32_t)col << 8);                                      // :55-57 resting: a move
+                else {                                                                                                         // :55-57 resting: a move
+                    if (n < cap) out[n++] = (uint16_t)((uint32_t)y | (uint32_t)col << 8);
+                    if (stop != nullptr && ((stop[col] >> y) & 1u)) {                     // tie break: the first visited move of the stop set
+                        out[0] = (uint16_t)((uint32_t)y | (uint32_t)col << 8);
+                        return 1;
+                    }
+                }
             } else if (stage == 1) {
                 stack[sp - 1] = (uint16_t)((fr & 0x0FFFu) | 0x2000u);
                 if (col > 0) stack[sp++] = (uint16_t)((uint32_t)y | (uint32_t)(col - 1) << 8);          // :63-64
@@ -451,6 +459,45 @@ TB_HD int wiggle_rot(const uint32_t* fm, int w, const uint16_t* starts, int nsta
         }
     }
     return n;
+}
+
+// Set-only companion of wiggle_rot: the cells reachable from the starts by down / left / right moves through free
+// cells, by bit-parallel flood fill (no visiting order).  The resting cells among them are the moves of the wiggle move
+// sets as a SET; the kernels use it when the best move is unique and fall back to wiggle_rot only to break ties.
+TB_HD uint32_t fill_down(uint32_t seed, uint32_t free)      // cells reachable from seed (subset of free) by moving down through free cells
+{
+    uint32_t r = seed, f = free;
+    r |= (r >> 1) & f; f &= f >> 1;
+    r |= (r >> 2) & f; f &= f >> 2;
+    r |= (r >> 4) & f; f &= f >> 4;
+    r |= (r >> 8) & f; f &= f >> 8;
+    r |= (r >> 16) & f;
+    return r;
+}
+
+TB_HD void wiggle_reach(const uint32_t* fm, int w, const uint16_t* starts, int nstarts, uint32_t* reach)
+{
+    const int ncol = COLS - w + 1;
+    for (int i = 0; i <= COLS; ++i) reach[i] = 0u;
+    for (int i = 0; i < nstarts; ++i) {
+        const int y = (int)(starts[i] & 31u), col = (int)(starts[i] >> 8);
+        reach[col] |= fm[col] & (1u << y);
+    }
+    bool changed = true;
+    while (changed) {
+        changed = false;
+        for (int col = 0; col < ncol; ++col) {
+            const uint32_t seed = (reach[col] | (col > 0 ? reach[col - 1] : 0u) | (col + 1 < ncol ? reach[col + 1] : 0u)) & fm[col];
+            const uint32_t r = fill_down(seed, fm[col]);
+            if (r != reach[col]) { reach[col] = r; changed = true; }
+        }
+        for (int col = ncol - 1; col >= 0; --col) {
+            const uint32_t seed = (reach[col] | (col > 0 ? reach[col - 1] : 0u) | (col + 1 < ncol ? reach[col + 1] : 0u)) & fm[col];
+            const uint32_t r = fill_down(seed, fm[col]);
+            if (r != reach[col]) { reach[col] = r; changed = true; }
+        }
+    }
+    for (int col = 0; col <= COLS; ++col) reach[col] &= ~(fm[col] << 1);     // keep the resting cells: free, and the cell below is not
 }
 
 TB_HD bool place_slot(const uint32_t c[COLS], const Heights& H, const SlotDesc& d, Placement& p)

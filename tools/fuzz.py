@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Differential fuzzing of the CUDA path against the plain-C oracle: random feature lists / weights / lane widths /
 lookahead / move sets / pressure parameters / initial boards / sequence lengths; every output field and every move is
-compared.  usage: fuzz.py [iterations] [seed]"""
+compared.  usage: fuzz.py [iterations] [seed]   (FUZZ_MOVE_SETS=wiggle_top,wiggle_drop restricts the move sets)"""
 import os, sys, random, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -41,7 +41,7 @@ def main():
             names = NAMES
         else:
             names = rng.sample(NAMES, rng.randint(1, 14))
-        ms_name = rng.choice(["drop", "drop", "drop", "slide", "wiggle_top", "wiggle_drop"])
+        ms_name = rng.choice(os.environ.get("FUZZ_MOVE_SETS", "drop,drop,drop,slide,wiggle_top,wiggle_drop").split(","))
         la = 2 if rng.random() < 0.25 else 1
         pressure = None
         if rng.random() < 0.3:
