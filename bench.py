@@ -277,6 +277,7 @@ def run_gpu_arm(args):
     sync_all()
     kernel_ms = sum(kms) / len(kms)
     lanes_used = eng.last_timing()["lanes"]
+    launches_per_step = int(eng.last_timing()["kernels_launched"])      # play kernels (1, or 3 re-spreading stages) + fitness
     res = np.frombuffer(d_res.cpu().numpy().tobytes(), dtype=_lib.RESULT_DTYPE)
     placements = int(res["placements"].sum())
     pieces = int(res["pieces"].sum())
@@ -342,13 +343,16 @@ def run_gpu_arm(args):
         "placements_per_step": placements_all, "pieces_per_step": pieces_all, "lanes_per_game": lanes_used,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(tm["h2d_bytes"]), "d2h_bytes_per_step": int(tm["d2h_bytes"]),
                 "ms_per_step": 1e3 * e2e_s / args.steps, "api": "PopulationEvaluator.evaluate -> tb200_play_games (host buffers, pinned)"},
-        "gpu_launches": 2 * args.steps,
+        "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "int-issue", "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tops/s (thread integer ops)",
                      "frac": achieved / int_peak, "traffic": traffic,
-                     "kernel": {64: "play_games_w6pair_kernel", 32: "play_games_w6fast_kernel"}.get(lanes_used, "play_games_w6grp_kernel<%d>" % lanes_used),
+                     "kernel": ("play_games_w6fast_kernel<staged> x2 + play_games_w6pair_kernel (re-spreading stages of one play, one event pair around all three)"
+                                if launches_per_step > 2 else
+                                {64: "play_games_w6pair_kernel", 32: "play_games_w6fast_kernel"}.get(lanes_used, "play_games_w6grp_kernel<%d>" % lanes_used)),
                      "kernel_ms": kernel_ms, "kernel_launches_averaged": len(kms),
-                     "note": "1000 games = 1000-2000 warps on 592 warp schedulers: the run time of this workload is the serial chain of its "
-                             "longest game, so the fraction is low by construction; see throughput_regime for the same kernels with the machine full",
+                     "note": "1000 games on 592 warp schedulers: the run time of this workload is the serial chain of its longest game "
+                             "(1000 pieces x 1230-1900 cycles per piece depending on how many live games share a scheduler), so the fraction is "
+                             "low by construction; see throughput_regime for the same evaluation code with the machine full",
                      "algorithmic_ops_per_placement": W6_OPS_PER_PLACEMENT,
                      "peak_source": "measured: bin/int_peak on this pool's B200 (profiles/INT_PEAK_r01.json)",
                      "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9,

@@ -232,6 +232,39 @@ def test_properties_full_size(eng):
     assert (base["pieces"] <= T).all()
 
 
+@pytest.mark.parametrize("n,T,spread", [(1000, 400, 6.0), (600, 300, 8.0), (2300, 200, 5.0), (400, 256, 10.0), (1000, 1000, 0.5)])
+def test_k2_respread_stages_vs_single_launch_and_coracle(eng, n, T, spread):
+    """Latency regime (automatic lanes, 2..16 games per SM): the play is split into stream-ordered stages that hand the
+    surviving games — board, counters, position in the piece stream — to sparser launches.  Every output must equal the
+    single-launch kernel's (lanes = 32) and the C oracle's: results, every move, every winning score, final boards."""
+    rng = np.random.default_rng(n + T)
+    w = np.array(W6_VALS)[None, :] + rng.normal(0, spread, size=(n, 6))          # wide spread: games die at very different ages
+    fids = [pyoracle.FEATURE_ID[x] for x in W6_NAMES]
+    eng.set_features(W6_NAMES)
+    seqid = (np.arange(n, dtype=np.int32) * 7) % 64
+    init = np.zeros((n, 20), dtype=np.uint16)
+    init[::3, 19] = 0x1EF; init[::5, 18] = 0x3F0; init[::5, 19] |= 0x3F0
+    lines0 = (np.arange(n, dtype=np.uint32) * 13) % 57
+    kw = dict(T=T, seed=21, seq_of_game=seqid, init_rows=init, init_lines=lines0, want_trace=True, want_scores=True, want_final=True)
+    a = eng.play_games(w, 1, **kw)                       # staged
+    assert eng.last_timing()["kernels_launched"] >= 3
+    b = eng.play_games(w, 1, lanes=32, **kw)             # one launch
+    assert eng.last_timing()["kernels_launched"] <= 2
+    assert (a["results"] == b["results"]).all()
+    assert (a["final"] == b["final"]).all()
+    for g in range(n):
+        k = int(a["results"]["pieces"][g])
+        assert a["trace"][g, :k].tobytes() == b["trace"][g, :k].tobytes()
+        assert bits(a["scores"][g, :k]).tobytes() == bits(b["scores"][g, :k]).tobytes()
+    # the oracle's batch entry starts from empty boards: same population without the initial boards / lines
+    res = eng.play_games(w, 1, T=T, seed=21, seq_of_game=seqid)["results"]
+    assert eng.last_timing()["kernels_launched"] >= 3
+    o = coracle.play_games(fids, w, 1, T=T, seed=21, seq_of_game=seqid, threads=16)
+    assert (res["pieces"] == o["pieces"]).all() and (res["lines"] == o["lines"]).all()
+    assert (res["score"] == o["score"]).all() and (res["placements"] == o["placements"]).all()
+    assert (res["hist"] == o["hist"]).all()
+
+
 # ------------------------------------------------------------------------------------------------
 # edge cases: tiny / ragged shapes, immediate game over, max_moves, explicit sequence maps, many tickets
 # ------------------------------------------------------------------------------------------------

@@ -62,6 +62,20 @@ struct PlayParams {
     int32_t   move_set;              // bit 0: overhang slides, bit 1: pressure filter (extended generic kernels only)
     Pressure  press;                 // move_with_pressure parameters (press.on mirrors bit 1)
     uint8_t   ids[TB200_MAX_WEIGHTED];
+    // re-spreading stages of the latency regime (K2f / K2p only; st_ctl == null: off) — see launch_play
+    uint32_t* st_ctl;                // [0..2] ticket of stage s, [3] games finished so far, [4 + s] games handed to stage s
+    const uint32_t* st_list_in;      // game ids handed to this stage, or null: all games, fresh
+    uint32_t* st_list_out;           // survivors of this stage (null in the last stage)
+    struct GameSave* st_save;        // [n_games] state of the handed-over games
+    int32_t   st_stage;
+    uint32_t  st_cut;                // leave the stage once (games not yet finished) <= st_cut; 0: run to the end
+};
+
+// state of a game handed from one stage to the next (80 bytes)
+struct GameSave {
+    uint32_t c[COLS];
+    uint32_t t, lines, h1, h2, h3, h4, cnt, pad;
+    uint64_t gscore;
 };
 
 // ---- argmax over a LANES-wide group: maximise key, ties -> smallest tag (first in enumeration order)
@@ -532,8 +546,22 @@ __global__ void __launch_bounds__(BLOCK) play_games_w32_kernel(const PlayParams 
 // Slots 32 and 33 of the 34-slot pieces run as a second, interleaved instruction stream.
 // ---------------------------------------------------------------------------------------------
 
+template <bool STAGED>
 __global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayParams prm)
 {
+    constexpr bool staged = STAGED;
+    uint32_t* const ticket = staged ? prm.st_ctl + prm.st_stage : prm.ticket;
+    uint32_t n_in = prm.n_games;
+    if (staged && prm.st_list_in) {
+        n_in = prm.st_ctl[4 + prm.st_stage];
+        if (n_in == 0u) return;                    // nothing was handed over: the earlier stage finished every game
+    }
+    const uint32_t* const finished = staged ? prm.st_ctl + 3 : nullptr;
+    auto poll_finished = [&]() -> uint32_t {           // relaxed, L2-coherent; asm volatile so it is re-read every time
+        uint32_t v;
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(finished) : "memory");
+        return v;
+    };
     __shared__ Tables s_tab;
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
@@ -546,14 +574,26 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayPara
 
     for (;;) {
         uint32_t game = 0;
-        if (lane == 0) game = atomicAdd(prm.ticket, 1u);
+        if (lane == 0) {
+            game = atomicAdd(ticket, 1u);
+            if (game < n_in && prm.st_list_in) game = prm.st_list_in[game]; else if (game >= n_in) game = 0xffffffffu;
+        }
         game = __shfl_sync(FULLMASK, game, 0);
-        if (game >= prm.n_games) break;
+        if (game == 0xffffffffu) break;
+        const bool resume = staged && prm.st_list_in != nullptr;
         const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : (prm.per_game_weights != 0 ? game : game % (uint32_t)prm.G);
         const uint64_t stream = sq;
         const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
         uint32_t c[COLS];
-        if (prm.init_rows) {
+        uint32_t t = 0, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+        uint64_t gscore = 0;
+        if (resume) {
+            const GameSave* sv = prm.st_save + game;
+#pragma unroll
+            for (int k = 0; k < COLS; ++k) c[k] = sv->c[k];
+            t = sv->t; lines = sv->lines; h1 = sv->h1; h2 = sv->h2; h3 = sv->h3; h4 = sv->h4; gscore = sv->gscore;
+            if (lane == 0) cnt = sv->cnt;
+        } else if (prm.init_rows) {
             uint16_t rows[ROWS];
             for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
             rows_to_cols(rows, c);
@@ -561,8 +601,9 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayPara
 #pragma unroll
             for (int k = 0; k < COLS; ++k) c[k] = 0;
         }
+        if (!resume && prm.init_lines) lines = prm.init_lines[game];
         GameStat g = game_stat(c);
-        const int cells0 = g.cells;
+        const int cells0 = g.cells - 4 * (int)t;       // g.cells = cells0 + 4 (pieces placed) - 10 (lines cleared since here)
         double w[6];
         {
             const size_t wrow = prm.per_game_weights > 0 ? (size_t)game : (prm.per_game_weights < 0 ? 0 : (size_t)(game / (uint32_t)prm.G));
@@ -575,18 +616,18 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayPara
             if (tt >= T) return 7u;
             return seq ? (uint32_t)__ldg(seq + tt) : (uint32_t)hashed_piece(prm.seed, stream, tt);
         };
-        uint32_t base = 0;
-        uint32_t win = load_piece((uint32_t)lane) | load_piece(32u + (uint32_t)lane) << 8;
+        uint32_t base = t;
+        uint32_t win = load_piece(base + (uint32_t)lane) | load_piece(base + 32u + (uint32_t)lane) << 8;
         auto piece_at = [&](uint32_t tt) -> int {          // base <= tt < base + 64, tt warp-uniform
             const uint32_t idx = tt - base;
             const uint32_t v = __shfl_sync(FULLMASK, win, (int)(idx & 31u));
             return (int)((v >> ((idx >> 5) * 8u)) & 255u);
         };
-        uint32_t t = 0, lines = prm.init_lines ? prm.init_lines[game] : 0u, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
         const uint32_t lines0 = lines;
-        uint64_t gscore = 0;
         const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
-        int p_cur = piece_at(0), p_next = piece_at(1);
+        int p_cur = piece_at(t), p_next = piece_at(t + 1u);
+        uint32_t fin_seen = staged ? poll_finished() : 0u;      // polled ahead of its use: the load never stalls the game
+        bool handed = staged && prm.n_games - fin_seen <= prm.st_cut;
         // descriptors of the current piece (prefetched one piece ahead, they do not depend on the board);
         // word 7 of every descriptor of a piece (padding slots included) is its slot count
         const int slotB = lane < 2 ? lane + 32 : 0;
@@ -596,7 +637,10 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayPara
 #ifdef TB_PHASES
         long long ph[8] = {0,0,0,0,0,0,0,0}; long long last_ = clock64();
 #endif
-        while (t < stop && p_cur < 7) {
+        bool over = false;                              // no legal placement
+        while (!handed && t < stop && p_cur < 7) {
+            uint32_t fin_next = fin_seen;
+            if (staged && (t & 3u) == 0u) fin_next = poll_finished();
             PH(5)
             if (t + 2u - base >= 64u) {              // advance the piece window
                 base += 32u;
@@ -643,7 +687,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayPara
             // ---- argmax: hi word by REDUX; the lo word / tag only when two lanes share the hi word ----
             const uint32_t hi = (uint32_t)(key >> 32);
             const uint32_t mhi = __reduce_max_sync(FULLMASK, hi);
-            if (mhi == 0u) break;                   // no legal placement: game over (simulator.py:187-189)
+            if (mhi == 0u) { over = true; break; }  // no legal placement: game over (simulator.py:187-189)
             const uint32_t tie = __ballot_sync(FULLMASK, hi == mhi);
             int src = __ffs((int)tie) - 1;
             if (tie & (tie - 1u)) {
@@ -683,13 +727,26 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayPara
             ++t;
             p_cur = p_next; p_next = p_after;
             dA = dA_next; dB = dB_next;
+            if (staged) { handed = prm.n_games - fin_seen <= prm.st_cut; fin_seen = fin_next; }
             PH(4)
         }
+        handed = handed && !over && t < stop && p_cur < 7;      // a game that ended anyway is finished, not handed over
 #ifdef TB_PHASES
         if (lane == 0) { for (int i = 0; i < 6; ++i) atomicAdd(&g_phase[i], (unsigned long long)ph[i]); atomicAdd(&g_phase[6], (unsigned long long)t); }
 #endif
         cnt = __reduce_add_sync(FULLMASK, cnt);
+        if (handed) {                                   // few enough games are left: hand this one to the next, sparser stage
+            if (lane == 0) {
+                GameSave* sv = prm.st_save + game;
+#pragma unroll
+                for (int k = 0; k < COLS; ++k) sv->c[k] = c[k];
+                sv->t = t; sv->lines = lines; sv->h1 = h1; sv->h2 = h2; sv->h3 = h3; sv->h4 = h4; sv->cnt = cnt; sv->gscore = gscore;
+                prm.st_list_out[atomicAdd(prm.st_ctl + 5 + prm.st_stage, 1u)] = game;
+            }
+            continue;
+        }
         if (lane == 0) {
+            if (staged) atomicAdd(prm.st_ctl + 3, 1u);
             tb200_game_result* r = prm.results + game;
             r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4;
             r->score = gscore; r->placements = cnt;
@@ -714,6 +771,13 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayPara
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) play_games_w6pair_kernel(const PlayParams prm)
 {
+    const bool staged = prm.st_ctl != nullptr;
+    uint32_t* const ticket = staged ? prm.st_ctl + prm.st_stage : prm.ticket;
+    uint32_t n_in = prm.n_games;
+    if (staged && prm.st_list_in) {
+        n_in = prm.st_ctl[4 + prm.st_stage];
+        if (n_in == 0u) return;
+    }
     __shared__ Tables s_tab;
     __shared__ uint4 s_x[2][2][5];
     __shared__ uint32_t s_game;
@@ -730,16 +794,29 @@ __global__ void __launch_bounds__(64) play_games_w6pair_kernel(const PlayParams 
     const uint32_t T = prm.T;
 
     for (;;) {
-        if (threadIdx.x == 0) s_game = atomicAdd(prm.ticket, 1u);
+        if (threadIdx.x == 0) {
+            uint32_t gi = atomicAdd(ticket, 1u);
+            if (gi < n_in && prm.st_list_in) gi = prm.st_list_in[gi]; else if (gi >= n_in) gi = 0xffffffffu;
+            s_game = gi;
+        }
         __syncthreads();
         const uint32_t game = s_game;
         __syncthreads();
-        if (game >= prm.n_games) break;
+        if (game == 0xffffffffu) break;
+        const bool resume = staged && prm.st_list_in != nullptr;
         const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : (prm.per_game_weights != 0 ? game : game % (uint32_t)prm.G);
         const uint64_t stream = sq;
         const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
         uint32_t c[COLS];
-        if (prm.init_rows) {
+        uint32_t t = 0, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+        uint64_t gscore = 0;
+        if (resume) {
+            const GameSave* sv = prm.st_save + game;
+#pragma unroll
+            for (int k = 0; k < COLS; ++k) c[k] = sv->c[k];
+            t = sv->t; lines = sv->lines; h1 = sv->h1; h2 = sv->h2; h3 = sv->h3; h4 = sv->h4; gscore = sv->gscore;
+            if (threadIdx.x == 0) cnt = sv->cnt;
+        } else if (prm.init_rows) {
             uint16_t rows[ROWS];
             for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
             rows_to_cols(rows, c);
@@ -747,8 +824,9 @@ __global__ void __launch_bounds__(64) play_games_w6pair_kernel(const PlayParams 
 #pragma unroll
             for (int k = 0; k < COLS; ++k) c[k] = 0;
         }
+        if (!resume && prm.init_lines) lines = prm.init_lines[game];
         GameStat g = game_stat(c);
-        const int cells0 = g.cells;
+        const int cells0 = g.cells - 4 * (int)t;
         double w[6];
         {
             const size_t wrow = prm.per_game_weights > 0 ? (size_t)game : (prm.per_game_weights < 0 ? 0 : (size_t)(game / (uint32_t)prm.G));
@@ -761,18 +839,16 @@ __global__ void __launch_bounds__(64) play_games_w6pair_kernel(const PlayParams 
             if (tt >= T) return 7u;
             return seq ? (uint32_t)__ldg(seq + tt) : (uint32_t)hashed_piece(prm.seed, stream, tt);
         };
-        uint32_t base = 0;
-        uint32_t win = load_piece((uint32_t)lane) | load_piece(32u + (uint32_t)lane) << 8;
+        uint32_t base = t;
+        uint32_t win = load_piece(base + (uint32_t)lane) | load_piece(base + 32u + (uint32_t)lane) << 8;
         auto piece_at = [&](uint32_t tt) -> int {          // base <= tt < base + 64, uniform tt
             const uint32_t idx = tt - base;
             const uint32_t v = __shfl_sync(FULLMASK, win, (int)(idx & 31u));
             return (int)((v >> ((idx >> 5) * 8u)) & 255u);
         };
-        uint32_t t = 0, lines = prm.init_lines ? prm.init_lines[game] : 0u, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
         const uint32_t lines0 = lines;
-        uint64_t gscore = 0;
         const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
-        int p_cur = piece_at(0), p_next = piece_at(1);
+        int p_cur = piece_at(t), p_next = piece_at(t + 1u);
         SlotDesc d = load_slot12(s_tab, p_cur < 7 ? p_cur : 0, myslot);
         uint32_t par = 0;
 
@@ -1736,7 +1812,7 @@ static play_fn pick_kernel(int mode, int lookahead, int lanes, int move_set)
     if (lookahead == 1 && mode == MODE_W6 && lanes == 2) return play_games_w6grp_kernel<2>;
     if (lookahead == 1 && mode == MODE_W6 && lanes == 1) return play_games_w6grp_kernel<1>;
     if (lookahead == 1 && lanes == 32) {
-        if (mode == MODE_W6) return play_games_w6fast_kernel;
+        if (mode == MODE_W6) return play_games_w6fast_kernel<false>;
         if (mode == MODE_ALL45) return play_games_w32_kernel<MODE_ALL45>;
         return play_games_w32_kernel<MODE_GENERIC>;
     }
@@ -1759,6 +1835,11 @@ struct tb200_ctx {
     uint64_t rmask = 0;
     uint8_t ids[TB200_MAX_WEIGHTED] = {0};
     uint32_t* d_ticket = nullptr;
+    // workspace of the re-spreading stages (launch_play): control words, two hand-over lists, saved game states
+    char* d_stage = nullptr;
+    uint32_t stage_cap = 0;              // games the workspace holds
+    bool staging_enabled = true;
+    int stage_cut1 = 0, stage_cut2 = 0;  // hand-over thresholds (games still unfinished): 4 and 2 per SM unless TB200_STAGE_CUTS=a,b
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool timing_valid = false;
@@ -1848,6 +1929,8 @@ int tb200_create(int device, tb200_ctx** out)
     static const tb::Tables host_tab = { TB_SLOT_TABLE_INIT, TB_NSLOTS_INIT };
     cudaError_t e = cudaMemcpyToSymbol(tb::c_tables, &host_tab, sizeof(tb::Tables));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_ticket, sizeof(uint32_t));
+    ctx->stage_cap = (uint32_t)(16 * ctx->sms);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_stage, 256 + (size_t)ctx->stage_cap * (2 * sizeof(uint32_t) + sizeof(tb::GameSave)));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e != cudaSuccess) {
@@ -1856,6 +1939,12 @@ int tb200_create(int device, tb200_ctx** out)
         return TB200_E_CUDA;
     }
     if (getenv("TB200_NO_GRAPHS")) ctx->graphs_enabled = false;
+    if (getenv("TB200_NO_STAGES")) ctx->staging_enabled = false;
+    ctx->stage_cut1 = 4 * ctx->sms; ctx->stage_cut2 = 2 * ctx->sms;
+    if (const char* e2 = getenv("TB200_STAGE_CUTS")) {          // tuning aid (tools/stage_probe.py)
+        int c1 = 0, c2 = 0;
+        if (sscanf(e2, "%d,%d", &c1, &c2) == 2 && c1 >= c2 && c2 >= 0 && c1 <= 4 * ctx->sms) { ctx->stage_cut1 = c1; ctx->stage_cut2 = c2; }
+    }
     *out = ctx;
     return TB200_OK;
 }
@@ -1874,6 +1963,7 @@ void tb200_destroy(tb200_ctx* ctx)
     cudaSetDevice(ctx->device);
     drop_graph(ctx);
     if (ctx->d_ticket) cudaFree(ctx->d_ticket);
+    if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->d_arena) cudaFree(ctx->d_arena);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -1932,6 +2022,7 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
     int lanes = a.lanes;
     const int move_set = a.move_set;
     const bool pair_ok = ctx->mode == tb::MODE_W6 && a.lookahead == 1 && move_set == 0;
+    const bool lanes_auto = !(lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32 || lanes == 64);
     if (move_set != 0 && (lanes == 64 || lanes == 4 || lanes == 2 || lanes == 1)) lanes = lanes == 64 ? 32 : 8;
     if (move_set & (TB200_MOVES_WIGGLE | TB200_MOVES_WIGGLE_DROP)) lanes = 32;
     if (lanes == 64 && !pair_ok) lanes = 32;
@@ -1971,19 +2062,55 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
     p.press.avg_lat = a.pressure_avg_lat; p.press.resp_time = a.pressure_resp_time; p.press.move_eff = a.pressure_move_eff;
     memcpy(p.ids, ctx->ids, sizeof p.ids);
 
+    // Latency regime (between 2 and 16 games per SM, w6, lookahead 1, automatic lanes): the kernel time is the serial chain
+    // of the longest games, and a game's per-piece latency depends on how many other live games share its warp scheduler
+    // (measured, tools/latency_probe.py: 1880 cycles per piece with two K2f warps per scheduler, 1495 alone, 1225 as a K2p
+    // pair with a scheduler per warp).  Games die at very different ages, so the survivors end up unevenly spread.  The
+    // play is therefore split into up to three stream-ordered stages: K2f on everything until at most 4 games per SM are
+    // unfinished, K2f again on the survivors — one block per SM, one warp per scheduler — until at most 2 per SM are
+    // left, then K2p with one scheduler per warp.  A stage ends by itself: every warp polls the finished-games counter
+    // and hands its game (board + counters, 80 bytes) to the next stage's list.  Results do not depend on the staging.
+    const uint32_t stop_moves = p.max_moves < p.T ? p.max_moves : p.T;
+    const bool staged = ctx->staging_enabled && lanes_auto && pair_ok && n_games > (uint32_t)(2 * ctx->sms) && n_games <= ctx->stage_cap && stop_moves >= 128u;
     TB_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(uint32_t), st));
     TB_CUDA(ctx, cudaMemsetAsync(a.results, 0, sizeof(tb200_game_result) * (size_t)n_games, st));
-    if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
-    fn<<<(unsigned)blocks, block, 0, st>>>(p);
-    TB_CUDA(ctx, cudaGetLastError());
-    if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
-    *launches += 1;
+    if (staged) {
+        uint32_t* ctl = reinterpret_cast<uint32_t*>(ctx->d_stage);
+        uint32_t* list1 = reinterpret_cast<uint32_t*>(ctx->d_stage + 256);
+        uint32_t* list2 = list1 + ctx->stage_cap;
+        p.st_ctl = ctl;
+        p.st_save = reinterpret_cast<tb::GameSave*>(list2 + ctx->stage_cap);
+        TB_CUDA(ctx, cudaMemsetAsync(ctl, 0, 64, st));
+        if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+        const bool dense = n_games > (uint32_t)ctx->stage_cut1;
+        if (dense) {
+            p.st_stage = 0; p.st_list_in = nullptr; p.st_list_out = list1; p.st_cut = (uint32_t)ctx->stage_cut1;
+            tb::play_games_w6fast_kernel<true><<<(unsigned)blocks, tb::BLOCK, 0, st>>>(p);
+            TB_CUDA(ctx, cudaGetLastError());
+            *launches += 1;
+        }
+        p.st_stage = 1; p.st_list_in = dense ? list1 : nullptr; p.st_list_out = list2; p.st_cut = (uint32_t)ctx->stage_cut2;
+        tb::play_games_w6fast_kernel<true><<<(unsigned)ctx->sms, tb::BLOCK, 0, st>>>(p);
+        TB_CUDA(ctx, cudaGetLastError());
+        p.st_stage = 2; p.st_list_in = list2; p.st_list_out = nullptr; p.st_cut = 0;
+        tb::play_games_w6pair_kernel<<<(unsigned)(2 * ctx->sms), 64, 0, st>>>(p);
+        TB_CUDA(ctx, cudaGetLastError());
+        *launches += 2;
+        if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+        if (!dense) blocks = ctx->sms;
+    } else {
+        if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+        fn<<<(unsigned)blocks, block, 0, st>>>(p);
+        TB_CUDA(ctx, cudaGetLastError());
+        if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+        *launches += 1;
+    }
     if (a.fitness) {
         tb::fitness_kernel<<<(a.n_candidates + 127) / 128, 128, 0, st>>>(a.n_candidates, a.games_per_candidate, a.results, a.fitness);
         TB_CUDA(ctx, cudaGetLastError());
         *launches += 1;
     }
-    ctx->timing.lanes = lanes; ctx->timing.grid = (int)blocks; ctx->timing.block = block;
+    ctx->timing.lanes = staged ? 32 : lanes; ctx->timing.grid = (int)blocks; ctx->timing.block = staged ? tb::BLOCK : block;
     return TB200_OK;
 }
 

@@ -51,6 +51,10 @@ def main():
         T = rng.randint(1, 30) if (la == 2 or ms_name.startswith("wiggle")) else rng.randint(1, 220)
         if la == 2 and ms_name.startswith("wiggle"):
             T = rng.randint(1, 10); C = min(C, 4)
+        if rng.random() < float(os.environ.get("FUZZ_STAGED", "0.03")):
+            # latency regime: automatic lanes, more than 2 games per SM, >= 128 pieces -> the re-spreading stages run
+            names, ms_name, la, pressure, lanes = W6, "drop", 1, None, 0
+            C, G, T = rng.randint(300, 700), 1, rng.randint(128, 200)
         if names is W6 and rng.random() < 0.6:
             w = np.array([[rng.gauss(v, 2.0) for v in W6V] for _ in range(C)])
         elif rng.random() < 0.2:
