@@ -329,7 +329,7 @@ def run_gpu_arm(args):
         pass
     alg_bytes = C * 6 * 8 + seqs.size + n_games * _lib.RESULT_DTYPE.itemsize + C * 8
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_r01_summary.json")
+    tpath = os.path.join(ROOT, "profiles", "ncu_r01_staged_summary.json" if launches_per_step > 2 else "ncu_r01_summary.json")
     if os.path.exists(tpath):
         try:
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
