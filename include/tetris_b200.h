@@ -15,7 +15,7 @@
  *                        State.future()        tetris/game.py:166-180  (+ Board.imprint/full/clear :62-87)
  *                        State.lines_cleared/level/score   tetris/game.py:150-164
  *                        the test_f / map_f call of cross_entropy()   learning.py:38
- *   tb200_best_move      one simulate() iteration: pool_stack + move_policy   simulator.py:156-180
+ *   tb200_best_move(_ex) one simulate() iteration: pool_stack + move_policy   simulator.py:156-180 (any move_gen of simulator.py:3-120)
  *   tb200_eval_features  feature.evaluate(state, features)   feature.py:50-55 over tetris/features.py:18-347
  *   tb200_hashed_pieces  the caller-supplied zoid_gen (simulator.py:152) as a counter-based stream
  *
@@ -149,6 +149,24 @@ int tb200_best_move(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
                     const uint16_t* boards, const uint8_t* piece, const uint8_t* next,
                     const double* weights, int32_t per_board_weights, int32_t lookahead,
                     uint8_t* out_move, double* out_score, uint32_t* out_count, uint16_t* out_rows);
+
+/* the same decision under the other move generators of the reference (simulator.py:15-120): opts->move_set and the
+ * pressure_* fields mean what they mean in tb200_play_args; opts->lines u32[N] = lines cleared so far on each board (the
+ * level the pressure filter reads, game.py:156-157), or NULL = 0.  opts == NULL is tb200_best_move. */
+typedef struct {
+    uint32_t struct_size;            /* = sizeof(tb200_move_opts) */
+    int32_t  move_set;
+    int32_t  pressure_two_but_rot;
+    int32_t  reserved;
+    double   pressure_avg_lat;
+    double   pressure_resp_time;
+    double   pressure_move_eff;
+    const uint32_t* lines;
+} tb200_move_opts;
+int tb200_best_move_ex(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
+                       const uint16_t* boards, const uint8_t* piece, const uint8_t* next,
+                       const double* weights, int32_t per_board_weights, int32_t lookahead, const tb200_move_opts* opts,
+                       uint8_t* out_move, double* out_score, uint32_t* out_count, uint16_t* out_rows);
 
 /* all 45 features of prev.future(piece, rot, <drop row>, col) for N (board, placement) pairs (K3).
  * out_features f64[N][45] (ints are exact), out_info i32[N][3] = {legal, row, k}, out_rows u16[N][20]

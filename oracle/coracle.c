@@ -476,12 +476,13 @@ typedef struct {
  * trace (optional) receives 4 bytes {rot,row,col,k} per move. */
 static void play_game(const int* fids, const double* w, int F, const uint8_t* pieces, uint32_t T,
                       uint64_t seed, uint64_t stream_id, int lookahead, int move_set, const double* press, const uint16_t* init_rows,
-                      game_result_t* res, uint8_t* trace, uint16_t* final_rows)
+                      uint32_t init_lines, game_result_t* res, uint8_t* trace, uint16_t* final_rows)
 {
     static const uint32_t POINTS[5] = {0, 40, 100, 300, 1200};         /* game.py:159 */
     board_t b; memset(&b, 0, sizeof b);
     if (init_rows) rows_to_board(init_rows, &b);
     memset(res, 0, sizeof *res);
+    res->lines = init_lines;              /* a continuing game: State.lines_cleared() of the states before it (game.py:150-157) */
     for (uint32_t t = 0; t < T; ++t) {
         int p  = pieces ? pieces[t] : hashed_piece(seed, stream_id, t);
         int nx = (lookahead >= 2 && t + 1 < T) ? (pieces ? pieces[t + 1] : hashed_piece(seed, stream_id, t + 1)) : -1;
@@ -514,7 +515,7 @@ static void* worker(void* arg)
         int seq = j->seq_of_game ? j->seq_of_game[g] : gi;
         const uint8_t* ps = j->pieces ? j->pieces + (size_t)seq * j->T : 0;
         play_game(j->fids, j->weights + (size_t)cand * j->F, j->F, ps, j->T, j->seed, (uint64_t)seq, j->lookahead, j->move_set, j->press, 0,
-                  &j->results[g], j->trace ? j->trace + (size_t)g * j->T * 4 : 0, 0);
+                  0, &j->results[g], j->trace ? j->trace + (size_t)g * j->T * 4 : 0, 0);
     }
     return 0;
 }
@@ -556,7 +557,20 @@ int co_play_one(const int* fids, int F, const double* w, const uint8_t* pieces, 
 {
     init_shapes();
     game_result_t r;
-    play_game(fids, w, F, pieces, T, 0, 0, lookahead, move_set, press, init_rows, &r, trace, final_rows);
+    play_game(fids, w, F, pieces, T, 0, 0, lookahead, move_set, press, init_rows, 0, &r, trace, final_rows);
+    result8[0] = r.pieces; result8[1] = r.lines; result8[2] = r.hist[0]; result8[3] = r.hist[1];
+    result8[4] = r.hist[2]; result8[5] = r.hist[3]; result8[6] = r.score; result8[7] = r.placements;
+    return 0;
+}
+
+/* same, for a game that already cleared init_lines lines (level of the score and of the pressure filter) */
+int co_play_one_ex(const int* fids, int F, const double* w, const uint8_t* pieces, uint32_t T, int lookahead,
+                   const uint16_t* init_rows, uint32_t init_lines, uint64_t* result8, uint8_t* trace, uint16_t* final_rows,
+                   int move_set, const double* press)
+{
+    init_shapes();
+    game_result_t r;
+    play_game(fids, w, F, pieces, T, 0, 0, lookahead, move_set, press, init_rows, init_lines, &r, trace, final_rows);
     result8[0] = r.pieces; result8[1] = r.lines; result8[2] = r.hist[0]; result8[3] = r.hist[1];
     result8[4] = r.hist[2]; result8[5] = r.hist[3]; result8[6] = r.score; result8[7] = r.placements;
     return 0;

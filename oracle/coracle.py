@@ -148,7 +148,7 @@ def play_games(fids, weights, G, pieces=None, T=None, seq_of_game=None, seed=0, 
     return out
 
 
-def play_one(fids, weights, pieces, lookahead=1, init_rows=None, move_set="drop", pressure=None):
+def play_one(fids, weights, pieces, lookahead=1, init_rows=None, move_set="drop", pressure=None, init_lines=0):
     fids = np.ascontiguousarray(fids, dtype=np.int32)
     w = np.ascontiguousarray(weights, dtype=np.float64)
     pieces = np.ascontiguousarray(pieces, dtype=np.uint8)
@@ -157,9 +157,9 @@ def play_one(fids, weights, pieces, lookahead=1, init_rows=None, move_set="drop"
     res = np.zeros(8, dtype=np.uint64)
     trace = np.zeros((max(T, 1), 4), dtype=np.uint8)
     final = np.zeros(20, dtype=np.uint16)
-    lib().co_play_one(_p(fids, ctypes.c_int32), len(fids), _p(w, ctypes.c_double), _p(pieces, ctypes.c_uint8), T, int(lookahead),
-                      _p(init, ctypes.c_uint16), _p(res, ctypes.c_uint64), _p(trace, ctypes.c_uint8), _p(final, ctypes.c_uint16),
-                      MOVE_SETS[move_set] | _pressure(pressure)[0], _p(_pressure(pressure)[1], ctypes.c_double))
+    lib().co_play_one_ex(_p(fids, ctypes.c_int32), len(fids), _p(w, ctypes.c_double), _p(pieces, ctypes.c_uint8), T, int(lookahead),
+                         _p(init, ctypes.c_uint16), ctypes.c_uint32(int(init_lines)), _p(res, ctypes.c_uint64), _p(trace, ctypes.c_uint8),
+                         _p(final, ctypes.c_uint16), MOVE_SETS[move_set] | _pressure(pressure)[0], _p(_pressure(pressure)[1], ctypes.c_double))
     n = int(res[0])
     return {"pieces": n, "lines": int(res[1]), "hist": [int(x) for x in res[2:6]], "score": int(res[6]),
             "placements": int(res[7]), "trace": trace[:n].copy(), "final": final}

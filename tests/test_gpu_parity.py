@@ -124,6 +124,41 @@ def test_k1_best_move_golden_steps(eng, golden_steps):
                     assert r["count"][i] == want["n_leaves"]
 
 
+@pytest.mark.parametrize("ms,bit", [("drop", 0), ("slide", 1), ("wiggle_top", 4), ("wiggle_drop", 8)])
+@pytest.mark.parametrize("lookahead", [1, 2])
+def test_k1_best_move_ex_move_sets_vs_coracle(eng, golden_steps, ms, bit, lookahead):
+    """tb200_best_move_ex: one decision per board under every move generator, with and without the pressure filter and
+    with lines already cleared (the level the filter reads) — against the C oracle's one-move game on the same board."""
+    names = ["max_ht", "row_trans", "pits", "landing_height", "cuml_wells", "col_trans"]
+    fids = [pyoracle.FEATURE_ID[n] for n in names]
+    rng = random.Random(17 + bit + lookahead)
+    boards = [s["board"] for s in golden_steps["steps"]][:60]
+    for _ in range(40):                                   # cave-rich random boards: slides and wiggles find extra moves
+        hmax = rng.randint(2, 14)
+        rows = [0] * 20
+        for r in range(20 - hmax, 20):
+            v = rng.getrandbits(10) | rng.getrandbits(10)
+            rows[r] = v if v != 0x3FF else 0x37F
+        boards.append(rows)
+    N = len(boards)
+    boards = np.array(boards, dtype=np.uint16)
+    piece = [rng.randrange(7) for _ in range(N)]
+    nxt = [rng.randrange(7) for _ in range(N)]
+    w = np.array([[rng.gauss(0, 2.0) - 1.0 for _ in names] for _ in range(N)])
+    lines = np.array([rng.choice([0, 0, 7, 35, 60, 95]) for _ in range(N)], dtype=np.uint32)
+    eng.set_features(names)
+    for pressure in (None, {"avg_lat": 200.0, "resp_time": 60.0, "move_eff": 1.1, "two_but_rot": True}):
+        r = eng.best_move(boards, piece, nxt if lookahead == 2 else None, w, lookahead=lookahead, want_rows=True,
+                          move_set=bit, pressure=pressure, lines=lines)
+        for i in range(N):
+            seq = [piece[i], nxt[i]] if lookahead == 2 else [piece[i]]
+            o = coracle.play_one(fids, w[i], seq, lookahead, init_rows=boards[i], move_set=ms, pressure=pressure, init_lines=int(lines[i]))
+            if len(o["trace"]) == 0:
+                assert r["move"][i][1] == 255, (i, pressure)
+                continue
+            assert tuple(int(x) for x in r["move"][i]) == tuple(int(x) for x in o["trace"][0]), (i, pressure)
+
+
 @pytest.mark.parametrize("lanes", [64, 32, 16, 8])
 def test_k2_golden_games(eng, golden_games, lanes):
     for g in golden_games["games"]:

@@ -2260,7 +2260,23 @@ int tb200_best_move(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
                     const double* weights, int32_t per_board_weights, int32_t lookahead,
                     uint8_t* out_move, double* out_score, uint32_t* out_count, uint16_t* out_rows)
 {
+    return tb200_best_move_ex(ctx, mem, stream, N, boards, piece, next, weights, per_board_weights, lookahead, nullptr,
+                              out_move, out_score, out_count, out_rows);
+}
+
+int tb200_best_move_ex(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
+                       const uint16_t* boards, const uint8_t* piece, const uint8_t* next,
+                       const double* weights, int32_t per_board_weights, int32_t lookahead, const tb200_move_opts* opts,
+                       uint8_t* out_move, double* out_score, uint32_t* out_count, uint16_t* out_rows)
+{
     if (!ctx) return TB200_E_BAD_ARG;
+    if (opts) {
+        if (opts->struct_size != sizeof(tb200_move_opts)) return fail(ctx, TB200_E_BAD_ARG, "best_move: bad opts struct_size");
+        const int ms = opts->move_set, inner = ms & ~TB200_MOVES_PRESSURE;
+        if (ms < 0 || (inner != 0 && inner != TB200_MOVES_OVERHANG_SLIDE && inner != TB200_MOVES_WIGGLE && inner != TB200_MOVES_WIGGLE_DROP))
+            return fail(ctx, TB200_E_BAD_ARG, "best_move: bad move_set");
+    }
+    const uint32_t* lines = opts ? opts->lines : nullptr;
     if (ctx->F <= 0) return fail(ctx, TB200_E_NO_FEATURES, "best_move: call tb200_set_features first");
     if (N < 1 || !boards || !piece || !weights || !out_move) return fail(ctx, TB200_E_BAD_ARG, "best_move: missing argument");
     if (lookahead != 1 && lookahead != 2) return fail(ctx, TB200_E_BAD_ARG, "best_move: lookahead must be 1 or 2");
@@ -2277,7 +2293,7 @@ int tb200_best_move(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
     const size_t o_b = take(host ? 40 * n : 0), o_p = take(host ? n : 0), o_n = take(host && next ? n : 0),
                  o_w = take(host ? sizeof(double) * nw * ctx->F : 0), o_mv = take(host ? 4 * n : 0),
                  o_sc = take(host && out_score ? 8 * n : 0), o_ct = take(host && out_count ? 4 * n : 0),
-                 o_rows = take(host && out_rows ? 40 * n : 0);
+                 o_rows = take(host && out_rows ? 40 * n : 0), o_ln = take(host && lines ? 4 * n : 0);
     int rc = ensure_arena(ctx, off);
     if (rc) return rc;
     char* base = ctx->d_arena;
@@ -2291,6 +2307,10 @@ int tb200_best_move(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
         TB_CUDA(ctx, cudaMemcpyAsync((void*)d_piece, piece, n, cudaMemcpyHostToDevice, st));
         if (next) TB_CUDA(ctx, cudaMemcpyAsync((void*)d_next, next, n, cudaMemcpyHostToDevice, st));
         TB_CUDA(ctx, cudaMemcpyAsync((void*)d_w, weights, sizeof(double) * nw * ctx->F, cudaMemcpyHostToDevice, st));
+        if (lines) {
+            TB_CUDA(ctx, cudaMemcpyAsync(base + o_ln, lines, 4 * n, cudaMemcpyHostToDevice, st));
+            lines = (const uint32_t*)(base + o_ln);
+        }
     }
     // two-piece sequence per board: {piece, next}; T = 2 when a next piece is visible for lookahead 2, else 1.
     uint8_t* d_seq = (uint8_t*)(base + o_seq);
@@ -2303,6 +2323,11 @@ int tb200_best_move(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
     a.T = 2; a.max_moves = 1; a.lookahead = lookahead; a.lanes = 0; a.init_rows = d_boards;
     a.results = (tb200_game_result*)(base + o_res); a.trace = (uint8_t*)(base + o_tr); a.score_trace = (double*)(base + o_str);
     a.final_rows = d_rows;
+    if (opts) {
+        a.move_set = opts->move_set; a.pressure_two_but_rot = opts->pressure_two_but_rot;
+        a.pressure_avg_lat = opts->pressure_avg_lat; a.pressure_resp_time = opts->pressure_resp_time; a.pressure_move_eff = opts->pressure_move_eff;
+        a.init_lines = lines;
+    }
     int launches = 1;
     ctx->timing = tb200_timing{};
     rc = launch_play(ctx, a, st, per_board_weights ? 1 : -1, &launches);

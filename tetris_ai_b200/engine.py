@@ -181,7 +181,9 @@ class Engine:
         return {k: getattr(t, k) for k, _ in _lib.Timing._fields_}
 
     # ------------------------------------------------------------------ K1 one decision per board
-    def best_move(self, boards, piece, next_piece=None, weights=None, lookahead=1, want_rows=False):
+    def best_move(self, boards, piece, next_piece=None, weights=None, lookahead=1, want_rows=False, move_set=0, pressure=None, lines=None):
+        """One placement decision per board.  move_set / pressure as in play_games; lines = lines cleared so far on each
+        board (the level the pressure filter reads)."""
         boards = np.ascontiguousarray(boards, dtype=np.uint16).reshape(-1, 20)
         N = boards.shape[0]
         piece = np.ascontiguousarray(piece, dtype=np.uint8).reshape(N)
@@ -194,8 +196,14 @@ class Engine:
         score = np.zeros(N, dtype=np.float64)
         count = np.zeros(N, dtype=np.uint32)
         rows = np.zeros((N, 20), dtype=np.uint16) if want_rows else None
-        self._check(self._L.tb200_best_move(self._h, _lib.MEM_HOST, None, N, _ptr(boards), _ptr(piece), _ptr(nxt), _ptr(w),
-                                            per_board, int(lookahead), _ptr(move), _ptr(score), _ptr(count), _ptr(rows)))
+        opts = _lib.MoveOpts()
+        opts.struct_size = ctypes.sizeof(_lib.MoveOpts)
+        opts.move_set = int(move_set)
+        _set_pressure(opts, pressure)
+        ln = np.ascontiguousarray(lines, dtype=np.uint32).reshape(N) if lines is not None else None
+        opts.lines = _ptr(ln)
+        self._check(self._L.tb200_best_move_ex(self._h, _lib.MEM_HOST, None, N, _ptr(boards), _ptr(piece), _ptr(nxt), _ptr(w),
+                                               per_board, int(lookahead), ctypes.byref(opts), _ptr(move), _ptr(score), _ptr(count), _ptr(rows)))
         return {"move": move, "score": score, "count": count, "rows": rows}
 
     # ------------------------------------------------------------------ K3 features of placements
