@@ -59,6 +59,8 @@ struct PlayParams {
     int32_t   G;
     int32_t   F;
     int32_t   per_game_weights;      // K1 (one game per board, sequence id = game): weights row = game (1) or row 0 (-1); K2: 0
+    uint32_t  seq_major_C;           // kernels with several games per warp: != 0 => tickets run sequence-major (ticket = g * C + candidate), so the games that share a
+                                     // warp start on the same piece sequence and stay in step while they live (fewer idle lanes)
     int32_t   move_set;              // bit 0: overhang slides, bit 1: pressure filter (extended generic kernels only)
     Pressure  press;                 // move_with_pressure parameters (press.on mirrors bit 1)
     uint8_t   ids[TB200_MAX_WEIGHTED];
@@ -210,6 +212,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_kernel(const PlayParams prm)
         __syncwarp(FULLMASK);                    // previous game's reads of s_w are complete
         if (want) {
             if (g < prm.n_games) {
+                if (prm.seq_major_C) g = (g % prm.seq_major_C) * (uint32_t)prm.G + g / prm.seq_major_C;     // see PlayParams
                 game = g; active = true; t = 0; h1 = h2 = h3 = h4 = 0; cnt = 0; gscore = 0;
                 lines = prm.init_lines ? prm.init_lines[g] : 0u;
                 const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[g] : (prm.per_game_weights != 0 ? g : g % (uint32_t)prm.G);
@@ -990,8 +993,9 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6grp_kernel(const PlayParam
         tk = __shfl_sync(FULLMASK, tk, 0, LANES);
         if (want) {
             if (tk < prm.n_games) {
-                game = tk; active = true; t = 0; h1 = h2 = h3 = h4 = 0; cnt = 0; gscore = 0;
-                lines = prm.init_lines ? prm.init_lines[tk] : 0u; lines0 = lines;
+                game = prm.seq_major_C ? (tk % prm.seq_major_C) * (uint32_t)prm.G + tk / prm.seq_major_C : tk;
+                active = true; t = 0; h1 = h2 = h3 = h4 = 0; cnt = 0; gscore = 0;
+                lines = prm.init_lines ? prm.init_lines[game] : 0u; lines0 = lines;
                 const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : (prm.per_game_weights != 0 ? game : game % (uint32_t)prm.G);
                 stream = sq;
                 seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
@@ -2056,6 +2060,7 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
     p.ticket = ctx->d_ticket; p.seed = a.seed; p.rmask = ctx->rmask; p.n_games = n_games; p.T = a.T;
     p.max_moves = a.max_moves ? a.max_moves : a.T; p.G = a.games_per_candidate; p.F = ctx->F;
     p.per_game_weights = per_game_weights;
+    if (per_game_weights == 0 && !a.seq_of_game && a.games_per_candidate > 1 && !getenv("TB200_NO_SEQ_MAJOR")) p.seq_major_C = (uint32_t)a.n_candidates;
     p.move_set = move_set;
     p.press.on = (move_set & TB200_MOVES_PRESSURE) ? 1 : 0;
     p.press.two_but_rot = a.pressure_two_but_rot ? 1 : 0;
