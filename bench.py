@@ -361,7 +361,8 @@ def run_gpu_arm(args):
         "wall_s_timed_region": t_wall,
     }
     if world == 1 and not args.no_sweep:
-        line["throughput_regime"] = throughput_regime(eng, int_peak)
+        line["throughput_regime"] = throughput_regime(eng, int_peak, n=262144)
+        line["population_regime"] = population_regime(eng, int_peak)
     if not args.no_cpu:
         cores = os.cpu_count() or 1
         n_cand, n_games_s = pick_cpu_sample(cores, long=True)
@@ -390,6 +391,24 @@ def throughput_regime(eng, int_peak, n=65536, T=400):
     pl = int(out["results"]["placements"].sum())
     rate = pl / (best * 1e-3)
     return {"workload": "%d concurrent games, cap %d pieces, one candidate and one hashed piece stream per game, w6, lookahead 1" % (n, T),
+            "placements_per_s": rate, "kernel_ms": best, "placements": pl, "lanes_per_game": eng.last_timing()["lanes"],
+            "roofline_frac_int_issue": rate * W6_OPS_PER_PLACEMENT / int_peak}
+
+
+def population_regime(eng, int_peak, C=10000, G=30, T=1000):
+    """BASELINE configs[2] shape on ONE GPU (not the headline): C candidates x G games on G shared seeded piece sequences, weights =
+    w6 + N(0, 1) noise (a converged CE population: most games reach the cap); kernel-only timing."""
+    w6 = np.array([-4.500158825082766, 3.4181268101392694, -3.2178882868487753, -9.348695305445199, -7.899265427351652, -3.3855972247263626])
+    rng = np.random.default_rng(1)
+    w = w6[None, :] + rng.normal(0, 1.0, size=(C, 6))
+    seqs = np.array([[random.Random(100 + g).randrange(7) for _ in range(T)] for g in range(G)], dtype=np.uint8)
+    best, out = 1e9, None
+    for _ in range(2):
+        out = eng.play_games(w, G, pieces=seqs)
+        best = min(best, eng.last_timing()["kernel_ms"])
+    pl = int(out["results"]["placements"].sum())
+    rate = pl / (best * 1e-3)
+    return {"workload": "%d candidates x %d games on %d shared piece sequences, cap %d pieces, w6, lookahead 1 (the whole BASELINE configs[2] population on one GPU)" % (C, G, G, T),
             "placements_per_s": rate, "kernel_ms": best, "placements": pl, "lanes_per_game": eng.last_timing()["lanes"],
             "roofline_frac_int_issue": rate * W6_OPS_PER_PLACEMENT / int_peak}
 

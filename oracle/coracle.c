@@ -487,6 +487,8 @@ static void play_game(const int* fids, const double* w, int F, const uint8_t* pi
         int p  = pieces ? pieces[t] : hashed_piece(seed, stream_id, t);
         int nx = (lookahead >= 2 && t + 1 < T) ? (pieces ? pieces[t + 1] : hashed_piece(seed, stream_id, t + 1)) : -1;
         choice_t ch;
+        if (p < 0 || p > 6) break;            /* not a piece: the sequence ends here (harness convention, matches the library) */
+        if (nx > 6) nx = -1;
         if (!choose(&b, (int)res->lines, p, nx, lookahead, move_set, press, fids, w, F, &ch)) break;
         b = ch.st.board;
         res->placements += (uint64_t)ch.n_scored;

@@ -300,6 +300,71 @@ def test_k2_respread_stages_vs_single_launch_and_coracle(eng, n, T, spread):
     assert (res["hist"] == o["hist"]).all()
 
 
+@pytest.mark.parametrize("C,G,T,spread,explicit", [(500, 30, 200, 2.0, True), (3001, 5, 131, 6.0, True), (2000, 7, 160, 3.0, False), (13000, 4, 128, 8.0, True)])
+def test_k2_lockstep_population_vs_coracle(eng, C, G, T, spread, explicit):
+    """Population regime (more than 80 games per SM on G shared sequences, automatic lanes): the lockstep kernel K2s plays
+    stage by stage and re-packs the survivors of each sequence into full warps.  Ragged sizes (C not a multiple of the games
+    per warp, T not a multiple of the stage length), explicit and counter-based sequences: results, moves and winning
+    scores must equal the per-game kernel's (lanes = 8) and the C oracle's."""
+    rng = np.random.default_rng(C + G)
+    w = np.array(W6_VALS)[None, :] + rng.normal(0, spread, size=(C, 6))
+    fids = [pyoracle.FEATURE_ID[x] for x in W6_NAMES]
+    eng.set_features(W6_NAMES)
+    pieces = None
+    if explicit:
+        pieces = np.array([[random.Random(7 * g + 1).randrange(7) for _ in range(T)] for g in range(G)], dtype=np.uint8)
+    kw = dict(pieces=pieces, T=T, seed=77)
+    a = eng.play_games(w, G, want_trace=True, want_scores=True, want_final=True, **kw)
+    assert eng.last_timing()["kernels_launched"] == 2 and eng.last_timing()["lanes"] in (1, 2, 4, 8)
+    b = eng.play_games(w, G, lanes=8, want_trace=True, want_scores=True, want_final=True, **kw)
+    assert (a["results"] == b["results"]).all()
+    assert (a["final"] == b["final"]).all()
+    assert (a["fitness"] == b["fitness"]).all()
+    for g in range(0, C * G, 7):
+        k = int(a["results"]["pieces"][g])
+        assert a["trace"][g, :k].tobytes() == b["trace"][g, :k].tobytes()
+        assert bits(a["scores"][g, :k]).tobytes() == bits(b["scores"][g, :k]).tobytes()
+    o = coracle.play_games(fids, w, G, pieces=pieces, T=T, seed=77, threads=16, want_trace=True)
+    res = a["results"]
+    assert (res["pieces"] == o["pieces"]).all() and (res["lines"] == o["lines"]).all()
+    assert (res["score"] == o["score"]).all() and (res["placements"] == o["placements"]).all()
+    assert (res["hist"] == o["hist"]).all()
+    for g in range(0, C * G, 11):
+        k = int(res["pieces"][g])
+        assert a["trace"][g, :k].tobytes() == o["trace"][g, :k].tobytes()
+
+
+def test_k2_lockstep_initial_boards_lines_and_max_moves(eng):
+    """K2s with initial boards, lines already cleared and a max_moves stop that is not a stage boundary."""
+    rng = np.random.default_rng(3)
+    C, G, T = 700, 20, 400
+    w = np.array(W6_VALS)[None, :] + rng.normal(0, 3.0, size=(C, 6))
+    eng.set_features(W6_NAMES)
+    n = C * G
+    init = np.zeros((n, 20), dtype=np.uint16)
+    init[::3, 19] = 0x1EF; init[::5, 18] = 0x3F0; init[::5, 19] |= 0x3F0
+    lines0 = (np.arange(n, dtype=np.uint32) * 13) % 57
+    kw = dict(T=T, seed=5, init_rows=init, init_lines=lines0, max_moves=150, want_trace=True, want_final=True)
+    a = eng.play_games(w, G, **kw)
+    assert eng.last_timing()["kernels_launched"] == 2
+    b = eng.play_games(w, G, lanes=32, **kw)
+    assert (a["results"] == b["results"]).all() and (a["final"] == b["final"]).all()
+    assert (a["results"]["pieces"] <= 150).all()
+    for g in range(0, n, 5):
+        k = int(a["results"]["pieces"][g])
+        assert a["trace"][g, :k].tobytes() == b["trace"][g, :k].tobytes()
+    # explicit sequences, two of which end early (a piece id > 6 ends the game there — an extension of this library, so
+    # the comparison is against the per-game kernel only)
+    pieces = np.array([[random.Random(9 * g + 2).randrange(7) for _ in range(T)] for g in range(G)], dtype=np.uint8)
+    pieces[3, 200:] = 7
+    pieces[G - 1, 64:] = 7
+    a = eng.play_games(w, G, pieces=pieces, want_final=True)
+    assert eng.last_timing()["kernels_launched"] == 2
+    b = eng.play_games(w, G, pieces=pieces, lanes=16, want_final=True)
+    assert (a["results"] == b["results"]).all() and (a["final"] == b["final"]).all()
+    assert (a["results"]["pieces"].reshape(C, G)[:, 3] <= 200).all() and (a["results"]["pieces"].reshape(C, G)[:, G - 1] <= 64).all()
+
+
 # ------------------------------------------------------------------------------------------------
 # edge cases: tiny / ragged shapes, immediate game over, max_moves, explicit sequence maps, many tickets
 # ------------------------------------------------------------------------------------------------

@@ -71,6 +71,10 @@ struct PlayParams {
     struct GameSave* st_save;        // [n_games] state of the handed-over games
     int32_t   st_stage;
     uint32_t  st_cut;                // leave the stage once (games not yet finished) <= st_cut; 0: run to the end
+    // lockstep kernel K2s (see play_games_w6lock_kernel)
+    uint32_t* lk_ctl;                // [S][G][4] per (stage, sequence) bucket: {task ticket, tasks done, games entering the stage, -}
+    uint32_t* lk_list;               // [2][G][C] game ids entering a stage, by sequence; double-buffered by stage parity
+    uint32_t  lk_C, lk_K, lk_S;      // candidates, pieces per stage, stages
 };
 
 // state of a game handed from one stage to the next (80 bytes)
@@ -1096,6 +1100,204 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6grp_kernel(const PlayParam
 }
 
 // ---------------------------------------------------------------------------------------------
+// K2s: the lockstep throughput kernel for CE populations (BASELINE configs[2]): C candidates x G games on G SHARED piece
+// sequences, w6, lookahead 1.  All games of sequence g see the same piece at the same move, so a warp that holds only
+// games of one sequence at one move index runs every round with all of its lanes on the same piece: no lane waits for
+// another game's longer slot list (K2g on independent streams keeps 18 of 32 threads busy).  Games die, so the play is
+// cut into stages of K pieces; a task = (stage, sequence, chunk of 32 / LANES games); at the end of a task the
+// survivors are appended to the sequence's list for the next stage, which re-packs them into full warps.  One
+// persistent launch: warps walk the buckets (stage-major, sequence-minor) and claim tasks by ticket; bucket (s, g)
+// opens when every task of (s - 1, g) is done — 29 other buckets lie in between, so nobody actually waits except at
+// the very end, and a running task never waits, so the scheme cannot deadlock with a fully resident grid.
+// Hand-over state: GameSave (80 bytes per game) through L2 (__ldcg / fence + counter).
+// ---------------------------------------------------------------------------------------------
+template <int LANES>
+__global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayParams prm)
+{
+    constexpr uint32_t GPW = 32 / LANES;           // games per warp
+    __shared__ Tables s_tab;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (LANES - 1);
+    const uint32_t T = prm.T, C = prm.lk_C, K = prm.lk_K, S = prm.lk_S;
+    const uint32_t G = (uint32_t)prm.G;
+    const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
+
+    uint32_t st = 0, sq = 0;                       // current bucket
+    uint32_t n_in = C, ntasks = (C + GPW - 1) / GPW;
+    for (;;) {
+        uint32_t* ctl = prm.lk_ctl + ((size_t)st * G + sq) * 4;
+        uint32_t slot = 0;
+        if (lane == 0) slot = atomicAdd(ctl, 1u);
+        slot = __shfl_sync(FULLMASK, slot, 0);
+        if (slot >= ntasks) {                      // bucket handed out: open the next one
+            if (++sq == G) { sq = 0; if (++st == S) break; }
+            if (st > 0) {
+                if (lane == 0) {
+                    const uint32_t* prev = prm.lk_ctl + ((size_t)(st - 1) * G + sq) * 4;
+                    const uint32_t n_prev = st == 1 ? C : __ldcg(prev + 2);
+                    const uint32_t need = (n_prev + GPW - 1) / GPW;
+                    uint32_t spins = 0;
+                    while (*reinterpret_cast<volatile const uint32_t*>(prev + 1) < need) {
+                        __nanosleep(200);
+                        if (++spins > (1u << 23)) { atomicExch(prm.lk_ctl + (size_t)S * G * 4 + 3, 1u); break; }   // safety valve (> 1.5 s): never hang the device
+                    }
+                    __threadfence();
+                    n_in = spins > (1u << 23) ? 0u : __ldcg(prm.lk_ctl + ((size_t)st * G + sq) * 4 + 2);
+                }
+                n_in = __shfl_sync(FULLMASK, n_in, 0);
+            }
+            ntasks = (n_in + GPW - 1) / GPW;
+            continue;
+        }
+        // ---- task (st, sq, slot): up to GPW games of sequence sq, all at move st * K ----
+        const uint32_t idx = slot * GPW + (uint32_t)(lane / LANES);
+        bool active = idx < n_in;
+        uint32_t game = 0;
+        if (active) game = st == 0 ? idx * G + sq : __ldcg(prm.lk_list + ((size_t)(st & 1u) * G + sq) * C + idx);
+        const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
+        auto fetch_piece = [&](uint32_t tt) -> int {                     // warp-uniform
+            if (tt >= T) return 7;
+            return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, (uint64_t)sq, tt);
+        };
+        uint32_t c[COLS];
+        uint32_t t = st * K, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+        uint64_t gscore = 0;
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) c[k] = 0;
+        if (active) {
+            if (st > 0) {
+                const uint4* sv = reinterpret_cast<const uint4*>(prm.st_save + game);
+                const uint4 a0 = __ldcg(sv), a1 = __ldcg(sv + 1), a2 = __ldcg(sv + 2), a3 = __ldcg(sv + 3), a4 = __ldcg(sv + 4);
+                c[0] = a0.x; c[1] = a0.y; c[2] = a0.z; c[3] = a0.w; c[4] = a1.x; c[5] = a1.y; c[6] = a1.z; c[7] = a1.w; c[8] = a2.x; c[9] = a2.y;
+                lines = a2.w; h1 = a3.x; h2 = a3.y; h3 = a3.z; h4 = a3.w;
+                if (gl == 0) cnt = a4.x;
+                gscore = ((uint64_t)a4.w << 32) | a4.z;
+            } else {
+                if (prm.init_rows) {
+                    uint16_t rows[ROWS];
+                    for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
+                    rows_to_cols(rows, c);
+                }
+                if (prm.init_lines) lines = prm.init_lines[game];
+            }
+        }
+        GameStat g = game_stat(c);
+        const int cells0 = g.cells - 4 * (int)t;
+        const uint32_t lines0 = lines;
+        double w[6];
+        {
+            const double* wsrc = prm.weights + (size_t)(active ? game / G : 0u) * 6;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) w[i] = __ldg(wsrc + i);
+        }
+        const uint32_t t_end = (st + 1 == S || t + K > stop) ? stop : t + K;
+        int p_cur = fetch_piece(t), p_next = fetch_piece(t + 1u);
+        if (t >= stop || p_cur >= 7) {                                   // nothing to play (stop == 0 or the sequence ends here)
+            if (active && gl == 0) {
+                tb200_game_result* r = prm.results + game;
+                r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4; r->score = gscore;
+                if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&r->placements), (unsigned long long)cnt);
+                if (prm.final_rows) { uint16_t rows[ROWS]; cols_to_rows(c, rows); for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2]; }
+            }
+            active = false;
+        }
+        while (t < t_end && p_cur < 7 && __any_sync(FULLMASK, active)) {
+            const int p_after = fetch_piece(t + 2u);
+            const int ns = s_tab.nslots[p_cur];
+            uint64_t key = 0; uint32_t tag = 0;
+            for (int s2 = gl; s2 < ns; s2 += LANES) {                    // same piece, same trip count in every lane
+                const SlotDesc d = load_slot12(s_tab, p_cur, s2);
+                W6Cand A;
+                w6_pre(c, g, d, A);
+                if (A.legal && A.full != 0u) w6_clear(d, A);
+                Heights Hn;
+                const uint64_t k = w6_post(A, w, Hn);
+                cnt += (uint32_t)(A.legal && active);
+                if (k > key) { key = k; tag = (uint32_t)s2; }
+            }
+            group_argmax<LANES>(key, tag);
+            bool finish = false;
+            if (active) {
+                if (key == 0) {
+                    finish = true;                                       // no legal placement: game over (simulator.py:187-189)
+                } else {
+                    const SlotDesc d = load_slot12(s_tab, p_cur, (int)tag);
+                    W6Cand A;
+                    w6_pre(c, g, d, A);
+                    if (A.full != 0u) w6_clear(d, A);
+#pragma unroll
+                    for (int k = 0; k < COLS; ++k) { c[k] = A.P.n[k]; g.gh[k] = A.h[k]; }
+                    g.H.H0 = (uint32_t)A.h[0] | (uint32_t)A.h[1] << 8 | (uint32_t)A.h[2] << 16 | (uint32_t)A.h[3] << 24;
+                    g.H.H1 = (uint32_t)A.h[4] | (uint32_t)A.h[5] << 8 | (uint32_t)A.h[6] << 16 | (uint32_t)A.h[7] << 24;
+                    g.H.H2 = (uint32_t)A.h[8] | (uint32_t)A.h[9] << 8;
+                    const uint32_t wk = (uint32_t)A.P.k;
+                    if (wk != 0u) {
+                        lines += wk;
+                        h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
+                        const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
+                        gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
+                    }
+                    g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)(lines - lines0);
+                    if (gl == 0) {
+                        if (prm.trace) {
+                            const uint32_t row = (uint32_t)(ROWS - A.P.y - A.P.ph);
+                            reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = (uint32_t)A.P.rot | row << 8 | (uint32_t)A.P.c0 << 16 | wk << 24;
+                        }
+                        if (prm.score_trace) {
+                            const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
+                            prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
+                        }
+                    }
+                }
+            }
+            const uint32_t tn = t + 1u;
+            if (active && !finish && (tn >= stop || p_next >= 7)) finish = true;
+            if (finish) {
+                const uint32_t played = key == 0 ? t : tn;
+                if (gl == 0) {
+                    tb200_game_result* r = prm.results + game;
+                    r->pieces = played; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4; r->score = gscore;
+                    if (prm.final_rows) { uint16_t rows[ROWS]; cols_to_rows(c, rows); for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2]; }
+                }
+                if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&prm.results[game].placements), (unsigned long long)cnt);
+                active = false;
+            }
+            t = tn;
+            p_cur = p_next; p_next = p_after;
+        }
+        // ---- survivors (alive at move t_end < stop) go to the sequence's list of the next stage ----
+        {
+#pragma unroll
+            for (int off = LANES / 2; off > 0; off >>= 1) cnt += __shfl_xor_sync(FULLMASK, cnt, off);
+            const uint32_t live = __ballot_sync(FULLMASK, active && gl == 0);
+            if (live != 0u) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(prm.lk_ctl + ((size_t)(st + 1) * G + sq) * 4 + 2, (uint32_t)__popc(live));
+                base = __shfl_sync(FULLMASK, base, 0);
+                if (active && gl == 0) {
+                    uint4* sv = reinterpret_cast<uint4*>(prm.st_save + game);
+                    __stcg(sv, make_uint4(c[0], c[1], c[2], c[3]));
+                    __stcg(sv + 1, make_uint4(c[4], c[5], c[6], c[7]));
+                    __stcg(sv + 2, make_uint4(c[8], c[9], t, lines));
+                    __stcg(sv + 3, make_uint4(h1, h2, h3, h4));
+                    __stcg(sv + 4, make_uint4(cnt, 0u, (uint32_t)gscore, (uint32_t)(gscore >> 32)));
+                    const uint32_t rank = (uint32_t)__popc(live & ((1u << lane) - 1u));
+                    __stcg(prm.lk_list + ((size_t)((st + 1) & 1u) * G + sq) * C + base + rank, game);
+                }
+            }
+            __syncwarp(FULLMASK);
+            if (lane == 0) { __threadfence(); atomicAdd(ctl + 1, 1u); }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K2L: lookahead 2 with hard drops, one warp per game (BASELINE configs[3]).  The <= 34 legal layer-1 boards
 // (post-clear columns, packed heights, cached statistics, the move) are first built into shared memory by the
 // lanes; then the <= 34 x 34 leaves are FLATTENED over the 32 lanes (leaf -> (layer-1 rank, second slot)), so
@@ -1843,6 +2045,12 @@ struct tb200_ctx {
     char* d_stage = nullptr;
     uint32_t stage_cap = 0;              // games the workspace holds
     bool staging_enabled = true;
+    // workspace of the lockstep kernel K2s (grown on demand): saved games, two list buffers, bucket control words
+    char* d_lock = nullptr;
+    size_t lock_cap = 0;
+    bool lockstep_enabled = true;
+    int lock_lanes = 0, lock_K = 64;     // tuning aids: TB200_LOCK_LANES, TB200_LOCK_K
+    const uint32_t* lock_flag = nullptr; // device word set by K2s if a bucket wait ever timed out (checked after host-mode calls)
     int stage_cut1 = 0, stage_cut2 = 0;  // hand-over thresholds (games still unfinished): 4 and 2 per SM unless TB200_STAGE_CUTS=a,b
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1864,6 +2072,7 @@ struct tb200_ctx {
     uint8_t graph_ids[TB200_MAX_WEIGHTED] = {0};
     char* graph_arena = nullptr;
     tb200_timing graph_timing{};
+    const uint32_t* graph_lock_flag = nullptr;
 };
 
 static int fail(tb200_ctx* ctx, int code, const std::string& msg)
@@ -1944,6 +2153,9 @@ int tb200_create(int device, tb200_ctx** out)
     }
     if (getenv("TB200_NO_GRAPHS")) ctx->graphs_enabled = false;
     if (getenv("TB200_NO_STAGES")) ctx->staging_enabled = false;
+    if (getenv("TB200_NO_LOCKSTEP")) ctx->lockstep_enabled = false;
+    if (const char* e3 = getenv("TB200_LOCK_LANES")) ctx->lock_lanes = atoi(e3);
+    if (const char* e4 = getenv("TB200_LOCK_K")) { const int k = atoi(e4); if (k >= 8) ctx->lock_K = k; }
     ctx->stage_cut1 = 4 * ctx->sms; ctx->stage_cut2 = 2 * ctx->sms;
     if (const char* e2 = getenv("TB200_STAGE_CUTS")) {          // tuning aid (tools/stage_probe.py)
         int c1 = 0, c2 = 0;
@@ -1968,6 +2180,7 @@ void tb200_destroy(tb200_ctx* ctx)
     drop_graph(ctx);
     if (ctx->d_ticket) cudaFree(ctx->d_ticket);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
+    if (ctx->d_lock) cudaFree(ctx->d_lock);
     if (ctx->d_arena) cudaFree(ctx->d_arena);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -2015,6 +2228,37 @@ int tb200_last_timing(tb200_ctx* ctx, tb200_timing* out)
         else cudaGetLastError();         // never leave a stale error behind for the next launch check
     }
     *out = ctx->timing;
+    return TB200_OK;
+}
+
+// ---- lockstep kernel K2s: when it applies, and its workspace (allocated outside any stream capture) ----
+struct LockPlan { bool on; uint32_t K, S; size_t b_save, b_list, b_ctl; };
+static LockPlan lock_plan(const tb200_ctx* ctx, const tb200_play_args& a, int per_game_weights)
+{
+    LockPlan lp{};
+    const long long n_games = (long long)a.n_candidates * a.games_per_candidate;
+    const int l = a.lanes;
+    const bool lanes_auto = !(l == 1 || l == 2 || l == 4 || l == 8 || l == 16 || l == 32 || l == 64);
+    const uint32_t stop_moves = a.max_moves && a.max_moves < a.T ? a.max_moves : a.T;
+    lp.on = ctx->lockstep_enabled && lanes_auto && ctx->mode == tb::MODE_W6 && a.lookahead == 1 && a.move_set == 0 && per_game_weights == 0 &&
+            !a.seq_of_game && a.games_per_candidate >= 4 && a.games_per_candidate <= 4096 &&
+            (n_games + ctx->sms - 1) / ctx->sms > 80 && stop_moves >= (uint32_t)(2 * ctx->lock_K);
+    if (!lp.on) return lp;
+    lp.K = (uint32_t)ctx->lock_K; lp.S = (stop_moves + lp.K - 1) / lp.K;
+    lp.b_save = align_up(sizeof(tb::GameSave) * (size_t)n_games);
+    lp.b_list = align_up(2 * sizeof(uint32_t) * (size_t)n_games);
+    lp.b_ctl = align_up(16 * (size_t)(lp.S + 1) * (size_t)a.games_per_candidate);
+    return lp;
+}
+static int ensure_lock_ws(tb200_ctx* ctx, const tb200_play_args& a)
+{
+    const LockPlan lp = lock_plan(ctx, a, 0);
+    if (!lp.on || lp.b_save + lp.b_list + lp.b_ctl <= ctx->lock_cap) return TB200_OK;
+    drop_graph(ctx);
+    if (ctx->d_lock) { TB_CUDA(ctx, cudaFree(ctx->d_lock)); ctx->d_lock = nullptr; ctx->lock_cap = 0; }
+    const size_t cap = (lp.b_save + lp.b_list + lp.b_ctl) * 5 / 4;
+    TB_CUDA(ctx, cudaMalloc(&ctx->d_lock, cap));
+    ctx->lock_cap = cap;
     return TB200_OK;
 }
 
@@ -2077,9 +2321,37 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
     // and hands its game (board + counters, 80 bytes) to the next stage's list.  Results do not depend on the staging.
     const uint32_t stop_moves = p.max_moves < p.T ? p.max_moves : p.T;
     const bool staged = ctx->staging_enabled && lanes_auto && pair_ok && n_games > (uint32_t)(2 * ctx->sms) && n_games <= ctx->stage_cap && stop_moves >= 128u;
+    // Population regime (more than 80 games per SM, w6, lookahead 1, G shared sequences, automatic lanes): the lockstep
+    // kernel K2s keeps every warp on one sequence at one move index.
+    const long long per_sm_games = (n_games_ll + ctx->sms - 1) / ctx->sms;
+    const LockPlan lp = lock_plan(ctx, a, per_game_weights);
+    const bool lockstep = lp.on && lp.b_save + lp.b_list + lp.b_ctl <= ctx->lock_cap;      // workspace comes from ensure_lock_ws()
     TB_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(uint32_t), st));
     TB_CUDA(ctx, cudaMemsetAsync(a.results, 0, sizeof(tb200_game_result) * (size_t)n_games, st));
-    if (staged) {
+    if (lockstep) {
+        const uint32_t K = lp.K, S = lp.S;
+        const size_t b_save = lp.b_save, b_list = lp.b_list, b_ctl = lp.b_ctl;
+        p.st_save = reinterpret_cast<tb::GameSave*>(ctx->d_lock);
+        p.lk_list = reinterpret_cast<uint32_t*>(ctx->d_lock + b_save);
+        p.lk_ctl = reinterpret_cast<uint32_t*>(ctx->d_lock + b_save + b_list);
+        p.lk_C = (uint32_t)a.n_candidates; p.lk_K = K; p.lk_S = S;
+        ctx->lock_flag = p.lk_ctl + (size_t)S * (size_t)a.games_per_candidate * 4 + 3;
+        int ll = ctx->lock_lanes;
+        if (ll != 1 && ll != 2 && ll != 4 && ll != 8) ll = per_sm_games <= 320 ? 8 : (per_sm_games <= 760 ? 4 : (per_sm_games <= 1500 ? 2 : 1));   // tools/lock_probe.py
+        tb::play_fn lf = ll == 8 ? tb::play_games_w6lock_kernel<8> : (ll == 4 ? tb::play_games_w6lock_kernel<4> : (ll == 2 ? tb::play_games_w6lock_kernel<2> : tb::play_games_w6lock_kernel<1>));
+        int locc = 0;
+        TB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&locc, lf, tb::BLOCK, 0));
+        if (locc < 1) locc = 1;
+        long long lblocks = (n_games_ll * ll + tb::BLOCK - 1) / tb::BLOCK;           // the grid must be fully resident: tasks wait on tasks
+        if (lblocks > (long long)ctx->sms * locc) lblocks = (long long)ctx->sms * locc;
+        TB_CUDA(ctx, cudaMemsetAsync(p.lk_ctl, 0, b_ctl, st));
+        if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+        lf<<<(unsigned)lblocks, tb::BLOCK, 0, st>>>(p);
+        TB_CUDA(ctx, cudaGetLastError());
+        if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+        *launches += 1;
+        lanes = ll; blocks = lblocks;
+    } else if (staged) {
         uint32_t* ctl = reinterpret_cast<uint32_t*>(ctx->d_stage);
         uint32_t* list1 = reinterpret_cast<uint32_t*>(ctx->d_stage + 256);
         uint32_t* list2 = list1 + ctx->stage_cap;
@@ -2147,6 +2419,9 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
     TB_CUDA(ctx, cudaSetDevice(ctx->device));
     const tb200_play_args& a = *args;
     const size_t n_games = (size_t)a.n_candidates * a.games_per_candidate;
+    rc = ensure_lock_ws(ctx, a);
+    if (rc) return rc;
+    ctx->lock_flag = nullptr;
     ctx->timing = tb200_timing{};
     ctx->timing_valid = false;
     int launches = 0;
@@ -2216,7 +2491,7 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
                       ctx->graph_mode == ctx->mode && memcmp(ctx->graph_ids, ctx->ids, sizeof ctx->ids) == 0 && ctx->graph_arena == base;
     bool done = false;
     if (same) {
-        if (cudaGraphLaunch(ctx->graph_exec, st) == cudaSuccess) { ctx->timing = ctx->graph_timing; launches = ctx->graph_timing.kernels_launched; done = true; kernel_events = false; }
+        if (cudaGraphLaunch(ctx->graph_exec, st) == cudaSuccess) { ctx->timing = ctx->graph_timing; launches = ctx->graph_timing.kernels_launched; ctx->lock_flag = ctx->graph_lock_flag; done = true; kernel_events = false; }
         else { cudaGetLastError(); drop_graph(ctx); }
     } else if (ctx->graphs_enabled && is_pinned(a.weights) && is_pinned(a.pieces) && is_pinned(a.seq_of_game) && is_pinned(a.init_rows) && is_pinned(a.init_lines) &&
                is_pinned(a.results) && is_pinned(a.trace) && is_pinned(a.score_trace) && is_pinned(a.final_rows) && is_pinned(a.fitness)) {
@@ -2229,7 +2504,7 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
                 ctx->graph = gr; ctx->graph_args = a; ctx->graph_F = ctx->F; ctx->graph_mode = ctx->mode;
                 memcpy(ctx->graph_ids, ctx->ids, sizeof ctx->ids); ctx->graph_arena = base;
                 ctx->timing.kernels_launched = launches;
-                ctx->graph_timing = ctx->timing; ctx->graph_valid = true;
+                ctx->graph_timing = ctx->timing; ctx->graph_lock_flag = ctx->lock_flag; ctx->graph_valid = true;
                 if (cudaGraphLaunch(ctx->graph_exec, st) == cudaSuccess) { done = true; kernel_events = false; }
                 else { cudaGetLastError(); drop_graph(ctx); ctx->graphs_enabled = false; }
             } else {
@@ -2249,6 +2524,11 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
     }
     TB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     TB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (ctx->lock_flag) {                   // K2s ran: its bucket waits are bounded; a timeout means incomplete results
+        uint32_t flag = 0;
+        TB_CUDA(ctx, cudaMemcpy(&flag, ctx->lock_flag, sizeof flag, cudaMemcpyDeviceToHost));
+        if (flag) return fail(ctx, TB200_E_CUDA, "play_games: lockstep kernel timed out waiting for a stage (results incomplete)");
+    }
     ctx->kernel_events_valid = kernel_events;
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }

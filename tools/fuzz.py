@@ -55,6 +55,10 @@ def main():
             # latency regime: automatic lanes, more than 2 games per SM, >= 128 pieces -> the re-spreading stages run
             names, ms_name, la, pressure, lanes = W6, "drop", 1, None, 0
             C, G, T = rng.randint(300, 700), 1, rng.randint(128, 200)
+        if rng.random() < float(os.environ.get("FUZZ_LOCKSTEP", "0.02")):
+            # population regime: > 80 games per SM on shared sequences -> the lockstep kernel K2s
+            names, ms_name, la, pressure, lanes = W6, "drop", 1, None, 0
+            G = rng.randint(4, 12); C = 12200 // G + rng.randint(0, 300); T = rng.randint(128, 150)
         if names is W6 and rng.random() < 0.6:
             w = np.array([[rng.gauss(v, 2.0) for v in W6V] for _ in range(C)])
         elif rng.random() < 0.2:
