@@ -1104,13 +1104,17 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6grp_kernel(const PlayParam
 // sequences, w6, lookahead 1.  All games of sequence g see the same piece at the same move, so a warp that holds only
 // games of one sequence at one move index runs every round with all of its lanes on the same piece: no lane waits for
 // another game's longer slot list (K2g on independent streams keeps 18 of 32 threads busy).  Games die, so the play is
-// cut into stages of K pieces; a task = (stage, sequence, chunk of 32 / LANES games); at the end of a task the
+// cut into stages of K pieces (the first two shorter); a task = (stage, sequence, chunk of 32 / LANES games); at the end of a task the
 // survivors are appended to the sequence's list for the next stage, which re-packs them into full warps.  One
 // persistent launch: warps walk the buckets (stage-major, sequence-minor) and claim tasks by ticket; bucket (s, g)
 // opens when every task of (s - 1, g) is done — 29 other buckets lie in between, so nobody actually waits except at
 // the very end, and a running task never waits, so the scheme cannot deadlock with a fully resident grid.
 // Hand-over state: GameSave (80 bytes per game) through L2 (__ldcg / fence + counter).
 // ---------------------------------------------------------------------------------------------
+// first move of stage s: two short stages first (K/4, K/2) — a fresh CE population loses most of its games within a
+// few dozen pieces and they should be re-packed early — then K pieces per stage
+TB_HD uint32_t lock_stage_begin(uint32_t s, uint32_t K) { return s == 0u ? 0u : (s == 1u ? K / 4u : (s == 2u ? K / 2u : K * (s - 2u))); }
+
 template <int LANES>
 __global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayParams prm)
 {
@@ -1166,7 +1170,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayPara
             return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, (uint64_t)sq, tt);
         };
         uint32_t c[COLS];
-        uint32_t t = st * K, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+        uint32_t t = lock_stage_begin(st, K), lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
         uint64_t gscore = 0;
 #pragma unroll
         for (int k = 0; k < COLS; ++k) c[k] = 0;
@@ -1196,7 +1200,8 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayPara
 #pragma unroll
             for (int i = 0; i < 6; ++i) w[i] = __ldg(wsrc + i);
         }
-        const uint32_t t_end = (st + 1 == S || t + K > stop) ? stop : t + K;
+        const uint32_t t_next = lock_stage_begin(st + 1u, K);
+        const uint32_t t_end = (st + 1 == S || t_next > stop) ? stop : t_next;
         int p_cur = fetch_piece(t), p_next = fetch_piece(t + 1u);
         if (t >= stop || p_cur >= 7) {                                   // nothing to play (stop == 0 or the sequence ends here)
             if (active && gl == 0) {
@@ -2244,7 +2249,7 @@ static LockPlan lock_plan(const tb200_ctx* ctx, const tb200_play_args& a, int pe
             !a.seq_of_game && a.games_per_candidate >= 4 && a.games_per_candidate <= 4096 &&
             (n_games + ctx->sms - 1) / ctx->sms > 80 && stop_moves >= (uint32_t)(2 * ctx->lock_K);
     if (!lp.on) return lp;
-    lp.K = (uint32_t)ctx->lock_K; lp.S = (stop_moves + lp.K - 1) / lp.K;
+    lp.K = (uint32_t)ctx->lock_K; lp.S = (stop_moves + lp.K - 1) / lp.K + 2;      // see lock_stage_begin
     lp.b_save = align_up(sizeof(tb::GameSave) * (size_t)n_games);
     lp.b_list = align_up(2 * sizeof(uint32_t) * (size_t)n_games);
     lp.b_ctl = align_up(16 * (size_t)(lp.S + 1) * (size_t)a.games_per_candidate);
