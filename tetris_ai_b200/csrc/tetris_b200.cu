@@ -8,6 +8,9 @@
 //   K2f play_games_w6fast_kernel        one warp per game, lookahead 1, the w6 feature set: the latency path (config 2).
 //   K2p play_games_w6pair_kernel        two warps per game (tiny populations).
 //   K2g play_games_w6grp_kernel<LANES>  16 / 8 / 4 / 2 / 1 lanes per game: the throughput path (configs 3, 5).
+//   K2s play_games_w6lock_kernel<LANES> the lockstep population kernel (config 3): every warp holds games of one piece sequence at one
+//        move index; stages of 64 pieces, survivors re-packed per sequence, one persistent launch with per-bucket hand-over.
+//   K2f<staged> + K2p as re-spreading stages for the latency regime (config 2): see launch_play.
 //   K2w play_games_w32_kernel<MODE>     one warp per game, lookahead 1, all-45 / generic feature lists.
 //   K2L play_games_l2flat_kernel<MODE>  one warp per game, lookahead 2: layer-1 boards in shared memory, leaves flattened over lanes.
 //   K2x play_games_wiggle_kernel<MODE>  the wiggle move sets (8f rank 4): warp-parallel set flood fill + scoring; the reference-order search only breaks ties.
