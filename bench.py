@@ -48,6 +48,30 @@ METRIC, UNIT = "placements evaluated/sec (CE generation, 100 candidates x 10 gam
 
 
 # ---------------------------------------------------------------------------------------------
+# stdout hygiene: the contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner) write to fd 1, so fd 1
+# points at stderr while the benchmark runs and the JSON line goes to the saved descriptor.
+# ---------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
+# ---------------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------------
 def canonical_population(n_total):
@@ -150,7 +174,7 @@ def run_reference_arm(args):
         "note": "reference's CPU path = oracle/pyoracle.py, a numpy restatement of cogworks (pure-Python reference cannot travel to this box); "
                 "fork pool over all host cores, one candidate per task (learning.py:38 granularity)",
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -207,6 +231,7 @@ def run_gpu_arm(args):
     from tetris_ai_b200 import Engine, _lib
     from tetris_ai_b200.learning import PopulationEvaluator
 
+    guard_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -373,7 +398,7 @@ def run_gpu_arm(args):
         c_rate, c_dt = cpu_c_rate(pop, seqs, cores)
         line["cpu_baseline_c"] = {"value": c_rate, "unit": UNIT, "cores": cores, "kind": "port",
                                   "sample": "oracle/coracle.c (plain-C restatement, pthreads), the whole step (%d placements) in %.2f s" % (placements, c_dt)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
