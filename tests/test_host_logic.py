@@ -30,7 +30,7 @@ def test_c_abi_exports_every_declared_symbol():
 def test_c_abi_struct_layout_matches_header():
     import ctypes
     from tetris_ai_b200 import _lib
-    src = '#include <stdio.h>\n#include <stddef.h>\n#include "tetris_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(tb200_play_args), sizeof(tb200_game_result), sizeof(tb200_timing), offsetof(tb200_play_args, results), offsetof(tb200_play_args, fitness), offsetof(tb200_game_result, score));return 0;}\n'
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "tetris_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(tb200_play_args), sizeof(tb200_game_result), sizeof(tb200_timing), offsetof(tb200_play_args, results), offsetof(tb200_play_args, fitness), offsetof(tb200_game_result, score), sizeof(tb200_move_opts), offsetof(tb200_move_opts, lines));return 0;}\n'
     exe = os.path.join(ROOT, "tests", "emu", "abi_probe")
     subprocess.run(["gcc", "-x", "c", "-I", os.path.join(ROOT, "include"), "-o", exe, "-"], input=src.encode(), check=True)
     sizes = [int(x) for x in subprocess.check_output([exe]).split()]
@@ -39,6 +39,7 @@ def test_c_abi_struct_layout_matches_header():
     assert sizes[2] == ctypes.sizeof(_lib.Timing)
     assert sizes[3] == _lib.PlayArgs.results.offset and sizes[4] == _lib.PlayArgs.fitness.offset
     assert sizes[5] == _lib.RESULT_DTYPE.fields["score"][1]
+    assert sizes[6] == ctypes.sizeof(_lib.MoveOpts) and sizes[7] == _lib.MoveOpts.lines.offset
 
 
 def test_engine_fails_loudly_without_gpu():
