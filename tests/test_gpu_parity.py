@@ -365,6 +365,67 @@ def test_k2_lockstep_initial_boards_lines_and_max_moves(eng):
     assert (a["results"]["pieces"].reshape(C, G)[:, 3] <= 200).all() and (a["results"]["pieces"].reshape(C, G)[:, G - 1] <= 64).all()
 
 
+@pytest.mark.parametrize("n,T,explicit", [(33000, 70, False), (70001, 40, True), (300000, 24, False)])
+def test_k2_piece_binned_kernel_vs_coracle(eng, n, T, explicit):
+    """Independent piece streams, >= 32 768 games, automatic lanes: the piece-binned kernel K2b moves every game through
+    device-wide per-piece-type queues, one piece per task.  Results, moves, winning scores and final boards must equal the
+    per-game kernel's (lanes = 4) and the C oracle's; with explicit sequences some of them end early."""
+    rng = np.random.default_rng(n)
+    w = np.array(W6_VALS)[None, :] + rng.normal(0, 4.0, size=(n, 6))
+    fids = [pyoracle.FEATURE_ID[x] for x in W6_NAMES]
+    eng.set_features(W6_NAMES)
+    kw = dict(T=T, seed=31)
+    if explicit:
+        S = 257
+        pieces = np.array([[random.Random(3 * g + 1).randrange(7) for _ in range(T)] for g in range(S)], dtype=np.uint8)
+        kw = dict(pieces=pieces, seq_of_game=((np.arange(n, dtype=np.int64) * 11) % S).astype(np.int32))
+    else:
+        kw["seq_of_game"] = np.arange(n, dtype=np.int32)
+    a = eng.play_games(w, 1, want_trace=True, want_scores=True, want_final=True, **kw)
+    assert eng.last_timing()["kernels_launched"] == 3 and eng.last_timing()["lanes"] in (1, 2, 4)       # init + K2b + fitness
+    b = eng.play_games(w, 1, lanes=4, want_trace=True, want_scores=True, want_final=True, **kw)
+    assert eng.last_timing()["kernels_launched"] == 2
+    assert (a["results"] == b["results"]).all()
+    assert (a["final"] == b["final"]).all()
+    assert (a["fitness"] == b["fitness"]).all()
+    for g in range(0, n, 97):
+        k = int(a["results"]["pieces"][g])
+        assert a["trace"][g, :k].tobytes() == b["trace"][g, :k].tobytes()
+        assert bits(a["scores"][g, :k]).tobytes() == bits(b["scores"][g, :k]).tobytes()
+    o = coracle.play_games(fids, w, 1, threads=16, want_trace=True, **{k2: v for k2, v in kw.items()})
+    res = a["results"]
+    assert (res["pieces"] == o["pieces"]).all() and (res["lines"] == o["lines"]).all()
+    assert (res["score"] == o["score"]).all() and (res["placements"] == o["placements"]).all()
+    assert (res["hist"] == o["hist"]).all()
+    for g in range(0, n, 89):
+        k = int(res["pieces"][g])
+        assert a["trace"][g, :k].tobytes() == o["trace"][g, :k].tobytes()
+
+
+def test_k2_piece_binned_initial_boards_lines_max_moves_and_short_sequences(eng):
+    rng = np.random.default_rng(8)
+    n, T = 40000, 90
+    w = np.array(W6_VALS)[None, :] + rng.normal(0, 3.0, size=(n, 6))
+    eng.set_features(W6_NAMES)
+    init = np.zeros((n, 20), dtype=np.uint16)
+    init[::3, 19] = 0x1EF; init[::5, 18] = 0x3F0; init[::5, 19] |= 0x3F0
+    init[::7, 2:] = 0x2AA                                            # tall boards: some games end at once
+    lines0 = (np.arange(n, dtype=np.uint32) * 13) % 57
+    S = 64
+    pieces = np.array([[random.Random(5 * g + 2).randrange(7) for _ in range(T)] for g in range(S)], dtype=np.uint8)
+    pieces[5, 30:] = 7; pieces[6, 0:] = 7                            # a sequence that ends early and an empty one
+    kw = dict(pieces=pieces, seq_of_game=(np.arange(n, dtype=np.int32) % S), init_rows=init, init_lines=lines0, max_moves=50,
+              want_trace=True, want_final=True)
+    a = eng.play_games(w, 1, **kw)
+    assert eng.last_timing()["kernels_launched"] == 3
+    b = eng.play_games(w, 1, lanes=32, **kw)
+    assert (a["results"] == b["results"]).all() and (a["final"] == b["final"]).all()
+    assert (a["results"]["pieces"] <= 50).all() and (a["results"]["pieces"][6::S] == 0).all()
+    for g in range(0, n, 31):
+        k = int(a["results"]["pieces"][g])
+        assert a["trace"][g, :k].tobytes() == b["trace"][g, :k].tobytes()
+
+
 # ------------------------------------------------------------------------------------------------
 # edge cases: tiny / ragged shapes, immediate game over, max_moves, explicit sequence maps, many tickets
 # ------------------------------------------------------------------------------------------------

@@ -78,6 +78,10 @@ struct PlayParams {
     uint32_t* lk_ctl;                // [S][G][4] per (stage, sequence) bucket: {task ticket, tasks done, games entering the stage, -}
     uint32_t* lk_list;               // [2][G][C] game ids entering a stage, by sequence; double-buffered by stage parity
     uint32_t  lk_C, lk_K, lk_S;      // candidates, pieces per stage, stages
+    // piece-binned kernel K2b (see play_games_w6bin_kernel)
+    unsigned long long* pb_ctl;      // per shard 16 words: [0..6] queue tails (reserved), [8..14] queue heads; after the shards: games finished, error flag
+    uint32_t* pb_ring;               // [shards][7][pb_mask + 1] game ids waiting for a piece of type p; 0xffffffff = empty slot
+    uint32_t  pb_mask;               // ring capacity - 1 (a power of two >= games per shard)
 };
 
 // state of a game handed from one stage to the next (80 bytes)
@@ -85,6 +89,7 @@ struct GameSave {
     uint32_t c[COLS];
     uint32_t t, lines, h1, h2, h3, h4, cnt, pad;
     uint64_t gscore;
+    uint32_t H0, H1, H2, cells;      // K2b only: packed column heights and filled cells of the board (saves recomputing them every piece)
 };
 
 // ---- argmax over a LANES-wide group: maximise key, ties -> smallest tag (first in enumeration order)
@@ -1306,6 +1311,247 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayPara
 }
 
 // ---------------------------------------------------------------------------------------------
+// K2b: the piece-binned throughput kernel for INDEPENDENT piece streams (BASELINE configs[4]: every game its own
+// stream), w6, lookahead 1.  K2g keeps 18 of 32 threads busy there because the games of a warp are on different pieces
+// (9 / 17 / 34 slots).  Here a game is not bound to a warp: seven device-wide queues, one per piece type, hold the games
+// whose next piece has that type.  A warp pops up to 32 / LANES games from the fullest queue — all on the same piece —
+// plays exactly one piece for each of them with every lane in step, and pushes each survivor onto the queue of its
+// next piece.  Game state (80 bytes) travels through L2; with 4 warps per scheduler the pop / load latency hides behind
+// the other warps' arithmetic.  Queues are rings of game ids with 64-bit reserved-tail / head counters: a pusher
+// reserves slots by atomicAdd, writes the state, fences, then publishes the id into the slot; a popper claims by CAS
+// on the head and reads each slot once it is published.  All waits are bounded (error flag instead of a hang).
+// ---------------------------------------------------------------------------------------------
+#define PB_EMPTY 0xffffffffu
+constexpr uint32_t PB_SHARDS = 64;     // independent queue sets; a game always lives in shard game % PB_SHARDS, a warp's home shard is warp % PB_SHARDS
+
+TB_D void pb_write_state(GameSave* dst, const uint32_t c[COLS], uint32_t t, uint32_t lines, uint32_t h1, uint32_t h2, uint32_t h3, uint32_t h4,
+                         uint32_t cnt, uint64_t gscore, const Heights& H, int cells)
+{
+    uint4* sv = reinterpret_cast<uint4*>(dst);
+    __stcg(sv, make_uint4(c[0], c[1], c[2], c[3]));
+    __stcg(sv + 1, make_uint4(c[4], c[5], c[6], c[7]));
+    __stcg(sv + 2, make_uint4(c[8], c[9], t, lines));
+    __stcg(sv + 3, make_uint4(h1, h2, h3, h4));
+    __stcg(sv + 4, make_uint4(cnt, 0u, (uint32_t)gscore, (uint32_t)(gscore >> 32)));
+    __stcg(sv + 5, make_uint4(H.H0, H.H1, H.H2, (uint32_t)cells));
+}
+
+// publish `game` at queue position pos of piece type p (the slot is empty unless a slow popper still holds it)
+TB_D void pb_publish(const PlayParams& prm, uint32_t shard, int p, unsigned long long pos, uint32_t game)
+{
+    volatile uint32_t* slot = prm.pb_ring + ((size_t)shard * 7 + (size_t)p) * ((size_t)prm.pb_mask + 1) + (size_t)(pos & prm.pb_mask);
+    uint32_t spins = 0;
+    while (*slot != PB_EMPTY) { __nanosleep(100); if (++spins > (1u << 22)) { atomicExch(prm.pb_ctl + 16 * PB_SHARDS + 1, 1ull); break; } }
+    *slot = game;
+}
+
+// every game enters the queue of its first piece (or finishes at once when there is nothing to play)
+__global__ void pb_init_kernel(const PlayParams prm)
+{
+    const uint32_t game = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t T = prm.T;
+    const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
+    int p0 = 8;                                  // 8: no game in this thread
+    if (game < prm.n_games) {
+        const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : game % (uint32_t)prm.G;
+        uint32_t c[COLS];
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) c[k] = 0;
+        if (prm.init_rows) {
+            uint16_t rows[ROWS];
+            for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
+            rows_to_cols(rows, c);
+        }
+        const uint32_t lines = prm.init_lines ? prm.init_lines[game] : 0u;
+        p0 = stop == 0u ? 7 : (prm.pieces ? (int)prm.pieces[(size_t)sq * T] : hashed_piece(prm.seed, (uint64_t)sq, 0));
+        if (p0 >= 7) {
+            tb200_game_result* r = prm.results + game;
+            r->pieces = 0; r->lines = lines; r->score = 0;
+            if (prm.final_rows) { uint16_t rows[ROWS]; cols_to_rows(c, rows); for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2]; }
+            atomicAdd(prm.pb_ctl + 16 * PB_SHARDS, 1ull);
+            p0 = 8;
+        } else {
+            const GameStat g0 = game_stat(c);
+            pb_write_state(prm.st_save + game, c, 0u, lines, 0u, 0u, 0u, 0u, 0u, 0ull, g0.H, g0.cells);
+        }
+    }
+    if (p0 < 7) {
+        const uint32_t shard = game % PB_SHARDS;
+        const unsigned long long pos = atomicAdd(prm.pb_ctl + 16 * shard + p0, 1ull);
+        prm.pb_ring[((size_t)shard * 7 + (size_t)p0) * ((size_t)prm.pb_mask + 1) + (size_t)(pos & prm.pb_mask)] = game;
+    }
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(BLOCK) play_games_w6bin_kernel(const PlayParams prm)
+{
+    constexpr uint32_t GPW = 32 / LANES;
+    __shared__ Tables s_tab;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (LANES - 1);
+    const uint32_t T = prm.T;
+    const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
+    const size_t ring_stride = (size_t)prm.pb_mask + 1;
+    const uint32_t warp_id = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
+    unsigned long long* const fin_ctr = prm.pb_ctl + 16 * PB_SHARDS;
+    uint32_t idle = 0, probe = 0;
+    unsigned long long last_fin = 0;
+
+    for (;;) {
+        // ---- pop up to GPW games of one piece type from the home shard (or, when that is empty, from the next shard that
+        //      has work): lanes 0..6 look at one queue each, the fullest wins ----
+        const uint32_t shard = (warp_id + probe) % PB_SHARDS;
+        unsigned long long* const sctl = prm.pb_ctl + 16 * shard;
+        unsigned long long hd = 0, avail = 0;
+        if (lane < 7) { hd = *(volatile unsigned long long*)(sctl + 8 + lane); const unsigned long long tl = *(volatile unsigned long long*)(sctl + lane); avail = tl - hd; }
+        const uint32_t a32 = avail > 0xffffffull ? 0xffffffu : (uint32_t)avail;
+        // prefer full warps; among equally good queues rotate by warp so that the heads are not all hit at once
+        const uint32_t score = (lane < 7 && a32 != 0u) ? (1u << 20) + ((a32 >= GPW ? GPW : a32) << 8 | ((uint32_t)(lane + warp_id) % 7u)) : 0u;
+        const uint32_t best = __reduce_max_sync(FULLMASK, score);
+        if (best == 0u) {
+            if (++probe < PB_SHARDS) continue;                       // try the other shards before idling
+            probe = 0;
+            // nothing waiting anywhere: done when every game has finished, otherwise other warps are still playing
+            const unsigned long long fin = *(volatile unsigned long long*)fin_ctr;
+            if (fin >= (unsigned long long)prm.n_games) break;
+            __nanosleep(1000);
+            if ((++idle & 255u) == 0u && fin != last_fin) { last_fin = fin; idle = 0; }      // progress elsewhere: keep waiting
+            if (idle > (1u << 16)) { if (lane == 0) atomicExch(fin_ctr + 1, 1ull); break; }    // ~4 s without any game finishing
+            continue;
+        }
+        const int owner = __ffs((int)__ballot_sync(FULLMASK, score == best)) - 1;      // lane = piece type
+        uint32_t n = 0;
+        if (lane == owner) {
+            n = a32 < GPW ? a32 : GPW;
+            if (atomicCAS(sctl + 8 + lane, hd, hd + n) != hd) n = 0;                     // lost the race: look again
+        }
+        n = __shfl_sync(FULLMASK, n, owner);
+        if (n == 0u) continue;
+        idle = 0;
+        const unsigned long long base = __shfl_sync(FULLMASK, hd, owner);
+        const int p_cur = owner;
+        // ---- fetch the games ----
+        const uint32_t idx = (uint32_t)(lane / LANES);
+        bool active = idx < n;
+        uint32_t game = 0;
+        if (active) {
+            volatile uint32_t* slot = prm.pb_ring + ((size_t)shard * 7 + (size_t)p_cur) * ring_stride + (size_t)((base + idx) & prm.pb_mask);
+            uint32_t spins = 0;
+            while ((game = *slot) == PB_EMPTY) { __nanosleep(100); if (++spins > (1u << 22)) { atomicExch(fin_ctr + 1, 1ull); active = false; break; } }
+        }
+        __syncwarp(FULLMASK);
+        if (active && gl == 0) *(volatile uint32_t*)(prm.pb_ring + ((size_t)shard * 7 + (size_t)p_cur) * ring_stride + (size_t)((base + idx) & prm.pb_mask)) = PB_EMPTY;
+        __threadfence();
+        uint32_t c[COLS];
+        uint32_t t = 0, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+        uint64_t gscore = 0;
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) c[k] = 0;
+        uint32_t sq = 0;
+        GameStat g;
+        g.H.H0 = g.H.H1 = g.H.H2 = 0u; g.cells = 0;
+        if (active) {
+            const uint4* sv = reinterpret_cast<const uint4*>(prm.st_save + game);
+            const uint4 a0 = __ldcg(sv), a1 = __ldcg(sv + 1), a2 = __ldcg(sv + 2), a3 = __ldcg(sv + 3), a4 = __ldcg(sv + 4), a5 = __ldcg(sv + 5);
+            g.H.H0 = a5.x; g.H.H1 = a5.y; g.H.H2 = a5.z; g.cells = (int)a5.w;
+            c[0] = a0.x; c[1] = a0.y; c[2] = a0.z; c[3] = a0.w; c[4] = a1.x; c[5] = a1.y; c[6] = a1.z; c[7] = a1.w; c[8] = a2.x; c[9] = a2.y;
+            t = a2.z; lines = a2.w; h1 = a3.x; h2 = a3.y; h3 = a3.z; h4 = a3.w;
+            if (gl == 0) cnt = a4.x;
+            gscore = ((uint64_t)a4.w << 32) | a4.z;
+            sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : game % (uint32_t)prm.G;
+        }
+        const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
+        unpack_heights(g.H, g.gh);
+        double w[6];
+        {
+            const double* wsrc = prm.weights + (size_t)(active ? game / (uint32_t)prm.G : 0u) * 6;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) w[i] = __ldg(wsrc + i);
+        }
+        // ---- one piece, every lane in step ----
+        const int ns = s_tab.nslots[p_cur];
+        uint64_t key = 0; uint32_t tag = 0;
+        for (int s2 = gl; s2 < ns; s2 += LANES) {
+            const SlotDesc d = load_slot12(s_tab, p_cur, s2);
+            W6Cand A;
+            w6_pre(c, g, d, A);
+            if (A.legal && A.full != 0u) w6_clear(d, A);
+            Heights Hn;
+            const uint64_t k = w6_post(A, w, Hn);
+            cnt += (uint32_t)(A.legal && active);
+            if (k > key) { key = k; tag = (uint32_t)s2; }
+        }
+        group_argmax<LANES>(key, tag);
+#pragma unroll
+        for (int off = LANES / 2; off > 0; off >>= 1) cnt += __shfl_xor_sync(FULLMASK, cnt, off);
+        bool finish = false;
+        int p_next = 7;
+        if (active) {
+            if (key == 0) {
+                finish = true;                                           // no legal placement: game over (simulator.py:187-189)
+            } else {
+                const SlotDesc d = load_slot12(s_tab, p_cur, (int)tag);
+                W6Cand A;
+                w6_pre(c, g, d, A);
+                if (A.full != 0u) w6_clear(d, A);
+#pragma unroll
+                for (int k = 0; k < COLS; ++k) c[k] = A.P.n[k];
+                g.H.H0 = (uint32_t)A.h[0] | (uint32_t)A.h[1] << 8 | (uint32_t)A.h[2] << 16 | (uint32_t)A.h[3] << 24;
+                g.H.H1 = (uint32_t)A.h[4] | (uint32_t)A.h[5] << 8 | (uint32_t)A.h[6] << 16 | (uint32_t)A.h[7] << 24;
+                g.H.H2 = (uint32_t)A.h[8] | (uint32_t)A.h[9] << 8;
+                g.cells = A.cells;
+                const uint32_t wk = (uint32_t)A.P.k;
+                if (wk != 0u) {
+                    lines += wk;
+                    h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
+                    const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
+                    gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
+                }
+                if (gl == 0) {
+                    if (prm.trace) {
+                        const uint32_t row = (uint32_t)(ROWS - A.P.y - A.P.ph);
+                        reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = (uint32_t)A.P.rot | row << 8 | (uint32_t)A.P.c0 << 16 | wk << 24;
+                    }
+                    if (prm.score_trace) {
+                        const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
+                        prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
+                    }
+                }
+                ++t;
+                if (t < stop) p_next = seq ? (int)__ldg(seq + t) : hashed_piece(prm.seed, (uint64_t)sq, t);
+                if (p_next >= 7) finish = true;                          // cap reached or the sequence ends here
+            }
+        }
+        // ---- finished games write their results; survivors go to the queue of their next piece ----
+        const bool lead = active && gl == 0;
+        if (lead && finish) {
+            tb200_game_result* r = prm.results + game;
+            r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4; r->score = gscore; r->placements = cnt;
+            if (prm.final_rows) { uint16_t rows[ROWS]; cols_to_rows(c, rows); for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2]; }
+        }
+        if (lead && !finish) pb_write_state(prm.st_save + game, c, t, lines, h1, h2, h3, h4, cnt, gscore, g.H, g.cells);
+        __threadfence();
+        const uint32_t fin_mask = __ballot_sync(FULLMASK, lead && finish);
+        if (fin_mask != 0u && lane == 0) atomicAdd(fin_ctr, (unsigned long long)__popc(fin_mask));
+        const int my_next = (lead && !finish) ? p_next : 8;
+        const uint32_t peers = __match_any_sync(FULLMASK, my_next);       // the survivors that go to the same queue
+        if (my_next < 7) {
+            unsigned long long pos = 0;
+            const int leader = __ffs((int)peers) - 1;
+            if (lane == leader) pos = atomicAdd(sctl + my_next, (unsigned long long)__popc(peers));      // the games of this task all live in `shard`
+            pos = __shfl_sync(peers, pos, leader);
+            pb_publish(prm, shard, my_next, pos + (unsigned long long)__popc(peers & ((1u << lane) - 1u)), game);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K2L: lookahead 2 with hard drops, one warp per game (BASELINE configs[3]).  The <= 34 legal layer-1 boards
 // (post-clear columns, packed heights, cached statistics, the move) are first built into shared memory by the
 // lanes; then the <= 34 x 34 leaves are FLATTENED over the 32 lanes (leaf -> (layer-1 rank, second slot)), so
@@ -2058,6 +2304,8 @@ struct tb200_ctx {
     size_t lock_cap = 0;
     bool lockstep_enabled = true;
     int lock_lanes = 0, lock_K = 64;     // tuning aids: TB200_LOCK_LANES, TB200_LOCK_K
+    bool bin_enabled = true;             // K2b; TB200_NO_BINS, TB200_BIN_LANES, TB200_BIN_MIN_GAMES
+    int bin_lanes = 0; long long bin_min_games = 32768;
     const uint32_t* lock_flag = nullptr; // device word set by K2s if a bucket wait ever timed out (checked after host-mode calls)
     int stage_cut1 = 0, stage_cut2 = 0;  // hand-over thresholds (games still unfinished): 4 and 2 per SM unless TB200_STAGE_CUTS=a,b
     cudaStream_t own_stream = nullptr;
@@ -2162,6 +2410,9 @@ int tb200_create(int device, tb200_ctx** out)
     if (getenv("TB200_NO_GRAPHS")) ctx->graphs_enabled = false;
     if (getenv("TB200_NO_STAGES")) ctx->staging_enabled = false;
     if (getenv("TB200_NO_LOCKSTEP")) ctx->lockstep_enabled = false;
+    if (getenv("TB200_NO_BINS")) ctx->bin_enabled = false;
+    if (const char* e5 = getenv("TB200_BIN_LANES")) ctx->bin_lanes = atoi(e5);
+    if (const char* e6 = getenv("TB200_BIN_MIN_GAMES")) { const long long v = atoll(e6); if (v >= 1024) ctx->bin_min_games = v; }
     if (const char* e3 = getenv("TB200_LOCK_LANES")) ctx->lock_lanes = atoi(e3);
     if (const char* e4 = getenv("TB200_LOCK_K")) { const int k = atoi(e4); if (k >= 8) ctx->lock_K = k; }
     ctx->stage_cut1 = 4 * ctx->sms; ctx->stage_cut2 = 2 * ctx->sms;
@@ -2240,7 +2491,7 @@ int tb200_last_timing(tb200_ctx* ctx, tb200_timing* out)
 }
 
 // ---- lockstep kernel K2s: when it applies, and its workspace (allocated outside any stream capture) ----
-struct LockPlan { bool on; uint32_t K, S; size_t b_save, b_list, b_ctl; };
+struct LockPlan { bool on; int kind; uint32_t K, S; size_t b_save, b_list, b_ctl; uint32_t ring_cap; };   // kind 1: K2s, 2: K2b
 static LockPlan lock_plan(const tb200_ctx* ctx, const tb200_play_args& a, int per_game_weights)
 {
     LockPlan lp{};
@@ -2251,7 +2502,22 @@ static LockPlan lock_plan(const tb200_ctx* ctx, const tb200_play_args& a, int pe
     lp.on = ctx->lockstep_enabled && lanes_auto && ctx->mode == tb::MODE_W6 && a.lookahead == 1 && a.move_set == 0 && per_game_weights == 0 &&
             !a.seq_of_game && a.games_per_candidate >= 4 && a.games_per_candidate <= 4096 &&
             (n_games + ctx->sms - 1) / ctx->sms > 80 && stop_moves >= (uint32_t)(2 * ctx->lock_K);
-    if (!lp.on) return lp;
+    if (!lp.on) {
+        // independent piece streams (or too few games per sequence to stay in step): the piece-binned kernel K2b, once the
+        // population is several times what the machine holds in flight
+        const bool pb = ctx->bin_enabled && lanes_auto && ctx->mode == tb::MODE_W6 && a.lookahead == 1 && a.move_set == 0 && per_game_weights == 0 &&
+                        n_games >= (long long)ctx->bin_min_games && n_games <= 0x40000000LL;
+        if (!pb) return lp;
+        lp.on = true; lp.kind = 2;
+        uint32_t cap = 256;
+        while ((long long)cap * tb::PB_SHARDS < n_games + tb::PB_SHARDS) cap <<= 1;           // >= games per shard
+        lp.ring_cap = cap;
+        lp.b_save = align_up(sizeof(tb::GameSave) * (size_t)n_games);
+        lp.b_list = align_up(7 * sizeof(uint32_t) * (size_t)cap * tb::PB_SHARDS);
+        lp.b_ctl = align_up(8 * (16 * tb::PB_SHARDS + 16));
+        return lp;
+    }
+    lp.kind = 1;
     lp.K = (uint32_t)ctx->lock_K; lp.S = (stop_moves + lp.K - 1) / lp.K + 2;      // see lock_stage_begin
     lp.b_save = align_up(sizeof(tb::GameSave) * (size_t)n_games);
     lp.b_list = align_up(2 * sizeof(uint32_t) * (size_t)n_games);
@@ -2336,7 +2602,30 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
     const bool lockstep = lp.on && lp.b_save + lp.b_list + lp.b_ctl <= ctx->lock_cap;      // workspace comes from ensure_lock_ws()
     TB_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(uint32_t), st));
     TB_CUDA(ctx, cudaMemsetAsync(a.results, 0, sizeof(tb200_game_result) * (size_t)n_games, st));
-    if (lockstep) {
+    if (lockstep && lp.kind == 2) {
+        p.st_save = reinterpret_cast<tb::GameSave*>(ctx->d_lock);
+        p.pb_ring = reinterpret_cast<uint32_t*>(ctx->d_lock + lp.b_save);
+        p.pb_ctl = reinterpret_cast<unsigned long long*>(ctx->d_lock + lp.b_save + lp.b_list);
+        p.pb_mask = lp.ring_cap - 1u;
+        ctx->lock_flag = reinterpret_cast<const uint32_t*>(p.pb_ctl + 16 * tb::PB_SHARDS + 1);
+        int bl = ctx->bin_lanes;
+        if (bl != 1 && bl != 2 && bl != 4 && bl != 8) bl = per_sm_games <= 330 ? 4 : (per_sm_games <= 1300 ? 2 : 1);   // tools/bin_probe.py
+        tb::play_fn bf = bl == 8 ? tb::play_games_w6bin_kernel<8> : (bl == 4 ? tb::play_games_w6bin_kernel<4> : (bl == 2 ? tb::play_games_w6bin_kernel<2> : tb::play_games_w6bin_kernel<1>));
+        int bocc = 0;
+        TB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bocc, bf, tb::BLOCK, 0));
+        if (bocc < 1) bocc = 1;
+        const long long bblocks = (long long)ctx->sms * bocc;
+        TB_CUDA(ctx, cudaMemsetAsync(p.pb_ring, 0xff, lp.b_list, st));
+        TB_CUDA(ctx, cudaMemsetAsync(p.pb_ctl, 0, lp.b_ctl, st));
+        if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+        tb::pb_init_kernel<<<(unsigned)((n_games + 255u) / 256u), 256, 0, st>>>(p);
+        TB_CUDA(ctx, cudaGetLastError());
+        bf<<<(unsigned)bblocks, tb::BLOCK, 0, st>>>(p);
+        TB_CUDA(ctx, cudaGetLastError());
+        if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+        *launches += 2;
+        lanes = bl; blocks = bblocks;
+    } else if (lockstep) {
         const uint32_t K = lp.K, S = lp.S;
         const size_t b_save = lp.b_save, b_list = lp.b_list, b_ctl = lp.b_ctl;
         p.st_save = reinterpret_cast<tb::GameSave*>(ctx->d_lock);

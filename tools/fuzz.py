@@ -59,6 +59,11 @@ def main():
             # population regime: > 80 games per SM on shared sequences -> the lockstep kernel K2s
             names, ms_name, la, pressure, lanes = W6, "drop", 1, None, 0
             G = rng.randint(4, 12); C = 12200 // G + rng.randint(0, 300); T = rng.randint(128, 150)
+        binned = rng.random() < float(os.environ.get("FUZZ_BINNED", "0.01"))
+        if binned:
+            # independent streams, >= 32 768 games -> the piece-binned kernel K2b (per-game sequences come from seq_of_game = g % G with G = n)
+            names, ms_name, la, pressure, lanes = W6, "drop", 1, None, 0
+            C, G, T = 1, rng.randint(32768, 36000), rng.randint(8, 20)
         if names is W6 and rng.random() < 0.6:
             w = np.array([[rng.gauss(v, 2.0) for v in W6V] for _ in range(C)])
         elif rng.random() < 0.2:
