@@ -10,6 +10,8 @@
 //   K2g play_games_w6grp_kernel<LANES>  16 / 8 / 4 / 2 / 1 lanes per game: the throughput path (configs 3, 5).
 //   K2s play_games_w6lock_kernel<LANES> the lockstep population kernel (config 3): every warp holds games of one piece sequence at one
 //        move index; stages of 64 pieces, survivors re-packed per sequence, one persistent launch with per-bucket hand-over.
+//   K2b play_games_w6bin_kernel<LANES>  the piece-binned kernel (config 5, independent streams): games travel through device-wide
+//        per-piece-type queues; a warp pops 32 / LANES games on the same piece, plays one piece each, pushes the survivors.
 //   K2f<staged> + K2p as re-spreading stages for the latency regime (config 2): see launch_play.
 //   K2w play_games_w32_kernel<MODE>     one warp per game, lookahead 1, all-45 / generic feature lists.
 //   K2L play_games_l2flat_kernel<MODE>  one warp per game, lookahead 2: layer-1 boards in shared memory, leaves flattened over lanes.
