@@ -426,6 +426,40 @@ def test_k2_piece_binned_initial_boards_lines_max_moves_and_short_sequences(eng)
         assert a["trace"][g, :k].tobytes() == b["trace"][g, :k].tobytes()
 
 
+def test_k2_lockstep_and_binned_edge_shapes(eng):
+    """Corner cases of the two queue-driven kernels against the per-game kernel: the smallest G and stage count K2s takes,
+    a population in which most games die within the first stage (whole buckets stay empty), K2b at its smallest size with
+    one-piece and two-piece games, and K2b on boards where nothing can be placed."""
+    eng.set_features(W6_NAMES)
+    rng = np.random.default_rng(21)
+
+    def same(kw_a, kw_b, *args, **kw):
+        a = eng.play_games(*args, want_final=True, **kw, **kw_a)
+        la = eng.last_timing()["kernels_launched"]
+        b = eng.play_games(*args, want_final=True, **kw, **kw_b)
+        assert (a["results"] == b["results"]).all() and (a["final"] == b["final"]).all() and (a["fitness"] == b["fitness"]).all()
+        return a, la
+
+    # K2s: G = 4, exactly two full stages' worth of pieces
+    w = np.array(W6_VALS)[None, :] + rng.normal(0, 2.0, size=(3100, 6))
+    _, la = same({}, {"lanes": 8}, w, 4, T=128, seed=3)
+    assert la == 2
+    # K2s: hopeless candidates (they stack up and die in a few dozen pieces), a few good ones
+    w = rng.normal(0, 10.0, size=(2500, 6)); w[::97] = np.array(W6_VALS)
+    a, la = same({}, {"lanes": 16}, w, 6, T=300, seed=4)
+    assert la == 2 and a["results"]["pieces"].min() < 40 and a["results"]["pieces"].max() == 300
+    # K2b: smallest population, one and two pieces per game
+    w = np.array(W6_VALS)[None, :] + rng.normal(0, 2.0, size=(32768, 6))
+    ids = np.arange(32768, dtype=np.int32)
+    for T in (1, 2):
+        _, la = same({}, {"lanes": 8}, w, 1, T=T, seed=6, seq_of_game=ids)
+        assert la == 3
+    # K2b: boards filled to the top row (checkerboard, nothing ever clears): most pieces do not fit at all
+    init = np.zeros((32768, 20), dtype=np.uint16); init[:, 1::2] = 0x2AA; init[:, 2::2] = 0x155
+    a, la = same({}, {"lanes": 32}, w, 1, T=30, seed=7, seq_of_game=ids, init_rows=init)
+    assert la == 3 and (a["results"]["pieces"] < 30).all() and (a["results"]["pieces"] == 0).any()
+
+
 # ------------------------------------------------------------------------------------------------
 # edge cases: tiny / ragged shapes, immediate game over, max_moves, explicit sequence maps, many tickets
 # ------------------------------------------------------------------------------------------------
