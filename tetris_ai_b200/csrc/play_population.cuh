@@ -1,0 +1,604 @@
+// play_population.cuh — K2g, K2s (lockstep) and K2b (piece-binned): the w6 throughput kernels (BASELINE configs[2] and [4]) (part of libtetris_b200.so; included by tetris_b200.cu only).
+#pragma once
+
+#include "play_common.cuh"
+
+namespace tb {
+
+// ---------------------------------------------------------------------------------------------
+// K2g: the throughput kernel for the w6 set, lookahead 1: LANES (8 or 16) lanes per game, 32/LANES
+// games per warp, for populations larger than one resident wave (BASELINE configs[2] / [4]).
+// Same fast evaluation as K2f (w6_pre / w6_clear / w6_post: no clz, popc only for the transition
+// counts), slots in rounds of LANES with a per-lane running best, shuffle-butterfly argmax inside
+// the group, commit by re-placing the winning slot with w6_pre (its heights come out of the
+// placement arithmetic, so the commit needs no clz either).  Persistent, ticket per group.
+// ---------------------------------------------------------------------------------------------
+template <int LANES>
+__global__ void __launch_bounds__(BLOCK) play_games_w6grp_kernel(const PlayParams prm)
+{
+    __shared__ Tables s_tab;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (LANES - 1);
+    const uint32_t T = prm.T;
+    const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
+
+    bool active = false, exhausted = false;
+    uint32_t game = 0, t = 0, lines = 0, lines0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+    uint64_t gscore = 0, stream = 0;
+    const uint8_t* seq = nullptr;
+    uint32_t c[COLS];
+    GameStat g;
+    int cells0 = 0;
+    double w[6];
+    int p_cur = 7, p_next = 7;
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) { c[k] = 0; g.gh[k] = 0; }
+    g.H.H0 = g.H.H1 = g.H.H2 = 0; g.cells = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) w[i] = 0.0;
+
+    auto fetch_piece = [&](uint32_t tt) -> int {
+        if (tt >= T) return 7;
+        return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, stream, tt);
+    };
+
+    for (;;) {
+        const bool want = !active && !exhausted;
+        uint32_t tk = 0;
+        if (want && gl == 0) tk = atomicAdd(prm.ticket, 1u);
+        tk = __shfl_sync(FULLMASK, tk, 0, LANES);
+        if (want) {
+            if (tk < prm.n_games) {
+                game = prm.seq_major_C ? (tk % prm.seq_major_C) * (uint32_t)prm.G + tk / prm.seq_major_C : tk;
+                active = true; t = 0; h1 = h2 = h3 = h4 = 0; cnt = 0; gscore = 0;
+                lines = prm.init_lines ? prm.init_lines[game] : 0u; lines0 = lines;
+                const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : (prm.per_game_weights != 0 ? game : game % (uint32_t)prm.G);
+                stream = sq;
+                seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
+                if (prm.init_rows) {
+                    uint16_t rows[ROWS];
+                    for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
+                    rows_to_cols(rows, c);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < COLS; ++k) c[k] = 0;
+                }
+                g = game_stat(c);
+                cells0 = g.cells;
+                const size_t wrow = prm.per_game_weights > 0 ? (size_t)game : (prm.per_game_weights < 0 ? 0 : (size_t)(game / (uint32_t)prm.G));
+                const double* wsrc = prm.weights + wrow * 6;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) w[i] = __ldg(wsrc + i);
+                p_cur = fetch_piece(0); p_next = fetch_piece(1);
+                if (stop == 0 || p_cur >= 7) {            // nothing to play: finish immediately
+                    if (gl == 0) { tb200_game_result* r = prm.results + game; r->pieces = 0; r->lines = 0; r->score = 0; }
+                    active = false;
+                }
+            } else {
+                exhausted = true;
+            }
+        }
+        if (!__any_sync(FULLMASK, active)) break;
+
+        const int p_after = active ? fetch_piece(t + 2) : 7;
+        uint64_t key = 0; uint32_t tag = 0;
+        if (active) {
+            const int pc = p_cur < 7 ? p_cur : 0;
+            const int ns = p_cur < 7 ? s_tab.nslots[pc] : 0;
+            for (int s = gl; s < ns; s += LANES) {
+                const SlotDesc d = load_slot12(s_tab, pc, s);
+                W6Cand A;
+                w6_pre(c, g, d, A);
+                if (A.legal && A.full != 0u) w6_clear(d, A);
+                Heights Hn;
+                const uint64_t k = w6_post(A, w, Hn);
+                cnt += (uint32_t)A.legal;
+                if (k > key) { key = k; tag = (uint32_t)s; }
+            }
+        }
+        group_argmax<LANES>(key, tag);
+        if (active) {
+            bool finish = false;
+            if (key == 0) {
+                finish = true;                            // no legal placement: game over
+            } else {
+                const SlotDesc d = load_slot12(s_tab, p_cur, (int)tag);
+                W6Cand A;
+                w6_pre(c, g, d, A);
+                if (A.full != 0u) w6_clear(d, A);
+#pragma unroll
+                for (int k = 0; k < COLS; ++k) { c[k] = A.P.n[k]; g.gh[k] = A.h[k]; }
+                g.H.H0 = (uint32_t)A.h[0] | (uint32_t)A.h[1] << 8 | (uint32_t)A.h[2] << 16 | (uint32_t)A.h[3] << 24;
+                g.H.H1 = (uint32_t)A.h[4] | (uint32_t)A.h[5] << 8 | (uint32_t)A.h[6] << 16 | (uint32_t)A.h[7] << 24;
+                g.H.H2 = (uint32_t)A.h[8] | (uint32_t)A.h[9] << 8;
+                const uint32_t wk = (uint32_t)A.P.k;
+                if (wk != 0u) {
+                    lines += wk;
+                    h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
+                    const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
+                    gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
+                }
+                g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)(lines - lines0);
+                if (gl == 0) {
+                    if (prm.trace) {
+                        const uint32_t row = (uint32_t)(ROWS - A.P.y - A.P.ph);
+                        reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = (uint32_t)A.P.rot | row << 8 | (uint32_t)A.P.c0 << 16 | wk << 24;
+                    }
+                    if (prm.score_trace) {
+                        const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
+                        prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
+                    }
+                }
+                ++t;
+                p_cur = p_next; p_next = p_after;
+                if (t >= stop || p_cur >= 7) finish = true;
+            }
+            if (finish) {
+                if (gl == 0) {
+                    tb200_game_result* r = prm.results + game;
+                    r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4;
+                    r->score = gscore;
+                    if (prm.final_rows) {
+                        uint16_t rows[ROWS];
+                        cols_to_rows(c, rows);
+                        for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2];
+                    }
+                }
+                if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&prm.results[game].placements), (unsigned long long)cnt);
+                active = false;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2s: the lockstep throughput kernel for CE populations (BASELINE configs[2]): C candidates x G games on G SHARED piece
+// sequences, w6, lookahead 1.  All games of sequence g see the same piece at the same move, so a warp that holds only
+// games of one sequence at one move index runs every round with all of its lanes on the same piece: no lane waits for
+// another game's longer slot list (K2g on independent streams keeps 18 of 32 threads busy).  Games die, so the play is
+// cut into stages of K pieces (the first two shorter); a task = (stage, sequence, chunk of 32 / LANES games); at the end of a task the
+// survivors are appended to the sequence's list for the next stage, which re-packs them into full warps.  One
+// persistent launch: warps walk the buckets (stage-major, sequence-minor) and claim tasks by ticket; bucket (s, g)
+// opens when every task of (s - 1, g) is done — 29 other buckets lie in between, so nobody actually waits except at
+// the very end, and a running task never waits, so the scheme cannot deadlock with a fully resident grid.
+// Hand-over state: GameSave (80 bytes per game) through L2 (__ldcg / fence + counter).
+// ---------------------------------------------------------------------------------------------
+// first move of stage s: two short stages first (K/4, K/2) — a fresh CE population loses most of its games within a
+// few dozen pieces and they should be re-packed early — then K pieces per stage
+TB_HD uint32_t lock_stage_begin(uint32_t s, uint32_t K) { return s == 0u ? 0u : (s == 1u ? K / 4u : (s == 2u ? K / 2u : K * (s - 2u))); }
+
+template <int LANES>
+__global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayParams prm)
+{
+    constexpr uint32_t GPW = 32 / LANES;           // games per warp
+    __shared__ Tables s_tab;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (LANES - 1);
+    const uint32_t T = prm.T, C = prm.lk_C, K = prm.lk_K, S = prm.lk_S;
+    const uint32_t G = (uint32_t)prm.G;
+    const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
+
+    uint32_t st = 0, sq = 0;                       // current bucket
+    uint32_t n_in = C, ntasks = (C + GPW - 1) / GPW;
+    for (;;) {
+        uint32_t* ctl = prm.lk_ctl + ((size_t)st * G + sq) * 4;
+        uint32_t slot = 0;
+        if (lane == 0) slot = atomicAdd(ctl, 1u);
+        slot = __shfl_sync(FULLMASK, slot, 0);
+        if (slot >= ntasks) {                      // bucket handed out: open the next one
+            if (++sq == G) { sq = 0; if (++st == S) break; }
+            if (st > 0) {
+                if (lane == 0) {
+                    const uint32_t* prev = prm.lk_ctl + ((size_t)(st - 1) * G + sq) * 4;
+                    const uint32_t n_prev = st == 1 ? C : __ldcg(prev + 2);
+                    const uint32_t need = (n_prev + GPW - 1) / GPW;
+                    uint32_t spins = 0;
+                    while (*reinterpret_cast<volatile const uint32_t*>(prev + 1) < need) {
+                        __nanosleep(200);
+                        if (++spins > (1u << 23)) { atomicExch(prm.lk_ctl + (size_t)S * G * 4 + 3, 1u); break; }   // safety valve (> 1.5 s): never hang the device
+                    }
+                    __threadfence();
+                    n_in = spins > (1u << 23) ? 0u : __ldcg(prm.lk_ctl + ((size_t)st * G + sq) * 4 + 2);
+                }
+                n_in = __shfl_sync(FULLMASK, n_in, 0);
+            }
+            ntasks = (n_in + GPW - 1) / GPW;
+            continue;
+        }
+        // ---- task (st, sq, slot): up to GPW games of sequence sq, all at move st * K ----
+        const uint32_t idx = slot * GPW + (uint32_t)(lane / LANES);
+        bool active = idx < n_in;
+        uint32_t game = 0;
+        if (active) game = st == 0 ? idx * G + sq : __ldcg(prm.lk_list + ((size_t)(st & 1u) * G + sq) * C + idx);
+        const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
+        auto fetch_piece = [&](uint32_t tt) -> int {                     // warp-uniform
+            if (tt >= T) return 7;
+            return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, (uint64_t)sq, tt);
+        };
+        uint32_t c[COLS];
+        uint32_t t = lock_stage_begin(st, K), lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+        uint64_t gscore = 0;
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) c[k] = 0;
+        if (active) {
+            if (st > 0) {
+                const uint4* sv = reinterpret_cast<const uint4*>(prm.st_save + game);
+                const uint4 a0 = __ldcg(sv), a1 = __ldcg(sv + 1), a2 = __ldcg(sv + 2), a3 = __ldcg(sv + 3), a4 = __ldcg(sv + 4);
+                c[0] = a0.x; c[1] = a0.y; c[2] = a0.z; c[3] = a0.w; c[4] = a1.x; c[5] = a1.y; c[6] = a1.z; c[7] = a1.w; c[8] = a2.x; c[9] = a2.y;
+                lines = a2.w; h1 = a3.x; h2 = a3.y; h3 = a3.z; h4 = a3.w;
+                if (gl == 0) cnt = a4.x;
+                gscore = ((uint64_t)a4.w << 32) | a4.z;
+            } else {
+                if (prm.init_rows) {
+                    uint16_t rows[ROWS];
+                    for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
+                    rows_to_cols(rows, c);
+                }
+                if (prm.init_lines) lines = prm.init_lines[game];
+            }
+        }
+        GameStat g = game_stat(c);
+        const int cells0 = g.cells - 4 * (int)t;
+        const uint32_t lines0 = lines;
+        double w[6];
+        {
+            const double* wsrc = prm.weights + (size_t)(active ? game / G : 0u) * 6;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) w[i] = __ldg(wsrc + i);
+        }
+        const uint32_t t_next = lock_stage_begin(st + 1u, K);
+        const uint32_t t_end = (st + 1 == S || t_next > stop) ? stop : t_next;
+        int p_cur = fetch_piece(t), p_next = fetch_piece(t + 1u);
+        if (t >= stop || p_cur >= 7) {                                   // nothing to play (stop == 0 or the sequence ends here)
+            if (active && gl == 0) {
+                tb200_game_result* r = prm.results + game;
+                r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4; r->score = gscore;
+                if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&r->placements), (unsigned long long)cnt);
+                if (prm.final_rows) { uint16_t rows[ROWS]; cols_to_rows(c, rows); for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2]; }
+            }
+            active = false;
+        }
+        while (t < t_end && p_cur < 7 && __any_sync(FULLMASK, active)) {
+            const int p_after = fetch_piece(t + 2u);
+            const int ns = s_tab.nslots[p_cur];
+            uint64_t key = 0; uint32_t tag = 0;
+            for (int s2 = gl; s2 < ns; s2 += LANES) {                    // same piece, same trip count in every lane
+                const SlotDesc d = load_slot12(s_tab, p_cur, s2);
+                W6Cand A;
+                w6_pre(c, g, d, A);
+                if (A.legal && A.full != 0u) w6_clear(d, A);
+                Heights Hn;
+                const uint64_t k = w6_post(A, w, Hn);
+                cnt += (uint32_t)(A.legal && active);
+                if (k > key) { key = k; tag = (uint32_t)s2; }
+            }
+            group_argmax<LANES>(key, tag);
+            bool finish = false;
+            if (active) {
+                if (key == 0) {
+                    finish = true;                                       // no legal placement: game over (simulator.py:187-189)
+                } else {
+                    const SlotDesc d = load_slot12(s_tab, p_cur, (int)tag);
+                    W6Cand A;
+                    w6_pre(c, g, d, A);
+                    if (A.full != 0u) w6_clear(d, A);
+#pragma unroll
+                    for (int k = 0; k < COLS; ++k) { c[k] = A.P.n[k]; g.gh[k] = A.h[k]; }
+                    g.H.H0 = (uint32_t)A.h[0] | (uint32_t)A.h[1] << 8 | (uint32_t)A.h[2] << 16 | (uint32_t)A.h[3] << 24;
+                    g.H.H1 = (uint32_t)A.h[4] | (uint32_t)A.h[5] << 8 | (uint32_t)A.h[6] << 16 | (uint32_t)A.h[7] << 24;
+                    g.H.H2 = (uint32_t)A.h[8] | (uint32_t)A.h[9] << 8;
+                    const uint32_t wk = (uint32_t)A.P.k;
+                    if (wk != 0u) {
+                        lines += wk;
+                        h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
+                        const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
+                        gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
+                    }
+                    g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)(lines - lines0);
+                    if (gl == 0) {
+                        if (prm.trace) {
+                            const uint32_t row = (uint32_t)(ROWS - A.P.y - A.P.ph);
+                            reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = (uint32_t)A.P.rot | row << 8 | (uint32_t)A.P.c0 << 16 | wk << 24;
+                        }
+                        if (prm.score_trace) {
+                            const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
+                            prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
+                        }
+                    }
+                }
+            }
+            const uint32_t tn = t + 1u;
+            if (active && !finish && (tn >= stop || p_next >= 7)) finish = true;
+            if (finish) {
+                const uint32_t played = key == 0 ? t : tn;
+                if (gl == 0) {
+                    tb200_game_result* r = prm.results + game;
+                    r->pieces = played; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4; r->score = gscore;
+                    if (prm.final_rows) { uint16_t rows[ROWS]; cols_to_rows(c, rows); for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2]; }
+                }
+                if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&prm.results[game].placements), (unsigned long long)cnt);
+                active = false;
+            }
+            t = tn;
+            p_cur = p_next; p_next = p_after;
+        }
+        // ---- survivors (alive at move t_end < stop) go to the sequence's list of the next stage ----
+        {
+#pragma unroll
+            for (int off = LANES / 2; off > 0; off >>= 1) cnt += __shfl_xor_sync(FULLMASK, cnt, off);
+            const uint32_t live = __ballot_sync(FULLMASK, active && gl == 0);
+            if (live != 0u) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(prm.lk_ctl + ((size_t)(st + 1) * G + sq) * 4 + 2, (uint32_t)__popc(live));
+                base = __shfl_sync(FULLMASK, base, 0);
+                if (active && gl == 0) {
+                    uint4* sv = reinterpret_cast<uint4*>(prm.st_save + game);
+                    __stcg(sv, make_uint4(c[0], c[1], c[2], c[3]));
+                    __stcg(sv + 1, make_uint4(c[4], c[5], c[6], c[7]));
+                    __stcg(sv + 2, make_uint4(c[8], c[9], t, lines));
+                    __stcg(sv + 3, make_uint4(h1, h2, h3, h4));
+                    __stcg(sv + 4, make_uint4(cnt, 0u, (uint32_t)gscore, (uint32_t)(gscore >> 32)));
+                    const uint32_t rank = (uint32_t)__popc(live & ((1u << lane) - 1u));
+                    __stcg(prm.lk_list + ((size_t)((st + 1) & 1u) * G + sq) * C + base + rank, game);
+                }
+            }
+            __syncwarp(FULLMASK);
+            if (lane == 0) { __threadfence(); atomicAdd(ctl + 1, 1u); }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2b: the piece-binned throughput kernel for INDEPENDENT piece streams (BASELINE configs[4]: every game its own
+// stream), w6, lookahead 1.  K2g keeps 18 of 32 threads busy there because the games of a warp are on different pieces
+// (9 / 17 / 34 slots).  Here a game is not bound to a warp: seven device-wide queues, one per piece type, hold the games
+// whose next piece has that type.  A warp pops up to 32 / LANES games from the fullest queue — all on the same piece —
+// plays exactly one piece for each of them with every lane in step, and pushes each survivor onto the queue of its
+// next piece.  Game state (80 bytes) travels through L2; with 4 warps per scheduler the pop / load latency hides behind
+// the other warps' arithmetic.  Queues are rings of game ids with 64-bit reserved-tail / head counters: a pusher
+// reserves slots by atomicAdd, writes the state, fences, then publishes the id into the slot; a popper claims by CAS
+// on the head and reads each slot once it is published.  All waits are bounded (error flag instead of a hang).
+// ---------------------------------------------------------------------------------------------
+#define PB_EMPTY 0xffffffffu
+constexpr uint32_t PB_SHARDS = 64;     // independent queue sets; a game always lives in shard game % PB_SHARDS, a warp's home shard is warp % PB_SHARDS
+
+TB_D void pb_write_state(GameSave* dst, const uint32_t c[COLS], uint32_t t, uint32_t lines, uint32_t h1, uint32_t h2, uint32_t h3, uint32_t h4,
+                         uint32_t cnt, uint64_t gscore, const Heights& H, int cells)
+{
+    uint4* sv = reinterpret_cast<uint4*>(dst);
+    __stcg(sv, make_uint4(c[0], c[1], c[2], c[3]));
+    __stcg(sv + 1, make_uint4(c[4], c[5], c[6], c[7]));
+    __stcg(sv + 2, make_uint4(c[8], c[9], t, lines));
+    __stcg(sv + 3, make_uint4(h1, h2, h3, h4));
+    __stcg(sv + 4, make_uint4(cnt, 0u, (uint32_t)gscore, (uint32_t)(gscore >> 32)));
+    __stcg(sv + 5, make_uint4(H.H0, H.H1, H.H2, (uint32_t)cells));
+}
+
+// publish `game` at queue position pos of piece type p (the slot is empty unless a slow popper still holds it)
+TB_D void pb_publish(const PlayParams& prm, uint32_t shard, int p, unsigned long long pos, uint32_t game)
+{
+    volatile uint32_t* slot = prm.pb_ring + ((size_t)shard * 7 + (size_t)p) * ((size_t)prm.pb_mask + 1) + (size_t)(pos & prm.pb_mask);
+    uint32_t spins = 0;
+    while (*slot != PB_EMPTY) { __nanosleep(100); if (++spins > (1u << 22)) { atomicExch(prm.pb_ctl + 16 * PB_SHARDS + 1, 1ull); break; } }
+    *slot = game;
+}
+
+// every game enters the queue of its first piece (or finishes at once when there is nothing to play)
+__global__ void pb_init_kernel(const PlayParams prm)
+{
+    const uint32_t game = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t T = prm.T;
+    const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
+    int p0 = 8;                                  // 8: no game in this thread
+    if (game < prm.n_games) {
+        const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : game % (uint32_t)prm.G;
+        uint32_t c[COLS];
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) c[k] = 0;
+        if (prm.init_rows) {
+            uint16_t rows[ROWS];
+            for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
+            rows_to_cols(rows, c);
+        }
+        const uint32_t lines = prm.init_lines ? prm.init_lines[game] : 0u;
+        p0 = stop == 0u ? 7 : (prm.pieces ? (int)prm.pieces[(size_t)sq * T] : hashed_piece(prm.seed, (uint64_t)sq, 0));
+        if (p0 >= 7) {
+            tb200_game_result* r = prm.results + game;
+            r->pieces = 0; r->lines = lines; r->score = 0;
+            if (prm.final_rows) { uint16_t rows[ROWS]; cols_to_rows(c, rows); for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2]; }
+            atomicAdd(prm.pb_ctl + 16 * PB_SHARDS, 1ull);
+            p0 = 8;
+        } else {
+            const GameStat g0 = game_stat(c);
+            pb_write_state(prm.st_save + game, c, 0u, lines, 0u, 0u, 0u, 0u, 0u, 0ull, g0.H, g0.cells);
+        }
+    }
+    if (p0 < 7) {
+        const uint32_t shard = game % PB_SHARDS;
+        const unsigned long long pos = atomicAdd(prm.pb_ctl + 16 * shard + p0, 1ull);
+        prm.pb_ring[((size_t)shard * 7 + (size_t)p0) * ((size_t)prm.pb_mask + 1) + (size_t)(pos & prm.pb_mask)] = game;
+    }
+}
+
+template <int LANES>
+__global__ void __launch_bounds__(BLOCK) play_games_w6bin_kernel(const PlayParams prm)
+{
+    constexpr uint32_t GPW = 32 / LANES;
+    __shared__ Tables s_tab;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
+        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (LANES - 1);
+    const uint32_t T = prm.T;
+    const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
+    const size_t ring_stride = (size_t)prm.pb_mask + 1;
+    const uint32_t warp_id = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
+    unsigned long long* const fin_ctr = prm.pb_ctl + 16 * PB_SHARDS;
+    uint32_t idle = 0, probe = 0;
+    unsigned long long last_fin = 0;
+
+    for (;;) {
+        // ---- pop up to GPW games of one piece type from the home shard (or, when that is empty, from the next shard that
+        //      has work): lanes 0..6 look at one queue each, the fullest wins ----
+        const uint32_t shard = (warp_id + probe) % PB_SHARDS;
+        unsigned long long* const sctl = prm.pb_ctl + 16 * shard;
+        unsigned long long hd = 0, avail = 0;
+        if (lane < 7) { hd = *(volatile unsigned long long*)(sctl + 8 + lane); const unsigned long long tl = *(volatile unsigned long long*)(sctl + lane); avail = tl - hd; }
+        const uint32_t a32 = avail > 0xffffffull ? 0xffffffu : (uint32_t)avail;
+        // prefer full warps; among equally good queues rotate by warp so that the heads are not all hit at once
+        const uint32_t score = (lane < 7 && a32 != 0u) ? (1u << 20) + ((a32 >= GPW ? GPW : a32) << 8 | ((uint32_t)(lane + warp_id) % 7u)) : 0u;
+        const uint32_t best = __reduce_max_sync(FULLMASK, score);
+        if (best == 0u) {
+            if (++probe < PB_SHARDS) continue;                       // try the other shards before idling
+            probe = 0;
+            // nothing waiting anywhere: done when every game has finished, otherwise other warps are still playing
+            const unsigned long long fin = *(volatile unsigned long long*)fin_ctr;
+            if (fin >= (unsigned long long)prm.n_games) break;
+            __nanosleep(1000);
+            if ((++idle & 255u) == 0u && fin != last_fin) { last_fin = fin; idle = 0; }      // progress elsewhere: keep waiting
+            if (idle > (1u << 16)) { if (lane == 0) atomicExch(fin_ctr + 1, 1ull); break; }    // ~4 s without any game finishing
+            continue;
+        }
+        const int owner = __ffs((int)__ballot_sync(FULLMASK, score == best)) - 1;      // lane = piece type
+        uint32_t n = 0;
+        if (lane == owner) {
+            n = a32 < GPW ? a32 : GPW;
+            if (atomicCAS(sctl + 8 + lane, hd, hd + n) != hd) n = 0;                     // lost the race: look again
+        }
+        n = __shfl_sync(FULLMASK, n, owner);
+        if (n == 0u) continue;
+        idle = 0;
+        const unsigned long long base = __shfl_sync(FULLMASK, hd, owner);
+        const int p_cur = owner;
+        // ---- fetch the games ----
+        const uint32_t idx = (uint32_t)(lane / LANES);
+        bool active = idx < n;
+        uint32_t game = 0;
+        if (active) {
+            volatile uint32_t* slot = prm.pb_ring + ((size_t)shard * 7 + (size_t)p_cur) * ring_stride + (size_t)((base + idx) & prm.pb_mask);
+            uint32_t spins = 0;
+            while ((game = *slot) == PB_EMPTY) { __nanosleep(100); if (++spins > (1u << 22)) { atomicExch(fin_ctr + 1, 1ull); active = false; break; } }
+        }
+        __syncwarp(FULLMASK);
+        if (active && gl == 0) *(volatile uint32_t*)(prm.pb_ring + ((size_t)shard * 7 + (size_t)p_cur) * ring_stride + (size_t)((base + idx) & prm.pb_mask)) = PB_EMPTY;
+        __threadfence();
+        uint32_t c[COLS];
+        uint32_t t = 0, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+        uint64_t gscore = 0;
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) c[k] = 0;
+        uint32_t sq = 0;
+        GameStat g;
+        g.H.H0 = g.H.H1 = g.H.H2 = 0u; g.cells = 0;
+        if (active) {
+            const uint4* sv = reinterpret_cast<const uint4*>(prm.st_save + game);
+            const uint4 a0 = __ldcg(sv), a1 = __ldcg(sv + 1), a2 = __ldcg(sv + 2), a3 = __ldcg(sv + 3), a4 = __ldcg(sv + 4), a5 = __ldcg(sv + 5);
+            g.H.H0 = a5.x; g.H.H1 = a5.y; g.H.H2 = a5.z; g.cells = (int)a5.w;
+            c[0] = a0.x; c[1] = a0.y; c[2] = a0.z; c[3] = a0.w; c[4] = a1.x; c[5] = a1.y; c[6] = a1.z; c[7] = a1.w; c[8] = a2.x; c[9] = a2.y;
+            t = a2.z; lines = a2.w; h1 = a3.x; h2 = a3.y; h3 = a3.z; h4 = a3.w;
+            if (gl == 0) cnt = a4.x;
+            gscore = ((uint64_t)a4.w << 32) | a4.z;
+            sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : game % (uint32_t)prm.G;
+        }
+        const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
+        unpack_heights(g.H, g.gh);
+        double w[6];
+        {
+            const double* wsrc = prm.weights + (size_t)(active ? game / (uint32_t)prm.G : 0u) * 6;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) w[i] = __ldg(wsrc + i);
+        }
+        // ---- one piece, every lane in step ----
+        const int ns = s_tab.nslots[p_cur];
+        uint64_t key = 0; uint32_t tag = 0;
+        for (int s2 = gl; s2 < ns; s2 += LANES) {
+            const SlotDesc d = load_slot12(s_tab, p_cur, s2);
+            W6Cand A;
+            w6_pre(c, g, d, A);
+            if (A.legal && A.full != 0u) w6_clear(d, A);
+            Heights Hn;
+            const uint64_t k = w6_post(A, w, Hn);
+            cnt += (uint32_t)(A.legal && active);
+            if (k > key) { key = k; tag = (uint32_t)s2; }
+        }
+        group_argmax<LANES>(key, tag);
+#pragma unroll
+        for (int off = LANES / 2; off > 0; off >>= 1) cnt += __shfl_xor_sync(FULLMASK, cnt, off);
+        bool finish = false;
+        int p_next = 7;
+        if (active) {
+            if (key == 0) {
+                finish = true;                                           // no legal placement: game over (simulator.py:187-189)
+            } else {
+                const SlotDesc d = load_slot12(s_tab, p_cur, (int)tag);
+                W6Cand A;
+                w6_pre(c, g, d, A);
+                if (A.full != 0u) w6_clear(d, A);
+#pragma unroll
+                for (int k = 0; k < COLS; ++k) c[k] = A.P.n[k];
+                g.H.H0 = (uint32_t)A.h[0] | (uint32_t)A.h[1] << 8 | (uint32_t)A.h[2] << 16 | (uint32_t)A.h[3] << 24;
+                g.H.H1 = (uint32_t)A.h[4] | (uint32_t)A.h[5] << 8 | (uint32_t)A.h[6] << 16 | (uint32_t)A.h[7] << 24;
+                g.H.H2 = (uint32_t)A.h[8] | (uint32_t)A.h[9] << 8;
+                g.cells = A.cells;
+                const uint32_t wk = (uint32_t)A.P.k;
+                if (wk != 0u) {
+                    lines += wk;
+                    h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
+                    const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
+                    gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
+                }
+                if (gl == 0) {
+                    if (prm.trace) {
+                        const uint32_t row = (uint32_t)(ROWS - A.P.y - A.P.ph);
+                        reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = (uint32_t)A.P.rot | row << 8 | (uint32_t)A.P.c0 << 16 | wk << 24;
+                    }
+                    if (prm.score_trace) {
+                        const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
+                        prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
+                    }
+                }
+                ++t;
+                if (t < stop) p_next = seq ? (int)__ldg(seq + t) : hashed_piece(prm.seed, (uint64_t)sq, t);
+                if (p_next >= 7) finish = true;                          // cap reached or the sequence ends here
+            }
+        }
+        // ---- finished games write their results; survivors go to the queue of their next piece ----
+        const bool lead = active && gl == 0;
+        if (lead && finish) {
+            tb200_game_result* r = prm.results + game;
+            r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4; r->score = gscore; r->placements = cnt;
+            if (prm.final_rows) { uint16_t rows[ROWS]; cols_to_rows(c, rows); for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2]; }
+        }
+        if (lead && !finish) pb_write_state(prm.st_save + game, c, t, lines, h1, h2, h3, h4, cnt, gscore, g.H, g.cells);
+        __threadfence();
+        const uint32_t fin_mask = __ballot_sync(FULLMASK, lead && finish);
+        if (fin_mask != 0u && lane == 0) atomicAdd(fin_ctr, (unsigned long long)__popc(fin_mask));
+        const int my_next = (lead && !finish) ? p_next : 8;
+        const uint32_t peers = __match_any_sync(FULLMASK, my_next);       // the survivors that go to the same queue
+        if (my_next < 7) {
+            unsigned long long pos = 0;
+            const int leader = __ffs((int)peers) - 1;
+            if (lane == leader) pos = atomicAdd(sctl + my_next, (unsigned long long)__popc(peers));      // the games of this task all live in `shard`
+            pos = __shfl_sync(peers, pos, leader);
+            pb_publish(prm, shard, my_next, pos + (unsigned long long)__popc(peers & ((1u << lane) - 1u)), game);
+        }
+    }
+}
+
+}  // namespace tb

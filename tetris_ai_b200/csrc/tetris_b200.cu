@@ -1,4 +1,9 @@
-// tetris_b200.cu — kernels + C ABI of libtetris_b200.so (sm_100a only).
+// tetris_b200.cu — the single translation unit of libtetris_b200.so (sm_100a only): small kernels (K3, K4, fitness, K1 packers),
+// kernel selection, launch scheduling and the C ABI.  The play kernels live in the headers included below:
+//   play_common.cuh      PlayParams, GameSave, argmax / table helpers
+//   play_generic.cuh     K2 generic, K2w            play_latency.cuh     K2f, K2p
+//   play_population.cuh  K2g, K2s, K2b              play_lookahead2.cuh  K2L          play_wiggle.cuh  K2x
+//   tetris_core.cuh      the host/device core (placement, clear, 45 features, scorer) shared with the host emulation in tests/emu
 //
 //   K2  play_games_kernel<LANES,MODE,LOOKAHEAD,EXT>  persistent, one LANES-wide lane group per game (8 / 16 / 32), lookahead
 //        1 or 2, any feature list; placements fan out across the lanes, features by popc/clz bit formulas
@@ -29,2108 +34,14 @@
 #include <string>
 #include <new>
 
-#include "tetris_core.cuh"
-#include "../../include/tetris_b200.h"
+#include "play_common.cuh"
+#include "play_generic.cuh"
+#include "play_latency.cuh"
+#include "play_population.cuh"
+#include "play_lookahead2.cuh"
+#include "play_wiggle.cuh"
 
 namespace tb {
-
-#define FULLMASK 0xffffffffu
-constexpr int BLOCK = 128;
-
-__constant__ Tables c_tables;
-#ifdef TB_PHASES
-__device__ unsigned long long g_phase[8];
-#define PH(i) { const long long now_ = clock64(); ph[i] += now_ - last_; last_ = now_; }
-#else
-#define PH(i)
-#endif
-
-struct PlayParams {
-    const double*  weights;
-    const uint8_t* pieces;
-    const int32_t* seq_of_game;
-    const uint16_t* init_rows;
-    const uint32_t* init_lines;      // lines already cleared before the first move (level for score / pressure), or null
-    tb200_game_result* results;
-    uint8_t*  trace;
-    double*   score_trace;
-    uint16_t* final_rows;
-    uint32_t* ticket;
-    uint64_t  seed;
-    uint64_t  rmask;
-    uint32_t  n_games;
-    uint32_t  T;
-    uint32_t  max_moves;
-    int32_t   G;
-    int32_t   F;
-    int32_t   per_game_weights;      // K1 (one game per board, sequence id = game): weights row = game (1) or row 0 (-1); K2: 0
-    uint32_t  seq_major_C;           // kernels with several games per warp: != 0 => tickets run sequence-major (ticket = g * C + candidate), so the games that share a
-                                     // warp start on the same piece sequence and stay in step while they live (fewer idle lanes)
-    int32_t   move_set;              // bit 0: overhang slides, bit 1: pressure filter (extended generic kernels only)
-    Pressure  press;                 // move_with_pressure parameters (press.on mirrors bit 1)
-    uint8_t   ids[TB200_MAX_WEIGHTED];
-    // re-spreading stages of the latency regime (K2f / K2p only; st_ctl == null: off) — see launch_play
-    uint32_t* st_ctl;                // [0..2] ticket of stage s, [3] games finished so far, [4 + s] games handed to stage s
-    const uint32_t* st_list_in;      // game ids handed to this stage, or null: all games, fresh
-    uint32_t* st_list_out;           // survivors of this stage (null in the last stage)
-    struct GameSave* st_save;        // [n_games] state of the handed-over games
-    int32_t   st_stage;
-    uint32_t  st_cut;                // leave the stage once (games not yet finished) <= st_cut; 0: run to the end
-    // lockstep kernel K2s (see play_games_w6lock_kernel)
-    uint32_t* lk_ctl;                // [S][G][4] per (stage, sequence) bucket: {task ticket, tasks done, games entering the stage, -}
-    uint32_t* lk_list;               // [2][G][C] game ids entering a stage, by sequence; double-buffered by stage parity
-    uint32_t  lk_C, lk_K, lk_S;      // candidates, pieces per stage, stages
-    // piece-binned kernel K2b (see play_games_w6bin_kernel)
-    unsigned long long* pb_ctl;      // per shard 16 words: [0..6] queue tails (reserved), [8..14] queue heads; after the shards: games finished, error flag
-    uint32_t* pb_ring;               // [shards][7][pb_mask + 1] game ids waiting for a piece of type p; 0xffffffff = empty slot
-    uint32_t  pb_mask;               // ring capacity - 1 (a power of two >= games per shard)
-};
-
-// state of a game handed from one stage to the next (80 bytes)
-struct GameSave {
-    uint32_t c[COLS];
-    uint32_t t, lines, h1, h2, h3, h4, cnt, pad;
-    uint64_t gscore;
-    uint32_t H0, H1, H2, cells;      // K2b only: packed column heights and filled cells of the board (saves recomputing them every piece)
-};
-
-// ---- argmax over a LANES-wide group: maximise key, ties -> smallest tag (first in enumeration order)
-template <int LANES>
-TB_D void group_argmax(uint64_t& key, uint32_t& tag)
-{
-#pragma unroll
-    for (int off = LANES / 2; off > 0; off >>= 1) {
-        const uint32_t ohi = __shfl_xor_sync(FULLMASK, (uint32_t)(key >> 32), off);
-        const uint32_t olo = __shfl_xor_sync(FULLMASK, (uint32_t)key, off);
-        const uint32_t otag = __shfl_xor_sync(FULLMASK, tag, off);
-        const uint64_t okey = ((uint64_t)ohi << 32) | olo;
-        if (okey > key || (okey == key && otag < tag)) { key = okey; tag = otag; }
-    }
-}
-
-// same, carrying the placement to commit (mv = slot | height << 8) along with the winner
-template <int LANES>
-TB_D void group_argmax_mv(uint64_t& key, uint32_t& tag, uint32_t& mv)
-{
-#pragma unroll
-    for (int off = LANES / 2; off > 0; off >>= 1) {
-        const uint32_t ohi = __shfl_xor_sync(FULLMASK, (uint32_t)(key >> 32), off);
-        const uint32_t olo = __shfl_xor_sync(FULLMASK, (uint32_t)key, off);
-        const uint32_t otag = __shfl_xor_sync(FULLMASK, tag, off);
-        const uint32_t omv = __shfl_xor_sync(FULLMASK, mv, off);
-        const uint64_t okey = ((uint64_t)ohi << 32) | olo;
-        if (okey > key || (okey == key && otag < tag)) { key = okey; tag = otag; mv = omv; }
-    }
-}
-
-TB_D SlotDesc load_slot12(const Tables& tab, int piece, int s)
-{
-    const uint4* p = reinterpret_cast<const uint4*>(&tab.slot[piece][s]);
-    const uint4 a = p[0], b = p[1], e = p[2];
-    SlotDesc d;
-    d.w[0] = a.x; d.w[1] = a.y; d.w[2] = a.z; d.w[3] = a.w; d.w[4] = b.x; d.w[5] = b.y; d.w[6] = b.z; d.w[7] = b.w;
-    d.w[8] = e.x; d.w[9] = e.y; d.w[10] = e.z; d.w[11] = e.w;
-    return d;
-}
-
-// Moves derived from one legal hard-drop slot: the drop itself (index 0) and, with SLIDE, the overhang slides
-// (simulator.py:15-47) in the reference's order.  list[i] = slot | height << 8 of slide i + 1.
-template <int SLIDE>
-TB_D int collect_slides(const uint32_t c[COLS], const Heights& H, const Tables& tab, int piece, const SlotDesc& d0, int s0, int y0, bool slide_on, uint16_t* list)
-{
-    int n = 0;
-    if (SLIDE && slide_on)
-        for_each_slide(c, H, d0, s0, y0, [&](int s2) { return load_slot12(tab, piece, s2); },
-                       [&](const SlotDesc&, int s2, int yy, int) { list[n++] = (uint16_t)((uint32_t)s2 | (uint32_t)yy << 8); });
-    return n;
-}
-
-// layer search: every move of `piece` on board c (hard drops, plus overhang slides with SLIDE), each scored as a
-// leaf whose previous state is the board itself.  Lanes take slots gl, gl+LANES, ...; inside a lane moves are
-// visited in enumeration order, so a strict > keeps the earliest.  tag = tag_hi | slot << 5 | slide index;
-// mv = the placement to commit if this leaf wins: the leaf's own (leaf_is_first) or the caller's first move mv1.
-template <int LANES, int MODE, int SLIDE>
-TB_D void search_one(const uint32_t c[COLS], const Heights& H, const PrevStat& pv, int piece, int gl,
-                     const Tables& tab, const uint8_t* ids, const double* w, int F, uint64_t rmask,
-                     bool slide_on, const Pressure& pr, int level,
-                     uint32_t tag_hi, uint32_t mv1, bool leaf_is_first, uint64_t& key, uint32_t& tag, uint32_t& mv, uint32_t& cnt)
-{
-    const int ns = tab.nslots[piece];
-    for (int s = gl; s < ns; s += LANES) {
-        const SlotDesc d0 = load_slot12(tab, piece, s);
-        Placement P0;
-        if (!place_slot(c, H, d0, P0)) continue;
-        uint16_t list[SLIDE ? 18 : 1];
-        const int n = collect_slides<SLIDE>(c, H, tab, piece, d0, s, P0.y, slide_on, list);
-        for (int i = 0; i <= n; ++i) {
-            const uint32_t m = i == 0 ? ((uint32_t)s | (uint32_t)P0.y << 8) : (uint32_t)list[SLIDE ? i - 1 : 0];
-            Placement P; SlotDesc d;
-            if (SLIDE) {
-                d = load_slot12(tab, piece, (int)(m & 255u));
-                if (pr.on && !is_time(d, (int)(m >> 8), pr, level)) continue;      // move_with_pressure filter
-                uint32_t full;
-                place_at(c, d, (int)(m >> 8), P, &full);
-                if (full != 0u) place_clear(d, P, full);
-            } else {
-                d = d0; P = P0;
-            }
-            Feat f;
-            eval_features<ModeTraits<MODE>::CMASK>(P, d, pv, rmask, f);
-            const uint64_t k = score_key(score_features<MODE>(f, ids, w, F));
-            if (k > key) { key = k; tag = tag_hi | (uint32_t)s << 5 | (uint32_t)i; mv = leaf_is_first ? m : mv1; }
-            ++cnt;
-        }
-    }
-}
-
-template <int LANES, int MODE, int LOOKAHEAD, int SLIDE>
-__global__ void __launch_bounds__(BLOCK) play_games_kernel(const PlayParams prm)
-{
-    constexpr int GROUPS = BLOCK / LANES;
-    __shared__ Tables s_tab;
-    __shared__ double s_w[MODE == MODE_W6 ? 1 : GROUPS][MODE == MODE_W6 ? 1 : TB200_MAX_WEIGHTED];
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
-        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
-    }
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31;
-    const int gl = lane & (LANES - 1);
-    const int grp = threadIdx.x / LANES;
-    const int F = prm.F;
-    const uint32_t T = prm.T;
-
-    // per-game state (identical in every lane of the group)
-    bool active = false, exhausted = false;
-    uint32_t game = 0, t = 0, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
-    uint64_t gscore = 0, stream = 0;
-    const uint8_t* seq = nullptr;
-    uint32_t c[COLS];
-    Heights H; PrevStat pv;
-    double wreg[6];
-    int p_cur = 0, p_next = 0;
-
-    auto fetch_piece = [&](uint32_t tt) -> int {
-        if (tt >= T) return 0;
-        return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, stream, tt);
-    };
-
-    for (;;) {
-        // ---- ticket: groups without a game fetch the next one (shuffles stay warp-convergent) ----
-        const bool want = !active && !exhausted;
-        uint32_t g = 0;
-        if (want && gl == 0) g = atomicAdd(prm.ticket, 1u);
-        g = __shfl_sync(FULLMASK, g, 0, LANES);
-        __syncwarp(FULLMASK);                    // previous game's reads of s_w are complete
-        if (want) {
-            if (g < prm.n_games) {
-                if (prm.seq_major_C) g = (g % prm.seq_major_C) * (uint32_t)prm.G + g / prm.seq_major_C;     // see PlayParams
-                game = g; active = true; t = 0; h1 = h2 = h3 = h4 = 0; cnt = 0; gscore = 0;
-                lines = prm.init_lines ? prm.init_lines[g] : 0u;
-                const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[g] : (prm.per_game_weights != 0 ? g : g % (uint32_t)prm.G);
-                stream = sq;
-                seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
-                if (prm.init_rows) {
-                    uint16_t rows[ROWS];
-                    for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)g * ROWS + r];
-                    rows_to_cols(rows, c);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < COLS; ++k) c[k] = 0;
-                }
-                pv = prev_stat(c); H = pack_gh(pv.gh);
-                const size_t wrow = prm.per_game_weights > 0 ? (size_t)g : (prm.per_game_weights < 0 ? 0 : (size_t)(g / (uint32_t)prm.G));
-                const double* wsrc = prm.weights + wrow * (size_t)F;
-                if (MODE == MODE_W6) {
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) wreg[i] = __ldg(wsrc + i);
-                } else {
-                    for (int i = gl; i < F; i += LANES) s_w[MODE == MODE_W6 ? 0 : grp][i] = __ldg(wsrc + i);
-                }
-                p_cur = fetch_piece(0); p_next = fetch_piece(1);
-            } else {
-                exhausted = true;
-            }
-        }
-        __syncwarp(FULLMASK);                    // s_w of a freshly started game is visible to its group
-        if (!__any_sync(FULLMASK, active)) break;
-
-        const double* w = MODE == MODE_W6 ? wreg : s_w[MODE == MODE_W6 ? 0 : grp];
-        const int p_after = active ? fetch_piece(t + 2) : 0;      // prefetch: consumed two steps later
-
-        uint64_t key = 0; uint32_t tag = 0, mv = 0;
-        const bool slide_on = (prm.move_set & 1) != 0;
-        if (LOOKAHEAD == 2) {
-            if (active && t + 1 < T && p_cur < 7 && p_next < 7) {
-                // layer 1 (group-uniform): every move of the current piece in enumeration order, expanded by the next piece
-                const int ns1 = s_tab.nslots[p_cur];
-                for (int s1 = 0; s1 < ns1; ++s1) {
-                    const SlotDesc d0 = load_slot12(s_tab, p_cur, s1);
-                    Placement P0;
-                    if (!place_slot(c, H, d0, P0)) continue;
-                    uint16_t list[SLIDE ? 18 : 1];
-                    const int n = collect_slides<SLIDE>(c, H, s_tab, p_cur, d0, s1, P0.y, slide_on, list);
-                    for (int i = 0; i <= n; ++i) {
-                        const uint32_t m1 = i == 0 ? ((uint32_t)s1 | (uint32_t)P0.y << 8) : (uint32_t)list[SLIDE ? i - 1 : 0];
-                        Placement P1; SlotDesc d1;
-                        if (SLIDE) {
-                            d1 = load_slot12(s_tab, p_cur, (int)(m1 & 255u));
-                            if (prm.press.on && !is_time(d1, (int)(m1 >> 8), prm.press, (int)(lines / 10u))) continue;
-                            uint32_t full;
-                            place_at(c, d1, (int)(m1 >> 8), P1, &full);
-                            if (full != 0u) place_clear(d1, P1, full);
-                        } else {
-                            d1 = d0; P1 = P0;
-                        }
-                        const PrevStat pv1 = next_stat(pv, P1, d1);
-                        const Heights H1 = pack_gh(pv1.gh);
-                        search_one<LANES, MODE, SLIDE>(P1.n, H1, pv1, p_next, gl, s_tab, prm.ids, w, F, prm.rmask,
-                                                       slide_on, prm.press, (int)((lines + (uint32_t)P1.k) / 10u),
-                                                       ((uint32_t)s1 << 5 | (uint32_t)i) << 11, m1, false, key, tag, mv, cnt);
-                    }
-                }
-            }
-            group_argmax_mv<LANES>(key, tag, mv);
-        }
-        const bool need_l1 = active && p_cur < 7 && (LOOKAHEAD == 1 || key == 0);
-        if (LOOKAHEAD == 1 || __any_sync(FULLMASK, need_l1)) {
-            uint64_t k1 = 0; uint32_t t1 = 0, m1 = 0;
-            if (need_l1) search_one<LANES, MODE, SLIDE>(c, H, pv, p_cur, gl, s_tab, prm.ids, w, F, prm.rmask, slide_on, prm.press, (int)(lines / 10u), 0u, 0u, true, k1, t1, m1, cnt);
-            group_argmax_mv<LANES>(k1, t1, m1);
-            if (need_l1) { key = k1; tag = t1; mv = m1; }
-        }
-
-        if (active) {
-            bool finish = false;
-            if (key == 0) {
-                finish = true;                                   // no legal placement: game over (simulator.py:187-189)
-            } else {
-                const SlotDesc d1 = load_slot12(s_tab, p_cur, (int)(mv & 255u));
-                Placement P;
-                {
-                    uint32_t full;
-                    place_at(c, d1, (int)(mv >> 8), P, &full);
-                    if (full != 0u) place_clear(d1, P, full);
-                }
-#pragma unroll
-                for (int k = 0; k < COLS; ++k) c[k] = P.n[k];
-                pv = next_stat(pv, P, d1); H = pack_gh(pv.gh);
-                lines += (uint32_t)P.k;
-                h1 += P.k == 1; h2 += P.k == 2; h3 += P.k == 3; h4 += P.k == 4;
-                const uint32_t pts = P.k == 0 ? 0u : (P.k == 1 ? 40u : (P.k == 2 ? 100u : (P.k == 3 ? 300u : 1200u)));
-                gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);          // game.py:159-164
-                if (gl == 0) {
-                    if (prm.trace) {
-                        const uint32_t row = (uint32_t)(ROWS - P.y - P.ph);
-                        const uint32_t rec = (uint32_t)P.rot | row << 8 | (uint32_t)P.c0 << 16 | (uint32_t)P.k << 24;
-                        reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = rec;
-                    }
-                    if (prm.score_trace) {
-                        const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
-                        prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
-                    }
-                }
-                ++t;
-                p_cur = p_next; p_next = p_after;
-                if (t >= T || t >= prm.max_moves) finish = true;
-            }
-            if (finish) {
-                if (gl == 0) {
-                    tb200_game_result* r = prm.results + game;
-                    r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4;
-                    r->score = gscore;
-                    if (prm.final_rows) {
-                        uint16_t rows[ROWS];
-                        cols_to_rows(c, rows);
-                        for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2];
-                    }
-                }
-                if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&prm.results[game].placements), (unsigned long long)cnt);
-                active = false;
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K2w: the latency-optimised variant for lookahead 1 with one full warp per game.  Used when the
-// population fits in one resident wave (BASELINE config 2: 1000 games), where the run time is the
-// serial chain of the longest game, so what matters is the per-piece latency of a single warp:
-//   * slots s and s+32 of a 34-slot piece (T, L, J) are evaluated as two interleaved straight-line
-//     instruction streams in ONE pass instead of two dependent passes,
-//   * argmax by three REDUX (hi word, lo word, tag) instead of a 5-step shuffle butterfly,
-//   * commit by broadcasting the winning lane's candidate board (SHFL) instead of recomputing it,
-//   * the ticket fetch is outside the per-piece loop.
-// ---------------------------------------------------------------------------------------------
-TB_D void warp_argmax32(uint64_t& key, uint32_t& tag)
-{
-    const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
-    const uint32_t mhi = __reduce_max_sync(FULLMASK, hi);
-    const uint32_t mlo = __reduce_max_sync(FULLMASK, hi == mhi ? lo : 0u);
-    const bool win = hi == mhi && lo == mlo;
-    tag = __reduce_min_sync(FULLMASK, win ? tag : 0xffffffffu);
-    key = ((uint64_t)mhi << 32) | mlo;
-}
-
-template <int MODE>
-TB_D uint64_t eval_key(const Placement& P, const SlotDesc& d, bool legal, const PrevStat& pv, const uint8_t* ids, const double* w, int F, uint64_t rmask)
-{
-    Feat f;
-    eval_features<ModeTraits<MODE>::CMASK>(P, d, pv, rmask, f);
-    const uint64_t k = score_key(score_features<MODE>(f, ids, w, F));
-    return legal ? k : 0ull;
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(BLOCK) play_games_w32_kernel(const PlayParams prm)
-{
-    constexpr int GROUPS = BLOCK / 32;
-    __shared__ Tables s_tab;
-    __shared__ double s_w[MODE == MODE_W6 ? 1 : GROUPS][MODE == MODE_W6 ? 1 : TB200_MAX_WEIGHTED];
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
-        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int grp = threadIdx.x >> 5;
-    const int F = prm.F;
-    const uint32_t T = prm.T;
-    double wreg[6];
-    const double* w = MODE == MODE_W6 ? wreg : s_w[MODE == MODE_W6 ? 0 : grp];
-
-    for (;;) {
-        uint32_t game = 0;
-        if (lane == 0) game = atomicAdd(prm.ticket, 1u);
-        game = __shfl_sync(FULLMASK, game, 0);
-        if (game >= prm.n_games) break;
-        const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : (prm.per_game_weights != 0 ? game : game % (uint32_t)prm.G);
-        const uint64_t stream = sq;
-        const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
-        uint32_t c[COLS];
-        if (prm.init_rows) {
-            uint16_t rows[ROWS];
-            for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
-            rows_to_cols(rows, c);
-        } else {
-#pragma unroll
-            for (int k = 0; k < COLS; ++k) c[k] = 0;
-        }
-        PrevStat pv = prev_stat(c);
-        Heights H = pack_gh(pv.gh);
-        {
-            const size_t wrow = prm.per_game_weights > 0 ? (size_t)game : (prm.per_game_weights < 0 ? 0 : (size_t)(game / (uint32_t)prm.G));
-            const double* wsrc = prm.weights + wrow * (size_t)F;
-            if (MODE == MODE_W6) {
-#pragma unroll
-                for (int i = 0; i < 6; ++i) wreg[i] = __ldg(wsrc + i);
-            } else {
-                __syncwarp(FULLMASK);
-                for (int i = lane; i < F; i += 32) s_w[MODE == MODE_W6 ? 0 : grp][i] = __ldg(wsrc + i);
-                __syncwarp(FULLMASK);
-            }
-        }
-        auto fetch_piece = [&](uint32_t tt) -> int {
-            if (tt >= T) return 7;
-            return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, stream, tt);
-        };
-        uint32_t t = 0, lines = prm.init_lines ? prm.init_lines[game] : 0u, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
-        const uint32_t lines0 = lines;
-        uint64_t gscore = 0;
-        int p_cur = fetch_piece(0), p_next = fetch_piece(1);
-        const uint32_t max_moves = prm.max_moves;
-
-#ifdef TB_PHASES
-        long long ph[8] = {0,0,0,0,0,0,0,0}; long long last_ = clock64();
-#endif
-        while (t < T && t < max_moves && p_cur < 7) {
-            PH(5)
-            const int p_after = fetch_piece(t + 2);
-            const int ns = s_tab.nslots[p_cur];
-            // ---- stream A: slot = lane ----
-            const bool hasA = lane < ns;
-            const SlotDesc dA = load_slot12(s_tab, p_cur, hasA ? lane : 0);
-            Placement PA; uint32_t fA;
-            const bool legalA = place_pre(c, H, dA, PA, &fA) && hasA;
-            uint64_t key; uint32_t tag = (uint32_t)lane;
-            PH(0)
-            if (MODE == MODE_W6 && ns > 32) {
-                // ---- stream B: slot = lane + 32 (only lanes 0, 1 of the 34-slot pieces), interleaved with A ----
-                const bool hasB = lane + 32 < ns;
-                const SlotDesc dB = load_slot12(s_tab, p_cur, hasB ? lane + 32 : 0);
-                Placement PB; uint32_t fB;
-                const bool legalB = place_pre(c, H, dB, PB, &fB) && hasB;
-                if ((legalA && fA != 0u) || (legalB && fB != 0u)) {
-                    if (legalA && fA != 0u) place_clear(dA, PA, fA);
-                    if (legalB && fB != 0u) place_clear(dB, PB, fB);
-                }
-                const uint64_t kA = eval_key<MODE>(PA, dA, legalA, pv, prm.ids, w, F, prm.rmask);
-                const uint64_t kB = eval_key<MODE>(PB, dB, legalB, pv, prm.ids, w, F, prm.rmask);
-                cnt += (uint32_t)legalA + (uint32_t)legalB;
-                key = kA;
-                if (kB > kA) {                      // strict: the earlier slot keeps ties
-                    key = kB; tag = (uint32_t)lane + 32u;
-#pragma unroll
-                    for (int k = 0; k < COLS; ++k) PA.n[k] = PB.n[k];
-                    PA.y = PB.y; PA.k = PB.k; PA.rot = PB.rot; PA.c0 = PB.c0; PA.ph = PB.ph;
-                }
-            } else {
-                if (legalA && fA != 0u) place_clear(dA, PA, fA);
-                key = eval_key<MODE>(PA, dA, legalA, pv, prm.ids, w, F, prm.rmask);
-                cnt += (uint32_t)legalA;
-                if (MODE != MODE_W6 && ns > 32) {   // big feature sets: second pass after the first (register budget)
-                    const bool hasB = lane + 32 < ns;
-                    const SlotDesc dB = load_slot12(s_tab, p_cur, hasB ? lane + 32 : 0);
-                    Placement PB;
-                    const bool legalB = place_slot(c, H, dB, PB) && hasB;
-                    if (__any_sync(FULLMASK, legalB)) {
-                        const uint64_t kB = eval_key<MODE>(PB, dB, legalB, pv, prm.ids, w, F, prm.rmask);
-                        cnt += (uint32_t)legalB;
-                        if (kB > key) {
-                            key = kB; tag = (uint32_t)lane + 32u;
-#pragma unroll
-                            for (int k = 0; k < COLS; ++k) PA.n[k] = PB.n[k];
-                            PA.y = PB.y; PA.k = PB.k; PA.rot = PB.rot; PA.c0 = PB.c0; PA.ph = PB.ph;
-                        }
-                    }
-                }
-            }
-            PH(ns > 32 ? 2 : 1)
-            warp_argmax32(key, tag);
-            PH(3)
-            if (key == 0) break;                    // no legal placement: game over (simulator.py:187-189)
-            // ---- commit: broadcast the winner's candidate board ----
-            const int src = (int)(tag & 31u);
-#pragma unroll
-            for (int k = 0; k < COLS; ++k) c[k] = __shfl_sync(FULLMASK, PA.n[k], src);
-            const uint32_t info = __shfl_sync(FULLMASK, (uint32_t)PA.y | (uint32_t)PA.k << 8 | (uint32_t)PA.rot << 12 | (uint32_t)PA.c0 << 16 | (uint32_t)PA.ph << 24, src);
-            const uint32_t wk = (info >> 8) & 15u;
-            {   // statistics of the committed board: arithmetic from the winner's move unless it cleared rows
-                Placement Pw;
-                Pw.y = (int)(info & 255u); Pw.k = (int)wk;
-#pragma unroll
-                for (int k = 0; k < COLS; ++k) Pw.n[k] = c[k];
-                const SlotDesc dw = load_slot12(s_tab, p_cur, (int)tag);
-                pv = next_stat(pv, Pw, dw);
-                H = pack_gh(pv.gh);
-            }
-            lines += wk;
-            h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
-            const uint32_t pts = wk == 0 ? 0u : (wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u)));
-            gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
-            if (lane == 0) {
-                if (prm.trace) {
-                    const uint32_t wy = info & 255u, wph = info >> 24;
-                    const uint32_t row = (uint32_t)ROWS - wy - wph;
-                    reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = ((info >> 12) & 15u) | row << 8 | ((info >> 16) & 255u) << 16 | wk << 24;
-                }
-                if (prm.score_trace) {
-                    const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
-                    prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
-                }
-            }
-            ++t;
-            p_cur = p_next; p_next = p_after;
-            PH(4)
-        }
-#ifdef TB_PHASES
-        if (lane == 0) { for (int i = 0; i < 6; ++i) atomicAdd(&g_phase[i], (unsigned long long)ph[i]); atomicAdd(&g_phase[6], (unsigned long long)t); }
-#endif
-        // ---- game finished (over, cap reached or max_moves) ----
-        cnt = __reduce_add_sync(FULLMASK, cnt);
-        if (lane == 0) {
-            tb200_game_result* r = prm.results + game;
-            r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4;
-            r->score = gscore; r->placements = cnt;
-            if (prm.final_rows) {
-                uint16_t rows[ROWS];
-                cols_to_rows(c, rows);
-                for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2];
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K2f: one warp per game, lookahead 1, the w6 feature set — the BASELINE config-2 hot kernel.
-// Per piece: [descriptors for this piece were prefetched] -> w6_pre (landing, legality, imprint,
-// arithmetic heights) -> rare clear fix-up -> w6_post (transitions by popc, wells, fp64 score)
-// -> REDUX argmax (+ ballot; the lo-word / tag REDUX only on a tie of the hi word) -> commit by
-// broadcasting the winner's board, packed heights and move (14 SHFL, no clz, no popc).
-// Slots 32 and 33 of the 34-slot pieces run as a second, interleaved instruction stream.
-// ---------------------------------------------------------------------------------------------
-
-template <bool STAGED>
-__global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayParams prm)
-{
-    constexpr bool staged = STAGED;
-    uint32_t* const ticket = staged ? prm.st_ctl + prm.st_stage : prm.ticket;
-    uint32_t n_in = prm.n_games;
-    if (staged && prm.st_list_in) {
-        n_in = prm.st_ctl[4 + prm.st_stage];
-        if (n_in == 0u) return;                    // nothing was handed over: the earlier stage finished every game
-    }
-    const uint32_t* const finished = staged ? prm.st_ctl + 3 : nullptr;
-    auto poll_finished = [&]() -> uint32_t {           // relaxed, L2-coherent; asm volatile so it is re-read every time
-        uint32_t v;
-        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(finished) : "memory");
-        return v;
-    };
-    __shared__ Tables s_tab;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
-        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const uint32_t T = prm.T;
-
-    for (;;) {
-        uint32_t game = 0;
-        if (lane == 0) {
-            game = atomicAdd(ticket, 1u);
-            if (game < n_in && prm.st_list_in) game = prm.st_list_in[game]; else if (game >= n_in) game = 0xffffffffu;
-        }
-        game = __shfl_sync(FULLMASK, game, 0);
-        if (game == 0xffffffffu) break;
-        const bool resume = staged && prm.st_list_in != nullptr;
-        const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : (prm.per_game_weights != 0 ? game : game % (uint32_t)prm.G);
-        const uint64_t stream = sq;
-        const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
-        uint32_t c[COLS];
-        uint32_t t = 0, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
-        uint64_t gscore = 0;
-        if (resume) {
-            const GameSave* sv = prm.st_save + game;
-#pragma unroll
-            for (int k = 0; k < COLS; ++k) c[k] = sv->c[k];
-            t = sv->t; lines = sv->lines; h1 = sv->h1; h2 = sv->h2; h3 = sv->h3; h4 = sv->h4; gscore = sv->gscore;
-            if (lane == 0) cnt = sv->cnt;
-        } else if (prm.init_rows) {
-            uint16_t rows[ROWS];
-            for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
-            rows_to_cols(rows, c);
-        } else {
-#pragma unroll
-            for (int k = 0; k < COLS; ++k) c[k] = 0;
-        }
-        if (!resume && prm.init_lines) lines = prm.init_lines[game];
-        GameStat g = game_stat(c);
-        const int cells0 = g.cells - 4 * (int)t;       // g.cells = cells0 + 4 (pieces placed) - 10 (lines cleared since here)
-        double w[6];
-        {
-            const size_t wrow = prm.per_game_weights > 0 ? (size_t)game : (prm.per_game_weights < 0 ? 0 : (size_t)(game / (uint32_t)prm.G));
-            const double* wsrc = prm.weights + wrow * 6;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) w[i] = __ldg(wsrc + i);
-        }
-        // piece window: lane i holds pieces base+i (byte 0) and base+32+i (byte 1); handed out by shuffle
-        auto load_piece = [&](uint32_t tt) -> uint32_t {
-            if (tt >= T) return 7u;
-            return seq ? (uint32_t)__ldg(seq + tt) : (uint32_t)hashed_piece(prm.seed, stream, tt);
-        };
-        uint32_t base = t;
-        uint32_t win = load_piece(base + (uint32_t)lane) | load_piece(base + 32u + (uint32_t)lane) << 8;
-        auto piece_at = [&](uint32_t tt) -> int {          // base <= tt < base + 64, tt warp-uniform
-            const uint32_t idx = tt - base;
-            const uint32_t v = __shfl_sync(FULLMASK, win, (int)(idx & 31u));
-            return (int)((v >> ((idx >> 5) * 8u)) & 255u);
-        };
-        const uint32_t lines0 = lines;
-        const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
-        int p_cur = piece_at(t), p_next = piece_at(t + 1u);
-        uint32_t fin_seen = staged ? poll_finished() : 0u;      // polled ahead of its use: the load never stalls the game
-        bool handed = staged && prm.n_games - fin_seen <= prm.st_cut;
-        // descriptors of the current piece (prefetched one piece ahead, they do not depend on the board);
-        // word 7 of every descriptor of a piece (padding slots included) is its slot count
-        const int slotB = lane < 2 ? lane + 32 : 0;
-        SlotDesc dA = load_slot12(s_tab, p_cur < 7 ? p_cur : 0, lane);
-        SlotDesc dB = load_slot12(s_tab, p_cur < 7 ? p_cur : 0, slotB);
-
-#ifdef TB_PHASES
-        long long ph[8] = {0,0,0,0,0,0,0,0}; long long last_ = clock64();
-#endif
-        bool over = false;                              // no legal placement
-        while (!handed && t < stop && p_cur < 7) {
-            uint32_t fin_next = fin_seen;
-            if (staged && (t & 3u) == 0u) fin_next = poll_finished();
-            PH(5)
-            if (t + 2u - base >= 64u) {              // advance the piece window
-                base += 32u;
-                win = (win >> 8) | load_piece(base + 32u + (uint32_t)lane) << 8;
-            }
-            const int p_after = piece_at(t + 2u);
-            // prefetch the next piece's descriptors
-            const int pn = p_next < 7 ? p_next : 0;
-            const SlotDesc dA_next = load_slot12(s_tab, pn, lane);
-            const SlotDesc dB_next = load_slot12(s_tab, pn, slotB);
-            const int ns = (int)dA.w[7];
-
-            PH(0)
-            W6Cand A;
-            w6_pre(c, g, dA, A);
-            A.legal = A.legal && lane < ns;
-            uint64_t key; uint32_t tag = (uint32_t)lane;
-            Heights Hn;
-            if (ns > 32) {
-                W6Cand B;
-                w6_pre(c, g, dB, B);
-                B.legal = B.legal && lane + 32 < ns;
-                if ((A.legal && A.full != 0u) || (B.legal && B.full != 0u)) {
-                    if (A.legal && A.full != 0u) w6_clear(dA, A);
-                    if (B.legal && B.full != 0u) w6_clear(dB, B);
-                }
-                Heights HnB;
-                const uint64_t kA = w6_post(A, w, Hn);
-                const uint64_t kB = w6_post(B, w, HnB);
-                cnt += (uint32_t)A.legal + (uint32_t)B.legal;
-                key = kA;
-                if (kB > kA) {                      // strict: the earlier slot keeps ties
-                    key = kB; tag = (uint32_t)lane + 32u; Hn = HnB;
-#pragma unroll
-                    for (int k = 0; k < COLS; ++k) A.P.n[k] = B.P.n[k];
-                    A.P.y = B.P.y; A.P.k = B.P.k; A.P.rot = B.P.rot; A.P.c0 = B.P.c0; A.P.ph = B.P.ph;
-                }
-            } else {
-                if (A.legal && A.full != 0u) w6_clear(dA, A);
-                key = w6_post(A, w, Hn);
-                cnt += (uint32_t)A.legal;
-            }
-            PH(ns > 32 ? 2 : 1)
-            // ---- argmax: hi word by REDUX; the lo word / tag only when two lanes share the hi word ----
-            const uint32_t hi = (uint32_t)(key >> 32);
-            const uint32_t mhi = __reduce_max_sync(FULLMASK, hi);
-            if (mhi == 0u) { over = true; break; }  // no legal placement: game over (simulator.py:187-189)
-            const uint32_t tie = __ballot_sync(FULLMASK, hi == mhi);
-            int src = __ffs((int)tie) - 1;
-            if (tie & (tie - 1u)) {
-                const uint32_t lo = (uint32_t)key;
-                const uint32_t mlo = __reduce_max_sync(FULLMASK, hi == mhi ? lo : 0u);
-                const uint32_t mtag = __reduce_min_sync(FULLMASK, (hi == mhi && lo == mlo) ? tag : 0xffffffffu);
-                src = (int)(mtag & 31u);
-            }
-            PH(3)
-            // ---- commit: broadcast the winner's candidate board, heights and move ----
-#pragma unroll
-            for (int k = 0; k < COLS; ++k) c[k] = __shfl_sync(FULLMASK, A.P.n[k], src);
-            g.H.H0 = __shfl_sync(FULLMASK, Hn.H0, src);
-            g.H.H1 = __shfl_sync(FULLMASK, Hn.H1, src);
-            g.H.H2 = __shfl_sync(FULLMASK, Hn.H2, src);
-            const uint32_t info = __shfl_sync(FULLMASK, (uint32_t)A.P.y | (uint32_t)A.P.k << 8 | (uint32_t)A.P.rot << 12 | (uint32_t)A.P.c0 << 16 | (uint32_t)A.P.ph << 24, src);
-            unpack_heights(g.H, g.gh);
-            const uint32_t wk = (info >> 8) & 15u;
-            if (wk != 0u) {
-                lines += wk;
-                h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
-                const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
-                gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
-            }
-            g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)(lines - lines0);
-            if (prm.trace && lane == 0) {
-                const uint32_t wy = info & 255u, wph = info >> 24;
-                const uint32_t row = (uint32_t)ROWS - wy - wph;
-                reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = ((info >> 12) & 15u) | row << 8 | ((info >> 16) & 255u) << 16 | wk << 24;
-            }
-            if (prm.score_trace) {
-                const uint32_t khi = __shfl_sync(FULLMASK, (uint32_t)(key >> 32), src), klo = __shfl_sync(FULLMASK, (uint32_t)key, src);
-                const uint64_t kk = ((uint64_t)khi << 32) | klo;
-                const uint64_t b = (kk & 0x8000000000000000ull) ? (kk & 0x7FFFFFFFFFFFFFFFull) : ~kk;
-                if (lane == 0) prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
-            }
-            ++t;
-            p_cur = p_next; p_next = p_after;
-            dA = dA_next; dB = dB_next;
-            if (staged) { handed = prm.n_games - fin_seen <= prm.st_cut; fin_seen = fin_next; }
-            PH(4)
-        }
-        handed = handed && !over && t < stop && p_cur < 7;      // a game that ended anyway is finished, not handed over
-#ifdef TB_PHASES
-        if (lane == 0) { for (int i = 0; i < 6; ++i) atomicAdd(&g_phase[i], (unsigned long long)ph[i]); atomicAdd(&g_phase[6], (unsigned long long)t); }
-#endif
-        cnt = __reduce_add_sync(FULLMASK, cnt);
-        if (handed) {                                   // few enough games are left: hand this one to the next, sparser stage
-            if (lane == 0) {
-                GameSave* sv = prm.st_save + game;
-#pragma unroll
-                for (int k = 0; k < COLS; ++k) sv->c[k] = c[k];
-                sv->t = t; sv->lines = lines; sv->h1 = h1; sv->h2 = h2; sv->h3 = h3; sv->h4 = h4; sv->cnt = cnt; sv->gscore = gscore;
-                prm.st_list_out[atomicAdd(prm.st_ctl + 5 + prm.st_stage, 1u)] = game;
-            }
-            continue;
-        }
-        if (lane == 0) {
-            if (staged) atomicAdd(prm.st_ctl + 3, 1u);
-            tb200_game_result* r = prm.results + game;
-            r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4;
-            r->score = gscore; r->placements = cnt;
-            if (prm.final_rows) {
-                uint16_t rows[ROWS];
-                cols_to_rows(c, rows);
-                for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2];
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K2p: TWO warps per game (one 64-thread block per game), lookahead 1, w6 — for populations so
-// small that warp schedulers would otherwise idle (BASELINE config 2: 1000 games on 592
-// schedulers).  Slots are split even / odd between the two warps, so every piece — including the
-// 34-slot T, L, J — is ONE pass of at most 17 lanes per warp.  Each warp finds its best slot
-// (REDUX), its winning lane publishes {key, slot, move, board, heights} to shared memory, one
-// block barrier, then both warps read both records, pick the global winner (higher key, then lower
-// slot = first in enumeration order) and commit it.  Records are double-buffered by piece parity.
-// Pieces are prefetched 32 at a time (one per lane) and handed out by shuffle.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) play_games_w6pair_kernel(const PlayParams prm)
-{
-    const bool staged = prm.st_ctl != nullptr;
-    uint32_t* const ticket = staged ? prm.st_ctl + prm.st_stage : prm.ticket;
-    uint32_t n_in = prm.n_games;
-    if (staged && prm.st_list_in) {
-        n_in = prm.st_ctl[4 + prm.st_stage];
-        if (n_in == 0u) return;
-    }
-    __shared__ Tables s_tab;
-    __shared__ uint4 s_x[2][2][5];
-    __shared__ uint32_t s_game;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
-        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += 64) dst[i] = src[i];
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int slot = 2 * lane + warp;              // lanes 17.. have slot >= 34: never legal
-    const int myslot = slot < TB_MAX_SLOTS ? slot : 0;
-    const uint32_t T = prm.T;
-
-    for (;;) {
-        if (threadIdx.x == 0) {
-            uint32_t gi = atomicAdd(ticket, 1u);
-            if (gi < n_in && prm.st_list_in) gi = prm.st_list_in[gi]; else if (gi >= n_in) gi = 0xffffffffu;
-            s_game = gi;
-        }
-        __syncthreads();
-        const uint32_t game = s_game;
-        __syncthreads();
-        if (game == 0xffffffffu) break;
-        const bool resume = staged && prm.st_list_in != nullptr;
-        const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : (prm.per_game_weights != 0 ? game : game % (uint32_t)prm.G);
-        const uint64_t stream = sq;
-        const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
-        uint32_t c[COLS];
-        uint32_t t = 0, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
-        uint64_t gscore = 0;
-        if (resume) {
-            const GameSave* sv = prm.st_save + game;
-#pragma unroll
-            for (int k = 0; k < COLS; ++k) c[k] = sv->c[k];
-            t = sv->t; lines = sv->lines; h1 = sv->h1; h2 = sv->h2; h3 = sv->h3; h4 = sv->h4; gscore = sv->gscore;
-            if (threadIdx.x == 0) cnt = sv->cnt;
-        } else if (prm.init_rows) {
-            uint16_t rows[ROWS];
-            for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
-            rows_to_cols(rows, c);
-        } else {
-#pragma unroll
-            for (int k = 0; k < COLS; ++k) c[k] = 0;
-        }
-        if (!resume && prm.init_lines) lines = prm.init_lines[game];
-        GameStat g = game_stat(c);
-        const int cells0 = g.cells - 4 * (int)t;
-        double w[6];
-        {
-            const size_t wrow = prm.per_game_weights > 0 ? (size_t)game : (prm.per_game_weights < 0 ? 0 : (size_t)(game / (uint32_t)prm.G));
-            const double* wsrc = prm.weights + wrow * 6;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) w[i] = __ldg(wsrc + i);
-        }
-        // piece window: lane i holds pieces base+i (byte 0) and base+32+i (byte 1)
-        auto load_piece = [&](uint32_t tt) -> uint32_t {
-            if (tt >= T) return 7u;
-            return seq ? (uint32_t)__ldg(seq + tt) : (uint32_t)hashed_piece(prm.seed, stream, tt);
-        };
-        uint32_t base = t;
-        uint32_t win = load_piece(base + (uint32_t)lane) | load_piece(base + 32u + (uint32_t)lane) << 8;
-        auto piece_at = [&](uint32_t tt) -> int {          // base <= tt < base + 64, uniform tt
-            const uint32_t idx = tt - base;
-            const uint32_t v = __shfl_sync(FULLMASK, win, (int)(idx & 31u));
-            return (int)((v >> ((idx >> 5) * 8u)) & 255u);
-        };
-        const uint32_t lines0 = lines;
-        const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
-        int p_cur = piece_at(t), p_next = piece_at(t + 1u);
-        SlotDesc d = load_slot12(s_tab, p_cur < 7 ? p_cur : 0, myslot);
-        uint32_t par = 0;
-
-        while (t < stop && p_cur < 7) {
-            // advance the piece window when the look-ahead index leaves it
-            if (t + 2u - base >= 64u) {
-                base += 32u;
-                win = (win >> 8) | load_piece(base + 32u + (uint32_t)lane) << 8;
-            }
-            const int p_after = piece_at(t + 2u);
-            const SlotDesc d_next = load_slot12(s_tab, p_next < 7 ? p_next : 0, myslot);
-
-            W6Cand A;
-            w6_pre(c, g, d, A);
-            A.legal = A.legal && slot < (int)d.w[7];
-            if (A.legal && A.full != 0u) w6_clear(d, A);
-            Heights Hn;
-            const uint64_t key = w6_post(A, w, Hn);
-            cnt += (uint32_t)A.legal;
-            // ---- warp-local argmax ----
-            const uint32_t hi = (uint32_t)(key >> 32);
-            const uint32_t mhi = __reduce_max_sync(FULLMASK, hi);
-            const uint32_t tie = __ballot_sync(FULLMASK, hi == mhi);
-            int src = __ffs((int)tie) - 1;
-            if (mhi != 0u && (tie & (tie - 1u))) {
-                const uint32_t lo = (uint32_t)key;
-                const uint32_t mlo = __reduce_max_sync(FULLMASK, hi == mhi ? lo : 0u);
-                const uint32_t mtag = __reduce_min_sync(FULLMASK, (hi == mhi && lo == mlo) ? (uint32_t)slot : 0xffffffffu);
-                src = (int)(mtag >> 1);
-            }
-            if (lane == src) {
-                uint4* rec = s_x[par][warp];
-                const uint32_t info = (uint32_t)A.P.y | (uint32_t)A.P.k << 8 | (uint32_t)A.P.rot << 12 | (uint32_t)A.P.c0 << 16 | (uint32_t)A.P.ph << 24;
-                rec[0] = make_uint4(hi, (uint32_t)key, (uint32_t)slot, info);
-                rec[1] = make_uint4(A.P.n[0], A.P.n[1], A.P.n[2], A.P.n[3]);
-                rec[2] = make_uint4(A.P.n[4], A.P.n[5], A.P.n[6], A.P.n[7]);
-                rec[3] = make_uint4(A.P.n[8], A.P.n[9], Hn.H0, Hn.H1);
-                rec[4] = make_uint4(Hn.H2, 0u, 0u, 0u);
-            }
-            __syncthreads();
-            // ---- global winner of the two warps: higher key, then lower slot ----
-            const uint4 ra = s_x[par][0][0], rb = s_x[par][1][0];
-            const uint64_t ka = ((uint64_t)ra.x << 32) | ra.y, kb = ((uint64_t)rb.x << 32) | rb.y;
-            if ((ra.x | rb.x) == 0u) break;         // no legal placement in either half: game over (simulator.py:187-189)
-            const int wsel = (kb > ka || (kb == ka && rb.z < ra.z)) ? 1 : 0;
-            const uint4* rec = s_x[par][wsel];
-            const uint4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3], r4 = rec[4];
-            par ^= 1u;
-            c[0] = r1.x; c[1] = r1.y; c[2] = r1.z; c[3] = r1.w; c[4] = r2.x; c[5] = r2.y; c[6] = r2.z; c[7] = r2.w; c[8] = r3.x; c[9] = r3.y;
-            g.H.H0 = r3.z; g.H.H1 = r3.w; g.H.H2 = r4.x;
-            unpack_heights(g.H, g.gh);
-            const uint32_t info = r0.w;
-            const uint32_t wk = (info >> 8) & 15u;
-            if (wk != 0u) {
-                lines += wk;
-                h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
-                const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
-                gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
-            }
-            g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)(lines - lines0);
-            if (threadIdx.x == 0) {
-                if (prm.trace) {
-                    const uint32_t wy = info & 255u, wph = info >> 24;
-                    const uint32_t row = (uint32_t)ROWS - wy - wph;
-                    reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = ((info >> 12) & 15u) | row << 8 | ((info >> 16) & 255u) << 16 | wk << 24;
-                }
-                if (prm.score_trace) {
-                    const uint64_t kk = wsel ? kb : ka;
-                    const uint64_t b = (kk & 0x8000000000000000ull) ? (kk & 0x7FFFFFFFFFFFFFFFull) : ~kk;
-                    prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
-                }
-            }
-            ++t;
-            p_cur = p_next; p_next = p_after;
-            d = d_next;
-        }
-        cnt = __reduce_add_sync(FULLMASK, cnt);
-        if (lane == 0 && cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&prm.results[game].placements), (unsigned long long)cnt);
-        if (threadIdx.x == 0) {
-            tb200_game_result* r = prm.results + game;
-            r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4;
-            r->score = gscore;
-            if (prm.final_rows) {
-                uint16_t rows[ROWS];
-                cols_to_rows(c, rows);
-                for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2];
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K2g: the throughput kernel for the w6 set, lookahead 1: LANES (8 or 16) lanes per game, 32/LANES
-// games per warp, for populations larger than one resident wave (BASELINE configs[2] / [4]).
-// Same fast evaluation as K2f (w6_pre / w6_clear / w6_post: no clz, popc only for the transition
-// counts), slots in rounds of LANES with a per-lane running best, shuffle-butterfly argmax inside
-// the group, commit by re-placing the winning slot with w6_pre (its heights come out of the
-// placement arithmetic, so the commit needs no clz either).  Persistent, ticket per group.
-// ---------------------------------------------------------------------------------------------
-template <int LANES>
-__global__ void __launch_bounds__(BLOCK) play_games_w6grp_kernel(const PlayParams prm)
-{
-    __shared__ Tables s_tab;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
-        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int gl = lane & (LANES - 1);
-    const uint32_t T = prm.T;
-    const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
-
-    bool active = false, exhausted = false;
-    uint32_t game = 0, t = 0, lines = 0, lines0 = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
-    uint64_t gscore = 0, stream = 0;
-    const uint8_t* seq = nullptr;
-    uint32_t c[COLS];
-    GameStat g;
-    int cells0 = 0;
-    double w[6];
-    int p_cur = 7, p_next = 7;
-#pragma unroll
-    for (int k = 0; k < COLS; ++k) { c[k] = 0; g.gh[k] = 0; }
-    g.H.H0 = g.H.H1 = g.H.H2 = 0; g.cells = 0;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) w[i] = 0.0;
-
-    auto fetch_piece = [&](uint32_t tt) -> int {
-        if (tt >= T) return 7;
-        return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, stream, tt);
-    };
-
-    for (;;) {
-        const bool want = !active && !exhausted;
-        uint32_t tk = 0;
-        if (want && gl == 0) tk = atomicAdd(prm.ticket, 1u);
-        tk = __shfl_sync(FULLMASK, tk, 0, LANES);
-        if (want) {
-            if (tk < prm.n_games) {
-                game = prm.seq_major_C ? (tk % prm.seq_major_C) * (uint32_t)prm.G + tk / prm.seq_major_C : tk;
-                active = true; t = 0; h1 = h2 = h3 = h4 = 0; cnt = 0; gscore = 0;
-                lines = prm.init_lines ? prm.init_lines[game] : 0u; lines0 = lines;
-                const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : (prm.per_game_weights != 0 ? game : game % (uint32_t)prm.G);
-                stream = sq;
-                seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
-                if (prm.init_rows) {
-                    uint16_t rows[ROWS];
-                    for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
-                    rows_to_cols(rows, c);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < COLS; ++k) c[k] = 0;
-                }
-                g = game_stat(c);
-                cells0 = g.cells;
-                const size_t wrow = prm.per_game_weights > 0 ? (size_t)game : (prm.per_game_weights < 0 ? 0 : (size_t)(game / (uint32_t)prm.G));
-                const double* wsrc = prm.weights + wrow * 6;
-#pragma unroll
-                for (int i = 0; i < 6; ++i) w[i] = __ldg(wsrc + i);
-                p_cur = fetch_piece(0); p_next = fetch_piece(1);
-                if (stop == 0 || p_cur >= 7) {            // nothing to play: finish immediately
-                    if (gl == 0) { tb200_game_result* r = prm.results + game; r->pieces = 0; r->lines = 0; r->score = 0; }
-                    active = false;
-                }
-            } else {
-                exhausted = true;
-            }
-        }
-        if (!__any_sync(FULLMASK, active)) break;
-
-        const int p_after = active ? fetch_piece(t + 2) : 7;
-        uint64_t key = 0; uint32_t tag = 0;
-        if (active) {
-            const int pc = p_cur < 7 ? p_cur : 0;
-            const int ns = p_cur < 7 ? s_tab.nslots[pc] : 0;
-            for (int s = gl; s < ns; s += LANES) {
-                const SlotDesc d = load_slot12(s_tab, pc, s);
-                W6Cand A;
-                w6_pre(c, g, d, A);
-                if (A.legal && A.full != 0u) w6_clear(d, A);
-                Heights Hn;
-                const uint64_t k = w6_post(A, w, Hn);
-                cnt += (uint32_t)A.legal;
-                if (k > key) { key = k; tag = (uint32_t)s; }
-            }
-        }
-        group_argmax<LANES>(key, tag);
-        if (active) {
-            bool finish = false;
-            if (key == 0) {
-                finish = true;                            // no legal placement: game over
-            } else {
-                const SlotDesc d = load_slot12(s_tab, p_cur, (int)tag);
-                W6Cand A;
-                w6_pre(c, g, d, A);
-                if (A.full != 0u) w6_clear(d, A);
-#pragma unroll
-                for (int k = 0; k < COLS; ++k) { c[k] = A.P.n[k]; g.gh[k] = A.h[k]; }
-                g.H.H0 = (uint32_t)A.h[0] | (uint32_t)A.h[1] << 8 | (uint32_t)A.h[2] << 16 | (uint32_t)A.h[3] << 24;
-                g.H.H1 = (uint32_t)A.h[4] | (uint32_t)A.h[5] << 8 | (uint32_t)A.h[6] << 16 | (uint32_t)A.h[7] << 24;
-                g.H.H2 = (uint32_t)A.h[8] | (uint32_t)A.h[9] << 8;
-                const uint32_t wk = (uint32_t)A.P.k;
-                if (wk != 0u) {
-                    lines += wk;
-                    h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
-                    const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
-                    gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
-                }
-                g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)(lines - lines0);
-                if (gl == 0) {
-                    if (prm.trace) {
-                        const uint32_t row = (uint32_t)(ROWS - A.P.y - A.P.ph);
-                        reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = (uint32_t)A.P.rot | row << 8 | (uint32_t)A.P.c0 << 16 | wk << 24;
-                    }
-                    if (prm.score_trace) {
-                        const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
-                        prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
-                    }
-                }
-                ++t;
-                p_cur = p_next; p_next = p_after;
-                if (t >= stop || p_cur >= 7) finish = true;
-            }
-            if (finish) {
-                if (gl == 0) {
-                    tb200_game_result* r = prm.results + game;
-                    r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4;
-                    r->score = gscore;
-                    if (prm.final_rows) {
-                        uint16_t rows[ROWS];
-                        cols_to_rows(c, rows);
-                        for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2];
-                    }
-                }
-                if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&prm.results[game].placements), (unsigned long long)cnt);
-                active = false;
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K2s: the lockstep throughput kernel for CE populations (BASELINE configs[2]): C candidates x G games on G SHARED piece
-// sequences, w6, lookahead 1.  All games of sequence g see the same piece at the same move, so a warp that holds only
-// games of one sequence at one move index runs every round with all of its lanes on the same piece: no lane waits for
-// another game's longer slot list (K2g on independent streams keeps 18 of 32 threads busy).  Games die, so the play is
-// cut into stages of K pieces (the first two shorter); a task = (stage, sequence, chunk of 32 / LANES games); at the end of a task the
-// survivors are appended to the sequence's list for the next stage, which re-packs them into full warps.  One
-// persistent launch: warps walk the buckets (stage-major, sequence-minor) and claim tasks by ticket; bucket (s, g)
-// opens when every task of (s - 1, g) is done — 29 other buckets lie in between, so nobody actually waits except at
-// the very end, and a running task never waits, so the scheme cannot deadlock with a fully resident grid.
-// Hand-over state: GameSave (80 bytes per game) through L2 (__ldcg / fence + counter).
-// ---------------------------------------------------------------------------------------------
-// first move of stage s: two short stages first (K/4, K/2) — a fresh CE population loses most of its games within a
-// few dozen pieces and they should be re-packed early — then K pieces per stage
-TB_HD uint32_t lock_stage_begin(uint32_t s, uint32_t K) { return s == 0u ? 0u : (s == 1u ? K / 4u : (s == 2u ? K / 2u : K * (s - 2u))); }
-
-template <int LANES>
-__global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayParams prm)
-{
-    constexpr uint32_t GPW = 32 / LANES;           // games per warp
-    __shared__ Tables s_tab;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
-        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int gl = lane & (LANES - 1);
-    const uint32_t T = prm.T, C = prm.lk_C, K = prm.lk_K, S = prm.lk_S;
-    const uint32_t G = (uint32_t)prm.G;
-    const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
-
-    uint32_t st = 0, sq = 0;                       // current bucket
-    uint32_t n_in = C, ntasks = (C + GPW - 1) / GPW;
-    for (;;) {
-        uint32_t* ctl = prm.lk_ctl + ((size_t)st * G + sq) * 4;
-        uint32_t slot = 0;
-        if (lane == 0) slot = atomicAdd(ctl, 1u);
-        slot = __shfl_sync(FULLMASK, slot, 0);
-        if (slot >= ntasks) {                      // bucket handed out: open the next one
-            if (++sq == G) { sq = 0; if (++st == S) break; }
-            if (st > 0) {
-                if (lane == 0) {
-                    const uint32_t* prev = prm.lk_ctl + ((size_t)(st - 1) * G + sq) * 4;
-                    const uint32_t n_prev = st == 1 ? C : __ldcg(prev + 2);
-                    const uint32_t need = (n_prev + GPW - 1) / GPW;
-                    uint32_t spins = 0;
-                    while (*reinterpret_cast<volatile const uint32_t*>(prev + 1) < need) {
-                        __nanosleep(200);
-                        if (++spins > (1u << 23)) { atomicExch(prm.lk_ctl + (size_t)S * G * 4 + 3, 1u); break; }   // safety valve (> 1.5 s): never hang the device
-                    }
-                    __threadfence();
-                    n_in = spins > (1u << 23) ? 0u : __ldcg(prm.lk_ctl + ((size_t)st * G + sq) * 4 + 2);
-                }
-                n_in = __shfl_sync(FULLMASK, n_in, 0);
-            }
-            ntasks = (n_in + GPW - 1) / GPW;
-            continue;
-        }
-        // ---- task (st, sq, slot): up to GPW games of sequence sq, all at move st * K ----
-        const uint32_t idx = slot * GPW + (uint32_t)(lane / LANES);
-        bool active = idx < n_in;
-        uint32_t game = 0;
-        if (active) game = st == 0 ? idx * G + sq : __ldcg(prm.lk_list + ((size_t)(st & 1u) * G + sq) * C + idx);
-        const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
-        auto fetch_piece = [&](uint32_t tt) -> int {                     // warp-uniform
-            if (tt >= T) return 7;
-            return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, (uint64_t)sq, tt);
-        };
-        uint32_t c[COLS];
-        uint32_t t = lock_stage_begin(st, K), lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
-        uint64_t gscore = 0;
-#pragma unroll
-        for (int k = 0; k < COLS; ++k) c[k] = 0;
-        if (active) {
-            if (st > 0) {
-                const uint4* sv = reinterpret_cast<const uint4*>(prm.st_save + game);
-                const uint4 a0 = __ldcg(sv), a1 = __ldcg(sv + 1), a2 = __ldcg(sv + 2), a3 = __ldcg(sv + 3), a4 = __ldcg(sv + 4);
-                c[0] = a0.x; c[1] = a0.y; c[2] = a0.z; c[3] = a0.w; c[4] = a1.x; c[5] = a1.y; c[6] = a1.z; c[7] = a1.w; c[8] = a2.x; c[9] = a2.y;
-                lines = a2.w; h1 = a3.x; h2 = a3.y; h3 = a3.z; h4 = a3.w;
-                if (gl == 0) cnt = a4.x;
-                gscore = ((uint64_t)a4.w << 32) | a4.z;
-            } else {
-                if (prm.init_rows) {
-                    uint16_t rows[ROWS];
-                    for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
-                    rows_to_cols(rows, c);
-                }
-                if (prm.init_lines) lines = prm.init_lines[game];
-            }
-        }
-        GameStat g = game_stat(c);
-        const int cells0 = g.cells - 4 * (int)t;
-        const uint32_t lines0 = lines;
-        double w[6];
-        {
-            const double* wsrc = prm.weights + (size_t)(active ? game / G : 0u) * 6;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) w[i] = __ldg(wsrc + i);
-        }
-        const uint32_t t_next = lock_stage_begin(st + 1u, K);
-        const uint32_t t_end = (st + 1 == S || t_next > stop) ? stop : t_next;
-        int p_cur = fetch_piece(t), p_next = fetch_piece(t + 1u);
-        if (t >= stop || p_cur >= 7) {                                   // nothing to play (stop == 0 or the sequence ends here)
-            if (active && gl == 0) {
-                tb200_game_result* r = prm.results + game;
-                r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4; r->score = gscore;
-                if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&r->placements), (unsigned long long)cnt);
-                if (prm.final_rows) { uint16_t rows[ROWS]; cols_to_rows(c, rows); for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2]; }
-            }
-            active = false;
-        }
-        while (t < t_end && p_cur < 7 && __any_sync(FULLMASK, active)) {
-            const int p_after = fetch_piece(t + 2u);
-            const int ns = s_tab.nslots[p_cur];
-            uint64_t key = 0; uint32_t tag = 0;
-            for (int s2 = gl; s2 < ns; s2 += LANES) {                    // same piece, same trip count in every lane
-                const SlotDesc d = load_slot12(s_tab, p_cur, s2);
-                W6Cand A;
-                w6_pre(c, g, d, A);
-                if (A.legal && A.full != 0u) w6_clear(d, A);
-                Heights Hn;
-                const uint64_t k = w6_post(A, w, Hn);
-                cnt += (uint32_t)(A.legal && active);
-                if (k > key) { key = k; tag = (uint32_t)s2; }
-            }
-            group_argmax<LANES>(key, tag);
-            bool finish = false;
-            if (active) {
-                if (key == 0) {
-                    finish = true;                                       // no legal placement: game over (simulator.py:187-189)
-                } else {
-                    const SlotDesc d = load_slot12(s_tab, p_cur, (int)tag);
-                    W6Cand A;
-                    w6_pre(c, g, d, A);
-                    if (A.full != 0u) w6_clear(d, A);
-#pragma unroll
-                    for (int k = 0; k < COLS; ++k) { c[k] = A.P.n[k]; g.gh[k] = A.h[k]; }
-                    g.H.H0 = (uint32_t)A.h[0] | (uint32_t)A.h[1] << 8 | (uint32_t)A.h[2] << 16 | (uint32_t)A.h[3] << 24;
-                    g.H.H1 = (uint32_t)A.h[4] | (uint32_t)A.h[5] << 8 | (uint32_t)A.h[6] << 16 | (uint32_t)A.h[7] << 24;
-                    g.H.H2 = (uint32_t)A.h[8] | (uint32_t)A.h[9] << 8;
-                    const uint32_t wk = (uint32_t)A.P.k;
-                    if (wk != 0u) {
-                        lines += wk;
-                        h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
-                        const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
-                        gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
-                    }
-                    g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)(lines - lines0);
-                    if (gl == 0) {
-                        if (prm.trace) {
-                            const uint32_t row = (uint32_t)(ROWS - A.P.y - A.P.ph);
-                            reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = (uint32_t)A.P.rot | row << 8 | (uint32_t)A.P.c0 << 16 | wk << 24;
-                        }
-                        if (prm.score_trace) {
-                            const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
-                            prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
-                        }
-                    }
-                }
-            }
-            const uint32_t tn = t + 1u;
-            if (active && !finish && (tn >= stop || p_next >= 7)) finish = true;
-            if (finish) {
-                const uint32_t played = key == 0 ? t : tn;
-                if (gl == 0) {
-                    tb200_game_result* r = prm.results + game;
-                    r->pieces = played; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4; r->score = gscore;
-                    if (prm.final_rows) { uint16_t rows[ROWS]; cols_to_rows(c, rows); for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2]; }
-                }
-                if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&prm.results[game].placements), (unsigned long long)cnt);
-                active = false;
-            }
-            t = tn;
-            p_cur = p_next; p_next = p_after;
-        }
-        // ---- survivors (alive at move t_end < stop) go to the sequence's list of the next stage ----
-        {
-#pragma unroll
-            for (int off = LANES / 2; off > 0; off >>= 1) cnt += __shfl_xor_sync(FULLMASK, cnt, off);
-            const uint32_t live = __ballot_sync(FULLMASK, active && gl == 0);
-            if (live != 0u) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(prm.lk_ctl + ((size_t)(st + 1) * G + sq) * 4 + 2, (uint32_t)__popc(live));
-                base = __shfl_sync(FULLMASK, base, 0);
-                if (active && gl == 0) {
-                    uint4* sv = reinterpret_cast<uint4*>(prm.st_save + game);
-                    __stcg(sv, make_uint4(c[0], c[1], c[2], c[3]));
-                    __stcg(sv + 1, make_uint4(c[4], c[5], c[6], c[7]));
-                    __stcg(sv + 2, make_uint4(c[8], c[9], t, lines));
-                    __stcg(sv + 3, make_uint4(h1, h2, h3, h4));
-                    __stcg(sv + 4, make_uint4(cnt, 0u, (uint32_t)gscore, (uint32_t)(gscore >> 32)));
-                    const uint32_t rank = (uint32_t)__popc(live & ((1u << lane) - 1u));
-                    __stcg(prm.lk_list + ((size_t)((st + 1) & 1u) * G + sq) * C + base + rank, game);
-                }
-            }
-            __syncwarp(FULLMASK);
-            if (lane == 0) { __threadfence(); atomicAdd(ctl + 1, 1u); }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K2b: the piece-binned throughput kernel for INDEPENDENT piece streams (BASELINE configs[4]: every game its own
-// stream), w6, lookahead 1.  K2g keeps 18 of 32 threads busy there because the games of a warp are on different pieces
-// (9 / 17 / 34 slots).  Here a game is not bound to a warp: seven device-wide queues, one per piece type, hold the games
-// whose next piece has that type.  A warp pops up to 32 / LANES games from the fullest queue — all on the same piece —
-// plays exactly one piece for each of them with every lane in step, and pushes each survivor onto the queue of its
-// next piece.  Game state (80 bytes) travels through L2; with 4 warps per scheduler the pop / load latency hides behind
-// the other warps' arithmetic.  Queues are rings of game ids with 64-bit reserved-tail / head counters: a pusher
-// reserves slots by atomicAdd, writes the state, fences, then publishes the id into the slot; a popper claims by CAS
-// on the head and reads each slot once it is published.  All waits are bounded (error flag instead of a hang).
-// ---------------------------------------------------------------------------------------------
-#define PB_EMPTY 0xffffffffu
-constexpr uint32_t PB_SHARDS = 64;     // independent queue sets; a game always lives in shard game % PB_SHARDS, a warp's home shard is warp % PB_SHARDS
-
-TB_D void pb_write_state(GameSave* dst, const uint32_t c[COLS], uint32_t t, uint32_t lines, uint32_t h1, uint32_t h2, uint32_t h3, uint32_t h4,
-                         uint32_t cnt, uint64_t gscore, const Heights& H, int cells)
-{
-    uint4* sv = reinterpret_cast<uint4*>(dst);
-    __stcg(sv, make_uint4(c[0], c[1], c[2], c[3]));
-    __stcg(sv + 1, make_uint4(c[4], c[5], c[6], c[7]));
-    __stcg(sv + 2, make_uint4(c[8], c[9], t, lines));
-    __stcg(sv + 3, make_uint4(h1, h2, h3, h4));
-    __stcg(sv + 4, make_uint4(cnt, 0u, (uint32_t)gscore, (uint32_t)(gscore >> 32)));
-    __stcg(sv + 5, make_uint4(H.H0, H.H1, H.H2, (uint32_t)cells));
-}
-
-// publish `game` at queue position pos of piece type p (the slot is empty unless a slow popper still holds it)
-TB_D void pb_publish(const PlayParams& prm, uint32_t shard, int p, unsigned long long pos, uint32_t game)
-{
-    volatile uint32_t* slot = prm.pb_ring + ((size_t)shard * 7 + (size_t)p) * ((size_t)prm.pb_mask + 1) + (size_t)(pos & prm.pb_mask);
-    uint32_t spins = 0;
-    while (*slot != PB_EMPTY) { __nanosleep(100); if (++spins > (1u << 22)) { atomicExch(prm.pb_ctl + 16 * PB_SHARDS + 1, 1ull); break; } }
-    *slot = game;
-}
-
-// every game enters the queue of its first piece (or finishes at once when there is nothing to play)
-__global__ void pb_init_kernel(const PlayParams prm)
-{
-    const uint32_t game = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t T = prm.T;
-    const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
-    int p0 = 8;                                  // 8: no game in this thread
-    if (game < prm.n_games) {
-        const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : game % (uint32_t)prm.G;
-        uint32_t c[COLS];
-#pragma unroll
-        for (int k = 0; k < COLS; ++k) c[k] = 0;
-        if (prm.init_rows) {
-            uint16_t rows[ROWS];
-            for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
-            rows_to_cols(rows, c);
-        }
-        const uint32_t lines = prm.init_lines ? prm.init_lines[game] : 0u;
-        p0 = stop == 0u ? 7 : (prm.pieces ? (int)prm.pieces[(size_t)sq * T] : hashed_piece(prm.seed, (uint64_t)sq, 0));
-        if (p0 >= 7) {
-            tb200_game_result* r = prm.results + game;
-            r->pieces = 0; r->lines = lines; r->score = 0;
-            if (prm.final_rows) { uint16_t rows[ROWS]; cols_to_rows(c, rows); for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2]; }
-            atomicAdd(prm.pb_ctl + 16 * PB_SHARDS, 1ull);
-            p0 = 8;
-        } else {
-            const GameStat g0 = game_stat(c);
-            pb_write_state(prm.st_save + game, c, 0u, lines, 0u, 0u, 0u, 0u, 0u, 0ull, g0.H, g0.cells);
-        }
-    }
-    if (p0 < 7) {
-        const uint32_t shard = game % PB_SHARDS;
-        const unsigned long long pos = atomicAdd(prm.pb_ctl + 16 * shard + p0, 1ull);
-        prm.pb_ring[((size_t)shard * 7 + (size_t)p0) * ((size_t)prm.pb_mask + 1) + (size_t)(pos & prm.pb_mask)] = game;
-    }
-}
-
-template <int LANES>
-__global__ void __launch_bounds__(BLOCK) play_games_w6bin_kernel(const PlayParams prm)
-{
-    constexpr uint32_t GPW = 32 / LANES;
-    __shared__ Tables s_tab;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
-        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int gl = lane & (LANES - 1);
-    const uint32_t T = prm.T;
-    const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
-    const size_t ring_stride = (size_t)prm.pb_mask + 1;
-    const uint32_t warp_id = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
-    unsigned long long* const fin_ctr = prm.pb_ctl + 16 * PB_SHARDS;
-    uint32_t idle = 0, probe = 0;
-    unsigned long long last_fin = 0;
-
-    for (;;) {
-        // ---- pop up to GPW games of one piece type from the home shard (or, when that is empty, from the next shard that
-        //      has work): lanes 0..6 look at one queue each, the fullest wins ----
-        const uint32_t shard = (warp_id + probe) % PB_SHARDS;
-        unsigned long long* const sctl = prm.pb_ctl + 16 * shard;
-        unsigned long long hd = 0, avail = 0;
-        if (lane < 7) { hd = *(volatile unsigned long long*)(sctl + 8 + lane); const unsigned long long tl = *(volatile unsigned long long*)(sctl + lane); avail = tl - hd; }
-        const uint32_t a32 = avail > 0xffffffull ? 0xffffffu : (uint32_t)avail;
-        // prefer full warps; among equally good queues rotate by warp so that the heads are not all hit at once
-        const uint32_t score = (lane < 7 && a32 != 0u) ? (1u << 20) + ((a32 >= GPW ? GPW : a32) << 8 | ((uint32_t)(lane + warp_id) % 7u)) : 0u;
-        const uint32_t best = __reduce_max_sync(FULLMASK, score);
-        if (best == 0u) {
-            if (++probe < PB_SHARDS) continue;                       // try the other shards before idling
-            probe = 0;
-            // nothing waiting anywhere: done when every game has finished, otherwise other warps are still playing
-            const unsigned long long fin = *(volatile unsigned long long*)fin_ctr;
-            if (fin >= (unsigned long long)prm.n_games) break;
-            __nanosleep(1000);
-            if ((++idle & 255u) == 0u && fin != last_fin) { last_fin = fin; idle = 0; }      // progress elsewhere: keep waiting
-            if (idle > (1u << 16)) { if (lane == 0) atomicExch(fin_ctr + 1, 1ull); break; }    // ~4 s without any game finishing
-            continue;
-        }
-        const int owner = __ffs((int)__ballot_sync(FULLMASK, score == best)) - 1;      // lane = piece type
-        uint32_t n = 0;
-        if (lane == owner) {
-            n = a32 < GPW ? a32 : GPW;
-            if (atomicCAS(sctl + 8 + lane, hd, hd + n) != hd) n = 0;                     // lost the race: look again
-        }
-        n = __shfl_sync(FULLMASK, n, owner);
-        if (n == 0u) continue;
-        idle = 0;
-        const unsigned long long base = __shfl_sync(FULLMASK, hd, owner);
-        const int p_cur = owner;
-        // ---- fetch the games ----
-        const uint32_t idx = (uint32_t)(lane / LANES);
-        bool active = idx < n;
-        uint32_t game = 0;
-        if (active) {
-            volatile uint32_t* slot = prm.pb_ring + ((size_t)shard * 7 + (size_t)p_cur) * ring_stride + (size_t)((base + idx) & prm.pb_mask);
-            uint32_t spins = 0;
-            while ((game = *slot) == PB_EMPTY) { __nanosleep(100); if (++spins > (1u << 22)) { atomicExch(fin_ctr + 1, 1ull); active = false; break; } }
-        }
-        __syncwarp(FULLMASK);
-        if (active && gl == 0) *(volatile uint32_t*)(prm.pb_ring + ((size_t)shard * 7 + (size_t)p_cur) * ring_stride + (size_t)((base + idx) & prm.pb_mask)) = PB_EMPTY;
-        __threadfence();
-        uint32_t c[COLS];
-        uint32_t t = 0, lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
-        uint64_t gscore = 0;
-#pragma unroll
-        for (int k = 0; k < COLS; ++k) c[k] = 0;
-        uint32_t sq = 0;
-        GameStat g;
-        g.H.H0 = g.H.H1 = g.H.H2 = 0u; g.cells = 0;
-        if (active) {
-            const uint4* sv = reinterpret_cast<const uint4*>(prm.st_save + game);
-            const uint4 a0 = __ldcg(sv), a1 = __ldcg(sv + 1), a2 = __ldcg(sv + 2), a3 = __ldcg(sv + 3), a4 = __ldcg(sv + 4), a5 = __ldcg(sv + 5);
-            g.H.H0 = a5.x; g.H.H1 = a5.y; g.H.H2 = a5.z; g.cells = (int)a5.w;
-            c[0] = a0.x; c[1] = a0.y; c[2] = a0.z; c[3] = a0.w; c[4] = a1.x; c[5] = a1.y; c[6] = a1.z; c[7] = a1.w; c[8] = a2.x; c[9] = a2.y;
-            t = a2.z; lines = a2.w; h1 = a3.x; h2 = a3.y; h3 = a3.z; h4 = a3.w;
-            if (gl == 0) cnt = a4.x;
-            gscore = ((uint64_t)a4.w << 32) | a4.z;
-            sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : game % (uint32_t)prm.G;
-        }
-        const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
-        unpack_heights(g.H, g.gh);
-        double w[6];
-        {
-            const double* wsrc = prm.weights + (size_t)(active ? game / (uint32_t)prm.G : 0u) * 6;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) w[i] = __ldg(wsrc + i);
-        }
-        // ---- one piece, every lane in step ----
-        const int ns = s_tab.nslots[p_cur];
-        uint64_t key = 0; uint32_t tag = 0;
-        for (int s2 = gl; s2 < ns; s2 += LANES) {
-            const SlotDesc d = load_slot12(s_tab, p_cur, s2);
-            W6Cand A;
-            w6_pre(c, g, d, A);
-            if (A.legal && A.full != 0u) w6_clear(d, A);
-            Heights Hn;
-            const uint64_t k = w6_post(A, w, Hn);
-            cnt += (uint32_t)(A.legal && active);
-            if (k > key) { key = k; tag = (uint32_t)s2; }
-        }
-        group_argmax<LANES>(key, tag);
-#pragma unroll
-        for (int off = LANES / 2; off > 0; off >>= 1) cnt += __shfl_xor_sync(FULLMASK, cnt, off);
-        bool finish = false;
-        int p_next = 7;
-        if (active) {
-            if (key == 0) {
-                finish = true;                                           // no legal placement: game over (simulator.py:187-189)
-            } else {
-                const SlotDesc d = load_slot12(s_tab, p_cur, (int)tag);
-                W6Cand A;
-                w6_pre(c, g, d, A);
-                if (A.full != 0u) w6_clear(d, A);
-#pragma unroll
-                for (int k = 0; k < COLS; ++k) c[k] = A.P.n[k];
-                g.H.H0 = (uint32_t)A.h[0] | (uint32_t)A.h[1] << 8 | (uint32_t)A.h[2] << 16 | (uint32_t)A.h[3] << 24;
-                g.H.H1 = (uint32_t)A.h[4] | (uint32_t)A.h[5] << 8 | (uint32_t)A.h[6] << 16 | (uint32_t)A.h[7] << 24;
-                g.H.H2 = (uint32_t)A.h[8] | (uint32_t)A.h[9] << 8;
-                g.cells = A.cells;
-                const uint32_t wk = (uint32_t)A.P.k;
-                if (wk != 0u) {
-                    lines += wk;
-                    h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
-                    const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
-                    gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
-                }
-                if (gl == 0) {
-                    if (prm.trace) {
-                        const uint32_t row = (uint32_t)(ROWS - A.P.y - A.P.ph);
-                        reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = (uint32_t)A.P.rot | row << 8 | (uint32_t)A.P.c0 << 16 | wk << 24;
-                    }
-                    if (prm.score_trace) {
-                        const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
-                        prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
-                    }
-                }
-                ++t;
-                if (t < stop) p_next = seq ? (int)__ldg(seq + t) : hashed_piece(prm.seed, (uint64_t)sq, t);
-                if (p_next >= 7) finish = true;                          // cap reached or the sequence ends here
-            }
-        }
-        // ---- finished games write their results; survivors go to the queue of their next piece ----
-        const bool lead = active && gl == 0;
-        if (lead && finish) {
-            tb200_game_result* r = prm.results + game;
-            r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4; r->score = gscore; r->placements = cnt;
-            if (prm.final_rows) { uint16_t rows[ROWS]; cols_to_rows(c, rows); for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2]; }
-        }
-        if (lead && !finish) pb_write_state(prm.st_save + game, c, t, lines, h1, h2, h3, h4, cnt, gscore, g.H, g.cells);
-        __threadfence();
-        const uint32_t fin_mask = __ballot_sync(FULLMASK, lead && finish);
-        if (fin_mask != 0u && lane == 0) atomicAdd(fin_ctr, (unsigned long long)__popc(fin_mask));
-        const int my_next = (lead && !finish) ? p_next : 8;
-        const uint32_t peers = __match_any_sync(FULLMASK, my_next);       // the survivors that go to the same queue
-        if (my_next < 7) {
-            unsigned long long pos = 0;
-            const int leader = __ffs((int)peers) - 1;
-            if (lane == leader) pos = atomicAdd(sctl + my_next, (unsigned long long)__popc(peers));      // the games of this task all live in `shard`
-            pos = __shfl_sync(peers, pos, leader);
-            pb_publish(prm, shard, my_next, pos + (unsigned long long)__popc(peers & ((1u << lane) - 1u)), game);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K2L: lookahead 2 with hard drops, one warp per game (BASELINE configs[3]).  The <= 34 legal layer-1 boards
-// (post-clear columns, packed heights, cached statistics, the move) are first built into shared memory by the
-// lanes; then the <= 34 x 34 leaves are FLATTENED over the 32 lanes (leaf -> (layer-1 rank, second slot)), so
-// that lanes stay busy whatever the slot counts of the two pieces are (a per-first-move loop leaves half of the
-// lanes idle: 9 / 17 / 34 second slots on 32 lanes).  Leaf-only scoring, tag = rank << 6 | second slot keeps the
-// first-of-max order; when layer 2 is empty the layer-1 states are scored instead (simulator.py:170-174).
-// ---------------------------------------------------------------------------------------------
-struct L1Rec {                 // one legal first move
-    uint32_t n[COLS];          // board after it
-    uint32_t H0, H1, H2;       // packed heights
-    int max_ht, all_ht, pits, cells, possum;
-    uint32_t mv;               // slot | landing height << 8
-    uint32_t pad;
-};
-
-template <int MODE>
-__global__ void __launch_bounds__(BLOCK) play_games_l2flat_kernel(const PlayParams prm)
-{
-    constexpr int GROUPS = BLOCK / 32;
-    __shared__ Tables s_tab;
-    __shared__ L1Rec s_rec[GROUPS][TB_MAX_SLOTS];
-    __shared__ double s_w[GROUPS][TB200_MAX_WEIGHTED];
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
-        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int grp = threadIdx.x >> 5;
-    L1Rec* rec = s_rec[grp];
-    const int F = prm.F;
-    const uint32_t T = prm.T;
-    const double* w = s_w[grp];
-
-    auto score_leaf = [&](const uint32_t* c1, const Heights& H1, const PrevStat& pv1, const SlotDesc& d2, uint64_t& k, bool& legal) {
-        if (MODE == MODE_W6) {
-            GameStat g1;
-            g1.H = H1; g1.cells = pv1.cells;
-#pragma unroll
-            for (int q = 0; q < COLS; ++q) g1.gh[q] = pv1.gh[q];
-            W6Cand A;
-            w6_pre(c1, g1, d2, A);
-            if (A.legal && A.full != 0u) w6_clear(d2, A);
-            Heights Hn;
-            k = w6_post(A, w, Hn);
-            legal = A.legal;
-        } else {
-            Placement P2;
-            legal = place_slot(c1, H1, d2, P2);
-            Feat f;
-            eval_features<ModeTraits<MODE>::CMASK>(P2, d2, pv1, prm.rmask, f);
-            const uint64_t kk = score_key(score_features<MODE>(f, prm.ids, w, F));
-            k = legal ? kk : 0ull;
-        }
-    };
-
-    for (;;) {
-        uint32_t game = 0;
-        if (lane == 0) game = atomicAdd(prm.ticket, 1u);
-        game = __shfl_sync(FULLMASK, game, 0);
-        if (game >= prm.n_games) break;
-        const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : (prm.per_game_weights != 0 ? game : game % (uint32_t)prm.G);
-        const uint64_t stream = sq;
-        const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
-        uint32_t c[COLS];
-        if (prm.init_rows) {
-            uint16_t rows[ROWS];
-            for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
-            rows_to_cols(rows, c);
-        } else {
-#pragma unroll
-            for (int k = 0; k < COLS; ++k) c[k] = 0;
-        }
-        PrevStat pv = prev_stat(c);
-        Heights H = pack_gh(pv.gh);
-        {
-            const size_t wrow = prm.per_game_weights > 0 ? (size_t)game : (prm.per_game_weights < 0 ? 0 : (size_t)(game / (uint32_t)prm.G));
-            const double* wsrc = prm.weights + wrow * (size_t)F;
-            __syncwarp(FULLMASK);
-            for (int i = lane; i < F; i += 32) s_w[grp][i] = __ldg(wsrc + i);
-            __syncwarp(FULLMASK);
-        }
-        auto fetch_piece = [&](uint32_t tt) -> int {
-            if (tt >= T) return 7;
-            return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, stream, tt);
-        };
-        uint32_t t = 0, lines = prm.init_lines ? prm.init_lines[game] : 0u, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
-        uint64_t gscore = 0;
-        const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
-        int p_cur = fetch_piece(0), p_next = fetch_piece(1);
-
-        while (t < stop && p_cur < 7) {
-            const int p_after = fetch_piece(t + 2);
-            const int ns1 = s_tab.nslots[p_cur];
-            // ---- phase 1: legal first moves -> records in shared memory, in enumeration order ----
-            int nrec = 0;
-            __syncwarp(FULLMASK);
-            for (int base = 0; base < ns1; base += 32) {
-                const int s1 = base + lane;
-                const SlotDesc d1 = load_slot12(s_tab, p_cur, s1 < ns1 ? s1 : 0);
-                Placement P1;
-                const bool legal1 = place_slot(c, H, d1, P1) && s1 < ns1;
-                const uint32_t m = __ballot_sync(FULLMASK, legal1);
-                if (legal1) {
-                    const PrevStat pv1 = next_stat(pv, P1, d1);
-                    const Heights H1 = pack_gh(pv1.gh);
-                    L1Rec& r = rec[nrec + __popc(m & ((1u << lane) - 1u))];
-#pragma unroll
-                    for (int k = 0; k < COLS; ++k) r.n[k] = P1.n[k];
-                    r.H0 = H1.H0; r.H1 = H1.H1; r.H2 = H1.H2;
-                    r.max_ht = pv1.max_ht; r.all_ht = pv1.all_ht; r.pits = pv1.pits; r.cells = pv1.cells; r.possum = pv1.possum;
-                    r.mv = (uint32_t)s1 | (uint32_t)P1.y << 8;
-                }
-                nrec += __popc(m);
-            }
-            __syncwarp(FULLMASK);
-            uint64_t key = 0; uint32_t tag = 0;
-            bool leaf_is_first = true;
-            if (t + 1 < T && p_next < 7 && nrec > 0) {
-                // ---- phase 2: leaves flattened over the lanes: leaf idx -> (record r, second slot s2) ----
-                const int ns2 = s_tab.nslots[p_next];
-                const int total = nrec * ns2;
-                int r = 0, s2 = lane;
-                while (s2 >= ns2) { s2 -= ns2; ++r; }
-                for (int idx = lane; idx < total; idx += 32) {
-                    const L1Rec& R = rec[r];
-                    uint32_t c1[COLS];
-#pragma unroll
-                    for (int k = 0; k < COLS; ++k) c1[k] = R.n[k];
-                    Heights H1; H1.H0 = R.H0; H1.H1 = R.H1; H1.H2 = R.H2;
-                    PrevStat pv1;
-                    pv1.max_ht = R.max_ht; pv1.all_ht = R.all_ht; pv1.pits = R.pits; pv1.cells = R.cells; pv1.possum = R.possum;
-                    unpack_heights(H1, pv1.gh);
-                    const SlotDesc d2 = load_slot12(s_tab, p_next, s2);
-                    uint64_t k; bool legal2;
-                    score_leaf(c1, H1, pv1, d2, k, legal2);
-                    if (legal2) ++cnt;
-                    if (k > key) { key = k; tag = (uint32_t)r << 6 | (uint32_t)s2; }
-                    s2 += 32;
-                    while (s2 >= ns2) { s2 -= ns2; ++r; }
-                }
-                warp_argmax32(key, tag);
-                if (key != 0) leaf_is_first = false;
-            }
-            uint32_t mv;
-            if (leaf_is_first) {
-                // layer 2 empty (or the sequence ends): score the layer-1 states themselves
-                key = 0; tag = 0;
-                if (lane < nrec || lane + 32 < nrec) {
-                    for (int r = lane; r < nrec; r += 32) {
-                        const SlotDesc d1 = load_slot12(s_tab, p_cur, (int)(rec[r].mv & 255u));
-                        uint64_t k; bool legal1;
-                        score_leaf(c, H, pv, d1, k, legal1);
-                        if (legal1) ++cnt;
-                        if (k > key) { key = k; tag = (uint32_t)r; }
-                    }
-                }
-                warp_argmax32(key, tag);
-                if (key == 0) break;
-                mv = rec[tag].mv;
-            } else {
-                mv = rec[tag >> 6].mv;
-            }
-            // ---- commit the first move ----
-            const SlotDesc d = load_slot12(s_tab, p_cur, (int)(mv & 255u));
-            Placement P; uint32_t full;
-            place_at(c, d, (int)(mv >> 8), P, &full);
-            if (full != 0u) place_clear(d, P, full);
-#pragma unroll
-            for (int k = 0; k < COLS; ++k) c[k] = P.n[k];
-            pv = next_stat(pv, P, d); H = pack_gh(pv.gh);
-            const uint32_t wk = (uint32_t)P.k;
-            if (wk != 0u) {
-                lines += wk;
-                h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
-                const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
-                gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
-            }
-            if (lane == 0) {
-                if (prm.trace) {
-                    const uint32_t row = (uint32_t)(ROWS - P.y - P.ph);
-                    reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = (uint32_t)P.rot | row << 8 | (uint32_t)P.c0 << 16 | wk << 24;
-                }
-                if (prm.score_trace) {
-                    const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
-                    prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
-                }
-            }
-            ++t;
-            p_cur = p_next; p_next = p_after;
-        }
-        cnt = __reduce_add_sync(FULLMASK, cnt);
-        if (lane == 0) {
-            tb200_game_result* r = prm.results + game;
-            r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4;
-            r->score = gscore; r->placements = cnt;
-            if (prm.final_rows) {
-                uint16_t rows[ROWS];
-                cols_to_rows(c, rows);
-                for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2];
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// K2x: the wiggle move sets (simulator.py:49-85), one warp per game.
-// The moves of a piece are the resting cells reachable from the starts by down / left / right steps.  As a SET they come
-// from a warp-parallel bit flood fill (wiggle_rest: one (rotation, column) slot per lane, reachable heights as a bit
-// mask, fill_down + neighbour exchange until stable), and every lane scores the moves of its own slots.  The reference's
-// visiting ORDER (a depth-first recursion) only matters for its first-of-max tie rule, so the serial reference-order
-// search (wiggle_rot, explicit stack in shared memory) runs only when several moves of the deciding rotation tie at
-// the maximum, for that one rotation, and stops at the first tied move (wiggle_pick).  With lookahead 2 the first layer
-// is listed in reference order (wiggle_collect, one search per rotation on lanes 0..3) because the first move of the
-// winning pair is what gets committed; the second layer is order-free.
-// ---------------------------------------------------------------------------------------------
-struct WiggleShared {
-    uint32_t fm[4][12];        // free map per rotation and column (bit y)
-    uint32_t seen[4][12];
-    uint16_t stack[4][256];
-    uint16_t list[4][128];     // moves of each rotation in visiting order: y | col << 8
-    uint8_t  starty[4][12];    // hard-drop landing height per rotation and column, 255 = illegal
-    uint32_t tie[4][12];       // fast path: moves that tie at the maximum (bit y), per rotation and column
-    int cnt[4], base[4], wph[4];
-};
-
-// Move list of `piece` on board c (warp-cooperative): free maps + hard-drop landings by all lanes, one flood fill per
-// rotation by lanes 0..nrot-1.  off[r] = number of moves of rotations < r; returns the total.
-TB_D int wiggle_collect(WiggleShared& wg, const Tables& tab, const uint32_t c[COLS], const Heights& H, int piece, bool from_top, int lane, int off[5])
-{
-    const int ns = tab.nslots[piece];
-    const int nrot = (int)((tab.slot[piece][ns - 1].w[0] >> 4) & 3u) + 1;
-    __syncwarp(FULLMASK);
-    for (int i = lane; i < 48; i += 32) { wg.fm[i / 12][i % 12] = 0u; wg.starty[i / 12][i % 12] = 255; }
-    __syncwarp(FULLMASK);
-    for (int s = lane; s < ns; s += 32) {
-        const SlotDesc d = load_slot12(tab, piece, s);
-        const int rot = (int)((d.w[0] >> 4) & 3u), c0 = (int)(d.w[0] & 15u);
-        wg.fm[rot][c0] = free_mask(c, d);
-        Placement P; uint32_t full;
-        if (place_pre(c, H, d, P, &full)) wg.starty[rot][c0] = (uint8_t)P.y;
-        if (c0 == 0) { wg.base[rot] = s; wg.wph[rot] = (int)((d.w[0] >> 6) & 7u) | (int)((d.w[0] >> 9) & 7u) << 8; }
-    }
-    __syncwarp(FULLMASK);
-    if (lane < nrot) {
-        const int wd = wg.wph[lane] & 255, ph = wg.wph[lane] >> 8;
-        uint16_t starts[COLS]; int nst = 0;
-        for (int col = 0; col <= COLS - wd; ++col) {
-            if (from_top) starts[nst++] = (uint16_t)((uint32_t)(ROWS - ph) | (uint32_t)col << 8);
-            else if (wg.starty[lane][col] != 255) starts[nst++] = (uint16_t)((uint32_t)wg.starty[lane][col] | (uint32_t)col << 8);
-        }
-        wg.cnt[lane] = wiggle_rot(wg.fm[lane], wd, starts, nst, wg.stack[lane], wg.seen[lane], wg.list[lane], 128);
-    }
-    __syncwarp(FULLMASK);
-    off[0] = 0;
-    off[1] = wg.cnt[0];
-    off[2] = off[1] + (nrot > 1 ? wg.cnt[1] : 0);
-    off[3] = off[2] + (nrot > 2 ? wg.cnt[2] : 0);
-    off[4] = off[3] + (nrot > 3 ? wg.cnt[3] : 0);
-    return off[4];
-}
-
-TB_D void wiggle_move_at(const WiggleShared& wg, const int off[5], int idx, int& slot, int& y)
-{
-    const int r = idx < off[1] ? 0 : (idx < off[2] ? 1 : (idx < off[3] ? 2 : 3));
-    const uint32_t e = wg.list[r][idx - off[r]];
-    y = (int)(e & 31u); slot = wg.base[r] + (int)(e >> 8);
-}
-
-// score every move of the list as a leaf on board c (previous-state statistics pv); tag = tag_hi | position in the list
-template <int MODE>
-TB_D void wiggle_score(const WiggleShared& wg, const int off[5], const Tables& tab, const uint32_t c[COLS], const PrevStat& pv, int piece,
-                       const Pressure& pr, int level, const uint8_t* ids, const double* w, int F, uint64_t rmask, uint32_t tag_hi, int lane,
-                       uint64_t& key, uint32_t& tag, uint32_t& cnt)
-{
-    for (int idx = lane; idx < off[4]; idx += 32) {
-        int slot, y;
-        wiggle_move_at(wg, off, idx, slot, y);
-        const SlotDesc d = load_slot12(tab, piece, slot);
-        if (pr.on && !is_time(d, y, pr, level)) continue;
-        Placement P; uint32_t full;
-        place_at(c, d, y, P, &full);
-        if (full != 0u) place_clear(d, P, full);
-        Feat f;
-        eval_features<ModeTraits<MODE>::CMASK>(P, d, pv, rmask, f);
-        const uint64_t k = score_key(score_features<MODE>(f, ids, w, F));
-        if (k > key) { key = k; tag = tag_hi | (uint32_t)idx; }
-        ++cnt;
-    }
-}
-
-// Order-free fast path: the SET of resting cells of every slot by a warp-parallel flood fill.  Lane l owns slots l and
-// l + 32; each keeps the reachable cells of its slot as a bit mask (bit y), grows it downwards with fill_down and
-// sideways from its two neighbours of the same rotation (exchanged through wg.seen, index column + 1, zero padded)
-// until no lane changes.  rest[j] = reachable cells with no free cell below = the moves of slot l + 32 j.  Also leaves
-// the free maps, hard-drop landings and per-rotation slot bases in wg for the tie break.
-TB_D void wiggle_rest(WiggleShared& wg, const Tables& tab, const uint32_t c[COLS], const Heights& H, int piece, bool from_top, int lane, uint32_t rest[2])
-{
-    const int ns = tab.nslots[piece];
-    __syncwarp(FULLMASK);
-    for (int i = lane; i < 48; i += 32) { wg.seen[i / 12][i % 12] = 0u; wg.fm[i / 12][i % 12] = 0u; wg.starty[i / 12][i % 12] = 255; }
-    __syncwarp(FULLMASK);
-    uint32_t fm[2] = {0u, 0u}, rv[2] = {0u, 0u};
-    int at[2] = {0, 0};                      // rot * 12 + c0 + 1 of the lane's slots
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int sl = lane + 32 * j;
-        if (sl < ns) {
-            const SlotDesc d = load_slot12(tab, piece, sl);
-            const int rot = (int)((d.w[0] >> 4) & 3u), c0 = (int)(d.w[0] & 15u), ph = (int)((d.w[0] >> 9) & 7u);
-            fm[j] = free_mask(c, d);
-            wg.fm[rot][c0] = fm[j];
-            if (c0 == 0) { wg.base[rot] = sl; wg.wph[rot] = (int)((d.w[0] >> 6) & 7u) | ph << 8; }
-            uint32_t seed;
-            if (from_top) seed = 1u << (ROWS - ph);
-            else {
-                Placement P; uint32_t full;
-                const bool ok = place_pre(c, H, d, P, &full);
-                seed = ok ? 1u << P.y : 0u;
-                if (ok) wg.starty[rot][c0] = (uint8_t)P.y;
-            }
-            rv[j] = fill_down(seed & fm[j], fm[j]);
-            at[j] = rot * 12 + c0 + 1;
-            (&wg.seen[0][0])[at[j]] = rv[j];
-        }
-    }
-    for (;;) {
-        __syncwarp(FULLMASK);
-        uint32_t nv[2] = {0u, 0u};
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-            if (lane + 32 * j < ns) {
-                const uint32_t* sn = &wg.seen[0][0] + at[j];
-                nv[j] = fill_down((sn[-1] | sn[1] | rv[j]) & fm[j], fm[j]);
-            }
-        const bool changed = nv[0] != rv[0] || nv[1] != rv[1];
-        __syncwarp(FULLMASK);
-        if (!__any_sync(FULLMASK, changed)) break;
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-            if (nv[j] != rv[j]) { rv[j] = nv[j]; (&wg.seen[0][0])[at[j]] = nv[j]; }
-    }
-    rest[0] = rv[0] & ~(fm[0] << 1);
-    rest[1] = rv[1] & ~(fm[1] << 1);
-}
-
-// score the lane's moves (rest masks of wiggle_rest) as leaves on board c; tm[j] = the moves of slot lane + 32 j that
-// reach the lane's best key
-template <int MODE>
-TB_D void wiggle_score_rest(const uint32_t rest[2], const Tables& tab, const uint32_t c[COLS], const PrevStat& pv, int piece,
-                            const Pressure& pr, int level, const uint8_t* ids, const double* w, int F, uint64_t rmask, int lane,
-                            uint64_t& key, uint32_t tm[2], uint32_t& cnt)
-{
-    tm[0] = 0u; tm[1] = 0u;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        uint32_t m = rest[j];
-        if (m == 0u) continue;
-        const SlotDesc d = load_slot12(tab, piece, lane + 32 * j);
-        while (m != 0u) {
-            const int y = __ffs((int)m) - 1;
-            m &= m - 1u;
-            if (pr.on && !is_time(d, y, pr, level)) continue;
-            Placement P; uint32_t full;
-            place_at(c, d, y, P, &full);
-            if (full != 0u) place_clear(d, P, full);
-            Feat f;
-            eval_features<ModeTraits<MODE>::CMASK>(P, d, pv, rmask, f);
-            const uint64_t k = score_key(score_features<MODE>(f, ids, w, F));
-            ++cnt;
-            if (k > key) { key = k; tm[0] = 0u; tm[1] = 0u; tm[j] = 1u << y; }
-            else if (k == key) tm[j] |= 1u << y;
-        }
-    }
-}
-
-// The winner among the lanes' best moves under the reference's first-of-max rule.  A unique maximum needs no order;
-// otherwise the tied moves of the lowest rotation that has any decide: one such move wins outright, several are
-// ordered by running the reference-order search of that one rotation (lane 0) up to the first of them.
-// Returns false when there is no move at all; else slot / y of the winner and key = the maximum.
-TB_D bool wiggle_pick(WiggleShared& wg, const Tables& tab, int piece, bool from_top, int lane, uint64_t& key, const uint32_t tm_in[2], int& slot, int& y)
-{
-    const uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
-    const uint32_t mhi = __reduce_max_sync(FULLMASK, hi);
-    const uint32_t mlo = __reduce_max_sync(FULLMASK, hi == mhi ? lo : 0u);
-    key = ((uint64_t)mhi << 32) | mlo;
-    if (key == 0) return false;
-    const bool win = hi == mhi && lo == mlo;
-    const uint32_t tm[2] = {win ? tm_in[0] : 0u, win ? tm_in[1] : 0u};
-    // lowest tied slot (slots are rotation-major) -> the rotation that decides
-    const uint32_t smin = __reduce_min_sync(FULLMASK, tm[0] != 0u ? (uint32_t)lane : (tm[1] != 0u ? (uint32_t)lane + 32u : 99u));
-    const int rstar = (int)((tab.slot[piece][smin].w[0] >> 4) & 3u);
-    uint32_t mine = 0u, mymv = 0u;
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-        if (tm[j] != 0u && (int)((tab.slot[piece][lane + 32 * j].w[0] >> 4) & 3u) == rstar) {
-            mine += (uint32_t)__popc(tm[j]);
-            mymv = (uint32_t)(lane + 32 * j) | (uint32_t)(__ffs((int)tm[j]) - 1) << 8;
-        }
-    const uint32_t total = __reduce_add_sync(FULLMASK, mine);
-    if (total == 1u) {
-        const uint32_t who = __ballot_sync(FULLMASK, mine != 0u);
-        const uint32_t mv = __shfl_sync(FULLMASK, mymv, __ffs((int)who) - 1);
-        slot = (int)(mv & 255u); y = (int)(mv >> 8);
-        return true;
-    }
-    // several tied moves in rotation rstar: visiting order decides
-    __syncwarp(FULLMASK);
-    if (lane < 12) wg.tie[rstar][lane] = 0u;
-    __syncwarp(FULLMASK);
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-        if (tm[j] != 0u) {
-            const uint32_t w0 = tab.slot[piece][lane + 32 * j].w[0];
-            if ((int)((w0 >> 4) & 3u) == rstar) wg.tie[rstar][w0 & 15u] = tm[j];
-        }
-    __syncwarp(FULLMASK);
-    if (lane == 0) {
-        const int wd = wg.wph[rstar] & 255, ph = wg.wph[rstar] >> 8;
-        uint16_t starts[COLS]; int nst = 0;
-        for (int col = 0; col <= COLS - wd; ++col) {
-            if (from_top) starts[nst++] = (uint16_t)((uint32_t)(ROWS - ph) | (uint32_t)col << 8);
-            else if (wg.starty[rstar][col] != 255) starts[nst++] = (uint16_t)((uint32_t)wg.starty[rstar][col] | (uint32_t)col << 8);
-        }
-        wiggle_rot(wg.fm[rstar], wd, starts, nst, wg.stack[0], wg.seen[0], wg.list[0], 128, wg.tie[rstar]);
-    }
-    __syncwarp(FULLMASK);
-    const uint32_t e = wg.list[0][0];
-    y = (int)(e & 31u); slot = wg.base[rstar] + (int)(e >> 8);
-    return true;
-}
-
-template <int MODE, int LOOKAHEAD>
-__global__ void __launch_bounds__(BLOCK) play_games_wiggle_kernel(const PlayParams prm)
-{
-    constexpr int GROUPS = BLOCK / 32;
-    __shared__ Tables s_tab;
-    __shared__ WiggleShared s_wg[GROUPS][LOOKAHEAD];
-    __shared__ double s_w[GROUPS][TB200_MAX_WEIGHTED];
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
-        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
-    }
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int grp = threadIdx.x >> 5;
-    WiggleShared& wg1 = s_wg[grp][0];
-    WiggleShared& wg2 = s_wg[grp][LOOKAHEAD - 1];
-    const int F = prm.F;
-    const uint32_t T = prm.T;
-    const bool from_top = (prm.move_set & 4) != 0;
-    const double* w = s_w[grp];
-
-    for (;;) {
-        uint32_t game = 0;
-        if (lane == 0) game = atomicAdd(prm.ticket, 1u);
-        game = __shfl_sync(FULLMASK, game, 0);
-        if (game >= prm.n_games) break;
-        const uint32_t sq = prm.seq_of_game ? (uint32_t)prm.seq_of_game[game] : (prm.per_game_weights != 0 ? game : game % (uint32_t)prm.G);
-        const uint64_t stream = sq;
-        const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
-        uint32_t c[COLS];
-        if (prm.init_rows) {
-            uint16_t rows[ROWS];
-            for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
-            rows_to_cols(rows, c);
-        } else {
-#pragma unroll
-            for (int k = 0; k < COLS; ++k) c[k] = 0;
-        }
-        PrevStat pv = prev_stat(c);
-        Heights H = pack_gh(pv.gh);
-        {
-            const size_t wrow = prm.per_game_weights > 0 ? (size_t)game : (prm.per_game_weights < 0 ? 0 : (size_t)(game / (uint32_t)prm.G));
-            const double* wsrc = prm.weights + wrow * (size_t)F;
-            __syncwarp(FULLMASK);
-            for (int i = lane; i < F; i += 32) s_w[grp][i] = __ldg(wsrc + i);
-            __syncwarp(FULLMASK);
-        }
-        auto fetch_piece = [&](uint32_t tt) -> int {
-            if (tt >= T) return 7;
-            return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, stream, tt);
-        };
-        uint32_t t = 0, lines = prm.init_lines ? prm.init_lines[game] : 0u, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
-        uint64_t gscore = 0;
-        const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
-        int p_cur = fetch_piece(0), p_next = fetch_piece(1);
-
-        while (t < stop && p_cur < 7) {
-            const int p_after = fetch_piece(t + 2);
-            const int level = (int)(lines / 10u);
-            uint64_t key = 0;
-            int slot = 0, y = 0;
-            if (LOOKAHEAD == 1 || !(t + 1 < T && p_next < 7)) {
-                // order-free fast path: the move SET by warp-parallel flood fill; the reference's visiting order only
-                // matters when several moves tie at the maximum (wiggle_pick)
-                uint32_t rest[2], tm[2];
-                wiggle_rest(wg1, s_tab, c, H, p_cur, from_top, lane, rest);
-                wiggle_score_rest<MODE>(rest, s_tab, c, pv, p_cur, prm.press, level, prm.ids, w, F, prm.rmask, lane, key, tm, cnt);
-                if (!wiggle_pick(wg1, s_tab, p_cur, from_top, lane, key, tm, slot, y)) break;
-            } else {
-                // lookahead 2: every first move in the reference's list order (warp-uniform), expanded by the set flood fill of the next piece
-                int off1[5];
-                uint32_t tag = 0;
-                wiggle_collect(wg1, s_tab, c, H, p_cur, from_top, lane, off1);
-                for (int i1 = 0; i1 < off1[4]; ++i1) {
-                    int slot1, y1;
-                    wiggle_move_at(wg1, off1, i1, slot1, y1);
-                    const SlotDesc d1 = load_slot12(s_tab, p_cur, slot1);
-                    if (prm.press.on && !is_time(d1, y1, prm.press, level)) continue;
-                    Placement P1; uint32_t full;
-                    place_at(c, d1, y1, P1, &full);
-                    if (full != 0u) place_clear(d1, P1, full);
-                    const PrevStat pv1 = next_stat(pv, P1, d1);
-                    const Heights H1 = pack_gh(pv1.gh);
-                    // the second layer is order-free: only the FIRST move of the winning pair is committed, so among equal
-                    // keys the earliest i1 wins whatever the order inside its second layer
-                    uint32_t rest[2], tm[2];
-                    uint64_t k2 = 0;
-                    wiggle_rest(wg2, s_tab, P1.n, H1, p_next, from_top, lane, rest);
-                    wiggle_score_rest<MODE>(rest, s_tab, P1.n, pv1, p_next, prm.press, (int)((lines + (uint32_t)P1.k) / 10u), prm.ids, w, F, prm.rmask,
-                                            lane, k2, tm, cnt);
-                    if (k2 > key) { key = k2; tag = (uint32_t)i1 << 11; }
-                }
-                warp_argmax32(key, tag);
-                bool leaf_is_first = key == 0;
-                if (leaf_is_first) {              // no second-layer leaf anywhere: score the first layer itself
-                    tag = 0;
-                    wiggle_score<MODE>(wg1, off1, s_tab, c, pv, p_cur, prm.press, level, prm.ids, w, F, prm.rmask, 0u, lane, key, tag, cnt);
-                    warp_argmax32(key, tag);
-                }
-                if (key == 0) break;
-                wiggle_move_at(wg1, off1, (int)(leaf_is_first ? tag : (tag >> 11)), slot, y);
-            }
-            // ---- commit the (first) move of the winner ----
-            const SlotDesc d = load_slot12(s_tab, p_cur, slot);
-            Placement P; uint32_t full;
-            place_at(c, d, y, P, &full);
-            if (full != 0u) place_clear(d, P, full);
-#pragma unroll
-            for (int k = 0; k < COLS; ++k) c[k] = P.n[k];
-            pv = next_stat(pv, P, d); H = pack_gh(pv.gh);
-            const uint32_t wk = (uint32_t)P.k;
-            if (wk != 0u) {
-                lines += wk;
-                h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
-                const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
-                gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
-            }
-            if (lane == 0) {
-                if (prm.trace) {
-                    const uint32_t row = (uint32_t)(ROWS - P.y - P.ph);
-                    reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = (uint32_t)P.rot | row << 8 | (uint32_t)P.c0 << 16 | wk << 24;
-                }
-                if (prm.score_trace) {
-                    const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
-                    prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
-                }
-            }
-            ++t;
-            p_cur = p_next; p_next = p_after;
-        }
-        cnt = __reduce_add_sync(FULLMASK, cnt);
-        if (lane == 0) {
-            tb200_game_result* r = prm.results + game;
-            r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4;
-            r->score = gscore; r->placements = cnt;
-            if (prm.final_rows) {
-                uint16_t rows[ROWS];
-                cols_to_rows(c, rows);
-                for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2];
-            }
-        }
-    }
-}
 
 // K3: all 45 features of one placement per thread
 // at_row (optional): row of the piece's top bbox row; 255 / null => hard drop.  With an explicit row the placement only

@@ -70,23 +70,29 @@ class PopulationEvaluator:
         self.T = int(T if T is not None else self.pieces.shape[1])
         self.seed, self.lookahead, self.lanes = int(seed), int(lookahead), int(lanes)
         self._batch = []
+        self._keys_ok = None                  # key tuple of the last validated weights mapping
         self._bufs = None                     # page-locked staging buffers, reused every generation (-> CUDA-graph replay)
         self.last = None                      # raw device results of the last generation
         self.generations = 0
 
     # -- the two callables handed to cross_entropy ---------------------------------------------
     def test_f(self, weights):
-        keys = [getattr(k, "__name__", k) for k in weights.keys()]
-        if keys != self.names:
-            raise ValueError("weights mapping keys %r do not match the evaluator's feature order %r" % (keys, self.names))
-        self._batch.append([float(v) for v in weights.values()])
+        # called once per candidate (learning.py:38), 10 000 times per generation in BASELINE configs[2]: the key order is
+        # validated by name the first time a key tuple is seen and by identity afterwards
+        keys = tuple(weights)
+        if keys != self._keys_ok:
+            names = [getattr(k, "__name__", k) for k in keys]
+            if names != self.names:
+                raise ValueError("weights mapping keys %r do not match the evaluator's feature order %r" % (names, self.names))
+            self._keys_ok = keys
+        self._batch.append(list(weights.values()))
         return _Pending(len(self._batch) - 1)
 
     def map_f(self, fn, indices):
         self._batch = []
         tagged = [fn(i) for i in indices]                 # cheap: only records weights
-        fitness = self.evaluate(np.array(self._batch, dtype=np.float64))
-        return [(float(fitness[p.slot]), i) for p, i in tagged]
+        fitness = self.evaluate(np.array(self._batch, dtype=np.float64)).tolist()      # Python floats, same bits
+        return [(fitness[p.slot], i) for p, i in tagged]
 
     # -- batch evaluation ----------------------------------------------------------------------------
     def evaluate(self, weights):
@@ -142,14 +148,14 @@ class ShardedEvaluator:
         self.names = None
 
     def test_f(self, weights):
-        self._batch.append([float(v) for v in weights.values()])
+        self._batch.append(list(weights.values()))
         return _Pending(len(self._batch) - 1)
 
     def map_f(self, fn, indices):
         self._batch = []
         tagged = [fn(i) for i in indices]
-        fitness = self.evaluate(np.array(self._batch, dtype=np.float64))
-        return [(float(fitness[p.slot]), i) for p, i in tagged]
+        fitness = self.evaluate(np.array(self._batch, dtype=np.float64)).tolist()
+        return [(fitness[p.slot], i) for p, i in tagged]
 
     def evaluate(self, weights):
         import torch
