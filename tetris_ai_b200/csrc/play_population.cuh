@@ -272,10 +272,14 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayPara
         }
         while (t < t_end && p_cur < 7 && __any_sync(FULLMASK, active)) {
             const int p_after = fetch_piece(t + 2u);
-            const int ns = s_tab.nslots[p_cur];
+            // LANES == 1: every lane is on the same slot of the same piece, so the descriptor is warp-uniform: read it from
+            // constant memory with a provably uniform index (REDUX result) and let its field extraction run on the uniform
+            // datapath instead of the ALU pipe, which is the binding resource of this kernel
+            const int p_u = LANES == 1 ? (int)__reduce_max_sync(FULLMASK, (unsigned)p_cur) : p_cur;
+            const int ns = LANES == 1 ? c_tables.nslots[p_u] : s_tab.nslots[p_cur];
             uint64_t key = 0; uint32_t tag = 0;
             for (int s2 = gl; s2 < ns; s2 += LANES) {                    // same piece, same trip count in every lane
-                const SlotDesc d = load_slot12(s_tab, p_cur, s2);
+                const SlotDesc d = LANES == 1 ? c_tables.slot[p_u][s2] : load_slot12(s_tab, p_cur, s2);
                 W6Cand A;
                 w6_pre(c, g, d, A);
                 if (A.legal && A.full != 0u) w6_clear(d, A);
