@@ -334,6 +334,25 @@ def test_k2_lockstep_population_vs_coracle(eng, C, G, T, spread, explicit):
         assert a["trace"][g, :k].tobytes() == o["trace"][g, :k].tobytes()
 
 
+def test_k2_lockstep_one_lane_per_game_full_population(eng):
+    """The whole BASELINE configs[2] population (10 000 candidates x 30 games) on one GPU: K2s runs with ONE lane per game
+    (warp-uniform descriptors).  Every result against the per-game kernel; the first 150 candidates against the C oracle."""
+    rng = np.random.default_rng(10)
+    C, G, T = 10000, 30, 130
+    w = np.array(W6_VALS)[None, :] + rng.normal(0, 2.5, size=(C, 6))
+    fids = [pyoracle.FEATURE_ID[x] for x in W6_NAMES]
+    eng.set_features(W6_NAMES)
+    pieces = np.array([[random.Random(13 * g + 5).randrange(7) for _ in range(T)] for g in range(G)], dtype=np.uint8)
+    a = eng.play_games(w, G, pieces=pieces, want_final=True)
+    assert eng.last_timing()["kernels_launched"] == 2 and eng.last_timing()["lanes"] == 1
+    b = eng.play_games(w, G, pieces=pieces, lanes=8, want_final=True)
+    assert (a["results"] == b["results"]).all() and (a["final"] == b["final"]).all() and (a["fitness"] == b["fitness"]).all()
+    o = coracle.play_games(fids, w[:150], G, pieces=pieces, threads=16)
+    res = a["results"][:150 * G]
+    assert (res["pieces"] == o["pieces"]).all() and (res["lines"] == o["lines"]).all()
+    assert (res["score"] == o["score"]).all() and (res["placements"] == o["placements"]).all() and (res["hist"] == o["hist"]).all()
+
+
 def test_k2_lockstep_initial_boards_lines_and_max_moves(eng):
     """K2s with initial boards, lines already cleared and a max_moves stop that is not a stage boundary."""
     rng = np.random.default_rng(3)
