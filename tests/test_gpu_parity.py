@@ -440,6 +440,10 @@ def test_k2_piece_binned_initial_boards_lines_max_moves_and_short_sequences(eng)
     b = eng.play_games(w, 1, lanes=32, **kw)
     assert (a["results"] == b["results"]).all() and (a["final"] == b["final"]).all()
     assert (a["results"]["pieces"] <= 50).all() and (a["results"]["pieces"][6::S] == 0).all()
+    assert (a["results"]["lines"][6::S] == lines0[6::S]).all() and (a["final"][6::S] == init[6::S]).all()    # nothing played: state untouched
+    for lanes in (8, 2):                                              # the grouped kernel reports untouched games the same way
+        b2 = eng.play_games(w, 1, lanes=lanes, **kw)
+        assert (a["results"] == b2["results"]).all() and (a["final"] == b2["final"]).all()
     for g in range(0, n, 31):
         k = int(a["results"]["pieces"][g])
         assert a["trace"][g, :k].tobytes() == b["trace"][g, :k].tobytes()

@@ -77,7 +77,15 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6grp_kernel(const PlayParam
                 for (int i = 0; i < 6; ++i) w[i] = __ldg(wsrc + i);
                 p_cur = fetch_piece(0); p_next = fetch_piece(1);
                 if (stop == 0 || p_cur >= 7) {            // nothing to play: finish immediately
-                    if (gl == 0) { tb200_game_result* r = prm.results + game; r->pieces = 0; r->lines = 0; r->score = 0; }
+                    if (gl == 0) {
+                        tb200_game_result* r = prm.results + game;
+                        r->pieces = 0; r->lines = lines; r->score = 0;
+                        if (prm.final_rows) {
+                            uint16_t rows[ROWS];
+                            cols_to_rows(c, rows);
+                            for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2];
+                        }
+                    }
                     active = false;
                 }
             } else {
