@@ -90,7 +90,11 @@ typedef struct {
     const int32_t* seq_of_game;      /* i32[C*G] sequence / stream id of each game, or NULL => g % G */
     uint64_t seed;                   /* seed of the counter-based stream */
     int32_t  lookahead;              /* 1 or 2 (simulate(..., lookahead)) */
-    int32_t  lanes;                  /* lanes per game: 0 = auto, or 8 / 16 / 32; for the w6 set with lookahead 1 also 64 (two warps per game), 4, 2, 1 */
+    int32_t  lanes;                  /* lanes per game: 0 = auto, or 8 / 16 / 32; for the w6 set with lookahead 1 also 64 (two warps per game), 4, 2, 1.
+                                        An explicit value runs ONE persistent kernel of that width.  0 lets the library schedule the play: for the w6
+                                        set with lookahead 1 that can be several stream-ordered launches (2 - 16 games per SM), the lockstep kernel
+                                        (shared sequences, > 80 games per SM) or the piece-binned kernel (>= 32 768 games); results never depend on it.
+                                        Those two kernels bound every wait: a TB200_MEM_HOST call returns TB200_E_CUDA instead of hanging if one expires. */
     const uint16_t* init_rows;       /* u16[C*G][20] initial boards, or NULL => empty boards */
     tb200_game_result* results;      /* [C*G], required */
     uint8_t*  trace;                 /* u8[C*G][T][4] = {rot,row,col,k} per move, or NULL */

@@ -58,7 +58,7 @@ struct PlayParams {
     uint32_t  pb_mask;               // ring capacity - 1 (a power of two >= games per shard)
 };
 
-// state of a game handed from one stage to the next (80 bytes)
+// state of a game handed from one stage to the next (96 bytes)
 struct GameSave {
     uint32_t c[COLS];
     uint32_t t, lines, h1, h2, h3, h4, cnt, pad;

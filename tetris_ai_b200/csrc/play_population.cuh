@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6grp_kernel(const PlayParam
 // persistent launch: warps walk the buckets (stage-major, sequence-minor) and claim tasks by ticket; bucket (s, g)
 // opens when every task of (s - 1, g) is done — 29 other buckets lie in between, so nobody actually waits except at
 // the very end, and a running task never waits, so the scheme cannot deadlock with a fully resident grid.
-// Hand-over state: GameSave (80 bytes per game) through L2 (__ldcg / fence + counter).
+// Hand-over state: GameSave (96 bytes per game) through L2 (__ldcg / fence + counter).
 // ---------------------------------------------------------------------------------------------
 // first move of stage s: two short stages first (K/4, K/2) — a fresh CE population loses most of its games within a
 // few dozen pieces and they should be re-packed early — then K pieces per stage
@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayPara
 // (9 / 17 / 34 slots).  Here a game is not bound to a warp: seven device-wide queues, one per piece type, hold the games
 // whose next piece has that type.  A warp pops up to 32 / LANES games from the fullest queue — all on the same piece —
 // plays exactly one piece for each of them with every lane in step, and pushes each survivor onto the queue of its
-// next piece.  Game state (80 bytes) travels through L2; with 4 warps per scheduler the pop / load latency hides behind
+// next piece.  Game state (96 bytes) travels through L2; with 5 warps per scheduler the pop / load latency hides behind
 // the other warps' arithmetic.  Queues are rings of game ids with 64-bit reserved-tail / head counters: a pusher
 // reserves slots by atomicAdd, writes the state, fences, then publishes the id into the slot; a popper claims by CAS
 // on the head and reads each slot once it is published.  All waits are bounded (error flag instead of a hang).

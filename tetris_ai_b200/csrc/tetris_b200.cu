@@ -505,7 +505,7 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
     // play is therefore split into up to three stream-ordered stages: K2f on everything until at most 4 games per SM are
     // unfinished, K2f again on the survivors — one block per SM, one warp per scheduler — until at most 2 per SM are
     // left, then K2p with one scheduler per warp.  A stage ends by itself: every warp polls the finished-games counter
-    // and hands its game (board + counters, 80 bytes) to the next stage's list.  Results do not depend on the staging.
+    // and hands its game (board + counters, 96 bytes) to the next stage's list.  Results do not depend on the staging.
     const uint32_t stop_moves = p.max_moves < p.T ? p.max_moves : p.T;
     const bool staged = ctx->staging_enabled && lanes_auto && pair_ok && n_games > (uint32_t)(2 * ctx->sms) && n_games <= ctx->stage_cap && stop_moves >= 128u;
     // Population regime (more than 80 games per SM, w6, lookahead 1, G shared sequences, automatic lanes): the lockstep
