@@ -10,6 +10,18 @@ namespace tb {
 constexpr int BLOCK = 128;
 
 __constant__ Tables c_tables;
+// The same tables in global memory: every block copies them into shared memory at kernel start, and a copy out of constant
+// memory with per-thread addresses is serialised by the constant cache (it showed up as 2.5 % of the samples of a 0.4 ms
+// kernel); from global memory it is a few coalesced 128-bit loads per thread.
+__device__ Tables g_tables;
+static_assert(sizeof(Tables) % 16 == 0, "Tables must be a whole number of 128-bit words");
+template <int NT>
+__device__ __forceinline__ void load_tables(Tables& s_tab)
+{
+    const uint4* src = reinterpret_cast<const uint4*>(&g_tables);
+    uint4* dst = reinterpret_cast<uint4*>(&s_tab);
+    for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 16); i += NT) dst[i] = src[i];
+}
 #ifdef TB_PHASES
 __device__ unsigned long long g_phase[8];
 #define PH(i) { const long long now_ = clock64(); ph[i] += now_ - last_; last_ = now_; }

@@ -31,11 +31,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayPara
         return v;
     };
     __shared__ Tables s_tab;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
-        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
-    }
+    load_tables<BLOCK>(s_tab);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint32_t T = prm.T;
@@ -249,11 +245,7 @@ __global__ void __launch_bounds__(64) play_games_w6pair_kernel(const PlayParams 
     __shared__ Tables s_tab;
     __shared__ uint4 s_x[2][2][5];
     __shared__ uint32_t s_game;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
-        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += 64) dst[i] = src[i];
-    }
+    load_tables<64>(s_tab);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -377,7 +369,7 @@ __global__ void __launch_bounds__(64) play_games_w6pair_kernel(const PlayParams 
                 gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
             }
             g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)(lines - lines0);
-            if (threadIdx.x == 0) {
+            if ((prm.trace != nullptr || prm.score_trace != nullptr) && threadIdx.x == 0) {     // uniform test first: no divergent region per piece when nothing is traced
                 if (prm.trace) {
                     const uint32_t wy = info & 255u, wph = info >> 24;
                     const uint32_t row = (uint32_t)ROWS - wy - wph;

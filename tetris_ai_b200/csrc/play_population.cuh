@@ -17,11 +17,7 @@ template <int LANES>
 __global__ void __launch_bounds__(BLOCK) play_games_w6grp_kernel(const PlayParams prm)
 {
     __shared__ Tables s_tab;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
-        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
-    }
+    load_tables<BLOCK>(s_tab);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int gl = lane & (LANES - 1);
@@ -186,11 +182,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayPara
 {
     constexpr uint32_t GPW = 32 / LANES;           // games per warp
     __shared__ Tables s_tab;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
-        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
-    }
+    load_tables<BLOCK>(s_tab);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int gl = lane & (LANES - 1);
@@ -449,11 +441,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6bin_kernel(const PlayParam
 {
     constexpr uint32_t GPW = 32 / LANES;
     __shared__ Tables s_tab;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
-        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
-    }
+    load_tables<BLOCK>(s_tab);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int gl = lane & (LANES - 1);

@@ -239,11 +239,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_wiggle_kernel(const PlayPara
     __shared__ Tables s_tab;
     __shared__ WiggleShared s_wg[GROUPS][LOOKAHEAD];
     __shared__ double s_w[GROUPS][TB200_MAX_WEIGHTED];
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&c_tables);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_tab);
-        for (int i = threadIdx.x; i < (int)(sizeof(Tables) / 4); i += BLOCK) dst[i] = src[i];
-    }
+    load_tables<BLOCK>(s_tab);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int grp = threadIdx.x >> 5;

@@ -310,6 +310,7 @@ int tb200_create(int device, tb200_ctx** out)
     strncpy(ctx->name, prop.name, sizeof(ctx->name) - 1);
     static const tb::Tables host_tab = { TB_SLOT_TABLE_INIT, TB_NSLOTS_INIT };
     cudaError_t e = cudaMemcpyToSymbol(tb::c_tables, &host_tab, sizeof(tb::Tables));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(tb::g_tables, &host_tab, sizeof(tb::Tables));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_ticket, sizeof(uint32_t));
     ctx->stage_cap = (uint32_t)(16 * ctx->sms);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_stage, 256 + (size_t)ctx->stage_cap * (2 * sizeof(uint32_t) + sizeof(tb::GameSave)));

@@ -50,7 +50,7 @@ constexpr uint64_t W6_MASK = bit(F_LANDING_HEIGHT) | bit(F_ERODED_CELLS) | bit(F
 // tables
 // ---------------------------------------------------------------------------------------------
 struct SlotDesc { uint32_t w[12]; };         // layout: tools/gen_tables.py
-struct Tables {
+struct alignas(16) Tables {                  // 16-byte aligned and padded: copied into shared memory with 128-bit loads
     SlotDesc slot[7][TB_MAX_SLOTS];
     int nslots[7];
 };
