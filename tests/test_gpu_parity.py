@@ -353,6 +353,32 @@ def test_k2_lockstep_one_lane_per_game_full_population(eng):
     assert (res["score"] == o["score"]).all() and (res["placements"] == o["placements"]).all() and (res["hist"] == o["hist"]).all()
 
 
+@pytest.mark.parametrize("kind,C,G,T", [("8", 2100, 6, 140), ("all45", 1600, 8, 130), ("holes", 13000, 30, 128)])
+def test_k2_lockstep_other_feature_lists_vs_coracle(eng, kind, C, G, T):
+    """The lockstep kernel with feature lists other than w6 (general placement / feature / scorer code, run-time list or all 45):
+    against the per-game generic kernel (lanes = 8) and the C oracle."""
+    names = {"8": W6_NAMES + ["max_ht", "jaggedness"], "all45": NAMES, "holes": ["max_ht", "row_trans", "pits", "landing_height"]}[kind]
+    rng = np.random.default_rng(len(names) + C)
+    base = {"landing_height": -4.5, "eroded_cells": 3.4, "row_trans": -3.2, "col_trans": -9.3, "pits": -7.9, "cuml_wells": -3.4, "max_ht": -1.0, "jaggedness": -0.3}
+    w = np.array([[base.get(n, 0.0) for n in names]]) + rng.normal(0, 1.5 if kind != "all45" else 0.4, size=(C, len(names)))
+    fids = [pyoracle.FEATURE_ID[x] for x in names]
+    eng.set_features(names)
+    pieces = np.array([[random.Random(17 * g + 3).randrange(7) for _ in range(T)] for g in range(G)], dtype=np.uint8)
+    a = eng.play_games(w, G, pieces=pieces, want_trace=True, want_scores=True, want_final=True)
+    assert eng.last_timing()["kernels_launched"] == 2 and eng.last_timing()["lanes"] in (1, 2, 4, 8)
+    b = eng.play_games(w, G, pieces=pieces, lanes=8, want_trace=True, want_scores=True, want_final=True)
+    assert (a["results"] == b["results"]).all() and (a["final"] == b["final"]).all() and (a["fitness"] == b["fitness"]).all()
+    for g in range(0, C * G, 53):
+        k = int(a["results"]["pieces"][g])
+        assert a["trace"][g, :k].tobytes() == b["trace"][g, :k].tobytes()
+        assert bits(a["scores"][g, :k]).tobytes() == bits(b["scores"][g, :k]).tobytes()
+    n_o = min(C, 300)
+    o = coracle.play_games(fids, w[:n_o], G, pieces=pieces, threads=16)
+    res = a["results"][:n_o * G]
+    assert (res["pieces"] == o["pieces"]).all() and (res["lines"] == o["lines"]).all()
+    assert (res["score"] == o["score"]).all() and (res["placements"] == o["placements"]).all() and (res["hist"] == o["hist"]).all()
+
+
 def test_k2_lockstep_initial_boards_lines_and_max_moves(eng):
     """K2s with initial boards, lines already cleared and a max_moves stop that is not a stage boundary."""
     rng = np.random.default_rng(3)

@@ -177,9 +177,12 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6grp_kernel(const PlayParam
 // few dozen pieces and they should be re-packed early — then K pieces per stage
 TB_HD uint32_t lock_stage_begin(uint32_t s, uint32_t K) { return s == 0u ? 0u : (s == 1u ? K / 4u : (s == 2u ? K / 2u : K * (s - 2u))); }
 
-template <int LANES>
+// MODE_W6: the fast w6 evaluation.  MODE_ALL45 / MODE_GENERIC: the general placement / feature / scorer code of tetris_core.cuh,
+// weights read through L1 from the candidate's row (they do not fit in registers).
+template <int LANES, int MODE = MODE_W6>
 __global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayParams prm)
 {
+    constexpr bool W6 = MODE == MODE_W6;
     constexpr uint32_t GPW = 32 / LANES;           // games per warp
     __shared__ Tables s_tab;
     load_tables<BLOCK>(s_tab);
@@ -249,14 +252,20 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayPara
                 if (prm.init_lines) lines = prm.init_lines[game];
             }
         }
-        GameStat g = game_stat(c);
-        const int cells0 = g.cells - 4 * (int)t;
+        GameStat g;                                   // w6: heights / cells of the board
+        PrevStat pv; Heights H;                       // general: statistics of the board the piece is placed on
+        int cells0 = 0;
         const uint32_t lines0 = lines;
         double w[6];
-        {
-            const double* wsrc = prm.weights + (size_t)(active ? game / G : 0u) * 6;
+        const double* wrow = prm.weights + (size_t)(active ? game / G : 0u) * (size_t)prm.F;
+        if constexpr (W6) {
+            g = game_stat(c);
+            cells0 = g.cells - 4 * (int)t;
 #pragma unroll
-            for (int i = 0; i < 6; ++i) w[i] = __ldg(wsrc + i);
+            for (int i = 0; i < 6; ++i) w[i] = __ldg(wrow + i);
+        } else {
+            pv = prev_stat(c);
+            H = pack_gh(pv.gh);
         }
         const uint32_t t_next = lock_stage_begin(st + 1u, K);
         const uint32_t t_end = (st + 1 == S || t_next > stop) ? stop : t_next;
@@ -280,12 +289,22 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayPara
             uint64_t key = 0; uint32_t tag = 0;
             for (int s2 = gl; s2 < ns; s2 += LANES) {                    // same piece, same trip count in every lane
                 const SlotDesc d = LANES == 1 ? c_tables.slot[p_u][s2] : load_slot12(s_tab, p_cur, s2);
-                W6Cand A;
-                w6_pre(c, g, d, A);
-                if (A.legal && A.full != 0u) w6_clear(d, A);
-                Heights Hn;
-                const uint64_t k = w6_post(A, w, Hn);
-                cnt += (uint32_t)(A.legal && active);
+                uint64_t k = 0;
+                if constexpr (W6) {
+                    W6Cand A;
+                    w6_pre(c, g, d, A);
+                    if (A.legal && A.full != 0u) w6_clear(d, A);
+                    Heights Hn;
+                    k = w6_post(A, w, Hn);
+                } else {
+                    Placement P;
+                    if (place_slot(c, H, d, P)) {
+                        Feat f;
+                        eval_features<ModeTraits<MODE>::CMASK>(P, d, pv, prm.rmask, f);
+                        k = score_key(score_features<MODE>(f, prm.ids, wrow, prm.F));
+                    }
+                }
+                cnt += (uint32_t)(k != 0ull && active);
                 if (k > key) { key = k; tag = (uint32_t)s2; }
             }
             group_argmax<LANES>(key, tag);
@@ -296,13 +315,21 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayPara
                 } else {
                     const SlotDesc d = load_slot12(s_tab, p_cur, (int)tag);
                     W6Cand A;
-                    w6_pre(c, g, d, A);
-                    if (A.full != 0u) w6_clear(d, A);
+                    if constexpr (W6) {
+                        w6_pre(c, g, d, A);
+                        if (A.full != 0u) w6_clear(d, A);
 #pragma unroll
-                    for (int k = 0; k < COLS; ++k) { c[k] = A.P.n[k]; g.gh[k] = A.h[k]; }
-                    g.H.H0 = (uint32_t)A.h[0] | (uint32_t)A.h[1] << 8 | (uint32_t)A.h[2] << 16 | (uint32_t)A.h[3] << 24;
-                    g.H.H1 = (uint32_t)A.h[4] | (uint32_t)A.h[5] << 8 | (uint32_t)A.h[6] << 16 | (uint32_t)A.h[7] << 24;
-                    g.H.H2 = (uint32_t)A.h[8] | (uint32_t)A.h[9] << 8;
+                        for (int k = 0; k < COLS; ++k) { c[k] = A.P.n[k]; g.gh[k] = A.h[k]; }
+                        g.H.H0 = (uint32_t)A.h[0] | (uint32_t)A.h[1] << 8 | (uint32_t)A.h[2] << 16 | (uint32_t)A.h[3] << 24;
+                        g.H.H1 = (uint32_t)A.h[4] | (uint32_t)A.h[5] << 8 | (uint32_t)A.h[6] << 16 | (uint32_t)A.h[7] << 24;
+                        g.H.H2 = (uint32_t)A.h[8] | (uint32_t)A.h[9] << 8;
+                    } else {
+                        place_slot(c, H, d, A.P);
+#pragma unroll
+                        for (int k = 0; k < COLS; ++k) c[k] = A.P.n[k];
+                        pv = next_stat(pv, A.P, d);
+                        H = pack_gh(pv.gh);
+                    }
                     const uint32_t wk = (uint32_t)A.P.k;
                     if (wk != 0u) {
                         lines += wk;
@@ -310,7 +337,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayPara
                         const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
                         gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
                     }
-                    g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)(lines - lines0);
+                    if constexpr (W6) g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)(lines - lines0);
                     if (gl == 0) {
                         if (prm.trace) {
                             const uint32_t row = (uint32_t)(ROWS - A.P.y - A.P.ph);

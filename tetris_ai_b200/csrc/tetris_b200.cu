@@ -413,7 +413,7 @@ static LockPlan lock_plan(const tb200_ctx* ctx, const tb200_play_args& a, int pe
     const int l = a.lanes;
     const bool lanes_auto = !(l == 1 || l == 2 || l == 4 || l == 8 || l == 16 || l == 32 || l == 64);
     const uint32_t stop_moves = a.max_moves && a.max_moves < a.T ? a.max_moves : a.T;
-    lp.on = ctx->lockstep_enabled && lanes_auto && ctx->mode == tb::MODE_W6 && a.lookahead == 1 && a.move_set == 0 && per_game_weights == 0 &&
+    lp.on = ctx->lockstep_enabled && lanes_auto && a.lookahead == 1 && a.move_set == 0 && per_game_weights == 0 &&
             !a.seq_of_game && a.games_per_candidate >= 4 && a.games_per_candidate <= 4096 &&
             (n_games + ctx->sms - 1) / ctx->sms > 80 && stop_moves >= (uint32_t)(2 * ctx->lock_K);
     if (!lp.on) {
@@ -548,8 +548,19 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
         p.lk_C = (uint32_t)a.n_candidates; p.lk_K = K; p.lk_S = S;
         ctx->lock_flag = p.lk_ctl + (size_t)S * (size_t)a.games_per_candidate * 4 + 3;
         int ll = ctx->lock_lanes;
-        if (ll != 1 && ll != 2 && ll != 4 && ll != 8) ll = per_sm_games <= 320 ? 8 : (per_sm_games <= 760 ? 4 : (per_sm_games <= 1500 ? 2 : 1));   // tools/lock_probe.py
-        tb::play_fn lf = ll == 8 ? tb::play_games_w6lock_kernel<8> : (ll == 4 ? tb::play_games_w6lock_kernel<4> : (ll == 2 ? tb::play_games_w6lock_kernel<2> : tb::play_games_w6lock_kernel<1>));
+        if (ll != 1 && ll != 2 && ll != 4 && ll != 8) {
+            ll = per_sm_games <= 320 ? 8 : (per_sm_games <= 760 ? 4 : (per_sm_games <= 1500 ? 2 : 1));   // tools/lock_probe.py
+            if (ctx->mode != tb::MODE_W6 && ll < 2) ll = 2;     // the general evaluation is register-heavy: two lanes per game (tools/generic_pop_probe.py)
+        }
+        tb::play_fn lf;
+        if (ctx->mode == tb::MODE_W6)
+            lf = ll == 8 ? tb::play_games_w6lock_kernel<8> : (ll == 4 ? tb::play_games_w6lock_kernel<4> : (ll == 2 ? tb::play_games_w6lock_kernel<2> : tb::play_games_w6lock_kernel<1>));
+        else if (ctx->mode == tb::MODE_ALL45)
+            lf = ll == 8 ? tb::play_games_w6lock_kernel<8, tb::MODE_ALL45> : (ll == 4 ? tb::play_games_w6lock_kernel<4, tb::MODE_ALL45> :
+                 (ll == 2 ? tb::play_games_w6lock_kernel<2, tb::MODE_ALL45> : tb::play_games_w6lock_kernel<1, tb::MODE_ALL45>));
+        else
+            lf = ll == 8 ? tb::play_games_w6lock_kernel<8, tb::MODE_GENERIC> : (ll == 4 ? tb::play_games_w6lock_kernel<4, tb::MODE_GENERIC> :
+                 (ll == 2 ? tb::play_games_w6lock_kernel<2, tb::MODE_GENERIC> : tb::play_games_w6lock_kernel<1, tb::MODE_GENERIC>));
         int locc = 0;
         TB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&locc, lf, tb::BLOCK, 0));
         if (locc < 1) locc = 1;
