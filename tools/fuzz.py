@@ -57,7 +57,7 @@ def main():
             C, G, T = rng.randint(300, 700), 1, rng.randint(128, 200)
         if rng.random() < float(os.environ.get("FUZZ_LOCKSTEP", "0.02")):
             # population regime: > 80 games per SM on shared sequences -> the lockstep kernel K2s
-            names, ms_name, la, pressure, lanes = W6, "drop", 1, None, 0
+            names, ms_name, la, pressure, lanes = (W6 if rng.random() < 0.5 else names), "drop", 1, None, 0      # K2s exists for every feature mode
             G = rng.randint(4, 12); C = 12200 // G + rng.randint(0, 300); T = rng.randint(128, 150)
         binned = rng.random() < float(os.environ.get("FUZZ_BINNED", "0.01"))
         if binned:
