@@ -28,11 +28,21 @@
  *     its own device buffers and the call is synchronous) or TB200_MEM_DEVICE (pointers are device
  *     pointers; work is enqueued on `stream`, the call returns without synchronising);
  *   - a ctx is bound to one device, is not thread-safe, and different ctxs are independent;
+ *   - ONE CALL IN FLIGHT PER CTX: every call on a ctx shares one device workspace (game tickets, hand-over lists, queues, the
+ *     staging arena).  TB200_MEM_HOST calls return synchronised.  TB200_MEM_DEVICE calls only enqueue; the library orders
+ *     them itself — a later call on the same ctx, on any stream or in host mode, first waits (on the device, by event) for
+ *     the previous call's last kernel — so two calls never share the workspace, but they also never overlap.  Use one ctx
+ *     per stream for concurrency.  tb200_check_status(ctx) reports a bounded wait that expired inside an enqueued call;
  *   - there is NO CPU fallback: if no CUDA device is usable tb200_create fails with TB200_E_NO_DEVICE.
  *
  * Board exchange format (same as the reference's numpy grid, packed): uint16_t rows[20], rows[0]
  * is the TOP row, bit c of a row is column c.  Piece ids: I,T,L,J,O,Z,S = 0..6 (tetris/game.py:24-34).
- * Feature ids: 0..44 in tetris/features.py source order (see TB200_FEATURE_NAMES in tetris_b200_features.h).
+ * Feature ids: 0..44 in tetris/features.py source order (TB200_F_* and TB200_FEATURE_NAMES in tetris_b200_features.h).
+ *
+ * Limits (refused with TB200_E_BAD_ARG, never approximated): lookahead 1..TB200_MAX_LOOKAHEAD (simulate() accepts any
+ * lookahead > 0, simulator.py:153; the configs use 1 and 2); boards are 20 x 10 (game.py:38 takes any size; every config
+ * uses 20 x 10); weights must be finite with |w| <= 1e300 so that no score is NaN or infinite (all_max's NaN ordering,
+ * simulator.py:130-134, is therefore never exercised; checked for TB200_MEM_HOST, required for TB200_MEM_DEVICE).
  */
 #ifndef TETRIS_B200_H
 #define TETRIS_B200_H
@@ -48,6 +58,7 @@ extern "C" {
 #define TB200_COLS 10
 #define TB200_NUM_FEATURES 45
 #define TB200_MAX_WEIGHTED 48
+#define TB200_MAX_LOOKAHEAD 2
 
 #define TB200_MOVES_DROP            0
 #define TB200_MOVES_OVERHANG_SLIDE  1
@@ -111,6 +122,10 @@ typedef struct {
     double    pressure_move_eff;
     const uint32_t* init_lines;      /* u32[C*G] lines already cleared before the first move (continuing games: the level used
                                         by score and by the pressure filter; results.lines then reports the running total), or NULL */
+    uint32_t  points[5];             /* State.score(points) (game.py:159-164): results.score = sum over moves of points[rows cleared by
+                                        the move] * (level after the move + 1).  All five zero => the reference's default table
+                                        (0, 40, 100, 300, 1200).  points[0] may be non-zero (every non-clearing move then scores). */
+    uint32_t  reserved0;
 } tb200_play_args;
 
 /* timing of the last tb200_play_games call on this ctx (CUDA events on the launching stream) */
@@ -144,6 +159,11 @@ int tb200_set_features(tb200_ctx* ctx, const int32_t* feature_ids, int32_t F);
 /* whole games for a population: C candidates x G games (K2) */
 int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args);
 int tb200_last_timing(tb200_ctx* ctx, tb200_timing* out);
+
+/* Status of the work the last TB200_MEM_DEVICE call enqueued: waits for it (event of its last kernel), then returns TB200_OK, or
+ * TB200_E_CUDA if a CUDA error surfaced or one of the bounded device-side waits of the lockstep / piece-binned schedulers
+ * expired (results incomplete).  TB200_MEM_HOST calls check this themselves before they return. */
+int tb200_check_status(tb200_ctx* ctx);
 
 /* one placement decision per board (K1).  boards u16[N][20]; piece/next u8[N] (next[i] = 255 or
  * next == NULL => no visible second piece); weights f64[N][F] if per_board_weights else f64[1][F].

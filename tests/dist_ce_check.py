@@ -29,7 +29,7 @@ def main():
         seqs.append([r.randrange(7) for _ in range(ce["T"])])
     eng = Engine(local)
     local_ev = PopulationEvaluator(eng, feats, ce["games"], pieces=np.array(seqs, dtype=np.uint8))
-    ev = ShardedEvaluator(local_ev.evaluate, device=dev)
+    ev = ShardedEvaluator(local_ev, device=dev)          # device path: play -> all-gather of the device fitness -> one D2H
     gen = cross_entropy(feats, ce["stdev"], ce["width"], ce["keep"], random.Random(ce["rng_seed"]), ev.test_f, map_f=ev.map_f)
     ok = True
     for want in ce["generations"]:

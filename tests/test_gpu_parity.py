@@ -34,7 +34,7 @@ def bits(a):
 def assert_same_doubles(got, want, what=""):
     got = np.asarray(got, dtype=np.float64)
     want = np.asarray(want, dtype=np.float64)
-    ok = (bits(got) == bits(want)) | ((got == 0.0) & (want == 0.0))
+    ok = bits(got) == bits(want)              # strict: the sign of a zero counts too (the scorer never yields -0.0, tetris_core.cuh score_key)
     assert ok.all(), (what, np.argwhere(~ok)[:5], got[~ok][:5], want[~ok][:5])
 
 

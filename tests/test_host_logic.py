@@ -200,6 +200,37 @@ dist.destroy_process_group()
     assert r0["refits"] == want
 
 
+def test_sharded_evaluator_detects_desync_and_bad_keys(tmp_path):
+    """world_size 2 over gloo: ranks that sample different populations (different seeds) must raise, not refit silently;
+    a weights mapping whose key order differs from the evaluator's feature order must raise on every rank."""
+    script = tmp_path / "w2bad.py"
+    script.write_text('''
+import os, sys, random
+sys.path.insert(0, %r)
+import numpy as np
+import torch.distributed as dist
+from tetris_ai_b200.learning import ShardedEvaluator, cross_entropy
+dist.init_process_group("gloo")
+ev = ShardedEvaluator(lambda w: w.sum(axis=1), names=["a", "b", "c"])
+try:
+    ev.test_f({"a": 1.0, "c": 2.0, "b": 3.0})
+    print("KEYS_NOT_CHECKED")
+except ValueError:
+    print("KEYS_OK")
+gen = cross_entropy(["a", "b", "c"], 5.0, 8, 2, random.Random(3 + dist.get_rank()), ev.test_f, map_f=ev.map_f)
+try:
+    next(gen)
+    print("DESYNC_NOT_DETECTED")
+except RuntimeError as e:
+    print("DESYNC_OK" if "different weight batches" in str(e) else "OTHER %%s" %% e)
+dist.destroy_process_group()
+''' % (ROOT,))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29573", str(script)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.count("KEYS_OK") == 2 and out.stdout.count("DESYNC_OK") == 2, out.stdout
+
+
 def test_unmodified_reference_driver_with_evaluator_adapter(golden_ce):
     """INTEGRATION.md §1: the UNMODIFIED cogworks.learning.cross_entropy drives the batching adapter with the
     reference's own feature objects as mapping keys (evaluation by the C oracle here; by the GPU in test_gpu_api)."""
@@ -224,3 +255,101 @@ def test_unmodified_reference_driver_with_evaluator_adapter(golden_ce):
     mean, std = next(gen)
     assert [float(v).hex() for v in mean.values()] == ce["generations"][0]["mean"]
     assert [float(v).hex() for v in std.values()] == ce["generations"][0]["std"]
+
+
+class _SimFakeEngine:
+    """Engine stand-in for simulate(): one game per call, played by the C oracle (a checker, fine in tests)."""
+
+    def __init__(self):
+        self.launches = 0
+
+    def set_features(self, feats):
+        from oracle import pyoracle
+        self.fids = [pyoracle.FEATURE_ID[getattr(f, "__name__", f)] for f in feats]
+
+    def play_games(self, weights, G, pieces=None, lookahead=1, max_moves=0, init_rows=None, init_lines=0, **kw):
+        from oracle import coracle
+        self.launches += 1
+        o = coracle.play_one(self.fids, weights[0], pieces[0], lookahead=lookahead, init_rows=init_rows[0], init_lines=init_lines)
+        n = min(o["pieces"], max_moves) if max_moves else o["pieces"]
+        trace = np.zeros((1, pieces.shape[1], 4), dtype=np.uint8)
+        trace[0, :n] = o["trace"][:n]
+        return {"results": {"pieces": np.array([n])}, "trace": trace}
+
+
+@pytest.mark.parametrize("mode", ["stream", "chunk1"])
+def test_simulate_piece_consumption_matches_reference(mode):
+    """the reference pulls exactly `lookahead` pieces per move from zoid_gen (simulator.py:156).  With a PieceStream
+    (push-back) or chunk=1 a generator shared between successive games is left exactly where the reference leaves it
+    (counts and the next game's first piece from tests/golden/r2_extra.json, generated from the unmodified reference)."""
+    import collections
+    from conftest import load_golden
+    from oracle import pyoracle
+    from tetris_ai_b200.tetris import features as F
+    from tetris_ai_b200.tetris import simulator as sim
+    from tetris_ai_b200.tetris.game import Board, State, PIECES
+    for case in load_golden("r2_extra.json")["consumption"]:
+        eng = _SimFakeEngine()
+        pulled = [0]
+
+        def source():
+            for i in pyoracle.piece_sequence(case["seed"], case["total"]):
+                pulled[0] += 1
+                yield PIECES[i]
+        src = sim.PieceStream(source()) if mode == "stream" else source()
+        policy = sim.policy_best(sim.linear_scorer(collections.OrderedDict((getattr(F, n), w) for n, w in case["weights"])), sim.tie_first)
+        kw = {"chunk": 16} if mode == "stream" else {"chunk": 1}
+        gen = sim.simulate(State(None, Board(20, 10)), src, sim.move_drop, policy, lookahead=case["lookahead"], engine=eng, **kw)
+        moves = 0
+        for _ in gen:
+            moves += 1
+            if case["stop_after"] is not None and moves == case["stop_after"]:
+                break
+        gen.close()
+        assert moves == case["moves"], case
+        if mode == "chunk1":
+            assert pulled[0] == case["consumed"], (case, pulled[0])
+        gen2 = sim.simulate(State(None, Board(20, 10)), src, sim.move_drop, policy, lookahead=case["lookahead"], engine=eng, **kw)
+        first = next(gen2, None)
+        gen2.close()
+        assert (None if first is None else first.delta.zoid.name) == case["second_game_first_piece"], case
+
+
+def test_state_score_custom_points_matches_reference():
+    """State.score(points) (game.py:159-164) of the host State replay, custom tables incl. points[0] != 0."""
+    from conftest import load_golden
+    from oracle import pyoracle
+    from tetris_ai_b200.tetris.game import Board, State, PIECES
+    games = load_golden("games.json")["games"]
+    for rec in load_golden("r2_extra.json")["points"]:
+        g = games[rec["game"]]
+        ids = pyoracle.piece_sequence(g["seed"], g["T"])
+        tr = bytes.fromhex(g["trace_hex"])
+        st = State(None, Board(20, 10))
+        for t in range(g["pieces"]):
+            st = st.future(PIECES[ids[t]], tr[4 * t], tr[4 * t + 1], tr[4 * t + 2])
+        for pts, want in rec["scores"]:
+            assert st.score(points=tuple(pts)) == want
+
+
+def test_host_board_other_sizes_and_device_refusal():
+    """game.py:38-45 takes any size; the host model follows, the device boundary (rows16) refuses anything but 20 x 10."""
+    from tetris_ai_b200.tetris.game import Board, State, zoids
+    b = Board(8, 6)
+    assert b.rows() == 8 and b.cols() == 6 and b.data.shape == (8, 6)
+    st = State(None, b).future(zoids.classic.O, 0, 6, 0).future(zoids.classic.O, 0, 6, 2).future(zoids.classic.O, 0, 6, 4)
+    assert st.lines_cleared() == 2 and st.cleared[2] == 1 and st.board.masks == [0] * 8
+    st2 = pickle.loads(pickle.dumps(st))
+    assert st2.board.rows() == 8 and st2.board.masks == st.board.masks and st2.score() == st.score() == 100
+    with pytest.raises(ValueError):
+        b.rows16()
+
+
+def test_features_header_matches_tables():
+    from oracle import pyoracle
+    from tetris_ai_b200.tetris import features as F
+    h = open(os.path.join(ROOT, "include", "tetris_b200_features.h")).read()
+    ids = {m.group(1).lower(): int(m.group(2)) for m in re.finditer(r"TB200_F_([A-Z0-9_]+?)\s*=\s*(\d+),", h)}
+    assert ids == dict(F.FEATURE_ID) == dict(pyoracle.FEATURE_ID)
+    names = re.findall(r'"([a-z0-9_]+)"', h[h.index("TB200_FEATURE_NAMES {"):h.index("TB200_W6_FEATURE_IDS")])
+    assert names[:45] == list(F.FEATURE_NAMES)

@@ -34,6 +34,7 @@ class PlayArgs(ctypes.Structure):
         ("move_set", ctypes.c_int32), ("pressure_two_but_rot", ctypes.c_int32),
         ("pressure_avg_lat", ctypes.c_double), ("pressure_resp_time", ctypes.c_double), ("pressure_move_eff", ctypes.c_double),
         ("init_lines", ctypes.c_void_p),
+        ("points", ctypes.c_uint32 * 5), ("reserved0", ctypes.c_uint32),
     ]
 
 
@@ -57,6 +58,7 @@ EXPORTS = (
     "tb200_create", "tb200_destroy", "tb200_last_error", "tb200_version", "tb200_device_info",
     "tb200_set_features", "tb200_play_games", "tb200_last_timing", "tb200_best_move", "tb200_best_move_ex",
     "tb200_eval_features", "tb200_eval_features_at", "tb200_hashed_pieces", "tb200_alloc_pinned", "tb200_free_pinned",
+    "tb200_check_status",
 )
 
 _LIB = None
@@ -89,6 +91,8 @@ def load():
     L.tb200_play_games.restype = ctypes.c_int
     L.tb200_last_timing.argtypes = [vp, ctypes.POINTER(Timing)]
     L.tb200_last_timing.restype = ctypes.c_int
+    L.tb200_check_status.argtypes = [vp]
+    L.tb200_check_status.restype = ctypes.c_int
     L.tb200_best_move.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
     L.tb200_best_move.restype = ctypes.c_int
     L.tb200_best_move_ex.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, i32, i32, ctypes.POINTER(MoveOpts), vp, vp, vp, vp]

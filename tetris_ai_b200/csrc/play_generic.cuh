@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_kernel(const PlayParams prm)
                 pv = next_stat(pv, P, d1); H = pack_gh(pv.gh);
                 lines += (uint32_t)P.k;
                 h1 += P.k == 1; h2 += P.k == 2; h3 += P.k == 3; h4 += P.k == 4;
-                const uint32_t pts = P.k == 0 ? 0u : (P.k == 1 ? 40u : (P.k == 2 ? 100u : (P.k == 3 ? 300u : 1200u)));
+                const uint32_t pts = prm.pts[P.k];
                 gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);          // game.py:159-164
                 if (gl == 0) {
                     if (prm.trace) {
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_w32_kernel(const PlayParams 
             }
             lines += wk;
             h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
-            const uint32_t pts = wk == 0 ? 0u : (wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u)));
+            const uint32_t pts = prm.pts[wk];
             gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
             if (lane == 0) {
                 if (prm.trace) {

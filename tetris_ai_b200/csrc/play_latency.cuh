@@ -173,9 +173,9 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayPara
             if (wk != 0u) {
                 lines += wk;
                 h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
-                const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
+                const uint32_t pts = prm.pts[wk];
                 gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
-            }
+            } else if (prm.pts[0] != 0u) gscore += (uint64_t)prm.pts[0] * (uint64_t)(lines / 10u + 1u);      // State.score(points) with points[0] != 0
             g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)(lines - lines0);
             if (prm.trace && lane == 0) {
                 const uint32_t wy = info & 255u, wph = info >> 24;
@@ -365,9 +365,9 @@ __global__ void __launch_bounds__(64) play_games_w6pair_kernel(const PlayParams 
             if (wk != 0u) {
                 lines += wk;
                 h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
-                const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
+                const uint32_t pts = prm.pts[wk];
                 gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
-            }
+            } else if (prm.pts[0] != 0u) gscore += (uint64_t)prm.pts[0] * (uint64_t)(lines / 10u + 1u);      // State.score(points) with points[0] != 0
             g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)(lines - lines0);
             if ((prm.trace != nullptr || prm.score_trace != nullptr) && threadIdx.x == 0) {     // uniform test first: no divergent region per piece when nothing is traced
                 if (prm.trace) {

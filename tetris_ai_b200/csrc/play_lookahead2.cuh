@@ -178,9 +178,9 @@ __global__ void __launch_bounds__(BLOCK) play_games_l2flat_kernel(const PlayPara
             if (wk != 0u) {
                 lines += wk;
                 h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
-                const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
+                const uint32_t pts = prm.pts[wk];
                 gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
-            }
+            } else if (prm.pts[0] != 0u) gscore += (uint64_t)prm.pts[0] * (uint64_t)(lines / 10u + 1u);      // State.score(points) with points[0] != 0
             if (lane == 0) {
                 if (prm.trace) {
                     const uint32_t row = (uint32_t)(ROWS - P.y - P.ph);

@@ -125,9 +125,9 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6grp_kernel(const PlayParam
                 if (wk != 0u) {
                     lines += wk;
                     h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
-                    const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
+                    const uint32_t pts = prm.pts[wk];
                     gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
-                }
+                } else if (prm.pts[0] != 0u) gscore += (uint64_t)prm.pts[0] * (uint64_t)(lines / 10u + 1u);      // State.score(points) with points[0] != 0
                 g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)(lines - lines0);
                 if (gl == 0) {
                     if (prm.trace) {
@@ -334,9 +334,9 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayPara
                     if (wk != 0u) {
                         lines += wk;
                         h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
-                        const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
+                        const uint32_t pts = prm.pts[wk];
                         gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
-                    }
+                    } else if (prm.pts[0] != 0u) gscore += (uint64_t)prm.pts[0] * (uint64_t)(lines / 10u + 1u);      // State.score(points) with points[0] != 0
                     if constexpr (W6) g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)(lines - lines0);
                     if (gl == 0) {
                         if (prm.trace) {
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6bin_kernel(const PlayParam
     const size_t ring_stride = (size_t)prm.pb_mask + 1;
     const uint32_t warp_id = (blockIdx.x * BLOCK + threadIdx.x) >> 5;
     unsigned long long* const fin_ctr = prm.pb_ctl + 16 * PB_SHARDS;
-    uint32_t idle = 0, probe = 0;
+    uint32_t idle = 0, probe = 0, hsum = 0, last_hsum = 0;
     unsigned long long last_fin = 0;
 
     for (;;) {
@@ -492,14 +492,18 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6bin_kernel(const PlayParam
         const uint32_t score = (lane < 7 && a32 != 0u) ? (1u << 20) + ((a32 >= GPW ? GPW : a32) << 8 | ((uint32_t)(lane + warp_id) % 7u)) : 0u;
         const uint32_t best = __reduce_max_sync(FULLMASK, score);
         if (best == 0u) {
+            hsum += __reduce_add_sync(FULLMASK, lane < 7 ? (uint32_t)hd : 0u);       // queue heads seen during this sweep: they advance whenever a piece is played
             if (++probe < PB_SHARDS) continue;                       // try the other shards before idling
             probe = 0;
             // nothing waiting anywhere: done when every game has finished, otherwise other warps are still playing
             const unsigned long long fin = *(volatile unsigned long long*)fin_ctr;
             if (fin >= (unsigned long long)prm.n_games) break;
             __nanosleep(1000);
-            if ((++idle & 255u) == 0u && fin != last_fin) { last_fin = fin; idle = 0; }      // progress elsewhere: keep waiting
-            if (idle > (1u << 16)) { if (lane == 0) atomicExch(fin_ctr + 1, 1ull); break; }    // ~4 s without any game finishing
+            // progress = PIECES played anywhere (some queue head moved) or games finished, not games finished alone: a long
+            // tail of a few surviving games with a large cap keeps every idle warp waiting instead of raising the flag
+            if (hsum != last_hsum || fin != last_fin) { last_hsum = hsum; last_fin = fin; idle = 0; }
+            hsum = 0;
+            if (++idle > (1u << 16)) { if (lane == 0) atomicExch(fin_ctr + 1, 1ull); break; }    // seconds without a single piece played anywhere
             continue;
         }
         const int owner = __ffs((int)__ballot_sync(FULLMASK, score == best)) - 1;      // lane = piece type
@@ -587,9 +591,9 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6bin_kernel(const PlayParam
                 if (wk != 0u) {
                     lines += wk;
                     h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
-                    const uint32_t pts = wk == 1 ? 40u : (wk == 2 ? 100u : (wk == 3 ? 300u : 1200u));
+                    const uint32_t pts = prm.pts[wk];
                     gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
-                }
+                } else if (prm.pts[0] != 0u) gscore += (uint64_t)prm.pts[0] * (uint64_t)(lines / 10u + 1u);      // State.score(points) with points[0] != 0
                 if (gl == 0) {
                     if (prm.trace) {
                         const uint32_t row = (uint32_t)(ROWS - A.P.y - A.P.ph);

@@ -223,6 +223,10 @@ struct tb200_ctx {
     int stage_cut1 = 0, stage_cut2 = 0;  // hand-over thresholds (games still unfinished): 4 and 2 per SM unless TB200_STAGE_CUTS=a,b
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // one call in flight per ctx: `busy` is recorded after the last kernel of every call; the next call makes its stream wait for it
+    cudaEvent_t busy = nullptr;
+    bool busy_recorded = false;
+    bool seq_major = true;               // TB200_NO_SEQ_MAJOR clears it (read once at tb200_create)
     bool timing_valid = false;
     bool kernel_events_valid = true;     // false after a graph replay: ev[0] / ev[1] were not recorded by it
     tb200_timing timing{};
@@ -269,9 +273,29 @@ static bool is_pinned(const void* p)
     return at.type == cudaMemoryTypeHost;
 }
 
+// One call in flight per ctx (include/tetris_b200.h): the stream of a new call first waits for the last kernel of the
+// previous call on this ctx, whatever stream that ran on, because all calls share the ctx workspace.
+static int enter_call(tb200_ctx* ctx, cudaStream_t st)
+{
+    if (ctx->busy_recorded) TB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->busy, 0));
+    return TB200_OK;
+}
+static int leave_call(tb200_ctx* ctx, cudaStream_t st)
+{
+    TB_CUDA(ctx, cudaEventRecord(ctx->busy, st));
+    ctx->busy_recorded = true;
+    return TB200_OK;
+}
+// before any workspace buffer is freed or reallocated: nothing enqueued on this ctx may still use it
+static void quiesce(tb200_ctx* ctx)
+{
+    if (ctx->busy_recorded && cudaEventSynchronize(ctx->busy) != cudaSuccess) cudaGetLastError();
+}
+
 static int ensure_arena(tb200_ctx* ctx, size_t bytes)
 {
     if (bytes <= ctx->arena_cap) return TB200_OK;
+    quiesce(ctx);
     drop_graph(ctx);
     if (ctx->d_arena) { TB_CUDA(ctx, cudaFree(ctx->d_arena)); ctx->d_arena = nullptr; ctx->arena_cap = 0; }
     const size_t cap = bytes + bytes / 4 + (1u << 20);
@@ -316,6 +340,7 @@ int tb200_create(int device, tb200_ctx** out)
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_stage, 256 + (size_t)ctx->stage_cap * (2 * sizeof(uint32_t) + sizeof(tb::GameSave)));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->busy, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         fprintf(stderr, "tb200_create: %s\n", cudaGetErrorString(e));
         tb200_destroy(ctx);
@@ -325,6 +350,7 @@ int tb200_create(int device, tb200_ctx** out)
     if (getenv("TB200_NO_STAGES")) ctx->staging_enabled = false;
     if (getenv("TB200_NO_LOCKSTEP")) ctx->lockstep_enabled = false;
     if (getenv("TB200_NO_BINS")) ctx->bin_enabled = false;
+    if (getenv("TB200_NO_SEQ_MAJOR")) ctx->seq_major = false;
     if (const char* e5 = getenv("TB200_BIN_LANES")) ctx->bin_lanes = atoi(e5);
     if (const char* e6 = getenv("TB200_BIN_MIN_GAMES")) { const long long v = atoll(e6); if (v >= 1024) ctx->bin_min_games = v; }
     if (const char* e3 = getenv("TB200_LOCK_LANES")) ctx->lock_lanes = atoi(e3);
@@ -356,6 +382,7 @@ void tb200_destroy(tb200_ctx* ctx)
     if (ctx->d_lock) cudaFree(ctx->d_lock);
     if (ctx->d_arena) cudaFree(ctx->d_arena);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->busy) cudaEventDestroy(ctx->busy);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -442,6 +469,7 @@ static int ensure_lock_ws(tb200_ctx* ctx, const tb200_play_args& a)
 {
     const LockPlan lp = lock_plan(ctx, a, 0);
     if (!lp.on || lp.b_save + lp.b_list + lp.b_ctl <= ctx->lock_cap) return TB200_OK;
+    quiesce(ctx);
     drop_graph(ctx);
     if (ctx->d_lock) { TB_CUDA(ctx, cudaFree(ctx->d_lock)); ctx->d_lock = nullptr; ctx->lock_cap = 0; }
     const size_t cap = (lp.b_save + lp.b_list + lp.b_ctl) * 5 / 4;
@@ -492,12 +520,17 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
     p.ticket = ctx->d_ticket; p.seed = a.seed; p.rmask = ctx->rmask; p.n_games = n_games; p.T = a.T;
     p.max_moves = a.max_moves ? a.max_moves : a.T; p.G = a.games_per_candidate; p.F = ctx->F;
     p.per_game_weights = per_game_weights;
-    if (per_game_weights == 0 && !a.seq_of_game && a.games_per_candidate > 1 && !getenv("TB200_NO_SEQ_MAJOR")) p.seq_major_C = (uint32_t)a.n_candidates;
+    if (per_game_weights == 0 && !a.seq_of_game && a.games_per_candidate > 1 && ctx->seq_major) p.seq_major_C = (uint32_t)a.n_candidates;
     p.move_set = move_set;
     p.press.on = (move_set & TB200_MOVES_PRESSURE) ? 1 : 0;
     p.press.two_but_rot = a.pressure_two_but_rot ? 1 : 0;
     p.press.avg_lat = a.pressure_avg_lat; p.press.resp_time = a.pressure_resp_time; p.press.move_eff = a.pressure_move_eff;
     memcpy(p.ids, ctx->ids, sizeof p.ids);
+    {
+        static const uint32_t default_pts[5] = {0u, 40u, 100u, 300u, 1200u};          // game.py:159
+        const bool custom = (a.points[0] | a.points[1] | a.points[2] | a.points[3] | a.points[4]) != 0u;
+        memcpy(p.pts, custom ? a.points : default_pts, sizeof p.pts);
+    }
 
     // Latency regime (between 2 and 16 games per SM, w6, lookahead 1, automatic lanes): the kernel time is the serial chain
     // of the longest games, and a game's per-piece latency depends on how many other live games share its warp scheduler
@@ -613,6 +646,13 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
     return TB200_OK;
 }
 
+// Limits (include/tetris_b200.h): no NaN / infinite score can arise from weights that pass this
+static bool weights_ok(const double* w, size_t n)
+{
+    for (size_t i = 0; i < n; ++i) if (!(w[i] >= -1e300 && w[i] <= 1e300)) return false;
+    return true;
+}
+
 static int check_play_args(tb200_ctx* ctx, const tb200_play_args* a)
 {
     if (!a || a->struct_size != sizeof(tb200_play_args)) return fail(ctx, TB200_E_BAD_ARG, "play_games: bad struct_size");
@@ -621,7 +661,7 @@ static int check_play_args(tb200_ctx* ctx, const tb200_play_args* a)
     if ((long long)a->n_candidates * a->games_per_candidate > 0x7fffffffLL) return fail(ctx, TB200_E_BAD_ARG, "play_games: too many games");
     if (!a->weights || !a->results) return fail(ctx, TB200_E_BAD_ARG, "play_games: weights and results are required");
     if (a->T < 1) return fail(ctx, TB200_E_BAD_ARG, "play_games: T must be >= 1");
-    if (a->lookahead != 1 && a->lookahead != 2) return fail(ctx, TB200_E_BAD_ARG, "play_games: lookahead must be 1 or 2");
+    if (a->lookahead < 1 || a->lookahead > TB200_MAX_LOOKAHEAD) return fail(ctx, TB200_E_BAD_ARG, "play_games: lookahead must be 1 or 2 (TB200_MAX_LOOKAHEAD)");
     if (a->pieces && a->n_sequences < 1) return fail(ctx, TB200_E_BAD_ARG, "play_games: n_sequences must be >= 1 with explicit pieces");
     if (a->pieces && !a->seq_of_game && a->n_sequences < a->games_per_candidate) return fail(ctx, TB200_E_BAD_ARG, "play_games: need S >= G without seq_of_game");
     if (a->mem != TB200_MEM_HOST && a->mem != TB200_MEM_DEVICE) return fail(ctx, TB200_E_BAD_ARG, "play_games: bad mem");
@@ -648,7 +688,11 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
     ctx->timing_valid = false;
     int launches = 0;
     if (a.mem == TB200_MEM_DEVICE) {
+        rc = enter_call(ctx, (cudaStream_t)a.stream);
+        if (rc) return rc;
         rc = launch_play(ctx, a, (cudaStream_t)a.stream, 0, &launches);
+        if (rc) return rc;
+        rc = leave_call(ctx, (cudaStream_t)a.stream);
         if (rc) return rc;
         ctx->timing.kernels_launched = launches;
         ctx->timing_valid = true;
@@ -657,6 +701,7 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
     }
     // ---- host buffers: stage through the ctx arena on the ctx's own stream; synchronous ----------
     cudaStream_t st = ctx->own_stream;
+    if (!weights_ok(a.weights, (size_t)a.n_candidates * ctx->F)) return fail(ctx, TB200_E_BAD_ARG, "play_games: weights must be finite with |w| <= 1e300");
     const size_t b_w = sizeof(double) * (size_t)a.n_candidates * ctx->F;
     const size_t b_p = a.pieces ? (size_t)a.n_sequences * a.T : 0;
     const size_t b_s = a.seq_of_game ? sizeof(int32_t) * n_games : 0;
@@ -707,6 +752,9 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
         return TB200_OK;
     };
     bool kernel_events = true;
+    rc = enter_call(ctx, st);                  // outside any capture: a device-mode call may still be running on another stream
+    if (rc) return rc;
+    ctx->busy_recorded = false;                // this call ends synchronised
     TB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     // ---- graph replay: identical call (same pinned buffers, sizes, options, feature list) as last time ----
     const bool same = ctx->graph_valid && memcmp(&ctx->graph_args, &a, sizeof a) == 0 && ctx->graph_F == ctx->F &&
@@ -762,6 +810,19 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
     return TB200_OK;
 }
 
+int tb200_check_status(tb200_ctx* ctx)
+{
+    if (!ctx) return TB200_E_BAD_ARG;
+    TB_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->busy_recorded) TB_CUDA(ctx, cudaEventSynchronize(ctx->busy));
+    if (ctx->lock_flag) {
+        uint32_t flag = 0;
+        TB_CUDA(ctx, cudaMemcpy(&flag, ctx->lock_flag, sizeof flag, cudaMemcpyDeviceToHost));
+        if (flag) return fail(ctx, TB200_E_CUDA, "check_status: a bounded device-side wait of the lockstep / piece-binned scheduler expired (results incomplete)");
+    }
+    return TB200_OK;
+}
+
 int tb200_best_move(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
                     const uint16_t* boards, const uint8_t* piece, const uint8_t* next,
                     const double* weights, int32_t per_board_weights, int32_t lookahead,
@@ -786,7 +847,7 @@ int tb200_best_move_ex(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
     const uint32_t* lines = opts ? opts->lines : nullptr;
     if (ctx->F <= 0) return fail(ctx, TB200_E_NO_FEATURES, "best_move: call tb200_set_features first");
     if (N < 1 || !boards || !piece || !weights || !out_move) return fail(ctx, TB200_E_BAD_ARG, "best_move: missing argument");
-    if (lookahead != 1 && lookahead != 2) return fail(ctx, TB200_E_BAD_ARG, "best_move: lookahead must be 1 or 2");
+    if (lookahead < 1 || lookahead > TB200_MAX_LOOKAHEAD) return fail(ctx, TB200_E_BAD_ARG, "best_move: lookahead must be 1 or 2 (TB200_MAX_LOOKAHEAD)");
     if (mem != TB200_MEM_HOST && mem != TB200_MEM_DEVICE) return fail(ctx, TB200_E_BAD_ARG, "best_move: bad mem");
     TB_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool host = mem == TB200_MEM_HOST;
@@ -801,8 +862,12 @@ int tb200_best_move_ex(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
                  o_w = take(host ? sizeof(double) * nw * ctx->F : 0), o_mv = take(host ? 4 * n : 0),
                  o_sc = take(host && out_score ? 8 * n : 0), o_ct = take(host && out_count ? 4 * n : 0),
                  o_rows = take(host && out_rows ? 40 * n : 0), o_ln = take(host && lines ? 4 * n : 0);
+    if (host && !weights_ok(weights, nw * (size_t)ctx->F)) return fail(ctx, TB200_E_BAD_ARG, "best_move: weights must be finite with |w| <= 1e300");
     int rc = ensure_arena(ctx, off);
     if (rc) return rc;
+    rc = enter_call(ctx, st);
+    if (rc) return rc;
+    ctx->lock_flag = nullptr;
     char* base = ctx->d_arena;
     const uint16_t* d_boards = boards; const uint8_t* d_piece = piece; const uint8_t* d_next = next; const double* d_w = weights;
     uint8_t* d_mv = out_move; double* d_sc = out_score; uint32_t* d_ct = out_count; uint16_t* d_rows = out_rows;
@@ -850,8 +915,10 @@ int tb200_best_move_ex(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
         if (out_count) TB_CUDA(ctx, cudaMemcpyAsync(out_count, d_ct, 4 * n, cudaMemcpyDeviceToHost, st));
         if (out_rows) TB_CUDA(ctx, cudaMemcpyAsync(out_rows, d_rows, 40 * n, cudaMemcpyDeviceToHost, st));
         TB_CUDA(ctx, cudaStreamSynchronize(st));
+        ctx->busy_recorded = false;
+        return TB200_OK;
     }
-    return TB200_OK;
+    return leave_call(ctx, st);
 }
 
 int tb200_eval_features_at(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
@@ -875,6 +942,8 @@ int tb200_eval_features_at(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
                  o_ar = take(row ? n : 0);
     int rc = ensure_arena(ctx, off);
     if (rc) return rc;
+    rc = enter_call(ctx, st);
+    if (rc) return rc;
     char* base = ctx->d_arena;
     TB_CUDA(ctx, cudaMemcpyAsync(base + o_b, prev_boards, 40 * n, cudaMemcpyHostToDevice, st));
     TB_CUDA(ctx, cudaMemcpyAsync(base + o_p, piece, n, cudaMemcpyHostToDevice, st));
@@ -889,6 +958,7 @@ int tb200_eval_features_at(tb200_ctx* ctx, int32_t mem, void* stream, int32_t N,
     TB_CUDA(ctx, cudaMemcpyAsync(out_info, base + o_i, 12 * n, cudaMemcpyDeviceToHost, st));
     if (out_rows) TB_CUDA(ctx, cudaMemcpyAsync(out_rows, base + o_rows, 40 * n, cudaMemcpyDeviceToHost, st));
     TB_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->busy_recorded = false;
     return TB200_OK;
 }
 
@@ -915,10 +985,13 @@ int tb200_hashed_pieces(tb200_ctx* ctx, int32_t mem, void* stream, uint64_t seed
     int rc = ensure_arena(ctx, total);
     if (rc) return rc;
     cudaStream_t st = ctx->own_stream;
+    rc = enter_call(ctx, st);
+    if (rc) return rc;
     tb::hashed_pieces_kernel<<<grid, 256, 0, st>>>(seed, first_stream, n_streams, T, (uint8_t*)ctx->d_arena);
     TB_CUDA(ctx, cudaGetLastError());
     TB_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_arena, total, cudaMemcpyDeviceToHost, st));
     TB_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->busy_recorded = false;
     return TB200_OK;
 }
 

@@ -777,11 +777,14 @@ TB_HD double score_features(const Feat& f, const uint8_t* ids, const double* w, 
     return acc;
 }
 
-// order-preserving map double -> u64 (a < b  <=>  key(a) < key(b)); -0.0 is canonicalised to +0.0
-// first so that it ties with +0.0 exactly as Python's `<` does (simulator.py:130,134).
+// order-preserving map double -> u64 (a < b  <=>  key(a) < key(b)) for every score the canonical scorer can produce.
+// The one pair of doubles that compares equal with different bits is (-0.0, +0.0) (simulator.py:130,134 use `<`), and the
+// scorer cannot return -0.0: it starts from acc = +0.0 and in round-to-nearest a sum is -0.0 only when BOTH operands are
+// -0.0 ((+0.0) + (-0.0) = +0.0, x + (-x) = +0.0), so by induction acc is never -0.0.  Scores are therefore reported with
+// their exact sign and need no canonicalising add here.  NaN cannot occur either: weights are finite and bounded
+// (include/tetris_b200.h, Limits) and features are small integers.
 TB_HD uint64_t score_key(double s)
 {
-    s = dadd(s, 0.0);
 #if defined(__CUDA_ARCH__)
     const uint64_t b = (uint64_t)__double_as_longlong(s);
 #else

@@ -32,6 +32,19 @@ def _set_pressure(a, pressure):
     a.pressure_two_but_rot = 1 if pressure.get("two_but_rot", False) else 0
 
 
+def _set_points(a, points):
+    """points: None (the reference's default table) or State.score's `points` argument (game.py:159): five non-negative ints."""
+    if points is None:
+        return
+    pts = [int(x) for x in points]
+    if len(pts) != 5 or any(x < 0 or x >= 2 ** 32 or x != y for x, y in zip(pts, points)):
+        raise EngineError("points must be five non-negative integers below 2**32")
+    if not any(pts):
+        raise EngineError("an all-zero points table cannot be expressed at the C ABI (it selects the default table)")
+    for i, x in enumerate(pts):
+        a.points[i] = x
+
+
 def feature_ids(features):
     """Accepts ids, names, or feature objects carrying __name__ (the reference's protocol, feature.py:23)."""
     out = []
@@ -54,7 +67,6 @@ class Engine:
             raise EngineError("tb200_create(device=%d) failed with code %d: no usable CUDA device "
                               "(this engine has no CPU fallback)" % (device, rc))
         self._h = h
-        self._pinned = []
         self.device = int(device)
         self.features = None
         sms, khz = ctypes.c_int32(), ctypes.c_int32()
@@ -63,23 +75,24 @@ class Engine:
         self.sms, self.clock_khz, self.device_name = sms.value, khz.value, name.value.decode()
 
     def close(self):
+        """Destroy the ctx.  Pinned buffers handed out by pinned_empty() are NOT freed here: each one is released when the
+        last numpy view of it is garbage-collected (weakref.finalize), so arrays that outlive the Engine stay valid."""
         if getattr(self, "_h", None):
             self._L.tb200_destroy(self._h)
             self._h = None
-            for p in self._pinned:
-                self._L.tb200_free_pinned(p)
-            self._pinned = []
 
     def pinned_empty(self, shape, dtype):
-        """numpy array over page-locked host memory owned by this Engine (freed by close()).  Repeating a play_games call on
-        the same pinned buffers lets the library replay it as a CUDA graph."""
+        """numpy array over page-locked host memory.  The allocation lives exactly as long as the arrays that view it (the
+        base object carries a finalizer), independent of this Engine.  Repeating a play_games call on the same pinned
+        buffers lets the library replay it as a CUDA graph."""
+        import weakref
         dtype = np.dtype(dtype)
         n = int(np.prod(shape)) * dtype.itemsize
         p = ctypes.c_void_p()
         if self._L.tb200_alloc_pinned(max(n, 1), ctypes.byref(p)) != 0:
             raise EngineError("tb200_alloc_pinned(%d) failed" % n)
-        self._pinned.append(p)
         buf = (ctypes.c_char * max(n, 1)).from_address(p.value)
+        weakref.finalize(buf, self._L.tb200_free_pinned, ctypes.c_void_p(p.value))      # numpy keeps `buf` alive as the arrays' base
         return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     def __del__(self):
@@ -108,7 +121,7 @@ class Engine:
     # ------------------------------------------------------------------ K2 whole games
     def play_games(self, weights, games_per_candidate, pieces=None, T=None, seq_of_game=None, seed=0, lookahead=1,
                    lanes=0, max_moves=0, init_rows=None, want_trace=False, want_scores=False, want_final=False,
-                   want_fitness=True, out_results=None, out_fitness=None, move_set=0, pressure=None, init_lines=None):
+                   want_fitness=True, out_results=None, out_fitness=None, move_set=0, pressure=None, init_lines=None, points=None):
         """weights f64[C][F] -> dict(results=structured[C*G], fitness=f64[C], trace=..., ...)   (host buffers)."""
         w = np.ascontiguousarray(weights, dtype=np.float64)
         if w.ndim == 1:
@@ -152,6 +165,7 @@ class Engine:
         a.final_rows, a.fitness = _ptr(final), _ptr(fitness)
         a.move_set = int(move_set)
         _set_pressure(a, pressure)
+        _set_points(a, points)
         if init_lines is not None:
             init_lines = np.ascontiguousarray(np.broadcast_to(np.asarray(init_lines, dtype=np.uint32), (n,)), dtype=np.uint32)
             a.init_lines = _ptr(init_lines)
@@ -160,8 +174,10 @@ class Engine:
 
     def play_games_device(self, stream, n_candidates, games_per_candidate, weights_ptr, results_ptr, T, pieces_ptr=0,
                           n_sequences=0, seq_of_game_ptr=0, seed=0, lookahead=1, lanes=0, max_moves=0, init_rows_ptr=0,
-                          trace_ptr=0, score_trace_ptr=0, final_rows_ptr=0, fitness_ptr=0, move_set=0):
-        """All pointers are DEVICE pointers (ints); work is enqueued on `stream` (a cudaStream_t int) and not synchronised."""
+                          trace_ptr=0, score_trace_ptr=0, final_rows_ptr=0, fitness_ptr=0, move_set=0, points=None):
+        """All pointers are DEVICE pointers (ints); work is enqueued on `stream` (a cudaStream_t int) and not synchronised.
+        One call in flight per Engine: the library orders a later call behind this one (see include/tetris_b200.h);
+        check_status() waits for it and reports an expired device-side wait."""
         a = _lib.PlayArgs()
         a.struct_size = ctypes.sizeof(_lib.PlayArgs)
         a.mem = _lib.MEM_DEVICE
@@ -173,7 +189,12 @@ class Engine:
         a.results, a.trace, a.score_trace = results_ptr or None, trace_ptr or None, score_trace_ptr or None
         a.final_rows, a.fitness = final_rows_ptr or None, fitness_ptr or None
         a.move_set = int(move_set)
+        _set_points(a, points)
         self._check(self._L.tb200_play_games(self._h, ctypes.byref(a)))
+
+    def check_status(self):
+        """Wait for the last device-mode call and raise if one of its bounded device-side waits expired."""
+        self._check(self._L.tb200_check_status(self._h))
 
     def last_timing(self):
         t = _lib.Timing()

@@ -129,25 +129,43 @@ def shard_bounds(n, world, rank):
 
 
 class ShardedEvaluator:
-    """Candidate-sharded evaluation across the ranks of a torch.distributed process group.
+    """Candidate-sharded evaluation across the ranks of a torch.distributed process group (learning.py:38-41 on every rank).
 
-    local_eval(weights f64[c][F]) -> fitness f64[c] is the per-rank evaluator (on a GPU box:
-    PopulationEvaluator.evaluate).  The only collective is an all-gather of the fitness vector
-    (NCCL over NVLink when the group's backend is nccl; gloo in the CPU tests).
+    `local` is either
+      * a PopulationEvaluator (GPU ranks): the rank's slice is played with a device-mode call on torch's current stream, the
+        per-candidate fitness stays in HBM, ONE all_gather_into_tensor (NCCL over NVLink) collects f64[C] on every rank and ONE
+        device->host copy brings it back; every buffer is allocated once and reused; or
+      * a callable  weights f64[c][F] -> fitness f64[c]  (the CPU tests drive it with the oracle over gloo).
+    Every rank must run the same seeded driver.  The all-gather carries one extra slot per rank with a checksum of the FULL
+    weight batch, so a desynchronised driver raises instead of silently refitting different populations.
     """
 
-    def __init__(self, local_eval, group=None, device=None):
+    def __init__(self, local, group=None, device=None, names=None):
         import torch.distributed as dist
         self.dist = dist
-        self.local_eval = local_eval
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.device = device
+        self.pop = local if isinstance(local, PopulationEvaluator) else None
+        self.local_eval = None if self.pop is not None else local
+        self.names = list(self.pop.names) if self.pop is not None else ([getattr(f, "__name__", f) for f in names] if names is not None else None)
         self._batch = []
-        self.names = None
+        self._keys_ok = None
+        self._dev = None                      # device-path buffers, keyed by (C, F)
+        self.last_bytes = {"h2d": 0, "d2h": 0}
+        self.last_timing = {}                 # evaluate_ms / allgather_ms / d2h_ms (CUDA events), host_prep_ms, total_ms
+        self.collect_placements = False       # when set, last_timing["placements"] = scored leaves of the local shard (one small reduction)
 
+    # -- the two callables handed to cross_entropy ---------------------------------------------
     def test_f(self, weights):
+        keys = tuple(weights)
+        if keys != self._keys_ok:
+            if self.names is not None:
+                got = [getattr(k, "__name__", k) for k in keys]
+                if got != self.names:
+                    raise ValueError("weights mapping keys %r do not match the evaluator's feature order %r" % (got, self.names))
+            self._keys_ok = keys
         self._batch.append(list(weights.values()))
         return _Pending(len(self._batch) - 1)
 
@@ -157,19 +175,106 @@ class ShardedEvaluator:
         fitness = self.evaluate(np.array(self._batch, dtype=np.float64)).tolist()
         return [(fitness[p.slot], i) for p, i in tagged]
 
-    def evaluate(self, weights):
-        import torch
-        C = weights.shape[0]
-        lo, hi = shard_bounds(C, self.world, self.rank)
-        local = np.asarray(self.local_eval(weights[lo:hi]), dtype=np.float64) if hi > lo else np.zeros(0)
-        per = -(-C // self.world)                                    # padded shard length
-        buf = torch.zeros(per, dtype=torch.float64, device=self.device)
-        buf[: hi - lo] = torch.from_numpy(local).to(buf.device)
-        gathered = torch.empty(per * self.world, dtype=torch.float64, device=self.device)
-        self.dist.all_gather_into_tensor(gathered, buf, group=self.group)
-        g = gathered.cpu().numpy().reshape(self.world, per)
+    # -- batch evaluation ----------------------------------------------------------------------------
+    @staticmethod
+    def _checksum(weights):
+        """48-bit digest of the whole batch as an exactly representable double."""
+        import hashlib
+        return float(int.from_bytes(hashlib.sha256(np.ascontiguousarray(weights, dtype=np.float64).tobytes()).digest()[:6], "little"))
+
+    def _unpack(self, g, C):
+        per = g.shape[1] - 1
+        sums = g[:, per]
+        if not (sums == sums[0]).all():
+            raise RuntimeError("ShardedEvaluator: ranks evaluated different weight batches (checksums %r); every rank must run "
+                               "the same seeded cross_entropy driver" % (sums.tolist(),))
         out = np.empty(C, dtype=np.float64)
         for r in range(self.world):
             a, b = shard_bounds(C, self.world, r)
             out[a:b] = g[r, : b - a]
+        return out
+
+    def evaluate(self, weights):
+        weights = np.asarray(weights, dtype=np.float64)
+        if self.pop is not None and self.device is not None and getattr(self.device, "type", "cpu") == "cuda":
+            return self._evaluate_device(weights)
+        return self._evaluate_host(weights)
+
+    def _evaluate_host(self, weights):
+        import torch
+        C = weights.shape[0]
+        lo, hi = shard_bounds(C, self.world, self.rank)
+        ev = self.local_eval if self.local_eval is not None else self.pop.evaluate
+        local = np.asarray(ev(weights[lo:hi]), dtype=np.float64) if hi > lo else np.zeros(0)
+        per = -(-C // self.world)                                    # padded shard length
+        buf = torch.zeros(per + 1, dtype=torch.float64, device=self.device)
+        buf[: hi - lo] = torch.from_numpy(local).to(buf.device)
+        buf[per] = self._checksum(weights)
+        gathered = torch.empty((per + 1) * self.world, dtype=torch.float64, device=self.device)
+        self.dist.all_gather_into_tensor(gathered, buf, group=self.group)
+        return self._unpack(gathered.cpu().numpy().reshape(self.world, per + 1), C)
+
+    def _buffers(self, C, F):
+        import torch
+        from . import _lib
+        if self._dev is not None and self._dev["key"] == (C, F):
+            return self._dev
+        per = -(-C // self.world)
+        G, dev, pop = self.pop.games, self.device, self.pop
+        d = {"key": (C, F), "per": per,
+             "h_w": torch.empty((per, F), dtype=torch.float64).pin_memory(),
+             "d_w": torch.empty((per, F), dtype=torch.float64, device=dev),
+             "d_res": torch.zeros(per * G * _lib.RESULT_DTYPE.itemsize, dtype=torch.uint8, device=dev),
+             "d_fit": torch.zeros(per + 1, dtype=torch.float64, device=dev),
+             "d_all": torch.empty((per + 1) * self.world, dtype=torch.float64, device=dev),
+             "h_all": torch.empty((per + 1) * self.world, dtype=torch.float64).pin_memory(),
+             "h_pieces": torch.from_numpy(pop.pieces).pin_memory() if pop.pieces is not None else None,
+             "d_pieces": torch.empty(pop.pieces.shape, dtype=torch.uint8, device=dev) if pop.pieces is not None else None,
+             "ev": [torch.cuda.Event(enable_timing=True) for _ in range(4)]}
+        self._dev = d
+        return d
+
+    def _evaluate_device(self, weights):
+        import time
+        import torch
+        t0 = time.perf_counter()
+        pop, eng = self.pop, self.pop.engine
+        C, F = weights.shape
+        lo, hi = shard_bounds(C, self.world, self.rank)
+        c = hi - lo
+        b = self._buffers(C, F)
+        per = b["per"]
+        eng.set_features(pop.names)
+        stream = torch.cuda.current_stream(self.device)
+        b["h_w"].numpy()[:c] = weights[lo:hi]
+        chk = self._checksum(weights)
+        t1 = time.perf_counter()
+        ev = b["ev"]
+        ev[0].record(stream)
+        b["d_w"].copy_(b["h_w"], non_blocking=True)                  # this step's inputs: the rank's weights and the injected piece sequences
+        if b["d_pieces"] is not None:
+            b["d_pieces"].copy_(b["h_pieces"], non_blocking=True)
+        b["d_fit"][per:].fill_(chk)
+        if c > 0:
+            eng.play_games_device(stream.cuda_stream, c, pop.games, b["d_w"].data_ptr(), b["d_res"].data_ptr(), pop.T,
+                                  pieces_ptr=b["d_pieces"].data_ptr() if b["d_pieces"] is not None else 0,
+                                  n_sequences=pop.pieces.shape[0] if pop.pieces is not None else 0, seed=pop.seed,
+                                  lookahead=pop.lookahead, lanes=pop.lanes, fitness_ptr=b["d_fit"].data_ptr())
+        ev[1].record(stream)
+        self.dist.all_gather_into_tensor(b["d_all"], b["d_fit"], group=self.group)
+        ev[2].record(stream)
+        b["h_all"].copy_(b["d_all"], non_blocking=True)
+        ev[3].record(stream)
+        ev[3].synchronize()
+        if c > 0:
+            eng.check_status()
+        out = self._unpack(b["h_all"].numpy().reshape(self.world, per + 1), C)
+        self.last_timing = {"host_prep_ms": 1e3 * (t1 - t0), "evaluate_ms": ev[0].elapsed_time(ev[1]), "allgather_ms": ev[1].elapsed_time(ev[2]),
+                            "d2h_ms": ev[2].elapsed_time(ev[3]), "total_ms": 1e3 * (time.perf_counter() - t0), "local_candidates": c}
+        self.last_bytes = {"h2d": c * F * 8 + (pop.pieces.size if pop.pieces is not None else 0), "d2h": (per + 1) * self.world * 8}
+        if self.collect_placements:
+            from . import _lib
+            rec = b["d_res"][: c * pop.games * _lib.RESULT_DTYPE.itemsize].view(torch.int64).view(-1, 5)
+            self.last_timing["placements"] = int(rec[:, 4].sum().item())
+        pop.generations += 1
         return out

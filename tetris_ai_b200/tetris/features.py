@@ -25,16 +25,22 @@ FLOAT_FEATURES = frozenset(["mean_ht", "max_ht_diff", "min_ht_diff", "cuml_clear
 
 
 class Feature:
-    """Hashable handle usable as a weights-mapping key, like the reference's feature functions."""
-    __slots__ = ("__name__", "id")
+    """Hashable handle usable as a weights-mapping key, like the reference's feature functions.
+
+    accesses / misses mirror the counters of the reference's memo wrapper (feature.py:27,31,36-37): `accesses` counts every
+    evaluation request for this feature, `misses` the requests that had to compute it — here, the requests that were not
+    served from the per-evaluation cache of device values (one K3 launch fills all 45 at once)."""
+    __slots__ = ("__name__", "id", "accesses", "misses")
 
     def __init__(self, name, fid):
         self.__name__ = name
         self.id = fid
+        self.accesses = 0
+        self.misses = 0
 
     def __call__(self, state, cache=None):
-        from ..feature import evaluate
-        return evaluate(state, [self])[self]
+        from ..feature import feature_value
+        return feature_value(self, state, cache)
 
     def __repr__(self):
         return "<feature %s #%d>" % (self.__name__, self.id)

@@ -57,8 +57,8 @@ PIECES = tuple(zoids.classic)                     # piece id -> Zoid (I,T,L,J,O,
 
 class Board:
     def __init__(self, rows=20, cols=10, zero=True, masks=None):
-        if (rows, cols) != (20, 10):
-            raise ValueError("the B200 engine is specialised to the 20 x 10 board of the reference configs")
+        if rows < 1 or cols < 1:
+            raise ValueError("a board needs at least one row and one column")
         self._nrows, self._ncols = rows, cols
         self.masks = list(masks) if masks is not None else [0] * rows
         self.heights = self._heights()
@@ -88,6 +88,12 @@ class Board:
         return np.array([[(m >> c) & 1 for c in range(self._ncols)] for m in self.masks], dtype=np.bool_)
 
     def rows16(self):
+        """The board in the exchange format of include/tetris_b200.h.  The host model (replay, scoring, pickling) works for
+        any size like the reference's (game.py:38-45); the device kernels are specialised to the 20 x 10 board every
+        reference config uses, so this — the only way a board reaches the device — refuses other sizes."""
+        if (self._nrows, self._ncols) != (20, 10):
+            raise ValueError("the B200 engine is specialised to the 20 x 10 board of the reference configs (this board is %d x %d)"
+                             % (self._nrows, self._ncols))
         return np.array(self.masks, dtype=np.uint16)
 
     def row(self, r):
@@ -191,11 +197,12 @@ class State:
             d = node.delta
             moves.append((d.zoid.id, d.rot, d.row, d.col))
             node = node.prev
-        return (list(node.board.masks), dict(node.cleared), moves[::-1])
+        return (list(node.board.masks), dict(node.cleared), moves[::-1], (node.board.rows(), node.board.cols()))
 
     def __setstate__(self, saved):
-        masks, hist, moves = saved
-        node = State(None, Board(masks=masks), cleared=collections.defaultdict(int, hist))
+        masks, hist, moves = saved[:3]
+        rows, cols = saved[3] if len(saved) > 3 else (20, 10)
+        node = State(None, Board(rows, cols, masks=masks), cleared=collections.defaultdict(int, hist))
         for pid, rot, row, col in moves:
             node = node.future(PIECES[pid], rot, row, col)
         self.prev, self.board, self.cleared, self.delta = node.prev, node.board, node.cleared, node.delta

@@ -11,6 +11,7 @@ tie_first); anything else raises, because this engine has no CPU fallback.
 """
 from __future__ import annotations
 
+import collections
 import collections.abc
 import itertools
 
@@ -139,10 +140,43 @@ def policy_best(scorer, tie_breaker=tie_first):
     return BestPolicy(scorer, tie_breaker)
 
 
-def simulate(state, zoid_gen, move_gen, move_policy, lookahead=1, engine=None):
-    """Generator of successive States, identical to the reference's for the accepted arguments."""
+class PieceStream:
+    """Iterator with push-back for piece generators that are SHARED between successive simulate() calls.
+
+    The reference's simulate() pulls exactly `lookahead` pieces from zoid_gen per move (simulator.py:156).  This engine
+    hands the device a whole chunk of pieces per launch, so it reads ahead; when zoid_gen is a PieceStream, simulate()
+    returns every piece beyond the reference's own consumption point to it on exit (normal end, game over, or the caller
+    closing the generator), so the next game sees exactly the pieces it would see with the reference.  Plain iterators
+    cannot take pieces back: pass chunk=1 to simulate() for reference-identical consumption, or accept the read-ahead.
+    """
+
+    def __init__(self, iterable):
+        self._it = iter(iterable)
+        self._front = collections.deque()
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self._front:
+            return self._front.popleft()
+        return next(self._it)
+
+    def push_back(self, pieces):
+        self._front.extendleft(reversed(list(pieces)))
+
+
+def simulate(state, zoid_gen, move_gen, move_policy, lookahead=1, engine=None, chunk=None):
+    """Generator of successive States, identical to the reference's for the accepted arguments.
+
+    chunk: pieces handed to the device per launch (default CHUNK).  Read-ahead (documented deviation): up to
+    `chunk` pieces are taken from zoid_gen before each launch, where the reference takes `lookahead` per move.  The
+    yielded States never depend on it.  To keep a shared generator in step with the reference, wrap it in PieceStream
+    (unconsumed pieces are pushed back) or pass chunk=1 (one launch per move, reference-identical consumption).
+    """
     if lookahead not in (1, 2):
-        raise ValueError("lookahead must be 1 or 2")
+        raise ValueError("lookahead must be 1 or 2 on the B200 engine (TB200_MAX_LOOKAHEAD; the reference accepts any lookahead > 0, "
+                         "simulator.py:153, its configs use 1 and 2)")
     pressure = None
     if move_gen is move_drop:
         move_set = 0
@@ -156,28 +190,43 @@ def simulate(state, zoid_gen, move_gen, move_policy, lookahead=1, engine=None):
         raise TypeError("move_policy must come from policy_best(linear_scorer(weights), tie_first)")
     eng = engine or default_engine()
     sc = move_policy.scorer
+    size = max(int(chunk if chunk is not None else CHUNK), 1) + (lookahead - 1)      # pieces per launch incl. the look-ahead piece
+    source = zoid_gen if hasattr(zoid_gen, "push_back") else None
     zoid_gen = iter(zoid_gen)
-    carry = []
-    while True:
-        chunk = carry + list(itertools.islice(zoid_gen, 0, CHUNK - len(carry)))
-        if not chunk:
-            return
-        more = len(chunk) == CHUNK
-        # with lookahead 2 the last piece of a non-final chunk is only looked at, not placed
-        commit = len(chunk) - 1 if (more and lookahead == 2) else len(chunk)
-        ids = np.array([[z.id for z in chunk]], dtype=np.uint8)
-        eng.set_features(sc.features)
-        r = eng.play_games(np.array([sc.weights]), 1, pieces=ids, lookahead=lookahead, max_moves=commit,
-                           init_rows=[state.board.rows16()], want_trace=True, want_fitness=False, move_set=move_set, pressure=pressure,
-                           init_lines=state.lines_cleared())
-        placed = int(r["results"]["pieces"][0])
-        for t in range(placed):
-            rot, row, col, _k = (int(x) for x in r["trace"][0, t])
-            state = state.future(chunk[t], rot, row, col)
-            yield state
-        if placed < commit or not more:
-            return
-        carry = chunk[commit:]
+    window = []              # pieces read from zoid_gen and not yet placed
+    unread = 0               # how many pieces at the tail of `window` the reference would not have pulled yet
+    try:
+        while True:
+            window = window + list(itertools.islice(zoid_gen, 0, size - len(window)))
+            if not window:
+                return
+            more = len(window) == size
+            # with lookahead 2 the last piece of a non-final chunk is only looked at, not placed
+            commit = len(window) - 1 if (more and lookahead == 2) else len(window)
+            unread = len(window)
+            ids = np.array([[z.id for z in window]], dtype=np.uint8)
+            eng.set_features(sc.features)
+            r = eng.play_games(np.array([sc.weights]), 1, pieces=ids, lookahead=lookahead, max_moves=commit,
+                               init_rows=[state.board.rows16()], want_trace=True, want_fitness=False, move_set=move_set, pressure=pressure,
+                               init_lines=state.lines_cleared())
+            placed = int(r["results"]["pieces"][0])
+            for t in range(placed):
+                rot, row, col, _k = (int(x) for x in r["trace"][0, t])
+                state = state.future(window[t], rot, row, col)
+                # the reference has pulled t + lookahead pieces of this window when it yields move t (simulator.py:156,184)
+                unread = max(len(window) - (t + lookahead), 0)
+                yield state
+            if placed < commit:
+                unread = max(len(window) - (placed + lookahead), 0)      # game over: it pulled the `lookahead` visible pieces and stopped
+                return
+            if not more:
+                unread = 0
+                return
+            window = window[commit:]
+            unread = 0
+    finally:
+        if source is not None and unread:
+            source.push_back(window[len(window) - unread:])
 
 
-__all__ = ["move_drop", "move_with_overhang_slide", "move_with_pressure", "move_with_wiggle", "move_wiggle", "policy_best", "simulate", "linear_scorer", "tie_first", "LinearScorer", "BestPolicy", "PIECES"]
+__all__ = ["PieceStream", "move_drop", "move_with_overhang_slide", "move_with_pressure", "move_with_wiggle", "move_wiggle", "policy_best", "simulate", "linear_scorer", "tie_first", "LinearScorer", "BestPolicy", "PIECES"]

@@ -43,11 +43,13 @@ def main():
         stats["placements"] = int(local_ev.last["results"]["placements"].sum())
         return fit
     local_ev.evaluate = local_eval
+    ev = None
     if world > 1:
         import torch.distributed as dist
-        os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG", "INFO")             # ranks / transports visible in the log (stderr)
         dist.init_process_group("nccl", device_id=dev)
-        ev = ShardedEvaluator(local_eval, device=dev)
+        ev = ShardedEvaluator(local_ev, device=dev)            # device path: play -> all-gather of the device fitness -> one D2H
+        ev.collect_placements = True
         test_f, map_f = ev.test_f, ev.map_f
     else:
         test_f, map_f = local_ev.test_f, local_ev.map_f
@@ -65,6 +67,8 @@ def main():
         mean, std = next(gen)
         wall = time.perf_counter() - t0
         placements = stats["placements"]
+        if ev is not None:
+            placements = ev.last_timing["placements"]
         if world > 1:
             tot = torch.tensor([float(placements)], dtype=torch.float64, device=dev)
             dist.all_reduce(tot)
@@ -72,6 +76,7 @@ def main():
         digest = hashlib.sha256(("".join(float(v).hex() for v in list(mean.values()) + list(std.values()))).encode()).hexdigest()[:16]
         if rank == 0:
             print(json.dumps({"generation": g, "n_gpus": world, "width": width, "games_per_candidate": G, "wall_s": wall, "evaluate_s": times["map_s"],
+                              "sharded_timing": ({k: round(v, 3) for k, v in ev.last_timing.items()} if ev is not None else None),
                               "placements": placements, "placements_per_s_wall": placements / wall, "placements_per_s_evaluate": placements / times["map_s"],
                               "refit_digest": digest, "mean": [float(v) for v in mean.values()]}), flush=True)
     if world > 1:
