@@ -63,6 +63,14 @@ METRIC, UNIT = "placements evaluated/sec (CE generation, 100 candidates x 10 gam
 _REAL_STDOUT = None
 
 
+
+
+def seeded_sequence(seed, T):
+    """The canonical injected piece sequence: ONE random.Random(seed), T draws of randrange(7)."""
+    r = random.Random(seed)
+    return [r.randrange(7) for _ in range(T)]
+
+
 def guard_stdout():
     global _REAL_STDOUT
     if _REAL_STDOUT is None:
@@ -335,12 +343,12 @@ def population_sharded(eng, dev, world, int_peak, which, reps=3):
         fixture = json.load(gzip.open(fx, "rt")) if os.path.exists(fx) else None
         rng = random.Random(42)
         pop = [[rng.gauss(0, 10.0) for _ in range(6)] for _ in range(C)]
-        seqs = np.array([[random.Random(1000 + g).randrange(7) for _ in range(T)] for g in range(G)], dtype=np.uint8)
+        seqs = np.array([seeded_sequence(1000 + g, T) for g in range(G)], dtype=np.uint8)
         label = "generation 0 of the canonical configs[2] run (Random(42), sigma 10, seeds 1000..1029): a FRESH population, most games die within a few dozen pieces"
     else:
         rng = np.random.default_rng(1)
         pop = (np.array(W6_VALS)[None, :] + rng.normal(0, 1.0, size=(C, 6))).tolist()
-        seqs = np.array([[random.Random(100 + g).randrange(7) for _ in range(T)] for g in range(G)], dtype=np.uint8)
+        seqs = np.array([seeded_sequence(100 + g, T) for g in range(G)], dtype=np.uint8)
         label = "w6 + N(0,1) noise: a CONVERGED population, most games reach the cap (the population_regime population)"
     w = np.array(pop, dtype=np.float64)
     local_ev = PopulationEvaluator(eng, W6_NAMES, G, pieces=seqs)
@@ -634,7 +642,7 @@ def population_regime(eng, int_peak, C=10000, G=30, T=1000):
     w6 = np.array(W6_VALS)
     rng = np.random.default_rng(1)
     w = w6[None, :] + rng.normal(0, 1.0, size=(C, 6))
-    seqs = np.array([[random.Random(100 + g).randrange(7) for _ in range(T)] for g in range(G)], dtype=np.uint8)
+    seqs = np.array([seeded_sequence(100 + g, T) for g in range(G)], dtype=np.uint8)
     best, out = 1e9, None
     for _ in range(2):
         out = eng.play_games(w, G, pieces=seqs)

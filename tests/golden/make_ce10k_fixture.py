@@ -29,13 +29,21 @@ W6_NAMES = ["landing_height", "eroded_cells", "row_trans", "col_trans", "pits", 
 WIDTH, KEEP, G, T, SIGMA, RNG_SEED, SEED0 = 10000, 1000, 30, 1000, 10.0, 42, 1000
 
 
+
+
+def seeded_sequence(seed, T):
+    """The canonical injected piece sequence: ONE random.Random(seed), T draws of randrange(7)."""
+    r = random.Random(seed)
+    return [r.randrange(7) for _ in range(T)]
+
+
 def population():
     rng = random.Random(RNG_SEED)
     return np.array([[rng.gauss(0, SIGMA) for _ in range(6)] for _ in range(WIDTH)], dtype=np.float64)
 
 
 def sequences():
-    return np.array([[random.Random(SEED0 + g).randrange(7) for _ in range(T)] for g in range(G)], dtype=np.uint8)
+    return np.array([seeded_sequence(SEED0 + g, T) for g in range(G)], dtype=np.uint8)
 
 
 def refit(pop, fitness):

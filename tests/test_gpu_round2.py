@@ -112,7 +112,7 @@ def check_long(res, trace, want):
         assert hashlib.sha256(trace[: want["pieces"]].tobytes()).hexdigest() == want["trace_sha"]
 
 
-@pytest.mark.parametrize("lanes,family", [(32, "K2f one warp per game"), (64, "K2p two warps per game"), (8, "K2g 8 lanes"), (1, "K2g 1 lane")])
+@pytest.mark.parametrize("lanes,family", [(32, "K2f one warp per game"), (64, "K2p two warps per game"), (128, "K2q four warps per game"), (8, "K2g 8 lanes"), (1, "K2g 1 lane")])
 def test_long_game_single_launch_families(eng, long_oracle, lanes, family):
     streams = list(long_oracle)[:2]
     eng.set_features(W6_NAMES)
@@ -260,12 +260,14 @@ def test_custom_points_golden_games_every_family(eng, golden_games):
     n_checked = 0
     for rec in load_golden("r2_extra.json")["points"]:
         g = games[rec["game"]]
+        if g.get("tie") == "last":                 # golden game played with a last-of-max tie-breaker: not a device policy
+            continue
         names = [n for n, _ in g["weights"]]
         w = np.array([[x for _, x in g["weights"]]])
         seq = np.array([pyoracle.piece_sequence(g["seed"], g["T"])], dtype=np.uint8)
         eng.set_features(names)
         w6 = names == W6_NAMES and g["lookahead"] == 1
-        for lanes in ((64, 32, 16, 8, 4, 1) if w6 else (32, 16, 8)):
+        for lanes in ((128, 64, 32, 16, 8, 4, 1) if w6 else (32, 16, 8)):
             for pts, want in rec["scores"]:
                 r = eng.play_games(w, 1, pieces=seq, lookahead=g["lookahead"], lanes=lanes, points=pts)
                 assert int(r["results"]["score"][0]) == want, (rec["game"], lanes, pts)
@@ -353,7 +355,7 @@ def test_feature_handle_counters_and_piece_stream(eng):
     st = State(None, Board(20, 10)).future(PIECES[1], 0, 18, 3)
     a0, m0, b0, n0 = F.pits.accesses, F.pits.misses, F.max_ht.accesses, F.max_ht.misses
     cache = {}
-    assert F.pits(st, cache=cache) == 0 and F.max_ht(st, cache=cache) == 2 and F.pits(st, cache=cache) == 0
+    assert F.pits(st, cache=cache) == 2 and F.max_ht(st, cache=cache) == 2 and F.pits(st, cache=cache) == 2       # T pointing down on an empty board
     assert (F.pits.accesses - a0, F.pits.misses - m0) == (2, 1) and (F.max_ht.accesses - b0, F.max_ht.misses - n0) == (1, 1)
     feature.evaluate(st, [F.pits, F.max_ht])
     assert F.pits.accesses - a0 == 3 and F.pits.misses - m0 == 2
@@ -370,3 +372,56 @@ def test_feature_handle_counters_and_piece_stream(eng):
         assert moves == case["moves"]
         first = next(sim.simulate(State(None, Board(20, 10)), src, sim.move_drop, policy, lookahead=case["lookahead"], engine=eng, chunk=16), None)
         assert (None if first is None else first.delta.zoid.name) == case["second_game_first_piece"], case
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K2q: four warps per game, three lanes per placement
+# ---------------------------------------------------------------------------------------------------------------------
+def test_k2q_golden_games(eng, golden_games):
+    n = 0
+    for g in golden_games["games"]:
+        if g.get("tie") == "last" or g["lookahead"] != 1 or [x for x, _ in g["weights"]] != W6_NAMES:
+            continue
+        eng.set_features(W6_NAMES)
+        w = np.array([[x for _, x in g["weights"]]])
+        seq = np.array([pyoracle.piece_sequence(g["seed"], g["T"])], dtype=np.uint8)
+        r = eng.play_games(w, 1, pieces=seq, lanes=128, want_trace=True, want_final=True, want_scores=True)
+        res = r["results"][0]
+        assert int(res["pieces"]) == g["pieces"] and int(res["lines"]) == g["lines"] and [int(x) for x in res["hist"]] == g["hist"]
+        assert int(res["score"]) == g["score"] and int(res["placements"]) == g["scorer_calls"]
+        assert r["trace"][0, :g["pieces"]].tobytes().hex() == g["trace_hex"]
+        assert list(r["final"][0]) == g["final_board"]
+        n += 1
+    assert n >= 3
+
+
+@pytest.mark.parametrize("kind,C,G,T,spread", [("w6", 60, 4, 400, 1.0), ("w6", 150, 3, 300, 6.0), ("wide", 200, 2, 300, 10.0)])
+def test_k2q_vs_coracle_and_other_kernels(eng, kind, C, G, T, spread):
+    """Explicit lanes = 128 (one persistent K2q launch): results, every move, every winning score and the final boards
+    equal the C oracle's and the one-warp kernel's, from empty boards and from random initial boards with lines."""
+    rng = np.random.default_rng(C + T)
+    w = (np.array(W6_VALS)[None, :] + rng.normal(0, spread, size=(C, 6))) if kind == "w6" else rng.normal(0, spread, size=(C, 6))
+    fids = [pyoracle.FEATURE_ID[x] for x in W6_NAMES]
+    eng.set_features(W6_NAMES)
+    r = eng.play_games(w, G, T=T, seed=77, lanes=128, want_trace=True, want_scores=True, want_final=True)
+    assert eng.last_timing()["lanes"] == 128
+    o = coracle.play_games(fids, w, G, T=T, seed=77, threads=THREADS, want_trace=True)
+    same_results(r["results"], o)
+    for g in range(C * G):
+        k = int(o["pieces"][g])
+        assert r["trace"][g, :k].tobytes() == o["trace"][g, :k].tobytes(), g
+    b = eng.play_games(w, G, T=T, seed=77, lanes=32, want_trace=True, want_scores=True, want_final=True)
+    assert (b["results"] == r["results"]).all() and (b["final"] == r["final"]).all()
+    for g in range(C * G):
+        k = int(o["pieces"][g])
+        assert b["scores"][g, :k].tobytes() == r["scores"][g, :k].tobytes(), g
+    # initial boards (with garbage rows, some nearly full) and lines already cleared, ragged max_moves
+    n = C * G
+    init = np.zeros((n, 20), dtype=np.uint16)
+    init[::2, 19] = 0x3FE; init[::3, 18] = 0x1FF; init[::3, 19] |= 0x1FF; init[::7, 17] = 0x2AA; init[::7, 18] |= 0x155
+    lines0 = (np.arange(n, dtype=np.uint32) * 11) % 73
+    kw = dict(T=T, seed=78, init_rows=init, init_lines=lines0, max_moves=T - 13, want_trace=True, want_final=True, want_scores=True)
+    a = eng.play_games(w, G, lanes=128, **kw)
+    c = eng.play_games(w, G, lanes=32, **kw)
+    assert (a["results"] == c["results"]).all() and (a["final"] == c["final"]).all()
+    assert a["trace"].tobytes() == c["trace"].tobytes() and a["scores"].tobytes() == c["scores"].tobytes()

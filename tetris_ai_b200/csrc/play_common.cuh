@@ -55,7 +55,7 @@ struct PlayParams {
     uint8_t   ids[TB200_MAX_WEIGHTED];
     uint32_t  pts[5];                // State.score(points) table (game.py:159), default (0, 40, 100, 300, 1200)
     // re-spreading stages of the latency regime (K2f / K2p only; st_ctl == null: off) — see launch_play
-    uint32_t* st_ctl;                // [0..2] ticket of stage s, [3] games finished so far, [4 + s] games handed to stage s
+    uint32_t* st_ctl;                // [0..3] ticket of stage s, [4] games finished so far, [8 + s] games handed to stage s
     const uint32_t* st_list_in;      // game ids handed to this stage, or null: all games, fresh
     uint32_t* st_list_out;           // survivors of this stage (null in the last stage)
     struct GameSave* st_save;        // [n_games] state of the handed-over games

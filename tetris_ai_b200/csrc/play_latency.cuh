@@ -21,10 +21,10 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayPara
     uint32_t* const ticket = staged ? prm.st_ctl + prm.st_stage : prm.ticket;
     uint32_t n_in = prm.n_games;
     if (staged && prm.st_list_in) {
-        n_in = prm.st_ctl[4 + prm.st_stage];
+        n_in = prm.st_ctl[8 + prm.st_stage];
         if (n_in == 0u) return;                    // nothing was handed over: the earlier stage finished every game
     }
-    const uint32_t* const finished = staged ? prm.st_ctl + 3 : nullptr;
+    const uint32_t* const finished = staged ? prm.st_ctl + 4 : nullptr;
     auto poll_finished = [&]() -> uint32_t {           // relaxed, L2-coherent; asm volatile so it is re-read every time
         uint32_t v;
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(finished) : "memory");
@@ -205,12 +205,12 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6fast_kernel(const PlayPara
 #pragma unroll
                 for (int k = 0; k < COLS; ++k) sv->c[k] = c[k];
                 sv->t = t; sv->lines = lines; sv->h1 = h1; sv->h2 = h2; sv->h3 = h3; sv->h4 = h4; sv->cnt = cnt; sv->gscore = gscore;
-                prm.st_list_out[atomicAdd(prm.st_ctl + 5 + prm.st_stage, 1u)] = game;
+                prm.st_list_out[atomicAdd(prm.st_ctl + 9 + prm.st_stage, 1u)] = game;
             }
             continue;
         }
         if (lane == 0) {
-            if (staged) atomicAdd(prm.st_ctl + 3, 1u);
+            if (staged) atomicAdd(prm.st_ctl + 4, 1u);
             tb200_game_result* r = prm.results + game;
             r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4;
             r->score = gscore; r->placements = cnt;
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(64) play_games_w6pair_kernel(const PlayParams 
     uint32_t* const ticket = staged ? prm.st_ctl + prm.st_stage : prm.ticket;
     uint32_t n_in = prm.n_games;
     if (staged && prm.st_list_in) {
-        n_in = prm.st_ctl[4 + prm.st_stage];
+        n_in = prm.st_ctl[8 + prm.st_stage];
         if (n_in == 0u) return;
     }
     __shared__ Tables s_tab;

@@ -17,7 +17,8 @@
 //        move index; stages of 64 pieces, survivors re-packed per sequence, one persistent launch with per-bucket hand-over.
 //   K2b play_games_w6bin_kernel<LANES>  the piece-binned kernel (config 5, independent streams): games travel through device-wide
 //        per-piece-type queues; a warp pops 32 / LANES games on the same piece, plays one piece each, pushes the survivors.
-//   K2f<staged> + K2p as re-spreading stages for the latency regime (config 2): see launch_play.
+//   K2q play_games_w6quad_kernel        four warps per game, three lanes per placement (each a column range): the sparse stages of the latency regime.
+//   K2f<staged> + K2q as re-spreading stages for the latency regime (config 2): see launch_play.
 //   K2w play_games_w32_kernel<MODE>     one warp per game, lookahead 1, all-45 / generic feature lists.
 //   K2L play_games_l2flat_kernel<MODE>  one warp per game, lookahead 2: layer-1 boards in shared memory, leaves flattened over lanes.
 //   K2x play_games_wiggle_kernel<MODE>  the wiggle move sets (8f rank 4): warp-parallel set flood fill + scoring; the reference-order search only breaks ties.
@@ -37,6 +38,7 @@
 #include "play_common.cuh"
 #include "play_generic.cuh"
 #include "play_latency.cuh"
+#include "play_quad.cuh"
 #include "play_population.cuh"
 #include "play_lookahead2.cuh"
 #include "play_wiggle.cuh"
@@ -220,7 +222,8 @@ struct tb200_ctx {
     bool bin_enabled = true;             // K2b; TB200_NO_BINS, TB200_BIN_LANES, TB200_BIN_MIN_GAMES
     int bin_lanes = 0; long long bin_min_games = 32768;
     const uint32_t* lock_flag = nullptr; // device word set by K2s if a bucket wait ever timed out (checked after host-mode calls)
-    int stage_cut1 = 0, stage_cut2 = 0;  // hand-over thresholds (games still unfinished): 4 and 2 per SM unless TB200_STAGE_CUTS=a,b
+    int stage_cut1 = 0, stage_cut2 = 0, stage_cut3 = 0;  // hand-over thresholds (games still unfinished): 4, 2 and 1 per SM unless TB200_STAGE_CUTS=a,b[,c]
+    bool quad_enabled = true;            // K2q as the sparse stages (TB200_NO_QUAD: K2p as the last stage, the round-1 schedule)
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // one call in flight per ctx: `busy` is recorded after the last kernel of every call; the next call makes its stream wait for it
@@ -337,7 +340,7 @@ int tb200_create(int device, tb200_ctx** out)
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(tb::g_tables, &host_tab, sizeof(tb::Tables));
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_ticket, sizeof(uint32_t));
     ctx->stage_cap = (uint32_t)(16 * ctx->sms);
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_stage, 256 + (size_t)ctx->stage_cap * (2 * sizeof(uint32_t) + sizeof(tb::GameSave)));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_stage, 256 + (size_t)ctx->stage_cap * (3 * sizeof(uint32_t) + sizeof(tb::GameSave)));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->busy, cudaEventDisableTiming);
@@ -355,10 +358,15 @@ int tb200_create(int device, tb200_ctx** out)
     if (const char* e6 = getenv("TB200_BIN_MIN_GAMES")) { const long long v = atoll(e6); if (v >= 1024) ctx->bin_min_games = v; }
     if (const char* e3 = getenv("TB200_LOCK_LANES")) ctx->lock_lanes = atoi(e3);
     if (const char* e4 = getenv("TB200_LOCK_K")) { const int k = atoi(e4); if (k >= 8) ctx->lock_K = k; }
-    ctx->stage_cut1 = 4 * ctx->sms; ctx->stage_cut2 = 2 * ctx->sms;
+    ctx->stage_cut1 = 4 * ctx->sms; ctx->stage_cut2 = 2 * ctx->sms; ctx->stage_cut3 = ctx->sms;
+    if (getenv("TB200_NO_QUAD")) ctx->quad_enabled = false;
     if (const char* e2 = getenv("TB200_STAGE_CUTS")) {          // tuning aid (tools/stage_probe.py)
-        int c1 = 0, c2 = 0;
-        if (sscanf(e2, "%d,%d", &c1, &c2) == 2 && c1 >= c2 && c2 >= 0 && c1 <= 4 * ctx->sms) { ctx->stage_cut1 = c1; ctx->stage_cut2 = c2; }
+        int c1 = 0, c2 = 0, c3 = -1;
+        const int nr = sscanf(e2, "%d,%d,%d", &c1, &c2, &c3);
+        if (nr >= 2 && c1 >= c2 && c2 >= 1 && c1 <= 4 * ctx->sms) {
+            ctx->stage_cut1 = c1; ctx->stage_cut2 = c2;
+            if (nr == 3 && c3 >= 0 && c3 <= c2) ctx->stage_cut3 = c3; else if (ctx->stage_cut3 > c2) ctx->stage_cut3 = c2;
+        }
     }
     *out = ctx;
     return TB200_OK;
@@ -438,7 +446,7 @@ static LockPlan lock_plan(const tb200_ctx* ctx, const tb200_play_args& a, int pe
     LockPlan lp{};
     const long long n_games = (long long)a.n_candidates * a.games_per_candidate;
     const int l = a.lanes;
-    const bool lanes_auto = !(l == 1 || l == 2 || l == 4 || l == 8 || l == 16 || l == 32 || l == 64);
+    const bool lanes_auto = !(l == 1 || l == 2 || l == 4 || l == 8 || l == 16 || l == 32 || l == 64 || l == 128);
     const uint32_t stop_moves = a.max_moves && a.max_moves < a.T ? a.max_moves : a.T;
     lp.on = ctx->lockstep_enabled && lanes_auto && a.lookahead == 1 && a.move_set == 0 && per_game_weights == 0 &&
             !a.seq_of_game && a.games_per_candidate >= 4 && a.games_per_candidate <= 4096 &&
@@ -486,28 +494,31 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
     int lanes = a.lanes;
     const int move_set = a.move_set;
     const bool pair_ok = ctx->mode == tb::MODE_W6 && a.lookahead == 1 && move_set == 0;
-    const bool lanes_auto = !(lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32 || lanes == 64);
+    const bool lanes_auto = !(lanes == 1 || lanes == 2 || lanes == 4 || lanes == 8 || lanes == 16 || lanes == 32 || lanes == 64 || lanes == 128);
+    if (lanes == 128 && !pair_ok) lanes = 32;
     if (move_set != 0 && (lanes == 64 || lanes == 4 || lanes == 2 || lanes == 1)) lanes = lanes == 64 ? 32 : 8;
     if (move_set & (TB200_MOVES_WIGGLE | TB200_MOVES_WIGGLE_DROP)) lanes = 32;
     if (lanes == 64 && !pair_ok) lanes = 32;
     const bool narrow_ok = pair_ok && (lanes == 4 || lanes == 2 || lanes == 1);
-    if (!narrow_ok && lanes != 8 && lanes != 16 && lanes != 32 && lanes != 64) {
+    if (!narrow_ok && lanes != 8 && lanes != 16 && lanes != 32 && lanes != 64 && lanes != 128) {
         // auto (measured on B200, tools/lanes_sweep.py): two warps per game only while that still leaves warp
         // schedulers idle; one warp per game while the population is a few resident waves (lowest latency per
         // piece); narrower groups — more games per warp, better lane utilisation — as the population grows.
         const long long per_sm = (n_games_ll + ctx->sms - 1) / ctx->sms;
         if (a.lookahead == 2 && move_set == 0) lanes = 32;        // K2L: leaves flattened over a full warp
+        else if (pair_ok && ctx->quad_enabled && per_sm <= 2) lanes = 128;      // K2q: four warps per game while every warp can still have a scheduler (almost) to itself
         else if (pair_ok && per_sm <= 4) lanes = 64;
         else if (per_sm <= 80) lanes = 32;
         else if (pair_ok) lanes = per_sm <= 320 ? 8 : (per_sm <= 700 ? 4 : 2);
         else lanes = per_sm <= 160 ? 16 : 8;
     }
-    tb::play_fn fn = tb::pick_kernel(ctx->mode, a.lookahead, lanes, move_set);
+    tb::play_fn fn = lanes == 128 ? tb::play_games_w6quad_kernel : tb::pick_kernel(ctx->mode, a.lookahead, lanes, move_set);
     const int block = lanes == 64 ? 64 : tb::BLOCK;
+    const size_t dyn_smem = lanes == 128 ? sizeof(tb::QShared) : 0;
     int occ = 0;
-    TB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, block, 0));
+    TB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, block, dyn_smem));
     if (occ < 1) occ = 1;
-    const int groups_per_block = lanes == 64 ? 1 : tb::BLOCK / lanes;
+    const int groups_per_block = lanes >= 64 ? 1 : tb::BLOCK / lanes;
     long long blocks = (n_games_ll + groups_per_block - 1) / groups_per_block;
     const long long max_blocks = (long long)ctx->sms * occ;
     if (blocks > max_blocks) blocks = max_blocks;
@@ -610,8 +621,9 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
         uint32_t* ctl = reinterpret_cast<uint32_t*>(ctx->d_stage);
         uint32_t* list1 = reinterpret_cast<uint32_t*>(ctx->d_stage + 256);
         uint32_t* list2 = list1 + ctx->stage_cap;
+        uint32_t* list3 = list2 + ctx->stage_cap;
         p.st_ctl = ctl;
-        p.st_save = reinterpret_cast<tb::GameSave*>(list2 + ctx->stage_cap);
+        p.st_save = reinterpret_cast<tb::GameSave*>(list3 + ctx->stage_cap);
         TB_CUDA(ctx, cudaMemsetAsync(ctl, 0, 64, st));
         if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
         const bool dense = n_games > (uint32_t)ctx->stage_cut1;
@@ -624,15 +636,29 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
         p.st_stage = 1; p.st_list_in = dense ? list1 : nullptr; p.st_list_out = list2; p.st_cut = (uint32_t)ctx->stage_cut2;
         tb::play_games_w6fast_kernel<true><<<(unsigned)ctx->sms, tb::BLOCK, 0, st>>>(p);
         TB_CUDA(ctx, cudaGetLastError());
-        p.st_stage = 2; p.st_list_in = list2; p.st_list_out = nullptr; p.st_cut = 0;
-        tb::play_games_w6pair_kernel<<<(unsigned)(2 * ctx->sms), 64, 0, st>>>(p);
-        TB_CUDA(ctx, cudaGetLastError());
+        if (ctx->quad_enabled) {
+            // K2q, two games per SM (two warps per scheduler, each with a third of the per-piece instructions), then one game per SM
+            const bool two = ctx->stage_cut3 > 0 && ctx->stage_cut3 < ctx->stage_cut2;
+            if (two) {
+                p.st_stage = 2; p.st_list_in = list2; p.st_list_out = list3; p.st_cut = (uint32_t)ctx->stage_cut3;
+                tb::play_games_w6quad_kernel<<<(unsigned)ctx->stage_cut2, tb::QBLOCK, sizeof(tb::QShared), st>>>(p);      // one block per game still alive
+                TB_CUDA(ctx, cudaGetLastError());
+                *launches += 1;
+            }
+            p.st_stage = two ? 3 : 2; p.st_list_in = two ? list3 : list2; p.st_list_out = nullptr; p.st_cut = 0;
+            tb::play_games_w6quad_kernel<<<(unsigned)(two ? ctx->stage_cut3 : ctx->stage_cut2), tb::QBLOCK, sizeof(tb::QShared), st>>>(p);
+            TB_CUDA(ctx, cudaGetLastError());
+        } else {
+            p.st_stage = 2; p.st_list_in = list2; p.st_list_out = nullptr; p.st_cut = 0;
+            tb::play_games_w6pair_kernel<<<(unsigned)(2 * ctx->sms), 64, 0, st>>>(p);
+            TB_CUDA(ctx, cudaGetLastError());
+        }
         *launches += 2;
         if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
         if (!dense) blocks = ctx->sms;
     } else {
         if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
-        fn<<<(unsigned)blocks, block, 0, st>>>(p);
+        fn<<<(unsigned)blocks, block, dyn_smem, st>>>(p);
         TB_CUDA(ctx, cudaGetLastError());
         if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
         *launches += 1;

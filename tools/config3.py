@@ -21,6 +21,14 @@ sys.path.insert(0, ROOT)
 W6_NAMES = ["landing_height", "eroded_cells", "row_trans", "col_trans", "pits", "cuml_wells"]
 
 
+
+
+def seeded_sequence(seed, T):
+    """The canonical injected piece sequence: ONE random.Random(seed), T draws of randrange(7)."""
+    r = random.Random(seed)
+    return [r.randrange(7) for _ in range(T)]
+
+
 def main():
     import torch
     from tetris_ai_b200 import Engine
@@ -31,7 +39,7 @@ def main():
     dev = torch.device("cuda", local)
     width, keep, G, T = int(os.environ.get("CE_WIDTH", "10000")), int(os.environ.get("CE_KEEP", "1000")), 30, 1000
     feats = [getattr(F, n) for n in W6_NAMES]
-    seqs = np.array([[random.Random(1000 + g).randrange(7) for _ in range(T)] for g in range(G)], dtype=np.uint8)
+    seqs = np.array([seeded_sequence(1000 + g, T) for g in range(G)], dtype=np.uint8)
     eng = Engine(local)
     local_ev = PopulationEvaluator(eng, feats, G, pieces=seqs)
     stats = {"kernel_ms": 0.0, "placements": 0}

@@ -6,10 +6,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from tetris_ai_b200 import Engine
 from oracle import pyoracle
+
+
+def seeded_sequence(seed, T):
+    """The canonical injected piece sequence: ONE random.Random(seed), T draws of randrange(7)."""
+    r = random.Random(seed)
+    return [r.randrange(7) for _ in range(T)]
+
+
 C = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 300
 G = 30
-seqs = np.array([[random.Random(100 + g).randrange(7) for _ in range(T)] for g in range(G)], dtype=np.uint8)
+seqs = np.array([seeded_sequence(100 + g, T) for g in range(G)], dtype=np.uint8)
 eng = Engine(0)
 rng = np.random.default_rng(2)
 sets = {

@@ -7,12 +7,20 @@ CHILD = r'''
 import sys, random, numpy as np
 sys.path.insert(0, %r)
 from tetris_ai_b200 import Engine
+
+
+def seeded_sequence(seed, T):
+    """The canonical injected piece sequence (SURVEY.md §8c): ONE random.Random(seed), T draws of randrange(7)."""
+    r = random.Random(seed)
+    return [r.randrange(7) for _ in range(T)]
+
+
 W6 = ["landing_height", "eroded_cells", "row_trans", "col_trans", "pits", "cuml_wells"]
 W6V = [-4.500158825082766, 3.4181268101392694, -3.2178882868487753, -9.348695305445199, -7.899265427351652, -3.3855972247263626]
 C, spread = int(sys.argv[1]), float(sys.argv[2]); G, T = 30, 1000
 rng = np.random.default_rng(1)
 w = np.array(W6V)[None, :] + rng.normal(0, spread, size=(C, 6))
-seqs = np.array([[random.Random(100 + g).randrange(7) for _ in range(T)] for g in range(G)], dtype=np.uint8)
+seqs = np.array([seeded_sequence(100 + g, T) for g in range(G)], dtype=np.uint8)
 eng = Engine(0); eng.set_features(W6)
 best = 1e9
 for _ in range(3):

@@ -16,6 +16,14 @@ W6_NAMES = ["landing_height", "eroded_cells", "row_trans", "col_trans", "pits", 
 W6_VALS = [-4.500158825082766, 3.4181268101392694, -3.2178882868487753, -9.348695305445199, -7.899265427351652, -3.3855972247263626]
 
 
+
+
+def seeded_sequence(seed, T):
+    """The canonical injected piece sequence: ONE random.Random(seed), T draws of randrange(7)."""
+    r = random.Random(seed)
+    return [r.randrange(7) for _ in range(T)]
+
+
 def ce_populations():
     ce = json.load(open(os.path.join(ROOT, "tests", "golden", "ce.json")))["ce"]
     rng = random.Random(ce["rng_seed"])
@@ -63,7 +71,7 @@ def main():
     ce = _json.load(open(os.path.join(ROOT, "tests", "golden", "ce.json")))["ce"]
     mean = np.array([float.fromhex(x) for x in ce["generations"][0]["mean"]]); std = np.array([float.fromhex(x) for x in ce["generations"][0]["std"]])
     w3 = mean[None, :] + std[None, :] * rng.normal(0, 1.0, size=(1250, 6))
-    seqs30 = np.array([[random.Random(1000 + g).randrange(7) for _ in range(1000)] for g in range(30)], dtype=np.uint8)
+    seqs30 = np.array([seeded_sequence(1000 + g, 1000) for g in range(30)], dtype=np.uint8)
     for lanes in (0, 32, 8, 4):
         ms, out = timeit(eng, 2, weights=w3, games_per_candidate=30, pieces=seqs30, lanes=lanes)
         rows.append(("config3 shard 1250x30 T=1000", eng.last_timing()["lanes"], ms, int(out["results"]["placements"].sum()), int(out["results"]["pieces"].sum())))
