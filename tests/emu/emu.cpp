@@ -354,3 +354,49 @@ int emu_moves(const uint16_t* rows, int piece, int move_set, int* out)
 }
 
 }  // extern "C"
+
+
+// Window-local w6 evaluation (win_eval) against the general w6 evaluation (w6_pre / w6_post) for EVERY slot of every piece
+// on one board.  Returns the number of slots compared in the high 16 bits... no: returns mismatches; *compared receives the
+// number of legal, non-clearing slots whose keys were compared, *clearing the number of slots that complete a row.
+extern "C" int emu_win_check(const uint16_t* rows, const double* w6w, int* compared, int* clearing)
+{
+    const Tables& tab = host_tables();
+    uint32_t c[COLS];
+    rows_to_cols(rows, c);
+    const GameStat g = game_stat(c);
+    WinCache wc;
+    win_cache_init(c, wc);
+    int bad = 0, ncmp = 0, nclr = 0;
+    for (int piece = 0; piece < 7; ++piece) {
+        WinSlide ws;
+        win_reset(wc, ws);
+        for (int s = 0; s < tab.nslots[piece]; ++s) {
+            const SlotDesc& d = tab.slot[piece][s];
+            if ((d.w[0] & 15u) == 0u) win_reset(wc, ws);                 // new rotation: the windows slide from column 0 again
+            W6Cand A;
+            w6_pre(c, g, d, A);
+            const int c0 = (int)(d.w[0] & 15u), wd = (int)((d.w[0] >> 6) & 7u);
+            uint32_t and_out = 0xffffffffu;
+            for (int k = 0; k < COLS; ++k) if (k < c0 || k >= c0 + wd) and_out &= c[k];
+            uint32_t full = 0; bool legal = false;
+            const uint64_t kw = win_eval(wc, d, w6w, [&](int k) { return (k >= 0 && k < COLS) ? c[k] : 0xdeadbeefu; }, and_out, &full, &legal);
+            {   // the sliding windows the device uses must give the same key / full mask / legality
+                uint32_t full2 = 0; bool legal2 = false;
+                const uint64_t ks = win_eval_at(wc, ws, d, win_desc(d), w6w, [&](int k) { return (k >= 0 && k < COLS) ? c[k] : 0xdeadbeefu; }, and_out, &full2, &legal2);
+                if (ks != kw || full2 != full || legal2 != legal) ++bad;
+                win_advance(ws);
+            }
+            if (legal != A.legal) { ++bad; continue; }
+            if (!legal) { if (kw != 0ull) ++bad; continue; }
+            if (full != A.full) { ++bad; continue; }
+            if (full != 0u) { ++nclr; continue; }
+            Heights Hn;
+            const uint64_t k0 = w6_post(A, w6w, Hn);
+            ++ncmp;
+            if (k0 != kw) ++bad;
+        }
+    }
+    *compared = ncmp; *clearing = nclr;
+    return bad;
+}

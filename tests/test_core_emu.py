@@ -289,3 +289,36 @@ def test_emu_wiggle_set_equals_list_as_set():
         # the tie break: the early-out search returns the first listed move of any subset
         assert emu_lib.wiggle_stop_check(rows, p, True, rng.getrandbits(32)) == 0
         assert emu_lib.wiggle_stop_check(rows, p, False, rng.getrandbits(32)) == 0
+
+
+def test_emu_window_evaluation_equals_general_w6(golden_states):
+    """win_eval (window-local w6 evaluation used by the lockstep kernel) == w6_pre + w6_post, key for key, for every slot of
+    every piece on the golden boards and on random boards (flat, jagged, holey, nearly full rows), several weight sets."""
+    import ctypes
+    L = emu_lib.lib()
+    L.emu_win_check.restype = ctypes.c_int
+    rng = np.random.default_rng(11)
+    boards = [np.array(st["prev"], dtype=np.uint16) for st in golden_states["states"][::9]]
+    for i in range(1500):
+        rows = np.zeros(20, dtype=np.uint16)
+        top = int(rng.integers(0, 19))
+        dens = float(rng.uniform(0.35, 0.97))
+        for r in range(20 - top, 20):
+            m = 0
+            for k in range(10):
+                if rng.random() < dens:
+                    m |= 1 << k
+            rows[r] = m if m != 0x3FF else m & ~(1 << int(rng.integers(0, 10)))      # boards in play have no full rows
+        boards.append(rows)
+    wsets = [np.array([-4.500158825082766, 3.4181268101392694, -3.2178882868487753, -9.348695305445199, -7.899265427351652, -3.3855972247263626]),
+             np.array([1.0, -1.0, 1.0, 1.0, 1.0, 1.0]), rng.normal(0, 10, 6), np.array([0.0, 0.0, -1.0, 0.0, 0.0, 0.0]),
+             np.array([0.0, 0.0, 0.0, -1.0, 0.0, 0.0]), np.array([0.0, 0.0, 0.0, 0.0, -1.0, 0.0]), np.array([0.0, 0.0, 0.0, 0.0, 0.0, -1.0])]
+    total = clearing = 0
+    for bi, rows in enumerate(boards):
+        w = np.ascontiguousarray(wsets[bi % len(wsets)], dtype=np.float64)
+        ncmp, nclr = ctypes.c_int(0), ctypes.c_int(0)
+        bad = L.emu_win_check(rows.ctypes.data_as(ctypes.c_void_p), w.ctypes.data_as(ctypes.c_void_p), ctypes.byref(ncmp), ctypes.byref(nclr))
+        assert bad == 0, (bi, [int(x) for x in rows], bad)
+        total += ncmp.value
+        clearing += nclr.value
+    assert total > 100000 and clearing > 1000

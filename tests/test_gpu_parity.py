@@ -312,7 +312,7 @@ def test_k2_lockstep_population_vs_coracle(eng, C, G, T, spread, explicit):
     eng.set_features(W6_NAMES)
     pieces = None
     if explicit:
-        pieces = np.array([[random.Random(7 * g + 1).randrange(7) for _ in range(T)] for g in range(G)], dtype=np.uint8)
+        pieces = np.array([pyoracle.piece_sequence(7 * g + 1, T) for g in range(G)], dtype=np.uint8)
     kw = dict(pieces=pieces, T=T, seed=77)
     a = eng.play_games(w, G, want_trace=True, want_scores=True, want_final=True, **kw)
     assert eng.last_timing()["kernels_launched"] == 2 and eng.last_timing()["lanes"] in (1, 2, 4, 8)
@@ -342,7 +342,7 @@ def test_k2_lockstep_one_lane_per_game_full_population(eng):
     w = np.array(W6_VALS)[None, :] + rng.normal(0, 2.5, size=(C, 6))
     fids = [pyoracle.FEATURE_ID[x] for x in W6_NAMES]
     eng.set_features(W6_NAMES)
-    pieces = np.array([[random.Random(13 * g + 5).randrange(7) for _ in range(T)] for g in range(G)], dtype=np.uint8)
+    pieces = np.array([pyoracle.piece_sequence(13 * g + 5, T) for g in range(G)], dtype=np.uint8)
     a = eng.play_games(w, G, pieces=pieces, want_final=True)
     assert eng.last_timing()["kernels_launched"] == 2 and eng.last_timing()["lanes"] == 1
     b = eng.play_games(w, G, pieces=pieces, lanes=8, want_final=True)
@@ -363,7 +363,7 @@ def test_k2_lockstep_other_feature_lists_vs_coracle(eng, kind, C, G, T):
     w = np.array([[base.get(n, 0.0) for n in names]]) + rng.normal(0, 1.5 if kind != "all45" else 0.4, size=(C, len(names)))
     fids = [pyoracle.FEATURE_ID[x] for x in names]
     eng.set_features(names)
-    pieces = np.array([[random.Random(17 * g + 3).randrange(7) for _ in range(T)] for g in range(G)], dtype=np.uint8)
+    pieces = np.array([pyoracle.piece_sequence(17 * g + 3, T) for g in range(G)], dtype=np.uint8)
     a = eng.play_games(w, G, pieces=pieces, want_trace=True, want_scores=True, want_final=True)
     assert eng.last_timing()["kernels_launched"] == 2 and eng.last_timing()["lanes"] in (1, 2, 4, 8)
     b = eng.play_games(w, G, pieces=pieces, lanes=8, want_trace=True, want_scores=True, want_final=True)
@@ -400,7 +400,7 @@ def test_k2_lockstep_initial_boards_lines_and_max_moves(eng):
         assert a["trace"][g, :k].tobytes() == b["trace"][g, :k].tobytes()
     # explicit sequences, two of which end early (a piece id > 6 ends the game there — an extension of this library, so
     # the comparison is against the per-game kernel only)
-    pieces = np.array([[random.Random(9 * g + 2).randrange(7) for _ in range(T)] for g in range(G)], dtype=np.uint8)
+    pieces = np.array([pyoracle.piece_sequence(9 * g + 2, T) for g in range(G)], dtype=np.uint8)
     pieces[3, 200:] = 7
     pieces[G - 1, 64:] = 7
     a = eng.play_games(w, G, pieces=pieces, want_final=True)

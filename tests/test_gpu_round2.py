@@ -425,3 +425,68 @@ def test_k2q_vs_coracle_and_other_kernels(eng, kind, C, G, T, spread):
     c = eng.play_games(w, G, lanes=32, **kw)
     assert (a["results"] == c["results"]).all() and (a["final"] == c["final"]).all()
     assert a["trace"].tobytes() == c["trace"].tobytes() and a["scores"].tobytes() == c["scores"].tobytes()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# K2sW: the lockstep kernel with window-local evaluation (one lane per game)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def eng_lane1():
+    """An Engine whose lockstep kernel is forced to one lane per game (TB200_LOCK_LANES is read at tb200_create): every
+    lockstep launch below runs play_games_w6lockwin_kernel, whatever the population size."""
+    from tetris_ai_b200 import Engine
+    old = os.environ.get("TB200_LOCK_LANES")
+    os.environ["TB200_LOCK_LANES"] = "1"
+    try:
+        e = Engine(0)
+    finally:
+        if old is None:
+            del os.environ["TB200_LOCK_LANES"]
+        else:
+            os.environ["TB200_LOCK_LANES"] = old
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("C,G,T,spread,explicit", [(500, 30, 200, 1.0, True), (3001, 5, 131, 6.0, True), (2000, 7, 260, 2.0, False), (13000, 4, 128, 8.0, True), (420, 30, 1000, 0.7, True)])
+def test_k2sw_window_lockstep_vs_coracle_and_per_game_kernel(eng_lane1, C, G, T, spread, explicit):
+    eng = eng_lane1
+    rng = np.random.default_rng(C + G)
+    w = np.array(W6_VALS)[None, :] + rng.normal(0, spread, size=(C, 6))
+    fids = [pyoracle.FEATURE_ID[x] for x in W6_NAMES]
+    eng.set_features(W6_NAMES)
+    pieces = np.array([pyoracle.piece_sequence(7 * g + 1, T) for g in range(G)], dtype=np.uint8) if explicit else None
+    kw = dict(pieces=pieces, T=T, seed=77)
+    a = eng.play_games(w, G, want_trace=True, want_scores=True, want_final=True, **kw)
+    assert eng.last_timing()["kernels_launched"] == 2 and eng.last_timing()["lanes"] == 1
+    b = eng.play_games(w, G, lanes=8, want_trace=True, want_scores=True, want_final=True, **kw)
+    assert (a["results"] == b["results"]).all() and (a["final"] == b["final"]).all() and (a["fitness"] == b["fitness"]).all()
+    for g in range(0, C * G, 3):
+        k = int(a["results"]["pieces"][g])
+        assert a["trace"][g, :k].tobytes() == b["trace"][g, :k].tobytes(), g
+        assert a["scores"][g, :k].tobytes() == b["scores"][g, :k].tobytes(), g
+    n_o = min(C, 400)
+    o = coracle.play_games(fids, w[:n_o], G, pieces=pieces, T=T, seed=77, threads=THREADS, want_trace=True)
+    res = a["results"][: n_o * G]
+    same_results(res, o)
+    for g in range(0, n_o * G, 5):
+        k = int(res["pieces"][g])
+        assert a["trace"][g, :k].tobytes() == o["trace"][g, :k].tobytes(), g
+
+
+def test_k2sw_initial_boards_lines_points_and_max_moves(eng_lane1):
+    eng = eng_lane1
+    rng = np.random.default_rng(3)
+    C, G, T = 700, 20, 400
+    w = np.array(W6_VALS)[None, :] + rng.normal(0, 3.0, size=(C, 6))
+    eng.set_features(W6_NAMES)
+    n = C * G
+    init = np.zeros((n, 20), dtype=np.uint16)
+    init[::3, 19] = 0x1EF; init[::5, 18] = 0x3F0; init[::5, 19] |= 0x3F0; init[::11, 15] = 0x201; init[::11, 16] = 0x3FE; init[::11, 17] = 0x1FF
+    lines0 = (np.arange(n, dtype=np.uint32) * 13) % 57
+    kw = dict(T=T, seed=5, init_rows=init, init_lines=lines0, max_moves=150, want_trace=True, want_final=True, want_scores=True, points=(3, 40, 100, 300, 1200))
+    a = eng.play_games(w, G, **kw)
+    assert eng.last_timing()["kernels_launched"] == 2 and eng.last_timing()["lanes"] == 1
+    b = eng.play_games(w, G, lanes=32, **kw)
+    assert (a["results"] == b["results"]).all() and (a["final"] == b["final"]).all()
+    assert a["trace"].tobytes() == b["trace"].tobytes() and a["scores"].tobytes() == b["scores"].tobytes()

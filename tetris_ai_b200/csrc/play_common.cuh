@@ -14,6 +14,8 @@ __constant__ Tables c_tables;
 // memory with per-thread addresses is serialised by the constant cache (it showed up as 2.5 % of the samples of a 0.4 ms
 // kernel); from global memory it is a few coalesced 128-bit loads per thread.
 __device__ Tables g_tables;
+// board-independent window constants of every slot (tetris_core.cuh: win_desc), for the window-local lockstep kernel
+__constant__ WinDesc c_win[7][TB_MAX_SLOTS];
 static_assert(sizeof(Tables) % 16 == 0, "Tables must be a whole number of 128-bit words");
 template <int NT>
 __device__ __forceinline__ void load_tables(Tables& s_tab)

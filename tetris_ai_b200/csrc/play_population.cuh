@@ -179,6 +179,190 @@ TB_HD uint32_t lock_stage_begin(uint32_t s, uint32_t K) { return s == 0u ? 0u : 
 
 // MODE_W6: the fast w6 evaluation.  MODE_ALL45 / MODE_GENERIC: the general placement / feature / scorer code of tetris_core.cuh,
 // weights read through L1 from the candidate's row (they do not fit in registers).
+// One task of the lockstep schedule: up to 32 / LANES games of sequence sq, all at the first move of stage st, played to the end of
+// the stage (or of the game); survivors are appended to the sequence's list of the next stage.  `slot` = task index in the bucket.
+template <int LANES, int MODE>
+TB_D void lock_task(const PlayParams& prm, const Tables& s_tab, uint32_t st, uint32_t sq, uint32_t slot, uint32_t n_in, uint32_t* ctl)
+{
+    constexpr bool W6 = MODE == MODE_W6;
+    constexpr uint32_t GPW = 32 / LANES;           // games per warp
+    const int lane = threadIdx.x & 31;
+    const int gl = lane & (LANES - 1);
+    const uint32_t T = prm.T, C = prm.lk_C, K = prm.lk_K, S = prm.lk_S;
+    const uint32_t G = (uint32_t)prm.G;
+    const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
+    {
+    // ---- task (st, sq, slot): up to GPW games of sequence sq, all at move st * K ----
+    const uint32_t idx = slot * GPW + (uint32_t)(lane / LANES);
+    bool active = idx < n_in;
+    uint32_t game = 0;
+    if (active) game = st == 0 ? idx * G + sq : __ldcg(prm.lk_list + ((size_t)(st & 1u) * G + sq) * C + idx);
+    const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
+    auto fetch_piece = [&](uint32_t tt) -> int {                     // warp-uniform
+        if (tt >= T) return 7;
+        return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, (uint64_t)sq, tt);
+    };
+    uint32_t c[COLS];
+    uint32_t t = lock_stage_begin(st, K), lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+    uint64_t gscore = 0;
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) c[k] = 0;
+    if (active) {
+        if (st > 0) {
+            const uint4* sv = reinterpret_cast<const uint4*>(prm.st_save + game);
+            const uint4 a0 = __ldcg(sv), a1 = __ldcg(sv + 1), a2 = __ldcg(sv + 2), a3 = __ldcg(sv + 3), a4 = __ldcg(sv + 4);
+            c[0] = a0.x; c[1] = a0.y; c[2] = a0.z; c[3] = a0.w; c[4] = a1.x; c[5] = a1.y; c[6] = a1.z; c[7] = a1.w; c[8] = a2.x; c[9] = a2.y;
+            lines = a2.w; h1 = a3.x; h2 = a3.y; h3 = a3.z; h4 = a3.w;
+            if (gl == 0) cnt = a4.x;
+            gscore = ((uint64_t)a4.w << 32) | a4.z;
+        } else {
+            if (prm.init_rows) {
+                uint16_t rows[ROWS];
+                for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
+                rows_to_cols(rows, c);
+            }
+            if (prm.init_lines) lines = prm.init_lines[game];
+        }
+    }
+    GameStat g;                                   // w6: heights / cells of the board
+    PrevStat pv; Heights H;                       // general: statistics of the board the piece is placed on
+    int cells0 = 0;
+    const uint32_t lines0 = lines;
+    double w[6];
+    const double* wrow = prm.weights + (size_t)(active ? game / G : 0u) * (size_t)prm.F;
+    if constexpr (W6) {
+        g = game_stat(c);
+        cells0 = g.cells - 4 * (int)t;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) w[i] = __ldg(wrow + i);
+    } else {
+        pv = prev_stat(c);
+        H = pack_gh(pv.gh);
+    }
+    const uint32_t t_next = lock_stage_begin(st + 1u, K);
+    const uint32_t t_end = (st + 1 == S || t_next > stop) ? stop : t_next;
+    int p_cur = fetch_piece(t), p_next = fetch_piece(t + 1u);
+    if (t >= stop || p_cur >= 7) {                                   // nothing to play (stop == 0 or the sequence ends here)
+        if (active && gl == 0) {
+            tb200_game_result* r = prm.results + game;
+            r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4; r->score = gscore;
+            if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&r->placements), (unsigned long long)cnt);
+            if (prm.final_rows) { uint16_t rows[ROWS]; cols_to_rows(c, rows); for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2]; }
+        }
+        active = false;
+    }
+    while (t < t_end && p_cur < 7 && __any_sync(FULLMASK, active)) {
+        const int p_after = fetch_piece(t + 2u);
+        // LANES == 1: every lane is on the same slot of the same piece, so the descriptor is warp-uniform: read it from
+        // constant memory with a provably uniform index (REDUX result) and let its field extraction run on the uniform
+        // datapath instead of the ALU pipe, which is the binding resource of this kernel
+        const int p_u = LANES == 1 ? (int)__reduce_max_sync(FULLMASK, (unsigned)p_cur) : p_cur;
+        const int ns = LANES == 1 ? c_tables.nslots[p_u] : s_tab.nslots[p_cur];
+        uint64_t key = 0; uint32_t tag = 0;
+        for (int s2 = gl; s2 < ns; s2 += LANES) {                    // same piece, same trip count in every lane
+            const SlotDesc d = LANES == 1 ? c_tables.slot[p_u][s2] : load_slot12(s_tab, p_cur, s2);
+            uint64_t k = 0;
+            if constexpr (W6) {
+                W6Cand A;
+                w6_pre(c, g, d, A);
+                if (A.legal && A.full != 0u) w6_clear(d, A);
+                Heights Hn;
+                k = w6_post(A, w, Hn);
+            } else {
+                Placement P;
+                if (place_slot(c, H, d, P)) {
+                    Feat f;
+                    eval_features<ModeTraits<MODE>::CMASK>(P, d, pv, prm.rmask, f);
+                    k = score_key(score_features<MODE>(f, prm.ids, wrow, prm.F));
+                }
+            }
+            cnt += (uint32_t)(k != 0ull && active);
+            if (k > key) { key = k; tag = (uint32_t)s2; }
+        }
+        group_argmax<LANES>(key, tag);
+        bool finish = false;
+        if (active) {
+            if (key == 0) {
+                finish = true;                                       // no legal placement: game over (simulator.py:187-189)
+            } else {
+                const SlotDesc d = load_slot12(s_tab, p_cur, (int)tag);
+                W6Cand A;
+                if constexpr (W6) {
+                    w6_pre(c, g, d, A);
+                    if (A.full != 0u) w6_clear(d, A);
+#pragma unroll
+                    for (int k = 0; k < COLS; ++k) { c[k] = A.P.n[k]; g.gh[k] = A.h[k]; }
+                    g.H.H0 = (uint32_t)A.h[0] | (uint32_t)A.h[1] << 8 | (uint32_t)A.h[2] << 16 | (uint32_t)A.h[3] << 24;
+                    g.H.H1 = (uint32_t)A.h[4] | (uint32_t)A.h[5] << 8 | (uint32_t)A.h[6] << 16 | (uint32_t)A.h[7] << 24;
+                    g.H.H2 = (uint32_t)A.h[8] | (uint32_t)A.h[9] << 8;
+                } else {
+                    place_slot(c, H, d, A.P);
+#pragma unroll
+                    for (int k = 0; k < COLS; ++k) c[k] = A.P.n[k];
+                    pv = next_stat(pv, A.P, d);
+                    H = pack_gh(pv.gh);
+                }
+                const uint32_t wk = (uint32_t)A.P.k;
+                if (wk != 0u) {
+                    lines += wk;
+                    h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
+                    const uint32_t pts = prm.pts[wk];
+                    gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
+                } else if (prm.pts[0] != 0u) gscore += (uint64_t)prm.pts[0] * (uint64_t)(lines / 10u + 1u);      // State.score(points) with points[0] != 0
+                if constexpr (W6) g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)(lines - lines0);
+                if (gl == 0) {
+                    if (prm.trace) {
+                        const uint32_t row = (uint32_t)(ROWS - A.P.y - A.P.ph);
+                        reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = (uint32_t)A.P.rot | row << 8 | (uint32_t)A.P.c0 << 16 | wk << 24;
+                    }
+                    if (prm.score_trace) {
+                        const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
+                        prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
+                    }
+                }
+            }
+        }
+        const uint32_t tn = t + 1u;
+        if (active && !finish && (tn >= stop || p_next >= 7)) finish = true;
+        if (finish) {
+            const uint32_t played = key == 0 ? t : tn;
+            if (gl == 0) {
+                tb200_game_result* r = prm.results + game;
+                r->pieces = played; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4; r->score = gscore;
+                if (prm.final_rows) { uint16_t rows[ROWS]; cols_to_rows(c, rows); for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2]; }
+            }
+            if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&prm.results[game].placements), (unsigned long long)cnt);
+            active = false;
+        }
+        t = tn;
+        p_cur = p_next; p_next = p_after;
+    }
+    // ---- survivors (alive at move t_end < stop) go to the sequence's list of the next stage ----
+    {
+#pragma unroll
+        for (int off = LANES / 2; off > 0; off >>= 1) cnt += __shfl_xor_sync(FULLMASK, cnt, off);
+        const uint32_t live = __ballot_sync(FULLMASK, active && gl == 0);
+        if (live != 0u) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(prm.lk_ctl + ((size_t)(st + 1) * G + sq) * 4 + 2, (uint32_t)__popc(live));
+            base = __shfl_sync(FULLMASK, base, 0);
+            if (active && gl == 0) {
+                uint4* sv = reinterpret_cast<uint4*>(prm.st_save + game);
+                __stcg(sv, make_uint4(c[0], c[1], c[2], c[3]));
+                __stcg(sv + 1, make_uint4(c[4], c[5], c[6], c[7]));
+                __stcg(sv + 2, make_uint4(c[8], c[9], t, lines));
+                __stcg(sv + 3, make_uint4(h1, h2, h3, h4));
+                __stcg(sv + 4, make_uint4(cnt, 0u, (uint32_t)gscore, (uint32_t)(gscore >> 32)));
+                const uint32_t rank = (uint32_t)__popc(live & ((1u << lane) - 1u));
+                __stcg(prm.lk_list + ((size_t)((st + 1) & 1u) * G + sq) * C + base + rank, game);
+            }
+        }
+        __syncwarp(FULLMASK);
+        if (lane == 0) { __threadfence(); atomicAdd(ctl + 1, 1u); }
+    }
+    }
+}
+
 template <int LANES, int MODE = MODE_W6>
 __global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayParams prm)
 {
@@ -220,174 +404,327 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayPara
             ntasks = (n_in + GPW - 1) / GPW;
             continue;
         }
-        // ---- task (st, sq, slot): up to GPW games of sequence sq, all at move st * K ----
-        const uint32_t idx = slot * GPW + (uint32_t)(lane / LANES);
-        bool active = idx < n_in;
-        uint32_t game = 0;
-        if (active) game = st == 0 ? idx * G + sq : __ldcg(prm.lk_list + ((size_t)(st & 1u) * G + sq) * C + idx);
-        const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
-        auto fetch_piece = [&](uint32_t tt) -> int {                     // warp-uniform
-            if (tt >= T) return 7;
-            return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, (uint64_t)sq, tt);
-        };
-        uint32_t c[COLS];
-        uint32_t t = lock_stage_begin(st, K), lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
-        uint64_t gscore = 0;
+        lock_task<LANES, MODE>(prm, s_tab, st, sq, slot, n_in, ctl);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2sW: the lockstep kernel with WINDOW-LOCAL evaluation (one lane per game, w6, lookahead 1).  Same task / bucket / stage
+// machinery as K2s; what changes is the inner loop.  Every lane of a warp is on the same slot of the same piece, so the
+// slot's first column c0 and width are warp-uniform: a placement is scored from the window of columns it touches
+// (tetris_core.cuh: win_eval) — ~9 popc and ~140 instructions instead of ~19 popc and ~260 for all ten columns.
+// The boards live in shared memory, word-major ([word][lane]: every lane reads and writes only its own bank, no
+// conflicts, no synchronisation), so that a uniform run-time column index is a plain LDS; per game there are the ten
+// columns and the prefix / suffix ANDs of the columns (full-row test of a window placement = two loads and one AND).
+// The per-pair / per-column contributions of the current board and their totals (WinCache, 18 registers) are rebuilt at
+// every commit.  Placements that complete a row move every column: they are DEFERRED (one bit per slot) and evaluated
+// after the slot loop with the general w6 code, so the common path carries no divergent clear branch at all.
+// ---------------------------------------------------------------------------------------------
+constexpr int LW_WORDS = 30;           // per game: columns 0..9 | P[k] = AND of columns < k, k = 0..9 | S[k] = AND of columns >= k, k = 1..10
+
+TB_D void lw_store_board(uint32_t (*sb)[32], int lane, const uint32_t c[COLS])
+{
+    uint32_t acc = 0xffffffffu;
 #pragma unroll
-        for (int k = 0; k < COLS; ++k) c[k] = 0;
-        if (active) {
-            if (st > 0) {
-                const uint4* sv = reinterpret_cast<const uint4*>(prm.st_save + game);
-                const uint4 a0 = __ldcg(sv), a1 = __ldcg(sv + 1), a2 = __ldcg(sv + 2), a3 = __ldcg(sv + 3), a4 = __ldcg(sv + 4);
-                c[0] = a0.x; c[1] = a0.y; c[2] = a0.z; c[3] = a0.w; c[4] = a1.x; c[5] = a1.y; c[6] = a1.z; c[7] = a1.w; c[8] = a2.x; c[9] = a2.y;
-                lines = a2.w; h1 = a3.x; h2 = a3.y; h3 = a3.z; h4 = a3.w;
-                if (gl == 0) cnt = a4.x;
-                gscore = ((uint64_t)a4.w << 32) | a4.z;
-            } else {
-                if (prm.init_rows) {
-                    uint16_t rows[ROWS];
-                    for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
-                    rows_to_cols(rows, c);
-                }
-                if (prm.init_lines) lines = prm.init_lines[game];
-            }
-        }
-        GameStat g;                                   // w6: heights / cells of the board
-        PrevStat pv; Heights H;                       // general: statistics of the board the piece is placed on
-        int cells0 = 0;
-        const uint32_t lines0 = lines;
-        double w[6];
-        const double* wrow = prm.weights + (size_t)(active ? game / G : 0u) * (size_t)prm.F;
-        if constexpr (W6) {
-            g = game_stat(c);
-            cells0 = g.cells - 4 * (int)t;
+    for (int k = 0; k < COLS; ++k) { sb[k][lane] = c[k]; sb[10 + k][lane] = acc; acc &= c[k]; }
+    acc = 0xffffffffu;
 #pragma unroll
-            for (int i = 0; i < 6; ++i) w[i] = __ldg(wrow + i);
+    for (int k = COLS; k >= 1; --k) { sb[20 + k - 1][lane] = acc; acc &= c[k - 1]; }
+}
+
+// The window-local task: 32 games of sequence sq, one lane per game; sb = this warp's board words in shared memory.
+TB_D void lockwin_task(const PlayParams& prm, const Tables& s_tab, uint32_t (*sb)[32], uint32_t st, uint32_t sq, uint32_t slot, uint32_t n_in, uint32_t* ctl)
+{
+    constexpr uint32_t GPW = 32;
+    const int lane = threadIdx.x & 31;
+    const uint32_t T = prm.T, C = prm.lk_C, K = prm.lk_K, S = prm.lk_S;
+    const uint32_t G = (uint32_t)prm.G;
+    const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
+    {
+    // ---- task (st, sq, slot): up to 32 games of sequence sq, all at the first move of stage st ----
+    const uint32_t idx = slot * GPW + (uint32_t)lane;
+    bool active = idx < n_in;
+    uint32_t game = 0;
+    if (active) game = st == 0 ? idx * G + sq : __ldcg(prm.lk_list + ((size_t)(st & 1u) * G + sq) * C + idx);
+    const uint8_t* seq = prm.pieces ? prm.pieces + (size_t)sq * T : nullptr;
+    auto fetch_piece = [&](uint32_t tt) -> int {                     // warp-uniform
+        if (tt >= T) return 7;
+        return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, (uint64_t)sq, tt);
+    };
+    uint32_t c[COLS];
+    uint32_t t = lock_stage_begin(st, K), lines = 0, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
+    uint64_t gscore = 0;
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) c[k] = 0;
+    if (active) {
+        if (st > 0) {
+            const uint4* sv = reinterpret_cast<const uint4*>(prm.st_save + game);
+            const uint4 a0 = __ldcg(sv), a1 = __ldcg(sv + 1), a2 = __ldcg(sv + 2), a3 = __ldcg(sv + 3), a4 = __ldcg(sv + 4);
+            c[0] = a0.x; c[1] = a0.y; c[2] = a0.z; c[3] = a0.w; c[4] = a1.x; c[5] = a1.y; c[6] = a1.z; c[7] = a1.w; c[8] = a2.x; c[9] = a2.y;
+            lines = a2.w; h1 = a3.x; h2 = a3.y; h3 = a3.z; h4 = a3.w;
+            cnt = a4.x;
+            gscore = ((uint64_t)a4.w << 32) | a4.z;
         } else {
-            pv = prev_stat(c);
-            H = pack_gh(pv.gh);
-        }
-        const uint32_t t_next = lock_stage_begin(st + 1u, K);
-        const uint32_t t_end = (st + 1 == S || t_next > stop) ? stop : t_next;
-        int p_cur = fetch_piece(t), p_next = fetch_piece(t + 1u);
-        if (t >= stop || p_cur >= 7) {                                   // nothing to play (stop == 0 or the sequence ends here)
-            if (active && gl == 0) {
-                tb200_game_result* r = prm.results + game;
-                r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4; r->score = gscore;
-                if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&r->placements), (unsigned long long)cnt);
-                if (prm.final_rows) { uint16_t rows[ROWS]; cols_to_rows(c, rows); for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2]; }
+            if (prm.init_rows) {
+                uint16_t rows[ROWS];
+                for (int r = 0; r < ROWS; ++r) rows[r] = prm.init_rows[(size_t)game * ROWS + r];
+                rows_to_cols(rows, c);
             }
-            active = false;
+            if (prm.init_lines) lines = prm.init_lines[game];
         }
-        while (t < t_end && p_cur < 7 && __any_sync(FULLMASK, active)) {
-            const int p_after = fetch_piece(t + 2u);
-            // LANES == 1: every lane is on the same slot of the same piece, so the descriptor is warp-uniform: read it from
-            // constant memory with a provably uniform index (REDUX result) and let its field extraction run on the uniform
-            // datapath instead of the ALU pipe, which is the binding resource of this kernel
-            const int p_u = LANES == 1 ? (int)__reduce_max_sync(FULLMASK, (unsigned)p_cur) : p_cur;
-            const int ns = LANES == 1 ? c_tables.nslots[p_u] : s_tab.nslots[p_cur];
-            uint64_t key = 0; uint32_t tag = 0;
-            for (int s2 = gl; s2 < ns; s2 += LANES) {                    // same piece, same trip count in every lane
-                const SlotDesc d = LANES == 1 ? c_tables.slot[p_u][s2] : load_slot12(s_tab, p_cur, s2);
-                uint64_t k = 0;
-                if constexpr (W6) {
-                    W6Cand A;
-                    w6_pre(c, g, d, A);
-                    if (A.legal && A.full != 0u) w6_clear(d, A);
-                    Heights Hn;
-                    k = w6_post(A, w, Hn);
-                } else {
-                    Placement P;
-                    if (place_slot(c, H, d, P)) {
-                        Feat f;
-                        eval_features<ModeTraits<MODE>::CMASK>(P, d, pv, prm.rmask, f);
-                        k = score_key(score_features<MODE>(f, prm.ids, wrow, prm.F));
-                    }
-                }
-                cnt += (uint32_t)(k != 0ull && active);
+    }
+    WinCache wc;
+    win_cache_init(c, wc);
+    lw_store_board(sb, lane, c);
+    double w[6];
+    {
+        const double* wrow = prm.weights + (size_t)(active ? game / G : 0u) * 6;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) w[i] = __ldg(wrow + i);
+    }
+    const uint32_t t_next = lock_stage_begin(st + 1u, K);
+    const uint32_t t_end = (st + 1 == S || t_next > stop) ? stop : t_next;
+    int p_cur = fetch_piece(t), p_next = fetch_piece(t + 1u);
+    if (t >= stop || p_cur >= 7) {                                   // nothing to play (stop == 0 or the sequence ends here)
+        if (active) {
+            tb200_game_result* r = prm.results + game;
+            r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4; r->score = gscore;
+            if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&r->placements), (unsigned long long)cnt);
+            if (prm.final_rows) { uint16_t rows[ROWS]; cols_to_rows(c, rows); for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2]; }
+        }
+        active = false;
+    }
+    while (t < t_end && p_cur < 7 && __any_sync(FULLMASK, active)) {
+        const int p_after = fetch_piece(t + 2u);
+        const int p_u = (int)__reduce_max_sync(FULLMASK, (unsigned)p_cur);      // provably uniform: descriptors from constant memory, fields on the uniform datapath
+        const int ns = c_tables.nslots[p_u];
+        uint64_t key = 0; uint32_t tag = 0;
+        uint32_t dlo = 0u, dhi = 0u;                                 // slots deferred to the general evaluation (they complete a row)
+        // slots are enumerated rotation-major, column-minor: per rotation the windows start at column 0 and slide
+        for (int s2 = 0; s2 < ns;) {
+            WinSlide ws;
+            win_reset(wc, ws);
+            const int ncol = COLS + 1 - (int)((c_tables.slot[p_u][s2].w[0] >> 6) & 7u);      // columns of this rotation (uniform)
+#pragma unroll 1
+            for (int cc = 0; cc < ncol; ++cc, ++s2) {
+                const SlotDesc d = c_tables.slot[p_u][s2];
+                const WinDesc wdsc = c_win[p_u][s2];
+                const int c0 = (int)(d.w[0] & 15u), wdt = (int)((d.w[0] >> 6) & 7u);
+                const uint32_t and_out = sb[10 + c0][lane] & sb[20 + c0 + wdt - 1][lane];
+                uint32_t full; bool legal;
+                uint64_t k = win_eval_at(wc, ws, d, wdsc, w, [&](int kk) -> uint32_t { return sb[kk][lane]; }, and_out, &full, &legal);
+                win_advance(ws);
+                cnt += (uint32_t)(legal && active);
+                if (legal && full != 0u) { k = 0ull; if (s2 < 32) dlo |= 1u << s2; else dhi |= 1u << (s2 - 32); }
                 if (k > key) { key = k; tag = (uint32_t)s2; }
             }
-            group_argmax<LANES>(key, tag);
-            bool finish = false;
+        }
+        // ---- deferred placements: rows completed, every column moves -> general w6 evaluation ----
+        if (__any_sync(FULLMASK, (dlo | dhi) != 0u)) {
+            GameStat g;
+            g.H.H0 = funnel_r(wc.X[0], wc.X[1], 16u); g.H.H1 = funnel_r(wc.X[1], wc.X[2], 16u); g.H.H2 = funnel_r(wc.X[2], wc.X[3], 16u) & 0xffffu;
+            unpack_heights(g.H, g.gh);
+            g.cells = wc.cells;
+#pragma unroll
+            for (int k = 0; k < COLS; ++k) c[k] = sb[k][lane];
+            while ((dlo | dhi) != 0u) {
+                int s2;
+                if (dlo != 0u) { s2 = ctz(dlo); dlo &= dlo - 1u; } else { s2 = 32 + ctz(dhi); dhi &= dhi - 1u; }
+                const SlotDesc d = load_slot12(s_tab, p_cur, s2);
+                W6Cand A;
+                w6_pre(c, g, d, A);
+                w6_clear(d, A);
+                Heights Hn;
+                const uint64_t k = w6_post(A, w, Hn);
+                if (k > key || (k == key && (uint32_t)s2 < tag)) { key = k; tag = (uint32_t)s2; }       // first of max: the lower slot keeps a tie
+            }
+        }
+        bool finish = false;
+        if (active) {
+            if (key == 0) {
+                finish = true;                                       // no legal placement: game over (simulator.py:187-189)
+            } else {
+                const SlotDesc d = load_slot12(s_tab, p_cur, (int)tag);
+                GameStat g;
+                g.H.H0 = funnel_r(wc.X[0], wc.X[1], 16u); g.H.H1 = funnel_r(wc.X[1], wc.X[2], 16u); g.H.H2 = funnel_r(wc.X[2], wc.X[3], 16u) & 0xffffu;
+                unpack_heights(g.H, g.gh);
+                g.cells = wc.cells;
+#pragma unroll
+                for (int k = 0; k < COLS; ++k) c[k] = sb[k][lane];
+                W6Cand A;
+                w6_pre(c, g, d, A);
+                if (A.full != 0u) w6_clear(d, A);
+#pragma unroll
+                for (int k = 0; k < COLS; ++k) c[k] = A.P.n[k];
+                win_cache_init(c, wc);
+                lw_store_board(sb, lane, c);
+                const uint32_t wk = (uint32_t)A.P.k;
+                if (wk != 0u) {
+                    lines += wk;
+                    h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
+                    const uint32_t pts = prm.pts[wk];
+                    gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
+                } else if (prm.pts[0] != 0u) gscore += (uint64_t)prm.pts[0] * (uint64_t)(lines / 10u + 1u);      // State.score(points) with points[0] != 0
+                if (prm.trace) {
+                    const uint32_t row = (uint32_t)(ROWS - A.P.y - A.P.ph);
+                    reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = (uint32_t)A.P.rot | row << 8 | (uint32_t)A.P.c0 << 16 | wk << 24;
+                }
+                if (prm.score_trace) {
+                    const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
+                    prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
+                }
+            }
+        }
+        const uint32_t tn = t + 1u;
+        if (active && !finish && (tn >= stop || p_next >= 7)) finish = true;
+        if (finish) {
+            const uint32_t played = key == 0 ? t : tn;
+            tb200_game_result* r = prm.results + game;
+            r->pieces = played; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4; r->score = gscore;
+            if (prm.final_rows) {
+                uint16_t rows[ROWS];
+#pragma unroll
+                for (int k = 0; k < COLS; ++k) c[k] = sb[k][lane];
+                cols_to_rows(c, rows);
+                for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2];
+            }
+            if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&prm.results[game].placements), (unsigned long long)cnt);
+            active = false;
+        }
+        t = tn;
+        p_cur = p_next; p_next = p_after;
+    }
+    // ---- survivors (alive at move t_end < stop) go to the sequence's list of the next stage ----
+    {
+        const uint32_t live = __ballot_sync(FULLMASK, active);
+        if (live != 0u) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(prm.lk_ctl + ((size_t)(st + 1) * G + sq) * 4 + 2, (uint32_t)__popc(live));
+            base = __shfl_sync(FULLMASK, base, 0);
             if (active) {
-                if (key == 0) {
-                    finish = true;                                       // no legal placement: game over (simulator.py:187-189)
-                } else {
-                    const SlotDesc d = load_slot12(s_tab, p_cur, (int)tag);
-                    W6Cand A;
-                    if constexpr (W6) {
-                        w6_pre(c, g, d, A);
-                        if (A.full != 0u) w6_clear(d, A);
 #pragma unroll
-                        for (int k = 0; k < COLS; ++k) { c[k] = A.P.n[k]; g.gh[k] = A.h[k]; }
-                        g.H.H0 = (uint32_t)A.h[0] | (uint32_t)A.h[1] << 8 | (uint32_t)A.h[2] << 16 | (uint32_t)A.h[3] << 24;
-                        g.H.H1 = (uint32_t)A.h[4] | (uint32_t)A.h[5] << 8 | (uint32_t)A.h[6] << 16 | (uint32_t)A.h[7] << 24;
-                        g.H.H2 = (uint32_t)A.h[8] | (uint32_t)A.h[9] << 8;
-                    } else {
-                        place_slot(c, H, d, A.P);
-#pragma unroll
-                        for (int k = 0; k < COLS; ++k) c[k] = A.P.n[k];
-                        pv = next_stat(pv, A.P, d);
-                        H = pack_gh(pv.gh);
-                    }
-                    const uint32_t wk = (uint32_t)A.P.k;
-                    if (wk != 0u) {
-                        lines += wk;
-                        h1 += wk == 1; h2 += wk == 2; h3 += wk == 3; h4 += wk == 4;
-                        const uint32_t pts = prm.pts[wk];
-                        gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
-                    } else if (prm.pts[0] != 0u) gscore += (uint64_t)prm.pts[0] * (uint64_t)(lines / 10u + 1u);      // State.score(points) with points[0] != 0
-                    if constexpr (W6) g.cells = cells0 + 4 * (int)(t + 1) - 10 * (int)(lines - lines0);
-                    if (gl == 0) {
-                        if (prm.trace) {
-                            const uint32_t row = (uint32_t)(ROWS - A.P.y - A.P.ph);
-                            reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = (uint32_t)A.P.rot | row << 8 | (uint32_t)A.P.c0 << 16 | wk << 24;
-                        }
-                        if (prm.score_trace) {
-                            const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
-                            prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
-                        }
-                    }
-                }
+                for (int k = 0; k < COLS; ++k) c[k] = sb[k][lane];
+                uint4* sv = reinterpret_cast<uint4*>(prm.st_save + game);
+                __stcg(sv, make_uint4(c[0], c[1], c[2], c[3]));
+                __stcg(sv + 1, make_uint4(c[4], c[5], c[6], c[7]));
+                __stcg(sv + 2, make_uint4(c[8], c[9], t, lines));
+                __stcg(sv + 3, make_uint4(h1, h2, h3, h4));
+                __stcg(sv + 4, make_uint4(cnt, 0u, (uint32_t)gscore, (uint32_t)(gscore >> 32)));
+                const uint32_t rank = (uint32_t)__popc(live & ((1u << lane) - 1u));
+                __stcg(prm.lk_list + ((size_t)((st + 1) & 1u) * G + sq) * C + base + rank, game);
             }
-            const uint32_t tn = t + 1u;
-            if (active && !finish && (tn >= stop || p_next >= 7)) finish = true;
-            if (finish) {
-                const uint32_t played = key == 0 ? t : tn;
-                if (gl == 0) {
-                    tb200_game_result* r = prm.results + game;
-                    r->pieces = played; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4; r->score = gscore;
-                    if (prm.final_rows) { uint16_t rows[ROWS]; cols_to_rows(c, rows); for (int r2 = 0; r2 < ROWS; ++r2) prm.final_rows[(size_t)game * ROWS + r2] = rows[r2]; }
-                }
-                if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&prm.results[game].placements), (unsigned long long)cnt);
-                active = false;
-            }
-            t = tn;
-            p_cur = p_next; p_next = p_after;
         }
-        // ---- survivors (alive at move t_end < stop) go to the sequence's list of the next stage ----
-        {
-#pragma unroll
-            for (int off = LANES / 2; off > 0; off >>= 1) cnt += __shfl_xor_sync(FULLMASK, cnt, off);
-            const uint32_t live = __ballot_sync(FULLMASK, active && gl == 0);
-            if (live != 0u) {
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(prm.lk_ctl + ((size_t)(st + 1) * G + sq) * 4 + 2, (uint32_t)__popc(live));
-                base = __shfl_sync(FULLMASK, base, 0);
-                if (active && gl == 0) {
-                    uint4* sv = reinterpret_cast<uint4*>(prm.st_save + game);
-                    __stcg(sv, make_uint4(c[0], c[1], c[2], c[3]));
-                    __stcg(sv + 1, make_uint4(c[4], c[5], c[6], c[7]));
-                    __stcg(sv + 2, make_uint4(c[8], c[9], t, lines));
-                    __stcg(sv + 3, make_uint4(h1, h2, h3, h4));
-                    __stcg(sv + 4, make_uint4(cnt, 0u, (uint32_t)gscore, (uint32_t)(gscore >> 32)));
-                    const uint32_t rank = (uint32_t)__popc(live & ((1u << lane) - 1u));
-                    __stcg(prm.lk_list + ((size_t)((st + 1) & 1u) * G + sq) * C + base + rank, game);
+        __syncwarp(FULLMASK);
+        if (lane == 0) { __threadfence(); atomicAdd(ctl + 1, 1u); }
+    }
+    }
+}
+
+__global__ void __launch_bounds__(BLOCK, 5) play_games_w6lockwin_kernel(const PlayParams prm)
+{
+    constexpr uint32_t GPW = 32;                   // games per warp
+    __shared__ Tables s_tab;
+    __shared__ uint32_t s_board[BLOCK / 32][LW_WORDS][32];
+    load_tables<BLOCK>(s_tab);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    uint32_t (*sb)[32] = s_board[threadIdx.x >> 5];
+    const uint32_t T = prm.T, C = prm.lk_C, K = prm.lk_K, S = prm.lk_S;
+    const uint32_t G = (uint32_t)prm.G;
+    const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
+
+    uint32_t st = 0, sq = 0;                       // current bucket
+    uint32_t n_in = C, ntasks = (C + GPW - 1) / GPW;
+    for (;;) {
+        uint32_t* ctl = prm.lk_ctl + ((size_t)st * G + sq) * 4;
+        uint32_t slot = 0;
+        if (lane == 0) slot = atomicAdd(ctl, 1u);
+        slot = __shfl_sync(FULLMASK, slot, 0);
+        if (slot >= ntasks) {                      // bucket handed out: open the next one
+            if (++sq == G) { sq = 0; if (++st == S) break; }
+            if (st > 0) {
+                if (lane == 0) {
+                    const uint32_t* prev = prm.lk_ctl + ((size_t)(st - 1) * G + sq) * 4;
+                    const uint32_t n_prev = st == 1 ? C : __ldcg(prev + 2);
+                    const uint32_t need = (n_prev + GPW - 1) / GPW;
+                    uint32_t spins = 0;
+                    while (*reinterpret_cast<volatile const uint32_t*>(prev + 1) < need) {
+                        __nanosleep(200);
+                        if (++spins > (1u << 23)) { atomicExch(prm.lk_ctl + (size_t)S * G * 4 + 3, 1u); break; }   // safety valve (> 1.5 s): never hang the device
+                    }
+                    __threadfence();
+                    n_in = spins > (1u << 23) ? 0u : __ldcg(prm.lk_ctl + ((size_t)st * G + sq) * 4 + 2);
                 }
+                n_in = __shfl_sync(FULLMASK, n_in, 0);
             }
-            __syncwarp(FULLMASK);
-            if (lane == 0) { __threadfence(); atomicAdd(ctl + 1, 1u); }
+            ntasks = (n_in + GPW - 1) / GPW;
+            continue;
         }
+        lockwin_task(prm, s_tab, sb, st, sq, slot, n_in, ctl);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2sA: lanes per game chosen PER BUCKET from the live count ("choose lanes per game per stage").  A CE population
+// thins out as it plays — a fresh one loses most of its games within a few dozen pieces — and a rank's shard of a sharded
+// population is small to begin with, so one launch-wide width is wrong for part of every play: with few games alive one
+// lane per game leaves most warps without work (and the rest latency-bound), with many alive eight lanes per game waste
+// lanes.  Here every (stage, sequence) bucket picks its own width from the number of games that enter it, n_in (every
+// warp reads the same counter once the bucket is open, so the choice — and hence the task count — is the same everywhere):
+//     games alive over all G sequences per resident warp  >= 48 : one lane per game, window-local evaluation (K2sW task)
+//                                                          >= 10 : four lanes per game        else : eight lanes per game
+// Tasks of different widths are the same device functions the fixed-width kernels run; results do not depend on the width.
+// ---------------------------------------------------------------------------------------------
+TB_D uint32_t lock_auto_lanes(uint32_t n_in, uint32_t G, uint32_t warps)
+{
+    const uint64_t alive = (uint64_t)n_in * G;                            // estimate: the other sequences thin out alike
+    return alive >= 48ull * warps ? 1u : (alive >= 10ull * warps ? 4u : 8u);
+}
+
+__global__ void __launch_bounds__(BLOCK, 5) play_games_w6lockauto_kernel(const PlayParams prm)
+{
+    __shared__ Tables s_tab;
+    __shared__ uint32_t s_board[BLOCK / 32][LW_WORDS][32];
+    load_tables<BLOCK>(s_tab);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    uint32_t (*sb)[32] = s_board[threadIdx.x >> 5];
+    const uint32_t C = prm.lk_C, S = prm.lk_S, G = (uint32_t)prm.G;
+    const uint32_t warps = gridDim.x * (BLOCK / 32);
+
+    uint32_t st = 0, sq = 0;                       // current bucket
+    uint32_t n_in = C;
+    uint32_t lanes = lock_auto_lanes(n_in, G, warps);
+    uint32_t ntasks = (n_in * lanes + 31u) / 32u;
+    for (;;) {
+        uint32_t* ctl = prm.lk_ctl + ((size_t)st * G + sq) * 4;
+        uint32_t slot = 0;
+        if (lane == 0) slot = atomicAdd(ctl, 1u);
+        slot = __shfl_sync(FULLMASK, slot, 0);
+        if (slot >= ntasks) {                      // bucket handed out: open the next one
+            if (++sq == G) { sq = 0; if (++st == S) break; }
+            if (st > 0) {
+                if (lane == 0) {
+                    const uint32_t* prev = prm.lk_ctl + ((size_t)(st - 1) * G + sq) * 4;
+                    const uint32_t n_prev = st == 1 ? C : __ldcg(prev + 2);
+                    const uint32_t need = (n_prev * lock_auto_lanes(n_prev, G, warps) + 31u) / 32u;      // tasks of the previous bucket of this sequence
+                    uint32_t spins = 0;
+                    while (*reinterpret_cast<volatile const uint32_t*>(prev + 1) < need) {
+                        __nanosleep(200);
+                        if (++spins > (1u << 23)) { atomicExch(prm.lk_ctl + (size_t)S * G * 4 + 3, 1u); break; }   // safety valve (> 1.5 s): never hang the device
+                    }
+                    __threadfence();
+                    n_in = spins > (1u << 23) ? 0u : __ldcg(prm.lk_ctl + ((size_t)st * G + sq) * 4 + 2);
+                }
+                n_in = __shfl_sync(FULLMASK, n_in, 0);
+            }
+            lanes = lock_auto_lanes(n_in, G, warps);
+            ntasks = (n_in * lanes + 31u) / 32u;
+            continue;
+        }
+        if (lanes == 1u) lockwin_task(prm, s_tab, sb, st, sq, slot, n_in, ctl);
+        else if (lanes == 4u) lock_task<4, MODE_W6>(prm, s_tab, st, sq, slot, n_in, ctl);
+        else lock_task<8, MODE_W6>(prm, s_tab, st, sq, slot, n_in, ctl);
     }
 }
 

@@ -218,12 +218,13 @@ struct tb200_ctx {
     char* d_lock = nullptr;
     size_t lock_cap = 0;
     bool lockstep_enabled = true;
+    bool win_enabled = true;             // K2sW: window-local evaluation in the one-lane-per-game lockstep kernel (TB200_NO_WIN: the all-columns K2s)
     int lock_lanes = 0, lock_K = 64;     // tuning aids: TB200_LOCK_LANES, TB200_LOCK_K
     bool bin_enabled = true;             // K2b; TB200_NO_BINS, TB200_BIN_LANES, TB200_BIN_MIN_GAMES
     int bin_lanes = 0; long long bin_min_games = 32768;
     const uint32_t* lock_flag = nullptr; // device word set by K2s if a bucket wait ever timed out (checked after host-mode calls)
     int stage_cut1 = 0, stage_cut2 = 0, stage_cut3 = 0;  // hand-over thresholds (games still unfinished): 4, 2 and 1 per SM unless TB200_STAGE_CUTS=a,b[,c]
-    bool quad_enabled = true;            // K2q as the sparse stages (TB200_NO_QUAD: K2p as the last stage, the round-1 schedule)
+    bool quad_enabled = false;           // K2q as the sparse stages: measured SLOWER than K2p (1450 vs 1170 cycles per piece), so off unless TB200_QUAD=1
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     // one call in flight per ctx: `busy` is recorded after the last kernel of every call; the next call makes its stream wait for it
@@ -338,6 +339,11 @@ int tb200_create(int device, tb200_ctx** out)
     static const tb::Tables host_tab = { TB_SLOT_TABLE_INIT, TB_NSLOTS_INIT };
     cudaError_t e = cudaMemcpyToSymbol(tb::c_tables, &host_tab, sizeof(tb::Tables));
     if (e == cudaSuccess) e = cudaMemcpyToSymbol(tb::g_tables, &host_tab, sizeof(tb::Tables));
+    if (e == cudaSuccess) {
+        static tb::WinDesc host_win[7][TB_MAX_SLOTS];
+        for (int p = 0; p < 7; ++p) for (int s2 = 0; s2 < TB_MAX_SLOTS; ++s2) host_win[p][s2] = tb::win_desc(host_tab.slot[p][s2]);
+        e = cudaMemcpyToSymbol(tb::c_win, host_win, sizeof host_win);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_ticket, sizeof(uint32_t));
     ctx->stage_cap = (uint32_t)(16 * ctx->sms);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_stage, 256 + (size_t)ctx->stage_cap * (3 * sizeof(uint32_t) + sizeof(tb::GameSave)));
@@ -352,6 +358,7 @@ int tb200_create(int device, tb200_ctx** out)
     if (getenv("TB200_NO_GRAPHS")) ctx->graphs_enabled = false;
     if (getenv("TB200_NO_STAGES")) ctx->staging_enabled = false;
     if (getenv("TB200_NO_LOCKSTEP")) ctx->lockstep_enabled = false;
+    if (getenv("TB200_NO_WIN")) ctx->win_enabled = false;
     if (getenv("TB200_NO_BINS")) ctx->bin_enabled = false;
     if (getenv("TB200_NO_SEQ_MAJOR")) ctx->seq_major = false;
     if (const char* e5 = getenv("TB200_BIN_LANES")) ctx->bin_lanes = atoi(e5);
@@ -359,7 +366,7 @@ int tb200_create(int device, tb200_ctx** out)
     if (const char* e3 = getenv("TB200_LOCK_LANES")) ctx->lock_lanes = atoi(e3);
     if (const char* e4 = getenv("TB200_LOCK_K")) { const int k = atoi(e4); if (k >= 8) ctx->lock_K = k; }
     ctx->stage_cut1 = 4 * ctx->sms; ctx->stage_cut2 = 2 * ctx->sms; ctx->stage_cut3 = ctx->sms;
-    if (getenv("TB200_NO_QUAD")) ctx->quad_enabled = false;
+    if (getenv("TB200_QUAD")) ctx->quad_enabled = true;
     if (const char* e2 = getenv("TB200_STAGE_CUTS")) {          // tuning aid (tools/stage_probe.py)
         int c1 = 0, c2 = 0, c3 = -1;
         const int nr = sscanf(e2, "%d,%d,%d", &c1, &c2, &c3);
@@ -597,7 +604,12 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
             if (ctx->mode != tb::MODE_W6 && ll < 2) ll = 2;     // the general evaluation is register-heavy: two lanes per game (tools/generic_pop_probe.py)
         }
         tb::play_fn lf;
-        if (ctx->mode == tb::MODE_W6)
+        const bool lock_auto = ctx->mode == tb::MODE_W6 && ctx->win_enabled && !(ctx->lock_lanes == 1 || ctx->lock_lanes == 2 || ctx->lock_lanes == 4 || ctx->lock_lanes == 8);
+        if (lock_auto)
+            lf = tb::play_games_w6lockauto_kernel;             // lanes per game chosen per (stage, sequence) bucket from the live count
+        else if (ctx->mode == tb::MODE_W6 && ll == 1 && ctx->win_enabled)
+            lf = tb::play_games_w6lockwin_kernel;
+        else if (ctx->mode == tb::MODE_W6)
             lf = ll == 8 ? tb::play_games_w6lock_kernel<8> : (ll == 4 ? tb::play_games_w6lock_kernel<4> : (ll == 2 ? tb::play_games_w6lock_kernel<2> : tb::play_games_w6lock_kernel<1>));
         else if (ctx->mode == tb::MODE_ALL45)
             lf = ll == 8 ? tb::play_games_w6lock_kernel<8, tb::MODE_ALL45> : (ll == 4 ? tb::play_games_w6lock_kernel<4, tb::MODE_ALL45> :
@@ -609,7 +621,11 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
         TB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&locc, lf, tb::BLOCK, 0));
         if (locc < 1) locc = 1;
         long long lblocks = (n_games_ll * ll + tb::BLOCK - 1) / tb::BLOCK;           // the grid must be fully resident: tasks wait on tasks
-        if (lblocks > (long long)ctx->sms * locc) lblocks = (long long)ctx->sms * locc;
+        if (lblocks > (long long)ctx->sms * locc || lock_auto) lblocks = (long long)ctx->sms * locc;
+        if (lock_auto) {                                        // reported width = the one the first stage plays with (tb::lock_auto_lanes)
+            const unsigned long long alive = (unsigned long long)n_games_ll, warps = (unsigned long long)lblocks * (tb::BLOCK / 32);
+            ll = alive >= 48ull * warps ? 1 : (alive >= 10ull * warps ? 4 : 8);
+        }
         TB_CUDA(ctx, cudaMemsetAsync(p.lk_ctl, 0, b_ctl, st));
         if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
         lf<<<(unsigned)lblocks, tb::BLOCK, 0, st>>>(p);

@@ -897,4 +897,205 @@ TB_HD uint64_t w6_post(const W6Cand& a, const double* w, Heights& Hn)
     return a.legal ? key : 0ull;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Window-local evaluation of the w6 set (lockstep kernel K2s, one lane per game).
+// A hard drop changes at most four columns, so of the six features only the contributions of a small window move:
+//   row_trans  : the column pairs that touch the piece's columns            (<= 5 of 9 pairs)
+//   col_trans  : the piece's columns                                         (<= 4 of 10 columns)
+//   pits       : sum of heights - cells, heights change only under the piece
+//   cuml_wells : the wells of the piece's columns and of their two neighbours (<= 6 of 10 columns)
+// WinCache keeps the per-pair / per-column contributions of the CURRENT board (packed bytes) and their totals; a
+// placement that completes no row is then scored from the window alone: (old total) - (old window part) + (new window part).
+// Placements that complete a row are NOT handled here (the caller defers them to the general evaluation): every column
+// moves when a row disappears.  Same values as w6_pre + w6_post, bit for bit (tests/test_core_emu.py checks every slot of
+// thousands of boards on the CPU; the GPU parity tests check whole games).
+// ---------------------------------------------------------------------------------------------
+struct WinCache {
+    uint32_t X[4];       // extended packed heights: byte i = height of column i - 2; bytes 0, 1 and 12, 13 (outside the board) = ROWS: walls
+    uint32_t RTp[3];     // byte k + 1 = popc(c_k ^ c_{k+1}) for the pair (k, k+1), k = 0..8; byte 0 = 0
+    uint32_t CTc[3];     // byte k = popc((c_k ^ 2 c_k) & 0xFFFFE)
+    uint32_t Wd[3];      // byte k + 1 = well depth of column k; byte 0 = 0
+    int RT, CT, CW2, SH, cells;      // totals: row_trans, col_trans, sum of d (d + 1) over the wells, sum of heights, filled cells
+};
+
+TB_HD int bytesum_sel(uint32_t v, uint32_t sel01)        // sum of the bytes of v selected by sel01 (0x01 in the chosen bytes)
+{
+#if defined(__CUDA_ARCH__)
+    return (int)__dp4a(v, sel01, 0u);
+#else
+    int s = 0;
+    for (int i = 0; i < 4; ++i) s += (int)((v >> (8 * i)) & 255u) * (int)((sel01 >> (8 * i)) & 255u);
+    return s;
+#endif
+}
+TB_HD int bytesq_sel(uint32_t v, uint32_t selff)         // sum of b * b + b over the bytes of v selected by selff (0xFF in the chosen bytes)
+{
+    const uint32_t m = v & selff;
+#if defined(__CUDA_ARCH__)
+    return (int)__dp4a(m, m, __dp4a(m, 0x01010101u, 0u));
+#else
+    int s = 0;
+    for (int i = 0; i < 4; ++i) { const int b = (int)((m >> (8 * i)) & 255u); s += b * b + b; }
+    return s;
+#endif
+}
+// bytes i .. i+3 of the byte array held in (a0, a1, a2, a3); i in 0..12 (bytes beyond the array read as 0)
+TB_HD uint32_t win_bytes4(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, int i)
+{
+    const int wi = i >> 2;
+    const uint32_t sh = 8u * (uint32_t)(i & 3);
+    const uint32_t lo = wi == 0 ? a0 : (wi == 1 ? a1 : (wi == 2 ? a2 : a3));
+    const uint32_t hi = wi == 0 ? a1 : (wi == 1 ? a2 : (wi == 2 ? a3 : 0u));
+    return funnel_r(lo, hi, sh);
+}
+TB_CX uint32_t low_bytes01(int n) { return n <= 0 ? 0u : (n >= 4 ? 0x01010101u : (0x01010101u >> (8 * (4 - n)))); }   // 0x01 in the n low bytes
+
+TB_HD void win_cache_init(const uint32_t c[COLS], WinCache& wc)
+{
+    int h[COLS];
+    wc.SH = 0; wc.cells = 0; wc.RT = 0; wc.CT = 0; wc.CW2 = 0;
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) { h[k] = fls(c[k]); wc.SH += h[k]; wc.cells += popc(c[k]); }
+    wc.X[0] = (uint32_t)ROWS | (uint32_t)ROWS << 8 | (uint32_t)h[0] << 16 | (uint32_t)h[1] << 24;
+    wc.X[1] = (uint32_t)h[2] | (uint32_t)h[3] << 8 | (uint32_t)h[4] << 16 | (uint32_t)h[5] << 24;
+    wc.X[2] = (uint32_t)h[6] | (uint32_t)h[7] << 8 | (uint32_t)h[8] << 16 | (uint32_t)h[9] << 24;
+    wc.X[3] = (uint32_t)ROWS | (uint32_t)ROWS << 8;
+    uint32_t rt[3] = {0u, 0u, 0u}, ct[3] = {0u, 0u, 0u}, wd[3] = {0u, 0u, 0u};
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) {
+        if (k + 1 < COLS) { const int v = popc(c[k] ^ c[k + 1]); wc.RT += v; rt[(k + 1) >> 2] |= (uint32_t)v << (8 * ((k + 1) & 3)); }
+        const int t = popc((c[k] ^ (c[k] * 2u)) & 0xFFFFEu); wc.CT += t; ct[k >> 2] |= (uint32_t)t << (8 * (k & 3));
+        const int l = k == 0 ? ROWS : h[k - 1], r = k == COLS - 1 ? ROWS : h[k + 1];
+        int d = (l < r ? l : r) - h[k]; d = d > 0 ? d : 0;
+        wc.CW2 += d * d + d; wd[(k + 1) >> 2] |= (uint32_t)d << (8 * ((k + 1) & 3));
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { wc.RTp[i] = rt[i]; wc.CTc[i] = ct[i]; wc.Wd[i] = wd[i]; }
+}
+
+// The windows a placement at first column c0 needs, cut out of the cache.  With slots enumerated column-minor (c0 = 0, 1,
+// 2, ... within a rotation) they SLIDE: every array moves down by one byte per slot (win_advance), so no run-time byte
+// indexing is needed on the device — a reset at c0 == 0 and three or four constant shifts per slot.
+struct WinSlide {
+    uint32_t x[4];       // byte 0 = height of column c0 - 2 (the 8-byte heights window is x[0], x[1])
+    uint32_t r[3];       // byte 0 = pair (c0 - 1, c0)   (0 when c0 == 0; pairs beyond the board read 0)
+    uint32_t t[3];       // byte 0 = col_trans of column c0
+    uint32_t d[3];       // byte 0 = well depth of column c0 - 1 (0 outside the board)
+};
+TB_HD void win_reset(const WinCache& wc, WinSlide& ws)
+{
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ws.x[i] = wc.X[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { ws.r[i] = wc.RTp[i]; ws.t[i] = wc.CTc[i]; ws.d[i] = wc.Wd[i]; }
+}
+TB_HD void win_advance(WinSlide& ws)
+{
+    ws.x[0] = funnel_r(ws.x[0], ws.x[1], 8u); ws.x[1] = funnel_r(ws.x[1], ws.x[2], 8u); ws.x[2] = funnel_r(ws.x[2], ws.x[3], 8u); ws.x[3] >>= 8;
+    ws.r[0] = funnel_r(ws.r[0], ws.r[1], 8u); ws.r[1] = funnel_r(ws.r[1], ws.r[2], 8u); ws.r[2] >>= 8;
+    ws.t[0] = funnel_r(ws.t[0], ws.t[1], 8u); ws.t[1] = funnel_r(ws.t[1], ws.t[2], 8u); ws.t[2] >>= 8;
+    ws.d[0] = funnel_r(ws.d[0], ws.d[1], 8u); ws.d[1] = funnel_r(ws.d[1], ws.d[2], 8u); ws.d[2] >>= 8;
+}
+// per-slot constants that do not depend on the board (uniform on the device): piece cells / tops of the piece's own four
+// columns, cut out of the slot descriptor
+struct WinDesc {
+    uint32_t pbw, tpw;               // piece cells / tops of the piece's columns 0..3
+    uint32_t mr0, mr1, mt, md0, md1; // byte selectors of the old contributions: first wdt + 1 pairs, wdt columns, wdt + 2 wells of the windows
+    uint32_t pad;
+};
+TB_HD WinDesc win_desc(const SlotDesc& d)
+{
+    const int c0 = (int)(d.w[0] & 15u), wdt = (int)((d.w[0] >> 6) & 7u);
+    WinDesc wd;
+    wd.pbw = win_bytes4(d.w[4], d.w[5], d.w[6], 0u, c0);       // piece cells of the piece's columns 0..3 (bit q = bbox row q)
+    wd.tpw = win_bytes4(d.w[8], d.w[9], d.w[10], 0u, c0);      // 32 + top of the piece's columns (0 beyond its width)
+    wd.mr0 = low_bytes01(wdt + 1); wd.mr1 = low_bytes01(wdt - 3);
+    wd.mt = low_bytes01(wdt);
+    wd.md0 = low_bytes01(wdt + 2) * 255u; wd.md1 = low_bytes01(wdt - 2) * 255u;
+    wd.pad = 0u;
+    return wd;
+}
+
+// One hard drop scored from its window.  ws: the windows at the slot's first column; col(k): column word k of the current
+// board (k = 0..9; only the piece's columns and their two neighbours are asked for); and_out: AND of every column OUTSIDE
+// the piece's columns (for the full-row test).  Returns the comparison key (0 = illegal); *full = rows the placement
+// completes: when it is not 0 the returned key is meaningless and the caller must evaluate the placement with
+// w6_pre / w6_clear / w6_post.
+template <class ColFn>
+TB_HD uint64_t win_eval_at(const WinCache& wc, const WinSlide& ws, const SlotDesc& d, const WinDesc& wdsc, const double* w, ColFn col,
+                           uint32_t and_out, uint32_t* full, bool* legal_out)
+{
+    const int c0 = (int)(d.w[0] & 15u), wdt = (int)((d.w[0] >> 6) & 7u);
+    const uint32_t W0 = ws.x[0], W1 = ws.x[1];                            // heights of columns c0-2 .. c0+5
+    const uint32_t hw = funnel_r(W0, W1, 16u);                            // columns c0 .. c0+3
+    const bool legal = ((hw + d.w[2]) & 0x80808080u) == 0u;
+    const uint32_t v = hw + d.w[1];
+    uint32_t m01 = byte_of(v, 0), b1 = byte_of(v, 1), b2 = byte_of(v, 2), b3 = v >> 24;
+    m01 = m01 > b1 ? m01 : b1; b2 = b2 > b3 ? b2 : b3; m01 = m01 > b2 ? m01 : b2;
+    const int y = (int)m01 - 32;
+    *legal_out = legal;
+    const uint32_t pbw = wdsc.pbw, tpw = wdsc.tpw;
+    const uint32_t one_y = 1u << (y & 31);
+    // imprint + transitions of the window (the piece is 1..4 columns wide)
+    const uint32_t n0 = byte_of(pbw, 0) * one_y + col(c0);
+    uint32_t nl = n0;                                                     // last (right-most) piece column
+    uint32_t f = and_out & n0;
+    int rtn = 0, ctn = popc((n0 ^ (n0 * 2u)) & 0xFFFFEu);
+    if (c0 > 0) rtn += popc(col(c0 - 1) ^ n0);
+    if (wdt > 1) { const uint32_t n1 = byte_of(pbw, 1) * one_y + col(c0 + 1); f &= n1; rtn += popc(nl ^ n1); ctn += popc((n1 ^ (n1 * 2u)) & 0xFFFFEu); nl = n1; }
+    if (wdt > 2) { const uint32_t n2 = byte_of(pbw, 2) * one_y + col(c0 + 2); f &= n2; rtn += popc(nl ^ n2); ctn += popc((n2 ^ (n2 * 2u)) & 0xFFFFEu); nl = n2; }
+    if (wdt > 3) { const uint32_t n3 = (pbw >> 24) * one_y + col(c0 + 3); f &= n3; rtn += popc(nl ^ n3); ctn += popc((n3 ^ (n3 * 2u)) & 0xFFFFEu); nl = n3; }
+    if (c0 + wdt < COLS) rtn += popc(nl ^ col(c0 + wdt));
+    *full = f;
+    // old contributions of the same pairs / columns: the first wdt + 1 pairs, wdt columns, wdt + 2 wells of the windows
+    // (entries outside the board are 0 in the arrays, so the edges need no special case)
+    const int rto = bytesum_sel(ws.r[0], wdsc.mr0) + bytesum_sel(ws.r[1], wdsc.mr1);
+    const int cto = bytesum_sel(ws.t[0], wdsc.mt);
+    const int cwo = bytesq_sel(ws.d[0], wdsc.md0) + bytesq_sel(ws.d[1], wdsc.md1);
+    // heights under the piece
+    const int yb = y - 32;
+    int q[8];
+    q[0] = (int)byte_of(W0, 0); q[1] = (int)byte_of(W0, 1); q[2] = (int)byte_of(W0, 2); q[3] = (int)(W0 >> 24);
+    q[4] = (int)byte_of(W1, 0); q[5] = (int)byte_of(W1, 1); q[6] = (int)byte_of(W1, 2); q[7] = (int)(W1 >> 24);
+    int dsh = 0;
+    { const int t = (int)byte_of(tpw, 0) + yb; const int hn = t > q[2] ? t : q[2]; dsh += hn - q[2]; q[2] = hn; }
+    { const int t = (int)byte_of(tpw, 1) + yb; const int hn = t > q[3] ? t : q[3]; dsh += hn - q[3]; q[3] = hn; }      // top byte 0 beyond the width: t < 0 <= q
+    { const int t = (int)byte_of(tpw, 2) + yb; const int hn = t > q[4] ? t : q[4]; dsh += hn - q[4]; q[4] = hn; }
+    { const int t = (int)(tpw >> 24) + yb;     const int hn = t > q[5] ? t : q[5]; dsh += hn - q[5]; q[5] = hn; }
+    // wells of columns c0-1 .. c0+wdt (window positions 1 .. wdt+2); positions outside the board are walls, not wells
+    int cwn = 0;
+#pragma unroll
+    for (int p = 1; p <= 6; ++p) {
+        int dd = (q[p - 1] < q[p + 1] ? q[p - 1] : q[p + 1]) - q[p]; dd = dd > 0 ? dd : 0;
+        // positions outside the board are walls of height ROWS in the window, so their "depth" is 0 by itself
+        cwn += p <= wdt + 2 ? dd * dd + dd : 0;
+    }
+    const int rt = wc.RT - rto + rtn, ct = wc.CT - cto + ctn;
+    const int pits = wc.SH + dsh - (wc.cells + 4);
+    const int cw = (wc.CW2 - cwo + cwn) >> 1;
+    double acc = 0.0;                                                              // canonical order
+    acc = dadd(acc, dmul(u2d(y), w[0]));                                           // landing_height
+    // eroded_cells = 0 here (no row completed): the reference adds 0.0 * w[1] = +-0.0, which never changes the bits of acc
+    // (x + (+-0) = x, and acc is never -0.0: see score_key), so the term is skipped
+    acc = dadd(acc, dmul(u2d(rt), w[2]));
+    acc = dadd(acc, dmul(u2d(ct), w[3]));
+    acc = dadd(acc, dmul(u2d(pits), w[4]));
+    acc = dadd(acc, dmul(u2d(cw), w[5]));
+    const uint64_t key = score_key(acc);
+    return legal ? key : 0ull;
+}
+
+// the same for a stand-alone slot (host tests): windows cut out by byte index
+template <class ColFn>
+TB_HD uint64_t win_eval(const WinCache& wc, const SlotDesc& d, const double* w, ColFn col, uint32_t and_out, uint32_t* full, bool* legal_out)
+{
+    const int c0 = (int)(d.w[0] & 15u);
+    WinSlide ws;
+    ws.x[0] = win_bytes4(wc.X[0], wc.X[1], wc.X[2], wc.X[3], c0); ws.x[1] = win_bytes4(wc.X[0], wc.X[1], wc.X[2], wc.X[3], c0 + 4); ws.x[2] = ws.x[3] = 0u;
+    ws.r[0] = win_bytes4(wc.RTp[0], wc.RTp[1], wc.RTp[2], 0u, c0); ws.r[1] = win_bytes4(wc.RTp[0], wc.RTp[1], wc.RTp[2], 0u, c0 + 4); ws.r[2] = 0u;
+    ws.t[0] = win_bytes4(wc.CTc[0], wc.CTc[1], wc.CTc[2], 0u, c0); ws.t[1] = ws.t[2] = 0u;
+    ws.d[0] = win_bytes4(wc.Wd[0], wc.Wd[1], wc.Wd[2], 0u, c0); ws.d[1] = win_bytes4(wc.Wd[0], wc.Wd[1], wc.Wd[2], 0u, c0 + 4); ws.d[2] = 0u;
+    return win_eval_at(wc, ws, d, win_desc(d), w, col, and_out, full, legal_out);
+}
+
 }  // namespace tb

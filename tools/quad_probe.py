@@ -2,7 +2,7 @@
 """K2q (four warps per game, three lanes per placement) against K2f / K2p:
   (1) per-piece latency of all-surviving identical w6 games by games in flight and kernel (lanes 32 = K2f, 64 = K2p, 128 = K2q);
   (2) kernel time of the BASELINE config-2 generation (bench.py's headline step) under different stage schedules
-      (TB200_NO_QUAD=1 = the round-1 schedule; TB200_STAGE_CUTS=a,b,c = hand-over thresholds of stages 0 / 1 / 2).
+      (TB200_QUAD=1 = K2q as the sparse stages; TB200_STAGE_CUTS=a,b,c = hand-over thresholds of stages 0 / 1 / 2).
 usage: python tools/quad_probe.py  (spawns one process per setting for part 2)"""
 import os, subprocess, sys, random
 import numpy as np
@@ -49,9 +49,9 @@ def latency():
 
 def main():
     latency()
-    settings = [("round-1 schedule", {"TB200_NO_QUAD": "1"}), ("default", {})]
+    settings = [("default (K2p last)", {}), ("K2q stages", {"TB200_QUAD": "1"})]
     for cuts in sys.argv[1:] or ["592,296,0", "592,296,100", "592,400,148", "592,444,148", "592,592,148", "592,592,296", "500,350,148"]:
-        settings.append(("cuts " + cuts, {"TB200_STAGE_CUTS": cuts}))
+        settings.append(("K2q cuts " + cuts, {"TB200_STAGE_CUTS": cuts, "TB200_QUAD": "1"}))
     print("%-20s %10s %10s %8s %12s" % ("setting", "min_ms", "median_ms", "launches", "placements"))
     for name, env in settings:
         e = dict(os.environ); e.update(env)
