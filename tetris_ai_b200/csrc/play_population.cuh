@@ -432,6 +432,75 @@ TB_D void lw_store_board(uint32_t (*sb)[32], int lane, const uint32_t c[COLS])
     for (int k = COLS; k >= 1; --k) { sb[20 + k - 1][lane] = acc; acc &= c[k - 1]; }
 }
 
+// Best placement of piece p_cur (warp-uniform) for the game of this lane, window-local evaluation + deferred row-completing
+// placements; key = 0: no legal placement.  cnt counts the legal placements of active lanes (= scorer calls).
+TB_D void lw_search(const Tables& s_tab, uint32_t (*sb)[32], int lane, const WinCache& wc, const double* w, int p_cur, bool active,
+                    uint32_t& cnt, uint64_t& key, uint32_t& tag)
+{
+    uint32_t c[COLS];
+    const int p_u = (int)__reduce_max_sync(FULLMASK, (unsigned)p_cur);      // provably uniform: descriptors from constant memory, fields on the uniform datapath
+    const int ns = c_tables.nslots[p_u];
+    uint32_t dlo = 0u, dhi = 0u;                                 // slots deferred to the general evaluation (they complete a row)
+    // slots are enumerated rotation-major, column-minor: per rotation the windows start at column 0 and slide
+    for (int s2 = 0; s2 < ns;) {
+        WinSlide ws;
+        win_reset(wc, ws);
+        const int ncol = COLS + 1 - (int)((c_tables.slot[p_u][s2].w[0] >> 6) & 7u);      // columns of this rotation (uniform)
+#pragma unroll 1
+        for (int cc = 0; cc < ncol; ++cc, ++s2) {
+            const SlotDesc d = c_tables.slot[p_u][s2];
+            const WinDesc wdsc = c_win[p_u][s2];
+            const int c0 = (int)(d.w[0] & 15u), wdt = (int)((d.w[0] >> 6) & 7u);
+            const uint32_t and_out = sb[10 + c0][lane] & sb[20 + c0 + wdt - 1][lane];
+            uint32_t full; bool legal;
+            uint64_t k = win_eval_at(wc, ws, d, wdsc, w, [&](int kk) -> uint32_t { return sb[kk][lane]; }, and_out, &full, &legal);
+            win_advance(ws);
+            cnt += (uint32_t)(legal && active);
+            if (legal && full != 0u) { k = 0ull; if (s2 < 32) dlo |= 1u << s2; else dhi |= 1u << (s2 - 32); }
+            if (k > key) { key = k; tag = (uint32_t)s2; }
+        }
+    }
+    // ---- deferred placements: rows completed, every column moves -> general w6 evaluation ----
+    if (__any_sync(FULLMASK, (dlo | dhi) != 0u)) {
+        GameStat g;
+        g.H.H0 = funnel_r(wc.X[0], wc.X[1], 16u); g.H.H1 = funnel_r(wc.X[1], wc.X[2], 16u); g.H.H2 = funnel_r(wc.X[2], wc.X[3], 16u) & 0xffffu;
+        unpack_heights(g.H, g.gh);
+        g.cells = wc.cells;
+#pragma unroll
+        for (int k = 0; k < COLS; ++k) c[k] = sb[k][lane];
+        while ((dlo | dhi) != 0u) {
+            int s2;
+            if (dlo != 0u) { s2 = ctz(dlo); dlo &= dlo - 1u; } else { s2 = 32 + ctz(dhi); dhi &= dhi - 1u; }
+            const SlotDesc d = load_slot12(s_tab, p_cur, s2);
+            W6Cand A;
+            w6_pre(c, g, d, A);
+            w6_clear(d, A);
+            Heights Hn;
+            const uint64_t k = w6_post(A, w, Hn);
+            if (k > key || (k == key && (uint32_t)s2 < tag)) { key = k; tag = (uint32_t)s2; }       // first of max: the lower slot keeps a tie
+        }
+    }
+}
+
+// Commit the winning slot `tag`: apply the placement to the lane's board (shared memory), rebuild the window cache.
+TB_D void lw_commit(const Tables& s_tab, uint32_t (*sb)[32], int lane, WinCache& wc, int p_cur, uint32_t tag, W6Cand& A)
+{
+    uint32_t c[COLS];
+    const SlotDesc d = load_slot12(s_tab, p_cur, (int)tag);
+    GameStat g;
+    g.H.H0 = funnel_r(wc.X[0], wc.X[1], 16u); g.H.H1 = funnel_r(wc.X[1], wc.X[2], 16u); g.H.H2 = funnel_r(wc.X[2], wc.X[3], 16u) & 0xffffu;
+    unpack_heights(g.H, g.gh);
+    g.cells = wc.cells;
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) c[k] = sb[k][lane];
+    w6_pre(c, g, d, A);
+    if (A.full != 0u) w6_clear(d, A);
+#pragma unroll
+    for (int k = 0; k < COLS; ++k) c[k] = A.P.n[k];
+    win_cache_init(c, wc);
+    lw_store_board(sb, lane, c);
+}
+
 // The window-local task: 32 games of sequence sq, one lane per game; sb = this warp's board words in shared memory.
 TB_D void lockwin_task(const PlayParams& prm, const Tables& s_tab, uint32_t (*sb)[32], uint32_t st, uint32_t sq, uint32_t slot, uint32_t n_in, uint32_t* ctl)
 {
@@ -496,68 +565,15 @@ TB_D void lockwin_task(const PlayParams& prm, const Tables& s_tab, uint32_t (*sb
     }
     while (t < t_end && p_cur < 7 && __any_sync(FULLMASK, active)) {
         const int p_after = fetch_piece(t + 2u);
-        const int p_u = (int)__reduce_max_sync(FULLMASK, (unsigned)p_cur);      // provably uniform: descriptors from constant memory, fields on the uniform datapath
-        const int ns = c_tables.nslots[p_u];
         uint64_t key = 0; uint32_t tag = 0;
-        uint32_t dlo = 0u, dhi = 0u;                                 // slots deferred to the general evaluation (they complete a row)
-        // slots are enumerated rotation-major, column-minor: per rotation the windows start at column 0 and slide
-        for (int s2 = 0; s2 < ns;) {
-            WinSlide ws;
-            win_reset(wc, ws);
-            const int ncol = COLS + 1 - (int)((c_tables.slot[p_u][s2].w[0] >> 6) & 7u);      // columns of this rotation (uniform)
-#pragma unroll 1
-            for (int cc = 0; cc < ncol; ++cc, ++s2) {
-                const SlotDesc d = c_tables.slot[p_u][s2];
-                const WinDesc wdsc = c_win[p_u][s2];
-                const int c0 = (int)(d.w[0] & 15u), wdt = (int)((d.w[0] >> 6) & 7u);
-                const uint32_t and_out = sb[10 + c0][lane] & sb[20 + c0 + wdt - 1][lane];
-                uint32_t full; bool legal;
-                uint64_t k = win_eval_at(wc, ws, d, wdsc, w, [&](int kk) -> uint32_t { return sb[kk][lane]; }, and_out, &full, &legal);
-                win_advance(ws);
-                cnt += (uint32_t)(legal && active);
-                if (legal && full != 0u) { k = 0ull; if (s2 < 32) dlo |= 1u << s2; else dhi |= 1u << (s2 - 32); }
-                if (k > key) { key = k; tag = (uint32_t)s2; }
-            }
-        }
-        // ---- deferred placements: rows completed, every column moves -> general w6 evaluation ----
-        if (__any_sync(FULLMASK, (dlo | dhi) != 0u)) {
-            GameStat g;
-            g.H.H0 = funnel_r(wc.X[0], wc.X[1], 16u); g.H.H1 = funnel_r(wc.X[1], wc.X[2], 16u); g.H.H2 = funnel_r(wc.X[2], wc.X[3], 16u) & 0xffffu;
-            unpack_heights(g.H, g.gh);
-            g.cells = wc.cells;
-#pragma unroll
-            for (int k = 0; k < COLS; ++k) c[k] = sb[k][lane];
-            while ((dlo | dhi) != 0u) {
-                int s2;
-                if (dlo != 0u) { s2 = ctz(dlo); dlo &= dlo - 1u; } else { s2 = 32 + ctz(dhi); dhi &= dhi - 1u; }
-                const SlotDesc d = load_slot12(s_tab, p_cur, s2);
-                W6Cand A;
-                w6_pre(c, g, d, A);
-                w6_clear(d, A);
-                Heights Hn;
-                const uint64_t k = w6_post(A, w, Hn);
-                if (k > key || (k == key && (uint32_t)s2 < tag)) { key = k; tag = (uint32_t)s2; }       // first of max: the lower slot keeps a tie
-            }
-        }
+        lw_search(s_tab, sb, lane, wc, w, p_cur, active, cnt, key, tag);
         bool finish = false;
         if (active) {
             if (key == 0) {
                 finish = true;                                       // no legal placement: game over (simulator.py:187-189)
             } else {
-                const SlotDesc d = load_slot12(s_tab, p_cur, (int)tag);
-                GameStat g;
-                g.H.H0 = funnel_r(wc.X[0], wc.X[1], 16u); g.H.H1 = funnel_r(wc.X[1], wc.X[2], 16u); g.H.H2 = funnel_r(wc.X[2], wc.X[3], 16u) & 0xffffu;
-                unpack_heights(g.H, g.gh);
-                g.cells = wc.cells;
-#pragma unroll
-                for (int k = 0; k < COLS; ++k) c[k] = sb[k][lane];
                 W6Cand A;
-                w6_pre(c, g, d, A);
-                if (A.full != 0u) w6_clear(d, A);
-#pragma unroll
-                for (int k = 0; k < COLS; ++k) c[k] = A.P.n[k];
-                win_cache_init(c, wc);
-                lw_store_board(sb, lane, c);
+                lw_commit(s_tab, sb, lane, wc, p_cur, tag, A);
                 const uint32_t wk = (uint32_t)A.P.k;
                 if (wk != 0u) {
                     lines += wk;
@@ -671,17 +687,19 @@ __global__ void __launch_bounds__(BLOCK, 5) play_games_w6lockwin_kernel(const Pl
 // lane per game leaves most warps without work (and the rest latency-bound), with many alive eight lanes per game waste
 // lanes.  Here every (stage, sequence) bucket picks its own width from the number of games that enter it, n_in (every
 // warp reads the same counter once the bucket is open, so the choice — and hence the task count — is the same everywhere):
-//     games alive over all G sequences per resident warp  >= 48 : one lane per game, window-local evaluation (K2sW task)
-//                                                          >= 10 : four lanes per game        else : eight lanes per game
+//     games alive over all G sequences per resident warp  >= 24 : one lane per game, window-local evaluation (K2sW task)
+//                                >= 8 : four lanes per game     >= 2 : eight lanes per game     else : a whole warp per game
+// (prm.lk_thr; measured, tools/auto_probe.py: with many games per warp the lane utilisation decides, with few the per-piece latency)
 // Tasks of different widths are the same device functions the fixed-width kernels run; results do not depend on the width.
 // ---------------------------------------------------------------------------------------------
-TB_D uint32_t lock_auto_lanes(uint32_t n_in, uint32_t G, uint32_t warps)
+TB_D uint32_t lock_auto_lanes(const PlayParams& prm, uint32_t n_in, uint32_t G, uint32_t warps)
 {
     const uint64_t alive = (uint64_t)n_in * G;                            // estimate: the other sequences thin out alike
-    return alive >= 48ull * warps ? 1u : (alive >= 10ull * warps ? 4u : 8u);
+    return alive >= (uint64_t)prm.lk_thr[0] * warps ? 1u : (alive >= (uint64_t)prm.lk_thr[1] * warps ? 4u : (alive >= (uint64_t)prm.lk_thr[2] * warps ? 8u : 32u));
 }
 
-__global__ void __launch_bounds__(BLOCK, 5) play_games_w6lockauto_kernel(const PlayParams prm)
+template <int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) play_games_w6lockauto_kernel(const PlayParams prm)
 {
     __shared__ Tables s_tab;
     __shared__ uint32_t s_board[BLOCK / 32][LW_WORDS][32];
@@ -694,7 +712,7 @@ __global__ void __launch_bounds__(BLOCK, 5) play_games_w6lockauto_kernel(const P
 
     uint32_t st = 0, sq = 0;                       // current bucket
     uint32_t n_in = C;
-    uint32_t lanes = lock_auto_lanes(n_in, G, warps);
+    uint32_t lanes = lock_auto_lanes(prm, n_in, G, warps);
     uint32_t ntasks = (n_in * lanes + 31u) / 32u;
     for (;;) {
         uint32_t* ctl = prm.lk_ctl + ((size_t)st * G + sq) * 4;
@@ -707,7 +725,7 @@ __global__ void __launch_bounds__(BLOCK, 5) play_games_w6lockauto_kernel(const P
                 if (lane == 0) {
                     const uint32_t* prev = prm.lk_ctl + ((size_t)(st - 1) * G + sq) * 4;
                     const uint32_t n_prev = st == 1 ? C : __ldcg(prev + 2);
-                    const uint32_t need = (n_prev * lock_auto_lanes(n_prev, G, warps) + 31u) / 32u;      // tasks of the previous bucket of this sequence
+                    const uint32_t need = (n_prev * lock_auto_lanes(prm, n_prev, G, warps) + 31u) / 32u;      // tasks of the previous bucket of this sequence
                     uint32_t spins = 0;
                     while (*reinterpret_cast<volatile const uint32_t*>(prev + 1) < need) {
                         __nanosleep(200);
@@ -718,13 +736,14 @@ __global__ void __launch_bounds__(BLOCK, 5) play_games_w6lockauto_kernel(const P
                 }
                 n_in = __shfl_sync(FULLMASK, n_in, 0);
             }
-            lanes = lock_auto_lanes(n_in, G, warps);
+            lanes = lock_auto_lanes(prm, n_in, G, warps);
             ntasks = (n_in * lanes + 31u) / 32u;
             continue;
         }
         if (lanes == 1u) lockwin_task(prm, s_tab, sb, st, sq, slot, n_in, ctl);
         else if (lanes == 4u) lock_task<4, MODE_W6>(prm, s_tab, st, sq, slot, n_in, ctl);
-        else lock_task<8, MODE_W6>(prm, s_tab, st, sq, slot, n_in, ctl);
+        else if (lanes == 8u) lock_task<8, MODE_W6>(prm, s_tab, st, sq, slot, n_in, ctl);
+        else lock_task<32, MODE_W6>(prm, s_tab, st, sq, slot, n_in, ctl);
     }
 }
 
@@ -800,6 +819,8 @@ __global__ void pb_init_kernel(const PlayParams prm)
     }
 }
 
+// (Measured and not kept: the window-local evaluation of K2sW inside this kernel — the games of a task are on the same piece, so the
+// slot is warp-uniform here too — gave +1 %: a game is popped for ONE piece, so the window cache has to be rebuilt at every pop.)
 template <int LANES>
 __global__ void __launch_bounds__(BLOCK) play_games_w6bin_kernel(const PlayParams prm)
 {

@@ -24,12 +24,17 @@ for _ in range(3):
 import hashlib
 print("%%.3f %%.4e %%d %%s" %% (best, int(r["results"]["placements"].sum()) / best / 1e-3, eng.last_timing()["lanes"], hashlib.sha256(r["results"].tobytes()).hexdigest()[:12]))
 ''' % ROOT
-args = sys.argv[1:] or ["10000", "1.0", "1250", "1.0", "1250", "6.0"]
-for i in range(0, len(args), 2):
-    C, spread = args[i], args[i + 1]
-    print("C=%s spread=%s" % (C, spread))
-    for name, env in (("K2s  lanes 1 (all columns)", {"TB200_LOCK_LANES": "1", "TB200_NO_WIN": "1"}), ("K2sW lanes 1 (window)", {"TB200_LOCK_LANES": "1"}),
-                      ("K2s  lanes 4", {"TB200_LOCK_LANES": "4"}), ("auto", {})):
-        e = dict(os.environ); e.update(env)
-        out = subprocess.run([sys.executable, "-c", CHILD, C, spread], env=e, capture_output=True, text=True, timeout=600).stdout.split()
-        print("  %-28s %9s ms  %s placements/s  lanes %s  results %s" % (name, out[0], out[1], out[2], out[3]), flush=True)
+def main():
+  args = sys.argv[1:] or ["10000", "1.0", "1250", "1.0", "1250", "6.0"]
+  for i in range(0, len(args), 2):
+      C, spread = args[i], args[i + 1]
+      print("C=%s spread=%s" % (C, spread))
+      for name, env in (("K2s  lanes 1 (all columns)", {"TB200_LOCK_LANES": "1", "TB200_NO_WIN": "1"}), ("K2sW lanes 1 (window)", {"TB200_LOCK_LANES": "1"}),
+                        ("K2s  lanes 4", {"TB200_LOCK_LANES": "4"}), ("auto", {})):
+          e = dict(os.environ); e.update(env)
+          out = subprocess.run([sys.executable, "-c", CHILD, C, spread], env=e, capture_output=True, text=True, timeout=600).stdout.split()
+          print("  %-28s %9s ms  %s placements/s  lanes %s  results %s" % (name, out[0], out[1], out[2], out[3]), flush=True)
+
+
+if __name__ == "__main__":
+    main()
