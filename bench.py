@@ -353,6 +353,7 @@ def population_sharded(eng, dev, world, int_peak, which, reps=3):
     w = np.array(pop, dtype=np.float64)
     local_ev = PopulationEvaluator(eng, W6_NAMES, G, pieces=seqs)
     ev = ShardedEvaluator(local_ev, device=dev)
+    ev.collect_timing = True
     ev.collect_placements = True
     rows, digest, placements = [], None, 0
     for i in range(reps + 1):
@@ -429,7 +430,7 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local)
     # NCCL at every N (population_sharded runs at N = 1 too); INFO so that the ranks / transports are visible in the log
     # (fd 1 already points at stderr, so stdout stays the one JSON line)
-    os.environ.setdefault("NCCL_DEBUG", os.environ.get("TB_NCCL_DEBUG", "INFO"))
+    os.environ["NCCL_DEBUG"] = os.environ.get("TB_NCCL_DEBUG", "INFO")
     if world == 1 and "MASTER_ADDR" not in os.environ:
         os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(free_port()), "RANK": "0", "WORLD_SIZE": "1"})
     dist.init_process_group("nccl", device_id=dev, rank=rank, world_size=world)

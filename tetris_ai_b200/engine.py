@@ -69,6 +69,7 @@ class Engine:
         self._h = h
         self.device = int(device)
         self.features = None
+        self._last_features = None
         sms, khz = ctypes.c_int32(), ctypes.c_int32()
         name = ctypes.create_string_buffer(128)
         self._check(self._L.tb200_device_info(self._h, ctypes.byref(sms), ctypes.byref(khz), name, 128))
@@ -107,9 +108,13 @@ class Engine:
 
     # ------------------------------------------------------------------ scorer definition
     def set_features(self, features):
+        key = tuple(features)
+        if key == self._last_features:                # same list as last time (evaluators call this every generation)
+            return self
         ids = np.asarray(feature_ids(features), dtype=np.int32)
         self._check(self._L.tb200_set_features(self._h, _ptr(ids), len(ids)))
         self.features = [int(i) for i in ids]
+        self._last_features = key
         return self
 
     @property
@@ -178,6 +183,17 @@ class Engine:
         """All pointers are DEVICE pointers (ints); work is enqueued on `stream` (a cudaStream_t int) and not synchronised.
         One call in flight per Engine: the library orders a later call behind this one (see include/tetris_b200.h);
         check_status() waits for it and reports an expired device-side wait."""
+        self.run_prepared(self.prepare_device_call(stream, n_candidates, games_per_candidate, weights_ptr, results_ptr, T, pieces_ptr, n_sequences,
+                                                   seq_of_game_ptr, seed, lookahead, lanes, max_moves, init_rows_ptr, trace_ptr, score_trace_ptr,
+                                                   final_rows_ptr, fitness_ptr, move_set, points))
+
+    def run_prepared(self, args):
+        """Enqueue a device-mode call whose argument block was built once by prepare_device_call (latency-sensitive loops)."""
+        self._check(self._L.tb200_play_games(self._h, ctypes.byref(args)))
+
+    def prepare_device_call(self, stream, n_candidates, games_per_candidate, weights_ptr, results_ptr, T, pieces_ptr=0,
+                            n_sequences=0, seq_of_game_ptr=0, seed=0, lookahead=1, lanes=0, max_moves=0, init_rows_ptr=0,
+                            trace_ptr=0, score_trace_ptr=0, final_rows_ptr=0, fitness_ptr=0, move_set=0, points=None):
         a = _lib.PlayArgs()
         a.struct_size = ctypes.sizeof(_lib.PlayArgs)
         a.mem = _lib.MEM_DEVICE
@@ -190,7 +206,7 @@ class Engine:
         a.final_rows, a.fitness = final_rows_ptr or None, fitness_ptr or None
         a.move_set = int(move_set)
         _set_points(a, points)
-        self._check(self._L.tb200_play_games(self._h, ctypes.byref(a)))
+        return a
 
     def check_status(self):
         """Wait for the last device-mode call and raise if one of its bounded device-side waits expired."""

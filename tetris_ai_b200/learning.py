@@ -155,7 +155,8 @@ class ShardedEvaluator:
         self._dev = None                      # device-path buffers, keyed by (C, F)
         self.last_bytes = {"h2d": 0, "d2h": 0}
         self.last_timing = {}                 # evaluate_ms / allgather_ms / d2h_ms (CUDA events), host_prep_ms, total_ms
-        self.collect_placements = False       # when set, last_timing["placements"] = scored leaves of the local shard (one small reduction)
+        self.collect_timing = False           # when set, last_timing is filled from CUDA events around the play / the gather / the copy back
+        self.collect_placements = False       # with collect_timing: last_timing["placements"] = scored leaves of the local shard (one small reduction)
 
     # -- the two callables handed to cross_entropy ---------------------------------------------
     def test_f(self, weights):
@@ -246,35 +247,45 @@ class ShardedEvaluator:
         per = b["per"]
         eng.set_features(pop.names)
         stream = torch.cuda.current_stream(self.device)
-        b["h_w"].numpy()[:c] = weights[lo:hi]
-        chk = self._checksum(weights)
-        t1 = time.perf_counter()
+        timing = self.collect_timing
         ev = b["ev"]
-        ev[0].record(stream)
-        b["d_w"].copy_(b["h_w"], non_blocking=True)                  # this step's inputs: the rank's weights and the injected piece sequences
+        # ---- this step's inputs (the rank's weights, the injected piece sequences) and the play: enqueued first, so that the
+        #      GPU is busy while the host does the rest of its bookkeeping ----
+        b["h_w"].numpy()[:c] = weights[lo:hi]
+        if timing:
+            ev[0].record(stream)
+        b["d_w"].copy_(b["h_w"], non_blocking=True)
         if b["d_pieces"] is not None:
             b["d_pieces"].copy_(b["h_pieces"], non_blocking=True)
-        b["d_fit"][per:].fill_(chk)
         if c > 0:
-            eng.play_games_device(stream.cuda_stream, c, pop.games, b["d_w"].data_ptr(), b["d_res"].data_ptr(), pop.T,
-                                  pieces_ptr=b["d_pieces"].data_ptr() if b["d_pieces"] is not None else 0,
-                                  n_sequences=pop.pieces.shape[0] if pop.pieces is not None else 0, seed=pop.seed,
-                                  lookahead=pop.lookahead, lanes=pop.lanes, fitness_ptr=b["d_fit"].data_ptr())
-        ev[1].record(stream)
+            key = (stream.cuda_stream, c)
+            if b.get("call_key") != key:                    # argument block of the device-mode call, built once per (stream, slice size)
+                b["call"] = eng.prepare_device_call(stream.cuda_stream, c, pop.games, b["d_w"].data_ptr(), b["d_res"].data_ptr(), pop.T,
+                                                    pieces_ptr=b["d_pieces"].data_ptr() if b["d_pieces"] is not None else 0,
+                                                    n_sequences=pop.pieces.shape[0] if pop.pieces is not None else 0, seed=pop.seed,
+                                                    lookahead=pop.lookahead, lanes=pop.lanes, fitness_ptr=b["d_fit"].data_ptr())
+                b["call_key"] = key
+            eng.run_prepared(b["call"])
+        t1 = time.perf_counter()
+        if timing:
+            ev[1].record(stream)
+        b["d_fit"][per:].fill_(self._checksum(weights))     # slot `per` of my block: checksum of the WHOLE batch (stream-ordered before the gather)
         self.dist.all_gather_into_tensor(b["d_all"], b["d_fit"], group=self.group)
-        ev[2].record(stream)
+        if timing:
+            ev[2].record(stream)
         b["h_all"].copy_(b["d_all"], non_blocking=True)
         ev[3].record(stream)
         ev[3].synchronize()
         if c > 0:
             eng.check_status()
         out = self._unpack(b["h_all"].numpy().reshape(self.world, per + 1), C)
-        self.last_timing = {"host_prep_ms": 1e3 * (t1 - t0), "evaluate_ms": ev[0].elapsed_time(ev[1]), "allgather_ms": ev[1].elapsed_time(ev[2]),
-                            "d2h_ms": ev[2].elapsed_time(ev[3]), "total_ms": 1e3 * (time.perf_counter() - t0), "local_candidates": c}
         self.last_bytes = {"h2d": c * F * 8 + (pop.pieces.size if pop.pieces is not None else 0), "d2h": (per + 1) * self.world * 8}
-        if self.collect_placements:
-            from . import _lib
-            rec = b["d_res"][: c * pop.games * _lib.RESULT_DTYPE.itemsize].view(torch.int64).view(-1, 5)
-            self.last_timing["placements"] = int(rec[:, 4].sum().item())
+        if timing:
+            self.last_timing = {"host_prep_ms": 1e3 * (t1 - t0), "evaluate_ms": ev[0].elapsed_time(ev[1]), "allgather_ms": ev[1].elapsed_time(ev[2]),
+                                "d2h_ms": ev[2].elapsed_time(ev[3]), "total_ms": 1e3 * (time.perf_counter() - t0), "local_candidates": c}
+            if self.collect_placements:
+                from . import _lib
+                rec = b["d_res"][: c * pop.games * _lib.RESULT_DTYPE.itemsize].view(torch.int64).view(-1, 5)
+                self.last_timing["placements"] = int(rec[:, 4].sum().item())
         pop.generations += 1
         return out

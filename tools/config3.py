@@ -54,10 +54,11 @@ def main():
     ev = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG", "INFO")             # ranks / transports visible in the log (stderr)
+        os.environ["NCCL_DEBUG"] = os.environ.get("TB_NCCL_DEBUG", "INFO")      # ranks / transports visible in the log (stderr)
         dist.init_process_group("nccl", device_id=dev)
         ev = ShardedEvaluator(local_ev, device=dev)            # device path: play -> all-gather of the device fitness -> one D2H
-        ev.collect_placements = True
+        ev.collect_timing = True
+    ev.collect_placements = True
         test_f, map_f = ev.test_f, ev.map_f
     else:
         test_f, map_f = local_ev.test_f, local_ev.map_f
