@@ -47,8 +47,10 @@
 #ifndef TETRIS_B200_H
 #define TETRIS_B200_H
 
+#if !defined(__CUDACC_RTC__)      /* run-time compilation of the kernels has no host headers; tetris_core.cuh supplies the types */
 #include <stddef.h>
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -136,6 +138,8 @@ typedef struct {
     int32_t grid, block;             /* launch configuration */
     int32_t kernels_launched;        /* number of kernels of this library launched by the call */
     uint64_t h2d_bytes, d2h_bytes;   /* host mode: bytes staged each way */
+    int32_t specialised;             /* 1: the play kernel was one compiled at run time for the ctx's feature list (tb200_jit_build) */
+    int32_t reserved;
 } tb200_timing;
 
 /* page-locked host memory for staging buffers (optional).  A TB200_MEM_HOST play_games call whose buffers are
@@ -155,6 +159,16 @@ int tb200_device_info(tb200_ctx* ctx, int32_t* sms, int32_t* clock_khz, char* na
 /* weighted features of the linear scorer, in summation order (the key order of the weights
  * mapping handed to test_f, learning.py:38).  1 <= F <= TB200_MAX_WEIGHTED, ids in 0..44. */
 int tb200_set_features(tb200_ctx* ctx, const int32_t* feature_ids, int32_t F);
+
+/* Feature lists other than the two compiled into the library (the w6 set, all 45 in id order) are played by kernels that
+ * tb200_play_games specialises for the list at run time — the library's own CUDA sources (csrc/, next to the .so), compiled
+ * once more with NVRTC for sm_100a with the list known to the compiler, cached on disk ($TB200_JIT_CACHE, default
+ * /tmp/tetris_b200_jit-<uid>) — about 4x faster than the run-time-list code, identical results.  It happens on the first play
+ * of >= 2^22 game-moves with lookahead 1 and hard drops (~8 s once; TB200_JIT=1 always, =0 never); if NVRTC or the sources are
+ * missing the precompiled run-time-list kernels run instead (tb200_last_error says why).
+ * tb200_jit_build compiles (or finds in the cache) the kernels for a list without needing a device: returns the cubin size
+ * in KiB (> 0) or a negative TB200_E_* code; log (may be NULL) receives "compiled" / "cached" or the reason of the failure. */
+int tb200_jit_build(const int32_t* feature_ids, int32_t F, char* log, int32_t log_len);
 
 /* whole games for a population: C candidates x G games (K2) */
 int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args);

@@ -490,3 +490,66 @@ def test_k2sw_initial_boards_lines_points_and_max_moves(eng_lane1):
     b = eng.play_games(w, G, lanes=32, **kw)
     assert (a["results"] == b["results"]).all() and (a["final"] == b["final"]).all()
     assert a["trace"].tobytes() == b["trace"].tobytes() and a["scores"].tobytes() == b["scores"].tobytes()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# run-time specialised kernels for arbitrary feature lists (NVRTC, csrc/jit.inc)
+# ---------------------------------------------------------------------------------------------------------------------
+def _engine_with_env(**env):
+    from tetris_ai_b200 import Engine
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return Engine(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+@pytest.fixture(scope="module")
+def eng_jit():
+    e = _engine_with_env(TB200_JIT="1")
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng_nojit():
+    e = _engine_with_env(TB200_JIT="0")
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("kind", ["8", "holes", "floats", "one"])
+def test_jit_specialised_kernels_match_oracle_and_generic(eng_jit, eng_nojit, kind):
+    names = {"8": W6_NAMES + ["max_ht", "jaggedness"], "holes": ["max_ht", "row_trans", "pits", "landing_height"],
+             "floats": ["mean_ht", "max_ht_diff", "min_ht_diff", "mean_pit_depth", "d_mean_ht", "pits", "col_trans", "pattern_div", "tetris_progress", "cd_4", "cuml_eroded", "deep_wells"],
+             "one": ["pits"]}[kind]
+    base = {"landing_height": -4.5, "eroded_cells": 3.4, "row_trans": -3.2, "col_trans": -9.3, "pits": -7.9, "cuml_wells": -3.4, "max_ht": -1.0, "jaggedness": -0.3}
+    rng = np.random.default_rng(len(names))
+    fids = [pyoracle.FEATURE_ID[x] for x in names]
+    for C, G, T, lanes in ((2100, 6, 140, 0), (90, 4, 200, 8), (70, 3, 150, 16), (40, 2, 150, 32)):
+        w = np.array([[base.get(n, 0.0) for n in names]]) + rng.normal(0, 1.5, size=(C, len(names)))
+        pieces = np.array([pyoracle.piece_sequence(17 * g + 3, T) for g in range(G)], dtype=np.uint8)
+        out = {}
+        for tag, eng in (("jit", eng_jit), ("generic", eng_nojit)):
+            eng.set_features(names)
+            out[tag] = eng.play_games(w, G, pieces=pieces, lanes=lanes, want_trace=True, want_scores=True, want_final=True)
+            assert eng.last_timing()["specialised"] == (1 if tag == "jit" else 0), (tag, kind, lanes)
+        a, b = out["jit"], out["generic"]
+        assert (a["results"] == b["results"]).all() and (a["final"] == b["final"]).all() and (a["fitness"] == b["fitness"]).all()
+        assert a["trace"].tobytes() == b["trace"].tobytes() and a["scores"].tobytes() == b["scores"].tobytes()
+        n_o = min(C, 200)
+        o = coracle.play_games(fids, w[:n_o], G, pieces=pieces, threads=THREADS, want_trace=True)
+        res = a["results"][: n_o * G]
+        same_results(res, o)
+        for g in range(0, n_o * G, 7):
+            k = int(res["pieces"][g])
+            assert a["trace"][g, :k].tobytes() == o["trace"][g, :k].tobytes(), (kind, lanes, g)
+    # switching lists on the same ctx: the module follows the list; w6 never uses it
+    eng_jit.set_features(W6_NAMES)
+    eng_jit.play_games(np.array([W6_VALS] * 64), 1, T=50, seed=1)
+    assert eng_jit.last_timing()["specialised"] == 0

@@ -353,3 +353,21 @@ def test_features_header_matches_tables():
     assert ids == dict(F.FEATURE_ID) == dict(pyoracle.FEATURE_ID)
     names = re.findall(r'"([a-z0-9_]+)"', h[h.index("TB200_FEATURE_NAMES {"):h.index("TB200_W6_FEATURE_IDS")])
     assert names[:45] == list(F.FEATURE_NAMES)
+
+
+def test_jit_build_compiles_offline_and_caches(tmp_path, monkeypatch):
+    """tb200_jit_build: the library's own kernel sources, specialised for a feature list with NVRTC (sm_100a), no device needed;
+    the second call finds the cubin in the disk cache."""
+    import ctypes
+    from tetris_ai_b200 import _lib
+    monkeypatch.setenv("TB200_JIT_CACHE", str(tmp_path))
+    L = _lib.load()
+    ids = np.array([16, 1, 32, 37, 10], dtype=np.int32)          # pits, max_ht, jaggedness, landing_height, row_trans
+    log = ctypes.create_string_buffer(1024)
+    kib = L.tb200_jit_build(ids.ctypes.data_as(ctypes.c_void_p), len(ids), log, 1024)
+    assert kib > 100 and log.value == b"compiled", (kib, log.value)
+    kib2 = L.tb200_jit_build(ids.ctypes.data_as(ctypes.c_void_p), len(ids), log, 1024)
+    assert kib2 == kib and log.value == b"cached"
+    assert len(list(tmp_path.glob("*.cubin"))) == 1
+    bad = np.array([99], dtype=np.int32)
+    assert L.tb200_jit_build(bad.ctypes.data_as(ctypes.c_void_p), 1, log, 1024) < 0

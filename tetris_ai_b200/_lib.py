@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtetris_b200.so")
+LIB_PATH = os.environ.get("TB200_LIB") or os.path.join(_HERE, "libtetris_b200.so")      # TB200_LIB: an experiment build of the same library
 
 MEM_HOST, MEM_DEVICE = 0, 1
 MOVES_DROP, MOVES_OVERHANG_SLIDE, MOVES_PRESSURE, MOVES_WIGGLE, MOVES_WIGGLE_DROP = 0, 1, 2, 4, 8
@@ -51,6 +51,7 @@ class Timing(ctypes.Structure):
         ("kernel_ms", ctypes.c_float), ("total_ms", ctypes.c_float), ("lanes", ctypes.c_int32),
         ("grid", ctypes.c_int32), ("block", ctypes.c_int32), ("kernels_launched", ctypes.c_int32),
         ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64),
+        ("specialised", ctypes.c_int32), ("reserved", ctypes.c_int32),
     ]
 
 
@@ -58,7 +59,7 @@ EXPORTS = (
     "tb200_create", "tb200_destroy", "tb200_last_error", "tb200_version", "tb200_device_info",
     "tb200_set_features", "tb200_play_games", "tb200_last_timing", "tb200_best_move", "tb200_best_move_ex",
     "tb200_eval_features", "tb200_eval_features_at", "tb200_hashed_pieces", "tb200_alloc_pinned", "tb200_free_pinned",
-    "tb200_check_status",
+    "tb200_check_status", "tb200_jit_build",
 )
 
 _LIB = None
@@ -91,6 +92,8 @@ def load():
     L.tb200_play_games.restype = ctypes.c_int
     L.tb200_last_timing.argtypes = [vp, ctypes.POINTER(Timing)]
     L.tb200_last_timing.restype = ctypes.c_int
+    L.tb200_jit_build.argtypes = [vp, i32, ctypes.c_char_p, i32]
+    L.tb200_jit_build.restype = ctypes.c_int
     L.tb200_check_status.argtypes = [vp]
     L.tb200_check_status.restype = ctypes.c_int
     L.tb200_best_move.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]

@@ -42,6 +42,7 @@
 #include "play_population.cuh"
 #include "play_lookahead2.cuh"
 #include "play_wiggle.cuh"
+#include "jit.inc"
 
 namespace tb {
 
@@ -218,6 +219,10 @@ struct tb200_ctx {
     char* d_lock = nullptr;
     size_t lock_cap = 0;
     bool lockstep_enabled = true;
+    // run-time specialised kernels for the current (generic) feature list: see jit.inc
+    tbjit::Module* jit = nullptr;
+    bool jit_failed = false;             // compilation / loading failed for the current list: do not retry on every call
+    int jit_policy = -1;                 // TB200_JIT: 0 never, 1 always, unset: plays of >= 2^22 game-moves
     bool win_enabled = true;             // K2sW: window-local evaluation in the one-lane-per-game lockstep kernel (TB200_NO_WIN: the all-columns K2s)
     int lock_lanes = 0, lock_K = 64;     // tuning aids: TB200_LOCK_LANES, TB200_LOCK_K
     int lock_thr[3] = {24, 8, 2};        // K2sA width thresholds (games alive per resident warp): TB200_LOCK_THR=a,b,c
@@ -361,6 +366,7 @@ int tb200_create(int device, tb200_ctx** out)
     if (getenv("TB200_NO_STAGES")) ctx->staging_enabled = false;
     if (getenv("TB200_NO_LOCKSTEP")) ctx->lockstep_enabled = false;
     if (getenv("TB200_NO_WIN")) ctx->win_enabled = false;
+    if (const char* ej = getenv("TB200_JIT")) ctx->jit_policy = atoi(ej) != 0 ? 1 : 0;
     if (getenv("TB200_NO_BINS")) ctx->bin_enabled = false;
     if (getenv("TB200_NO_SEQ_MAJOR")) ctx->seq_major = false;
     if (const char* e5 = getenv("TB200_BIN_LANES")) ctx->bin_lanes = atoi(e5);
@@ -396,6 +402,7 @@ void tb200_destroy(tb200_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     drop_graph(ctx);
+    tbjit::unload(ctx->jit); ctx->jit = nullptr;
     if (ctx->d_ticket) cudaFree(ctx->d_ticket);
     if (ctx->d_stage) cudaFree(ctx->d_stage);
     if (ctx->d_lock) cudaFree(ctx->d_lock);
@@ -427,12 +434,25 @@ int tb200_set_features(tb200_ctx* ctx, const int32_t* feature_ids, int32_t F)
         ctx->ids[i] = (uint8_t)feature_ids[i];
         mask |= 1ull << feature_ids[i];
     }
+    if (ctx->jit && (ctx->jit->F != F || memcmp(ctx->jit->ids, ctx->ids, (size_t)F) != 0)) {      // another list: the specialised kernels go
+        quiesce(ctx); drop_graph(ctx);
+        tbjit::unload(ctx->jit); ctx->jit = nullptr;
+    }
+    if (ctx->F != F || ctx->rmask != mask) ctx->jit_failed = false;
     ctx->F = F; ctx->rmask = mask;
     static const int w6[6] = {tb::F_LANDING_HEIGHT, tb::F_ERODED_CELLS, tb::F_ROW_TRANS, tb::F_COL_TRANS, tb::F_PITS, tb::F_CUML_WELLS};
     bool is_w6 = F == 6, is_all = F == TB200_NUM_FEATURES;
     for (int i = 0; i < F && is_w6; ++i) is_w6 = feature_ids[i] == w6[i];
     for (int i = 0; i < F && is_all; ++i) is_all = feature_ids[i] == i;
     ctx->mode = is_w6 ? tb::MODE_W6 : (is_all ? tb::MODE_ALL45 : tb::MODE_GENERIC);
+#if defined(TB_JIT_MASK)        // experiment build: one extra feature list known at compile time (what the run-time compilation will specialise)
+    {
+        static const int jit_ids[TB_JIT_F] = TB_JIT_IDS;
+        bool is_jit = F == TB_JIT_F;
+        for (int i = 0; i < F && is_jit; ++i) is_jit = feature_ids[i] == jit_ids[i];
+        if (is_jit) ctx->mode = tb::MODE_JIT;
+    }
+#endif
     return TB200_OK;
 }
 
@@ -494,6 +514,44 @@ static int ensure_lock_ws(tb200_ctx* ctx, const tb200_play_args& a)
     const size_t cap = (lp.b_save + lp.b_list + lp.b_ctl) * 5 / 4;
     TB_CUDA(ctx, cudaMalloc(&ctx->d_lock, cap));
     ctx->lock_cap = cap;
+    return TB200_OK;
+}
+
+// ---- run-time specialised kernels (jit.inc): which plays use them, and their one-off compilation (outside any stream capture) ----
+static bool jit_applies(const tb200_ctx* ctx, const tb200_play_args& a)
+{
+    if (ctx->mode != tb::MODE_GENERIC || a.lookahead != 1 || a.move_set != 0 || ctx->jit_policy == 0) return false;
+    const uint32_t moves = a.max_moves && a.max_moves < a.T ? a.max_moves : a.T;
+    const unsigned long long work = (unsigned long long)a.n_candidates * a.games_per_candidate * moves;
+    return ctx->jit_policy == 1 || work >= (1ull << 22);
+}
+static void ensure_jit(tb200_ctx* ctx, const tb200_play_args& a)
+{
+    if (!jit_applies(ctx, a) || ctx->jit || ctx->jit_failed) return;
+    static const tb::Tables host_tab = { TB_SLOT_TABLE_INIT, TB_NSLOTS_INIT };
+    static tb::WinDesc host_win[7][TB_MAX_SLOTS];
+    for (int p = 0; p < 7; ++p) for (int s2 = 0; s2 < TB_MAX_SLOTS; ++s2) host_win[p][s2] = tb::win_desc(host_tab.slot[p][s2]);
+    std::string why;
+    quiesce(ctx);
+    drop_graph(ctx);
+    ctx->jit = tbjit::load_module(ctx->ids, ctx->F, host_tab, &host_win[0][0], sizeof host_win, why);
+    if (!ctx->jit) {
+        ctx->jit_failed = true;
+        ctx->err = "run-time specialisation unavailable (" + why + "): the precompiled generic kernels run instead";
+        fprintf(stderr, "tetris_b200: %s\n", ctx->err.c_str());
+    }
+}
+// launch a kernel of the library (fn) or its run-time specialised twin (cf != null)
+static int launch_any(tb200_ctx* ctx, tb::play_fn fn, CUfunction cf, unsigned grid, unsigned block, size_t smem, cudaStream_t st, tb::PlayParams& p)
+{
+    if (cf) {
+        void* params[] = { &p };
+        if (tbjit::g_api.LaunchKernel(cf, grid, 1, 1, block, 1, 1, (unsigned)smem, (CUstream)st, params, nullptr) != CUDA_SUCCESS)
+            return fail(ctx, TB200_E_CUDA, "cuLaunchKernel of a specialised kernel failed");
+        return TB200_OK;
+    }
+    fn<<<grid, block, smem, st>>>(p);
+    TB_CUDA(ctx, cudaGetLastError());
     return TB200_OK;
 }
 
@@ -569,6 +627,7 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
     const long long per_sm_games = (n_games_ll + ctx->sms - 1) / ctx->sms;
     const LockPlan lp = lock_plan(ctx, a, per_game_weights);
     const bool lockstep = lp.on && lp.b_save + lp.b_list + lp.b_ctl <= ctx->lock_cap;      // workspace comes from ensure_lock_ws()
+    bool used_jit = false;
     TB_CUDA(ctx, cudaMemsetAsync(ctx->d_ticket, 0, sizeof(uint32_t), st));
     TB_CUDA(ctx, cudaMemsetAsync(a.results, 0, sizeof(tb200_game_result) * (size_t)n_games, st));
     if (lockstep && lp.kind == 2) {
@@ -616,14 +675,26 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
             lf = tb::play_games_w6lockwin_kernel;
         else if (ctx->mode == tb::MODE_W6)
             lf = ll == 8 ? tb::play_games_w6lock_kernel<8> : (ll == 4 ? tb::play_games_w6lock_kernel<4> : (ll == 2 ? tb::play_games_w6lock_kernel<2> : tb::play_games_w6lock_kernel<1>));
+#if defined(TB_JIT_MASK)
+        else if (ctx->mode == tb::MODE_JIT)
+            lf = ll == 8 ? tb::play_games_w6lock_kernel<8, tb::MODE_JIT> : (ll == 4 ? tb::play_games_w6lock_kernel<4, tb::MODE_JIT> :
+                 (ll == 2 ? tb::play_games_w6lock_kernel<2, tb::MODE_JIT> : tb::play_games_w6lock_kernel<1, tb::MODE_JIT>));
+#endif
         else if (ctx->mode == tb::MODE_ALL45)
             lf = ll == 8 ? tb::play_games_w6lock_kernel<8, tb::MODE_ALL45> : (ll == 4 ? tb::play_games_w6lock_kernel<4, tb::MODE_ALL45> :
                  (ll == 2 ? tb::play_games_w6lock_kernel<2, tb::MODE_ALL45> : tb::play_games_w6lock_kernel<1, tb::MODE_ALL45>));
         else
             lf = ll == 8 ? tb::play_games_w6lock_kernel<8, tb::MODE_GENERIC> : (ll == 4 ? tb::play_games_w6lock_kernel<4, tb::MODE_GENERIC> :
                  (ll == 2 ? tb::play_games_w6lock_kernel<2, tb::MODE_GENERIC> : tb::play_games_w6lock_kernel<1, tb::MODE_GENERIC>));
+        CUfunction lcf = nullptr;
+        if (ctx->jit && jit_applies(ctx, a) && ctx->mode == tb::MODE_GENERIC) {
+            if (ll == 1) ll = 2;
+            lcf = ctx->jit->fn[ll == 8 ? tbjit::K_LOCK8 : (ll == 4 ? tbjit::K_LOCK4 : tbjit::K_LOCK2)];
+            used_jit = true;
+        }
         int locc = 0;
-        TB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&locc, lf, tb::BLOCK, 0));
+        if (lcf) { if (tbjit::g_api.Occupancy(&locc, lcf, tb::BLOCK, 0) != CUDA_SUCCESS) locc = 1; }
+        else TB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&locc, lf, tb::BLOCK, 0));
         if (locc < 1) locc = 1;
         long long lblocks = (n_games_ll * ll + tb::BLOCK - 1) / tb::BLOCK;           // the grid must be fully resident: tasks wait on tasks
         if (lblocks > (long long)ctx->sms * locc || lock_auto) lblocks = (long long)ctx->sms * locc;
@@ -633,8 +704,7 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
         }
         TB_CUDA(ctx, cudaMemsetAsync(p.lk_ctl, 0, b_ctl, st));
         if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
-        lf<<<(unsigned)lblocks, tb::BLOCK, 0, st>>>(p);
-        TB_CUDA(ctx, cudaGetLastError());
+        { const int rcl = launch_any(ctx, lf, lcf, (unsigned)lblocks, tb::BLOCK, 0, st, p); if (rcl) return rcl; }
         if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
         *launches += 1;
         lanes = ll; blocks = lblocks;
@@ -678,9 +748,19 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
         if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
         if (!dense) blocks = ctx->sms;
     } else {
+        CUfunction cf = nullptr;
+        if (ctx->jit && jit_applies(ctx, a) && (lanes == 8 || lanes == 16 || lanes == 32)) {
+            cf = ctx->jit->fn[lanes == 8 ? tbjit::K_GEN8 : (lanes == 16 ? tbjit::K_GEN16 : tbjit::K_W32)];
+            used_jit = true;
+            int jocc = 0;
+            if (tbjit::g_api.Occupancy(&jocc, cf, tb::BLOCK, 0) == CUDA_SUCCESS && jocc >= 1) {
+                const long long per_block = tb::BLOCK / lanes;
+                blocks = (n_games_ll + per_block - 1) / per_block;
+                if (blocks > (long long)ctx->sms * jocc) blocks = (long long)ctx->sms * jocc;
+            }
+        }
         if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
-        fn<<<(unsigned)blocks, block, dyn_smem, st>>>(p);
-        TB_CUDA(ctx, cudaGetLastError());
+        { const int rcl = launch_any(ctx, fn, cf, (unsigned)blocks, (unsigned)block, dyn_smem, st, p); if (rcl) return rcl; }
         if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
         *launches += 1;
     }
@@ -690,6 +770,7 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
         *launches += 1;
     }
     ctx->timing.lanes = staged ? 32 : lanes; ctx->timing.grid = (int)blocks; ctx->timing.block = staged ? tb::BLOCK : block;
+    ctx->timing.specialised = used_jit ? 1 : 0;
     return TB200_OK;
 }
 
@@ -730,6 +811,7 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
     const size_t n_games = (size_t)a.n_candidates * a.games_per_candidate;
     rc = ensure_lock_ws(ctx, a);
     if (rc) return rc;
+    ensure_jit(ctx, a);
     ctx->lock_flag = nullptr;
     ctx->timing = tb200_timing{};
     ctx->timing_valid = false;
@@ -855,6 +937,19 @@ int tb200_play_games(tb200_ctx* ctx, const tb200_play_args* args)
     ctx->timing.kernels_launched = launches;
     ctx->timing_valid = true;
     return TB200_OK;
+}
+
+int tb200_jit_build(const int32_t* feature_ids, int32_t F, char* log, int32_t log_len)
+{
+    if (!feature_ids || F < 1 || F > TB200_MAX_WEIGHTED) return TB200_E_BAD_ARG;
+    uint8_t ids[TB200_MAX_WEIGHTED];
+    for (int i = 0; i < F; ++i) { if (feature_ids[i] < 0 || feature_ids[i] >= TB200_NUM_FEATURES) return TB200_E_BAD_ARG; ids[i] = (uint8_t)feature_ids[i]; }
+    std::vector<char> cubin;
+    std::string why;
+    bool cached = false;
+    const bool ok = tbjit::build_cubin(ids, F, cubin, why, &cached);
+    if (log && log_len > 0) snprintf(log, (size_t)log_len, "%s", ok ? (cached ? "cached" : "compiled") : why.c_str());
+    return ok ? (int)(cubin.size() >> 10) : TB200_E_CUDA;
 }
 
 int tb200_check_status(tb200_ctx* ctx)

@@ -11,7 +11,12 @@
 // Everything is __host__ __device__ so that tests/emu can run the identical code on the CPU
 // against the oracles; the product only ever runs it on the GPU.
 #pragma once
+#if defined(__CUDACC_RTC__)      // run-time compilation (NVRTC) has no host headers
+typedef unsigned char uint8_t; typedef unsigned short uint16_t; typedef unsigned int uint32_t; typedef int int32_t;
+typedef unsigned long long uint64_t; typedef long long int64_t;
+#else
 #include <stdint.h>
+#endif
 #include "tetris_tables.h"
 
 #if defined(__CUDACC__)
@@ -749,11 +754,17 @@ TB_HD double feat_value(const Feat& f, int id)
 }
 
 // Scoring modes: the feature list and its order are compile-time for the two headline sets.
-enum : int { MODE_GENERIC = 0, MODE_W6 = 1, MODE_ALL45 = 2 };
+// MODE_JIT: a feature list fixed when the translation unit is compiled — TB_JIT_F features with ids TB_JIT_IDS (in summation
+// order) and mask TB_JIT_MASK, handed in as macros by the run-time compilation of csrc/jit.cuh (tb200_set_features): the
+// same code as MODE_GENERIC with the list known to the compiler, so unused features vanish and the scorer is unrolled.
+enum : int { MODE_GENERIC = 0, MODE_W6 = 1, MODE_ALL45 = 2, MODE_JIT = 3 };
 template <int MODE> struct ModeTraits;
 template <> struct ModeTraits<MODE_GENERIC> { static constexpr uint64_t CMASK = 0; };
 template <> struct ModeTraits<MODE_W6>      { static constexpr uint64_t CMASK = W6_MASK; };
 template <> struct ModeTraits<MODE_ALL45>   { static constexpr uint64_t CMASK = ALL45_MASK; };
+#if defined(TB_JIT_MASK)
+template <> struct ModeTraits<MODE_JIT>     { static constexpr uint64_t CMASK = TB_JIT_MASK; };
+#endif
 
 // canonical scorer: acc = 0.0; acc += float(f_i) * w_i in the caller's order,
 // one rounded multiply and one rounded add per feature.
@@ -771,6 +782,12 @@ TB_HD double score_features(const Feat& f, const uint8_t* ids, const double* w, 
     } else if (MODE == MODE_ALL45) {
 #pragma unroll
         for (int i = 0; i < NFEAT; ++i) acc = dadd(acc, dmul(feat_value(f, i), w[i]));
+#if defined(TB_JIT_MASK)
+    } else if (MODE == MODE_JIT) {
+        constexpr int jit_ids[TB_JIT_F] = TB_JIT_IDS;
+#pragma unroll
+        for (int i = 0; i < TB_JIT_F; ++i) acc = dadd(acc, dmul(feat_value(f, jit_ids[i]), w[i]));
+#endif
     } else {
         for (int i = 0; i < F; ++i) acc = dadd(acc, dmul(feat_value(f, ids[i]), w[i]));
     }

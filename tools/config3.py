@@ -58,7 +58,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
         ev = ShardedEvaluator(local_ev, device=dev)            # device path: play -> all-gather of the device fitness -> one D2H
         ev.collect_timing = True
-    ev.collect_placements = True
+        ev.collect_placements = True
         test_f, map_f = ev.test_f, ev.map_f
     else:
         test_f, map_f = local_ev.test_f, local_ev.map_f
