@@ -420,7 +420,9 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayPara
 // every commit.  Placements that complete a row move every column: they are DEFERRED (one bit per slot) and evaluated
 // after the slot loop with the general w6 code, so the common path carries no divergent clear branch at all.
 // ---------------------------------------------------------------------------------------------
-constexpr int LW_WORDS = 30;           // per game: columns 0..9 | P[k] = AND of columns < k, k = 0..9 | S[k] = AND of columns >= k, k = 1..10
+constexpr int LW_BOARD = 30;           // per game: columns 0..9 | P[k] = AND of columns < k, k = 0..9 | S[k] = AND of columns >= k, k = 1..10
+constexpr int LW_ITEMS = 256;          // deferred (game, slot) placements a warp shares per piece (more than that: their owners evaluate them)
+constexpr int LW_WORDS = LW_BOARD + LW_ITEMS / 32 + 2 * LW_ITEMS / 32;      // + item table (owner | slot << 8) + 64-bit keys of the items
 
 TB_D void lw_store_board(uint32_t (*sb)[32], int lane, const uint32_t c[COLS])
 {
@@ -460,26 +462,88 @@ TB_D void lw_search(const Tables& s_tab, uint32_t (*sb)[32], int lane, const Win
             if (k > key) { key = k; tag = (uint32_t)s2; }
         }
     }
-    // ---- deferred placements: rows completed, every column moves -> general w6 evaluation ----
-    if (__any_sync(FULLMASK, (dlo | dhi) != 0u)) {
-        GameStat g;
-        g.H.H0 = funnel_r(wc.X[0], wc.X[1], 16u); g.H.H1 = funnel_r(wc.X[1], wc.X[2], 16u); g.H.H2 = funnel_r(wc.X[2], wc.X[3], 16u) & 0xffffu;
-        unpack_heights(g.H, g.gh);
-        g.cells = wc.cells;
+    // ---- deferred placements: rows completed, every column moves -> general w6 evaluation.  The lanes of a warp hold very
+    //      different numbers of them (0 .. 10 per piece), so they are SHARED: every lane lists its (game, slot) items in shared
+    //      memory, the warp evaluates 32 items per round whatever game they belong to (the board comes from the owner's
+    //      shared-memory column, the weights / heights / cell count by shuffle from the owner's registers), and every owner
+    //      collects the keys of its own items in slot order. ----
+    const uint32_t mine = (uint32_t)__popc(dlo) + (uint32_t)__popc(dhi);
+    if (!__any_sync(FULLMASK, mine != 0u)) return;
+    uint32_t off = mine;                                         // inclusive prefix sum over the lanes
 #pragma unroll
-        for (int k = 0; k < COLS; ++k) c[k] = sb[k][lane];
-        while ((dlo | dhi) != 0u) {
+    for (int dlt = 1; dlt < 32; dlt <<= 1) { const uint32_t v = __shfl_up_sync(FULLMASK, off, dlt); if (lane >= dlt) off += v; }
+    const uint32_t total = __shfl_sync(FULLMASK, off, 31);
+    off -= mine;
+    uint32_t* const items = &sb[LW_BOARD][0];
+    unsigned long long* const keys = reinterpret_cast<unsigned long long*>(&sb[LW_BOARD + LW_ITEMS / 32][0]);
+    {
+        uint32_t a = dlo, b = dhi, i = off;
+        while ((a | b) != 0u) {
             int s2;
-            if (dlo != 0u) { s2 = ctz(dlo); dlo &= dlo - 1u; } else { s2 = 32 + ctz(dhi); dhi &= dhi - 1u; }
+            if (a != 0u) { s2 = ctz(a); a &= a - 1u; } else { s2 = 32 + ctz(b); b &= b - 1u; }
+            if (i < (uint32_t)LW_ITEMS) items[i] = (uint32_t)lane | (uint32_t)s2 << 8;
+            ++i;
+        }
+    }
+    __syncwarp(FULLMASK);
+    const uint32_t shared_n = total < (uint32_t)LW_ITEMS ? total : (uint32_t)LW_ITEMS;
+    for (uint32_t base = 0; base < shared_n; base += 32u) {
+        const uint32_t j = base + (uint32_t)lane;
+        const bool have = j < shared_n;
+        const uint32_t it = have ? items[j] : 0u;
+        const int owner = (int)(it & 31u), s2 = (int)(it >> 8);
+        double wo[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) wo[i] = __shfl_sync(FULLMASK, w[i], owner);
+        const uint32_t x0 = __shfl_sync(FULLMASK, wc.X[0], owner), x1 = __shfl_sync(FULLMASK, wc.X[1], owner),
+                       x2 = __shfl_sync(FULLMASK, wc.X[2], owner), x3 = __shfl_sync(FULLMASK, wc.X[3], owner);
+        GameStat g;
+        g.H.H0 = funnel_r(x0, x1, 16u); g.H.H1 = funnel_r(x1, x2, 16u); g.H.H2 = funnel_r(x2, x3, 16u) & 0xffffu;
+        unpack_heights(g.H, g.gh);
+        g.cells = __shfl_sync(FULLMASK, wc.cells, owner);
+        if (have) {
+#pragma unroll
+            for (int k = 0; k < COLS; ++k) c[k] = sb[k][owner];
             const SlotDesc d = load_slot12(s_tab, p_cur, s2);
             W6Cand A;
             w6_pre(c, g, d, A);
             w6_clear(d, A);
             Heights Hn;
-            const uint64_t k = w6_post(A, w, Hn);
+            keys[j] = w6_post(A, wo, Hn);
+        }
+    }
+    __syncwarp(FULLMASK);
+    if (mine != 0u) {
+        GameStat g;
+        bool loaded = false;
+        uint32_t i = off;
+        while ((dlo | dhi) != 0u) {
+            int s2;
+            if (dlo != 0u) { s2 = ctz(dlo); dlo &= dlo - 1u; } else { s2 = 32 + ctz(dhi); dhi &= dhi - 1u; }
+            uint64_t k;
+            if (i < (uint32_t)LW_ITEMS) {
+                k = keys[i];
+            } else {                                             // beyond the shared table: the owner evaluates it itself
+                if (!loaded) {
+                    g.H.H0 = funnel_r(wc.X[0], wc.X[1], 16u); g.H.H1 = funnel_r(wc.X[1], wc.X[2], 16u); g.H.H2 = funnel_r(wc.X[2], wc.X[3], 16u) & 0xffffu;
+                    unpack_heights(g.H, g.gh);
+                    g.cells = wc.cells;
+#pragma unroll
+                    for (int kk = 0; kk < COLS; ++kk) c[kk] = sb[kk][lane];
+                    loaded = true;
+                }
+                const SlotDesc d = load_slot12(s_tab, p_cur, s2);
+                W6Cand A;
+                w6_pre(c, g, d, A);
+                w6_clear(d, A);
+                Heights Hn;
+                k = w6_post(A, w, Hn);
+            }
+            ++i;
             if (k > key || (k == key && (uint32_t)s2 < tag)) { key = k; tag = (uint32_t)s2; }       // first of max: the lower slot keeps a tie
         }
     }
+    __syncwarp(FULLMASK);                                        // the item / key rows are reused by the next piece
 }
 
 // Commit the winning slot `tag`: apply the placement to the lane's board (shared memory), rebuild the window cache.
@@ -636,11 +700,11 @@ TB_D void lockwin_task(const PlayParams& prm, const Tables& s_tab, uint32_t (*sb
     }
 }
 
-__global__ void __launch_bounds__(BLOCK, 5) play_games_w6lockwin_kernel(const PlayParams prm)
+__global__ void __launch_bounds__(BLOCK, 4) play_games_w6lockwin_kernel(const PlayParams prm)
 {
     constexpr uint32_t GPW = 32;                   // games per warp
     __shared__ Tables s_tab;
-    __shared__ uint32_t s_board[BLOCK / 32][LW_WORDS][32];
+    __shared__ alignas(16) uint32_t s_board[BLOCK / 32][LW_WORDS][32];
     load_tables<BLOCK>(s_tab);
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -702,7 +766,7 @@ template <int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) play_games_w6lockauto_kernel(const PlayParams prm)
 {
     __shared__ Tables s_tab;
-    __shared__ uint32_t s_board[BLOCK / 32][LW_WORDS][32];
+    __shared__ alignas(16) uint32_t s_board[BLOCK / 32][LW_WORDS][32];
     load_tables<BLOCK>(s_tab);
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -710,16 +774,24 @@ __global__ void __launch_bounds__(BLOCK, MINB) play_games_w6lockauto_kernel(cons
     const uint32_t C = prm.lk_C, S = prm.lk_S, G = (uint32_t)prm.G;
     const uint32_t warps = gridDim.x * (BLOCK / 32);
 
+    // A stage has ntasks x G tasks.  When that is less than the resident warps, only as many warps as there are tasks
+    // take tickets, and they are chosen so that they spread evenly over the SMs (rank = warp-in-block major, block minor:
+    // consecutive ranks sit on different SMs) — otherwise the first warps to arrive pile the tasks onto a few SMs while the
+    // others idle (measured: 20.5 ms against 11.6 ms for a 37 500-game shard with one lane per game).
+    const uint32_t rank = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
     uint32_t st = 0, sq = 0;                       // current bucket
     uint32_t n_in = C;
     uint32_t lanes = lock_auto_lanes(prm, n_in, G, warps);
     uint32_t ntasks = (n_in * lanes + 31u) / 32u;
+    bool take = (uint64_t)rank < (uint64_t)ntasks * G;
     for (;;) {
         uint32_t* ctl = prm.lk_ctl + ((size_t)st * G + sq) * 4;
-        uint32_t slot = 0;
-        if (lane == 0) slot = atomicAdd(ctl, 1u);
-        slot = __shfl_sync(FULLMASK, slot, 0);
-        if (slot >= ntasks) {                      // bucket handed out: open the next one
+        uint32_t slot = 0xffffffffu;
+        if (take) {
+            if (lane == 0) slot = atomicAdd(ctl, 1u);
+            slot = __shfl_sync(FULLMASK, slot, 0);
+        }
+        if (slot >= ntasks) {                      // bucket handed out (or not mine): open the next one
             if (++sq == G) { sq = 0; if (++st == S) break; }
             if (st > 0) {
                 if (lane == 0) {
@@ -738,6 +810,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) play_games_w6lockauto_kernel(cons
             }
             lanes = lock_auto_lanes(prm, n_in, G, warps);
             ntasks = (n_in * lanes + 31u) / 32u;
+            take = (uint64_t)rank < (uint64_t)ntasks * G;
             continue;
         }
         if (lanes == 1u) lockwin_task(prm, s_tab, sb, st, sq, slot, n_in, ctl);

@@ -445,14 +445,6 @@ int tb200_set_features(tb200_ctx* ctx, const int32_t* feature_ids, int32_t F)
     for (int i = 0; i < F && is_w6; ++i) is_w6 = feature_ids[i] == w6[i];
     for (int i = 0; i < F && is_all; ++i) is_all = feature_ids[i] == i;
     ctx->mode = is_w6 ? tb::MODE_W6 : (is_all ? tb::MODE_ALL45 : tb::MODE_GENERIC);
-#if defined(TB_JIT_MASK)        // experiment build: one extra feature list known at compile time (what the run-time compilation will specialise)
-    {
-        static const int jit_ids[TB_JIT_F] = TB_JIT_IDS;
-        bool is_jit = F == TB_JIT_F;
-        for (int i = 0; i < F && is_jit; ++i) is_jit = feature_ids[i] == jit_ids[i];
-        if (is_jit) ctx->mode = tb::MODE_JIT;
-    }
-#endif
     return TB200_OK;
 }
 
@@ -675,11 +667,6 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
             lf = tb::play_games_w6lockwin_kernel;
         else if (ctx->mode == tb::MODE_W6)
             lf = ll == 8 ? tb::play_games_w6lock_kernel<8> : (ll == 4 ? tb::play_games_w6lock_kernel<4> : (ll == 2 ? tb::play_games_w6lock_kernel<2> : tb::play_games_w6lock_kernel<1>));
-#if defined(TB_JIT_MASK)
-        else if (ctx->mode == tb::MODE_JIT)
-            lf = ll == 8 ? tb::play_games_w6lock_kernel<8, tb::MODE_JIT> : (ll == 4 ? tb::play_games_w6lock_kernel<4, tb::MODE_JIT> :
-                 (ll == 2 ? tb::play_games_w6lock_kernel<2, tb::MODE_JIT> : tb::play_games_w6lock_kernel<1, tb::MODE_JIT>));
-#endif
         else if (ctx->mode == tb::MODE_ALL45)
             lf = ll == 8 ? tb::play_games_w6lock_kernel<8, tb::MODE_ALL45> : (ll == 4 ? tb::play_games_w6lock_kernel<4, tb::MODE_ALL45> :
                  (ll == 2 ? tb::play_games_w6lock_kernel<2, tb::MODE_ALL45> : tb::play_games_w6lock_kernel<1, tb::MODE_ALL45>));

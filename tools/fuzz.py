@@ -30,7 +30,19 @@ def random_board(rng):
 def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     rng = random.Random(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
-    eng = Engine(0)
+    # several ctxs with different scheduling switches (read at tb200_create): the lockstep kernel's per-bucket width rule is pushed
+    # to every width, the quad kernel takes over the sparse stages, the window evaluation is switched off
+    engines = []
+    for env in ({}, {"TB200_LOCK_THR": "0,0,0"}, {"TB200_LOCK_THR": "1000000,0,0"}, {"TB200_LOCK_THR": "1000000,1000000,0"},
+                {"TB200_LOCK_THR": "1000000,1000000,1000000"}, {"TB200_LOCK_THR": "60,20,6"}, {"TB200_QUAD": "1"}, {"TB200_NO_WIN": "1"}):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        engines.append(Engine(0))
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
     t0 = time.time()
     stats = {"games": 0, "pieces": 0, "placements": 0}
     for it in range(iters):
@@ -46,7 +58,8 @@ def main():
         pressure = None
         if rng.random() < 0.3:
             pressure = {"avg_lat": rng.uniform(100, 350), "resp_time": rng.uniform(30, 130), "move_eff": rng.uniform(0.9, 1.6), "two_but_rot": rng.random() < 0.5}
-        lanes = rng.choice([0, 64, 32, 16, 8, 4, 2, 1])
+        lanes = rng.choice([0, 128, 64, 32, 16, 8, 4, 2, 1])
+        eng = rng.choice(engines)
         C, G = rng.randint(1, 24), rng.randint(1, 3)
         T = rng.randint(1, 30) if (la == 2 or ms_name.startswith("wiggle")) else rng.randint(1, 220)
         if la == 2 and ms_name.startswith("wiggle"):
@@ -74,7 +87,7 @@ def main():
         use_pieces = rng.random() < 0.5
         pieces = np.array([[rng.randrange(7) for _ in range(T)] for _ in range(G)], dtype=np.uint8) if use_pieces else None
         init = None
-        if rng.random() < 0.4:
+        if rng.random() < 0.4 and n <= 2000:
             init = np.array([random_board(rng) for _ in range(n)], dtype=np.uint16)
         fids = [pyoracle.FEATURE_ID[x] for x in names]
         bit = {"drop": 0, "slide": 1, "wiggle_top": 4, "wiggle_drop": 8}[ms_name]
@@ -83,6 +96,20 @@ def main():
         r = eng.play_games(w, G, pieces=pieces, T=T, seed=seed, lookahead=la, lanes=lanes, init_rows=init, want_trace=True, want_final=True,
                            move_set=bit, pressure=pressure)
         res = r["results"]
+        if init is None and n > 64:
+            # big cases (staged / lockstep / binned populations): the oracle's multi-threaded batch entry, whole arrays compared
+            o = coracle.play_games(fids, w, G, pieces=pieces, T=T, seed=seed, lookahead=la, threads=os.cpu_count() or 8, want_trace=True,
+                                   move_set=ms_name, pressure=pressure)
+            ok = ((res["pieces"] == o["pieces"]).all() and (res["lines"] == o["lines"]).all() and (res["hist"] == o["hist"]).all()
+                  and (res["score"] == o["score"]).all() and (res["placements"] == o["placements"]).all())
+            if ok:
+                played = np.arange(T)[None, :, None] < o["pieces"].astype(np.int64)[:, None, None]
+                ok = bool((np.where(played, r["trace"], 0) == np.where(played, o["trace"], 0)).all())
+            if not ok:
+                print("MISMATCH iteration", it, dict(names=names, ms=ms_name, la=la, pressure=pressure, lanes=lanes, C=C, G=G, T=T, seed=seed, use_pieces=use_pieces))
+                sys.exit(1)
+            stats["games"] += n; stats["pieces"] += int(o["pieces"].sum()); stats["placements"] += int(o["placements"].sum())
+            continue
         for g in range(n):
             seq = pieces[g % G] if use_pieces else [pyoracle.hashed_piece(seed, g % G, t) for t in range(T)]
             o = coracle.play_one(fids, w[g // G], seq, la, init_rows=None if init is None else init[g], move_set=ms_name, pressure=pressure)
@@ -97,6 +124,9 @@ def main():
                 print(" cpu:", o["pieces"], o["lines"], o["hist"], o["score"], o["placements"], o["trace"].tolist()[:12])
                 sys.exit(1)
             stats["games"] += 1; stats["pieces"] += k; stats["placements"] += o["placements"]
+        if time.time() - t0 > float(os.environ.get("FUZZ_SECONDS", "1e9")):
+            iters = it + 1
+            break
     print("fuzz ok: %d iterations, %d games, %d pieces, %d placements, %.1f s" % (iters, stats["games"], stats["pieces"], stats["placements"], time.time() - t0))
 
 
