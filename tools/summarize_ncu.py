@@ -10,6 +10,7 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_outpu
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, row = rows[0], rows[1], rows[2]
 d = {h: (row[i], units[i]) for i, h in enumerate(hdr)}
+extra_launches = rows[3:]               # a report with several launches (e.g. the re-spreading stages of one play): summarised below
 keys = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__warps_active.avg.per_cycle_active", "smsp__warps_eligible.avg.per_cycle_active",
@@ -57,5 +58,18 @@ for r in srows:
                 pass
 s = sum(tot.values()) or 1
 res["warp_stall_samples_pct"] = {k: round(100.0 * v / s, 2) for k, v in tot.most_common(8)}
+if extra_launches:
+    res["launches"] = []
+    for r in [row] + extra_launches:
+        dd = {h: r[i] for i, h in enumerate(hdr) if i < len(r)}
+        one = {"kernel": dd.get("Kernel Name", "?")}
+        for k in keys:
+            if k in dd:
+                try:
+                    one[k] = float(dd[k])
+                except ValueError:
+                    one[k] = dd[k]
+        one["unit_of"] = {k: d[k][1] for k in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum") if k in d}
+        res["launches"].append(one)
 json.dump(res, open(out, "w"), indent=1)
 print(json.dumps(res, indent=1)[:1500])
