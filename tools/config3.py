@@ -30,6 +30,8 @@ def seeded_sequence(seed, T):
 
 
 def main():
+    real_stdout = os.dup(1)          # NCCL_DEBUG=INFO writes to fd 1: keep stdout for the JSON lines, send the rest to stderr
+    os.dup2(2, 1)
     import torch
     from tetris_ai_b200 import Engine
     from tetris_ai_b200.learning import PopulationEvaluator, ShardedEvaluator, cross_entropy
@@ -84,10 +86,10 @@ def main():
             placements = int(tot.item())
         digest = hashlib.sha256(("".join(float(v).hex() for v in list(mean.values()) + list(std.values()))).encode()).hexdigest()[:16]
         if rank == 0:
-            print(json.dumps({"generation": g, "n_gpus": world, "width": width, "games_per_candidate": G, "wall_s": wall, "evaluate_s": times["map_s"],
+            os.write(real_stdout, (json.dumps({"generation": g, "n_gpus": world, "width": width, "games_per_candidate": G, "wall_s": wall, "evaluate_s": times["map_s"],
                               "sharded_timing": ({k: round(v, 3) for k, v in ev.last_timing.items()} if ev is not None else None),
                               "placements": placements, "placements_per_s_wall": placements / wall, "placements_per_s_evaluate": placements / times["map_s"],
-                              "refit_digest": digest, "mean": [float(v) for v in mean.values()]}), flush=True)
+                              "refit_digest": digest, "mean": [float(v) for v in mean.values()]}) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
