@@ -553,3 +553,23 @@ def test_jit_specialised_kernels_match_oracle_and_generic(eng_jit, eng_nojit, ki
     eng_jit.set_features(W6_NAMES)
     eng_jit.play_games(np.array([W6_VALS] * 64), 1, T=50, seed=1)
     assert eng_jit.last_timing()["specialised"] == 0
+
+
+def test_jit_kernels_inside_the_evaluator_graph_replay(eng_jit):
+    """PopulationEvaluator with a generic feature list: pinned buffers -> the repeated host-mode call is replayed as a CUDA graph whose
+    play node is a run-time specialised kernel (launched through the driver API).  Three generations against the C oracle."""
+    from tetris_ai_b200.learning import PopulationEvaluator
+    names = W6_NAMES + ["max_ht", "jaggedness"]
+    fids = [pyoracle.FEATURE_ID[x] for x in names]
+    G, T, C = 5, 120, 300
+    pieces = np.array([pyoracle.piece_sequence(31 * g + 7, T) for g in range(G)], dtype=np.uint8)
+    ev = PopulationEvaluator(eng_jit, names, G, pieces=pieces)
+    rng = np.random.default_rng(4)
+    base = np.array(W6_VALS + [-0.5, -0.3])
+    for gen in range(3):
+        w = base[None, :] + rng.normal(0, 1.0, size=(C, len(names)))
+        fit = ev.evaluate(w)
+        assert eng_jit.last_timing()["specialised"] == 1
+        o = coracle.play_games(fids, w, G, pieces=pieces, threads=THREADS)
+        assert (fit == o["lines"].reshape(C, G).sum(axis=1) / G).all(), gen
+        same_results(ev.last["results"], o)
