@@ -573,3 +573,32 @@ def test_jit_kernels_inside_the_evaluator_graph_replay(eng_jit):
         o = coracle.play_games(fids, w, G, pieces=pieces, threads=THREADS)
         assert (fit == o["lines"].reshape(C, G).sum(axis=1) / G).all(), gen
         same_results(ev.last["results"], o)
+
+
+@pytest.mark.parametrize("C,G,T,spread,names", [(3000, 5, 200, 1.0, "w6"), (13000, 4, 150, 6.0, "w6"), (500, 30, 600, 0.7, "w6"), (700, 20, 1000, 0.5, "w6")])
+def test_pressure_filter_inside_the_lockstep_kernels(eng, C, G, T, spread, names):
+    """move_with_pressure(move_drop) (simulator.py:88-120) for a CE population: the per-move time predicate runs inside the lockstep
+    kernels (window evaluation and fixed widths), so a pressure population takes the same fast path as plain hard drops.  Against
+    the per-game extended generic kernel (lanes = 8) and the C oracle; default and custom pressure parameters."""
+    feat, base = W6_NAMES, np.array(W6_VALS)
+    rng = np.random.default_rng(C + T)
+    w = base[None, :] + rng.normal(0, spread, size=(C, len(feat)))
+    fids = [pyoracle.FEATURE_ID[x] for x in feat]
+    eng.set_features(feat)
+    pieces = np.array([pyoracle.piece_sequence(5 * g + 11, T) for g in range(G)], dtype=np.uint8)
+    for pressure in ({}, {"avg_lat": 120.0, "resp_time": 40.0, "move_eff": 1.05, "two_but_rot": True}):
+        a = eng.play_games(w, G, pieces=pieces, pressure=pressure, want_trace=True, want_scores=True, want_final=True)
+        assert eng.last_timing()["kernels_launched"] == 2 and eng.last_timing()["lanes"] in (1, 2, 4, 8), eng.last_timing()      # lockstep launch + fitness
+        b = eng.play_games(w, G, pieces=pieces, pressure=pressure, lanes=8, want_trace=True, want_scores=True, want_final=True)
+        assert (a["results"] == b["results"]).all() and (a["final"] == b["final"]).all() and (a["fitness"] == b["fitness"]).all()
+        assert a["trace"].tobytes() == b["trace"].tobytes() and a["scores"].tobytes() == b["scores"].tobytes()
+        n_o = min(C, 250)
+        o = coracle.play_games(fids, w[:n_o], G, pieces=pieces, threads=THREADS, want_trace=True, pressure=pressure)
+        res = a["results"][: n_o * G]
+        same_results(res, o)
+        for g in range(0, n_o * G, 9):
+            k = int(res["pieces"][g])
+            assert a["trace"][g, :k].tobytes() == o["trace"][g, :k].tobytes(), g
+    # the filter changes the play (and ends long games early: the level rises with the lines cleared)
+    free = eng.play_games(w, G, pieces=pieces)["results"]
+    assert int(a["results"]["pieces"].sum()) <= int(free["pieces"].sum()) and (a["results"] != free).any()

@@ -181,7 +181,7 @@ TB_HD uint32_t lock_stage_begin(uint32_t s, uint32_t K) { return s == 0u ? 0u : 
 // weights read through L1 from the candidate's row (they do not fit in registers).
 // One task of the lockstep schedule: up to 32 / LANES games of sequence sq, all at the first move of stage st, played to the end of
 // the stage (or of the game); survivors are appended to the sequence's list of the next stage.  `slot` = task index in the bucket.
-template <int LANES, int MODE>
+template <int LANES, int MODE, bool PRESS = false>      // PRESS: move_with_pressure(move_drop) — the per-move time predicate of simulator.py:88-120
 TB_D void lock_task(const PlayParams& prm, const Tables& s_tab, uint32_t st, uint32_t sq, uint32_t slot, uint32_t n_in, uint32_t* ctl)
 {
     constexpr bool W6 = MODE == MODE_W6;
@@ -265,12 +265,13 @@ TB_D void lock_task(const PlayParams& prm, const Tables& s_tab, uint32_t st, uin
             if constexpr (W6) {
                 W6Cand A;
                 w6_pre(c, g, d, A);
+                if (PRESS && A.legal && !is_time(d, A.P.y, prm.press, (int)(lines / 10u))) A.legal = false;      // a filtered move is never scored
                 if (A.legal && A.full != 0u) w6_clear(d, A);
                 Heights Hn;
                 k = w6_post(A, w, Hn);
             } else {
                 Placement P;
-                if (place_slot(c, H, d, P)) {
+                if (place_slot(c, H, d, P) && !(PRESS && !is_time(d, P.y, prm.press, (int)(lines / 10u)))) {
                     Feat f;
                     eval_features<ModeTraits<MODE>::CMASK>(P, d, pv, prm.rmask, f);
                     k = score_key(score_features<MODE>(f, prm.ids, wrow, prm.F));
@@ -436,8 +437,9 @@ TB_D void lw_store_board(uint32_t (*sb)[32], int lane, const uint32_t c[COLS])
 
 // Best placement of piece p_cur (warp-uniform) for the game of this lane, window-local evaluation + deferred row-completing
 // placements; key = 0: no legal placement.  cnt counts the legal placements of active lanes (= scorer calls).
+template <bool PRESS>
 TB_D void lw_search(const Tables& s_tab, uint32_t (*sb)[32], int lane, const WinCache& wc, const double* w, int p_cur, bool active,
-                    uint32_t& cnt, uint64_t& key, uint32_t& tag)
+                    const Pressure& press, int level, uint32_t& cnt, uint64_t& key, uint32_t& tag)
 {
     uint32_t c[COLS];
     const int p_u = (int)__reduce_max_sync(FULLMASK, (unsigned)p_cur);      // provably uniform: descriptors from constant memory, fields on the uniform datapath
@@ -454,9 +456,10 @@ TB_D void lw_search(const Tables& s_tab, uint32_t (*sb)[32], int lane, const Win
             const WinDesc wdsc = c_win[p_u][s2];
             const int c0 = (int)(d.w[0] & 15u), wdt = (int)((d.w[0] >> 6) & 7u);
             const uint32_t and_out = sb[10 + c0][lane] & sb[20 + c0 + wdt - 1][lane];
-            uint32_t full; bool legal;
-            uint64_t k = win_eval_at(wc, ws, d, wdsc, w, [&](int kk) -> uint32_t { return sb[kk][lane]; }, and_out, &full, &legal);
+            uint32_t full; bool legal; int y;
+            uint64_t k = win_eval_at(wc, ws, d, wdsc, w, [&](int kk) -> uint32_t { return sb[kk][lane]; }, and_out, &full, &legal, &y);
             win_advance(ws);
+            if (PRESS && legal && !is_time(d, y, press, level)) { legal = false; k = 0ull; }      // move_with_pressure: filtered before it is scored
             cnt += (uint32_t)(legal && active);
             if (legal && full != 0u) { k = 0ull; if (s2 < 32) dlo |= 1u << s2; else dhi |= 1u << (s2 - 32); }
             if (k > key) { key = k; tag = (uint32_t)s2; }
@@ -566,6 +569,7 @@ TB_D void lw_commit(const Tables& s_tab, uint32_t (*sb)[32], int lane, WinCache&
 }
 
 // The window-local task: 32 games of sequence sq, one lane per game; sb = this warp's board words in shared memory.
+template <bool PRESS = false>
 TB_D void lockwin_task(const PlayParams& prm, const Tables& s_tab, uint32_t (*sb)[32], uint32_t st, uint32_t sq, uint32_t slot, uint32_t n_in, uint32_t* ctl)
 {
     constexpr uint32_t GPW = 32;
@@ -630,7 +634,7 @@ TB_D void lockwin_task(const PlayParams& prm, const Tables& s_tab, uint32_t (*sb
     while (t < t_end && p_cur < 7 && __any_sync(FULLMASK, active)) {
         const int p_after = fetch_piece(t + 2u);
         uint64_t key = 0; uint32_t tag = 0;
-        lw_search(s_tab, sb, lane, wc, w, p_cur, active, cnt, key, tag);
+        lw_search<PRESS>(s_tab, sb, lane, wc, w, p_cur, active, prm.press, (int)(lines / 10u), cnt, key, tag);
         bool finish = false;
         if (active) {
             if (key == 0) {
@@ -762,7 +766,7 @@ TB_D uint32_t lock_auto_lanes(const PlayParams& prm, uint32_t n_in, uint32_t G, 
     return alive >= (uint64_t)prm.lk_thr[0] * warps ? 1u : (alive >= (uint64_t)prm.lk_thr[1] * warps ? 4u : (alive >= (uint64_t)prm.lk_thr[2] * warps ? 8u : 32u));
 }
 
-template <int MINB>
+template <int MINB, bool PRESS = false>
 __global__ void __launch_bounds__(BLOCK, MINB) play_games_w6lockauto_kernel(const PlayParams prm)
 {
     __shared__ Tables s_tab;
@@ -778,7 +782,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) play_games_w6lockauto_kernel(cons
     // take tickets, and they are chosen so that they spread evenly over the SMs (rank = warp-in-block major, block minor:
     // consecutive ranks sit on different SMs) — otherwise the first warps to arrive pile the tasks onto a few SMs while the
     // others idle (measured: 20.5 ms against 11.6 ms for a 37 500-game shard with one lane per game).
-    const uint32_t rank = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+    // (the blocks b, b + SMs, b + 2 SMs, ... normally share an SM and warp w of a block runs on scheduler w % 4: rotating the warp
+    //  index by the block's round keeps the chosen warps spread over the four schedulers of every SM as well)
+    const uint32_t sms = gridDim.x / (uint32_t)MINB;
+    const uint32_t rank = (((threadIdx.x >> 5) + blockIdx.x / (sms ? sms : 1u)) & 3u) * gridDim.x + blockIdx.x;
     uint32_t st = 0, sq = 0;                       // current bucket
     uint32_t n_in = C;
     uint32_t lanes = lock_auto_lanes(prm, n_in, G, warps);
@@ -813,10 +820,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) play_games_w6lockauto_kernel(cons
             take = (uint64_t)rank < (uint64_t)ntasks * G;
             continue;
         }
-        if (lanes == 1u) lockwin_task(prm, s_tab, sb, st, sq, slot, n_in, ctl);
-        else if (lanes == 4u) lock_task<4, MODE_W6>(prm, s_tab, st, sq, slot, n_in, ctl);
-        else if (lanes == 8u) lock_task<8, MODE_W6>(prm, s_tab, st, sq, slot, n_in, ctl);
-        else lock_task<32, MODE_W6>(prm, s_tab, st, sq, slot, n_in, ctl);
+        if (lanes == 1u) lockwin_task<PRESS>(prm, s_tab, sb, st, sq, slot, n_in, ctl);
+        else if (lanes == 4u) lock_task<4, MODE_W6, PRESS>(prm, s_tab, st, sq, slot, n_in, ctl);
+        else if (lanes == 8u) lock_task<8, MODE_W6, PRESS>(prm, s_tab, st, sq, slot, n_in, ctl);
+        else lock_task<32, MODE_W6, PRESS>(prm, s_tab, st, sq, slot, n_in, ctl);
     }
 }
 

@@ -471,7 +471,11 @@ static LockPlan lock_plan(const tb200_ctx* ctx, const tb200_play_args& a, int pe
     const int l = a.lanes;
     const bool lanes_auto = !(l == 1 || l == 2 || l == 4 || l == 8 || l == 16 || l == 32 || l == 64 || l == 128);
     const uint32_t stop_moves = a.max_moves && a.max_moves < a.T ? a.max_moves : a.T;
-    lp.on = ctx->lockstep_enabled && lanes_auto && a.lookahead == 1 && a.move_set == 0 && per_game_weights == 0 &&
+    // hard drops; inside move_with_pressure too, for the w6 set with the per-bucket-width kernel (the only one instantiated with the filter)
+    const bool press_ok = a.move_set == TB200_MOVES_PRESSURE && ctx->mode == tb::MODE_W6 && ctx->win_enabled &&
+                          !(ctx->lock_lanes == 1 || ctx->lock_lanes == 2 || ctx->lock_lanes == 4 || ctx->lock_lanes == 8);
+    lp.on = ctx->lockstep_enabled && lanes_auto && a.lookahead == 1 && (a.move_set == 0 || press_ok) && per_game_weights == 0 &&
+           
             !a.seq_of_game && a.games_per_candidate >= 4 && a.games_per_candidate <= 4096 &&
             (n_games + ctx->sms - 1) / ctx->sms > 80 && stop_moves >= (uint32_t)(2 * ctx->lock_K);
     if (!lp.on) {
@@ -662,7 +666,7 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
         tb::play_fn lf;
         const bool lock_auto = ctx->mode == tb::MODE_W6 && ctx->win_enabled && !(ctx->lock_lanes == 1 || ctx->lock_lanes == 2 || ctx->lock_lanes == 4 || ctx->lock_lanes == 8);
         if (lock_auto)
-            lf = ctx->lock_minb == 4 ? tb::play_games_w6lockauto_kernel<4> : tb::play_games_w6lockauto_kernel<5>;      // lanes per game chosen per (stage, sequence) bucket from the live count
+            lf = move_set == TB200_MOVES_PRESSURE ? tb::play_games_w6lockauto_kernel<4, true> : (ctx->lock_minb == 4 ? tb::play_games_w6lockauto_kernel<4> : tb::play_games_w6lockauto_kernel<5>);      // lanes per game chosen per (stage, sequence) bucket from the live count
         else if (ctx->mode == tb::MODE_W6 && ll == 1 && ctx->win_enabled)
             lf = tb::play_games_w6lockwin_kernel;
         else if (ctx->mode == tb::MODE_W6)

@@ -1040,7 +1040,7 @@ TB_HD WinDesc win_desc(const SlotDesc& d)
 // w6_pre / w6_clear / w6_post.
 template <class ColFn>
 TB_HD uint64_t win_eval_at(const WinCache& wc, const WinSlide& ws, const SlotDesc& d, const WinDesc& wdsc, const double* w, ColFn col,
-                           uint32_t and_out, uint32_t* full, bool* legal_out)
+                           uint32_t and_out, uint32_t* full, bool* legal_out, int* y_out = nullptr)
 {
     const int c0 = (int)(d.w[0] & 15u), wdt = (int)((d.w[0] >> 6) & 7u);
     const uint32_t W0 = ws.x[0], W1 = ws.x[1];                            // heights of columns c0-2 .. c0+5
@@ -1051,6 +1051,7 @@ TB_HD uint64_t win_eval_at(const WinCache& wc, const WinSlide& ws, const SlotDes
     m01 = m01 > b1 ? m01 : b1; b2 = b2 > b3 ? b2 : b3; m01 = m01 > b2 ? m01 : b2;
     const int y = (int)m01 - 32;
     *legal_out = legal;
+    if (y_out) *y_out = y;
     const uint32_t pbw = wdsc.pbw, tpw = wdsc.tpw;
     const uint32_t one_y = 1u << (y & 31);
     // imprint + transitions of the window (the piece is 1..4 columns wide)

@@ -9,7 +9,7 @@ import win_probe                                    # noqa: E402  (reuses its ch
 args = sys.argv[1:] or ["1250", "1.0", "1250", "6.0", "3000", "1.0", "3000", "6.0", "10000", "6.0", "10000", "1.0"]
 SETTINGS = [("fixed 1 (K2sW)", {"TB200_LOCK_LANES": "1"}), ("fixed 4", {"TB200_LOCK_LANES": "4"}), ("fixed 8", {"TB200_LOCK_LANES": "8"}),
             ("auto (default)", {}), ("auto 24,8,2", {"TB200_LOCK_THR": "24,8,2"}), ("auto 12,6,2", {"TB200_LOCK_THR": "12,6,2"}),
-            ("auto 10,5,2", {"TB200_LOCK_THR": "10,5,2"}), ("auto 8,4,1", {"TB200_LOCK_THR": "8,4,1"}), ("auto 12,8,2", {"TB200_LOCK_THR": "12,8,2"})]
+            ("auto 12,8,2", {"TB200_LOCK_THR": "12,8,2"}), ("auto 16,8,2", {"TB200_LOCK_THR": "16,8,2"})]
 for i in range(0, len(args), 2):
     C, spread = args[i], args[i + 1]
     print("C=%s spread=%s" % (C, spread))
