@@ -385,6 +385,13 @@ extern "C" int emu_win_check(const uint16_t* rows, const double* w6w, int* compa
                 uint32_t full2 = 0; bool legal2 = false;
                 const uint64_t ks = win_eval_at(wc, ws, d, win_desc(d), w6w, [&](int k) { return (k >= 0 && k < COLS) ? c[k] : 0xdeadbeefu; }, and_out, &full2, &legal2);
                 if (ks != kw || full2 != full || legal2 != legal) ++bad;
+                {   // K2sP starts the windows in the middle of a rotation: win_skip(c0) == c0 slides
+                    WinSlide wk;
+                    win_reset(wc, wk);
+                    win_skip(wk, c0);
+                    for (int i = 0; i < 4; ++i) if (wk.x[i] != ws.x[i]) ++bad;
+                    for (int i = 0; i < 3; ++i) if (wk.r[i] != ws.r[i] || wk.t[i] != ws.t[i] || wk.d[i] != ws.d[i]) ++bad;
+                }
                 win_advance(ws);
             }
             if (legal != A.legal) { ++bad; continue; }

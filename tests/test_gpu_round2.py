@@ -492,9 +492,6 @@ def test_k2sw_initial_boards_lines_points_and_max_moves(eng_lane1):
     assert a["trace"].tobytes() == b["trace"].tobytes() and a["scores"].tobytes() == b["scores"].tobytes()
 
 
-# ---------------------------------------------------------------------------------------------------------------------
-# run-time specialised kernels for arbitrary feature lists (NVRTC, csrc/jit.inc)
-# ---------------------------------------------------------------------------------------------------------------------
 def _engine_with_env(**env):
     from tetris_ai_b200 import Engine
     old = {k: os.environ.get(k) for k in env}
@@ -509,6 +506,75 @@ def _engine_with_env(**env):
                 os.environ[k] = v
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# K2sP: two warps share the slots of 32 games (opt-in experiment for shards that do not fill the machine: TB200_LOCK_PAIR)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def eng_pair():
+    """An Engine whose per-bucket-width kernel plays EVERY bucket that has at least one game per resident warp with pairs of
+    warps (and the thinner ones with a warp per game), so that the pair task, the hand-over between pair and plain buckets and
+    the pairs' shared ticket are exercised whatever the population size."""
+    e = _engine_with_env(TB200_LOCK_THR="1000000,1,1", TB200_LOCK_PAIR="1")
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("C,G,T,spread,explicit", [(3001, 5, 131, 6.0, True), (2000, 7, 260, 2.0, False), (420, 30, 400, 0.7, True)])
+def test_k2sp_pairs_of_warps_vs_coracle_and_per_game_kernel(eng_pair, C, G, T, spread, explicit):
+    """simulate() for a CE population (simulator.py:152-190, learning.py:38) played by pairs of warps that split each piece's slots:
+    results, traces, winning scores and final boards equal the per-game kernel's and the C oracle's, scorer-call counts included
+    (each warp counts its own share)."""
+    eng = eng_pair
+    rng = np.random.default_rng(C + G)
+    w = np.array(W6_VALS)[None, :] + rng.normal(0, spread, size=(C, 6))
+    fids = [pyoracle.FEATURE_ID[x] for x in W6_NAMES]
+    eng.set_features(W6_NAMES)
+    pieces = np.array([pyoracle.piece_sequence(7 * g + 1, T) for g in range(G)], dtype=np.uint8) if explicit else None
+    kw = dict(pieces=pieces, T=T, seed=77)
+    a = eng.play_games(w, G, want_trace=True, want_scores=True, want_final=True, **kw)
+    assert eng.last_timing()["kernels_launched"] == 2 and eng.last_timing()["lanes"] == 2, eng.last_timing()
+    b = eng.play_games(w, G, lanes=8, want_trace=True, want_scores=True, want_final=True, **kw)
+    assert (a["results"] == b["results"]).all() and (a["final"] == b["final"]).all() and (a["fitness"] == b["fitness"]).all()
+    for g in range(0, C * G, 3):
+        k = int(a["results"]["pieces"][g])
+        assert a["trace"][g, :k].tobytes() == b["trace"][g, :k].tobytes(), g
+        assert a["scores"][g, :k].tobytes() == b["scores"][g, :k].tobytes(), g
+    n_o = min(C, 300)
+    o = coracle.play_games(fids, w[:n_o], G, pieces=pieces, T=T, seed=77, threads=THREADS, want_trace=True)
+    res = a["results"][: n_o * G]
+    same_results(res, o)
+    for g in range(0, n_o * G, 5):
+        k = int(res["pieces"][g])
+        assert a["trace"][g, :k].tobytes() == o["trace"][g, :k].tobytes(), g
+    # repeatable (the pairs meet at an mbarrier every piece; tickets are taken by one warp for both)
+    a2 = eng.play_games(w, G, **kw)
+    assert (a2["results"] == a["results"]).all()
+
+
+def test_k2sp_initial_boards_lines_points_max_moves_and_pressure(eng_pair):
+    eng = eng_pair
+    rng = np.random.default_rng(3)
+    C, G, T = 700, 20, 400
+    w = np.array(W6_VALS)[None, :] + rng.normal(0, 3.0, size=(C, 6))
+    eng.set_features(W6_NAMES)
+    n = C * G
+    init = np.zeros((n, 20), dtype=np.uint16)
+    init[::3, 19] = 0x1EF; init[::5, 18] = 0x3F0; init[::5, 19] |= 0x3F0; init[::11, 15] = 0x201; init[::11, 16] = 0x3FE; init[::11, 17] = 0x1FF
+    lines0 = (np.arange(n, dtype=np.uint32) * 13) % 57
+    for pressure in (None, {"avg_lat": 120.0, "resp_time": 40.0, "move_eff": 1.05, "two_but_rot": True}):
+        kw = dict(T=T, seed=5, init_rows=init, init_lines=lines0, max_moves=150, want_trace=True, want_final=True, want_scores=True, points=(3, 40, 100, 300, 1200))
+        if pressure is not None:
+            kw["pressure"] = pressure
+        a = eng.play_games(w, G, **kw)
+        assert eng.last_timing()["kernels_launched"] == 2 and eng.last_timing()["lanes"] == 2, eng.last_timing()
+        b = eng.play_games(w, G, lanes=32, **kw)
+        assert (a["results"] == b["results"]).all() and (a["final"] == b["final"]).all()
+        assert a["trace"].tobytes() == b["trace"].tobytes() and a["scores"].tobytes() == b["scores"].tobytes()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# run-time specialised kernels for arbitrary feature lists (NVRTC, csrc/jit.inc)
+# ---------------------------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def eng_jit():
     e = _engine_with_env(TB200_JIT="1")

@@ -67,7 +67,9 @@ struct PlayParams {
     uint32_t* lk_ctl;                // [S][G][4] per (stage, sequence) bucket: {task ticket, tasks done, games entering the stage, -}
     uint32_t* lk_list;               // [2][G][C] game ids entering a stage, by sequence; double-buffered by stage parity
     uint32_t  lk_C, lk_K, lk_S;      // candidates, pieces per stage, stages
-    uint32_t  lk_thr[3];             // K2sA: games alive per resident warp from which a bucket plays with 1 / 4 / 8 lanes per game (below: a warp per game)
+    uint32_t  lk_thr[5];             // K2sA: games alive per resident warp from which a bucket plays with 1 / 4 / 8 lanes per game (below: a warp per game);
+                                     // [3]: from which it plays with one lane per game in each of two warps (K2sP; lk_thr[1] <= lk_thr[3] <= lk_thr[0]);
+                                     // [4]: the one-lane threshold of a STEADY bucket (>= 15/16 of the previous stage's games still alive)
     // piece-binned kernel K2b (see play_games_w6bin_kernel)
     unsigned long long* pb_ctl;      // per shard 16 words: [0..6] queue tails (reserved), [8..14] queue heads; after the shards: games finished, error flag
     uint32_t* pb_ring;               // [shards][7][pb_mask + 1] game ids waiting for a piece of type p; 0xffffffff = empty slot

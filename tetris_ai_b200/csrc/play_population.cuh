@@ -423,7 +423,43 @@ __global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayPara
 // ---------------------------------------------------------------------------------------------
 constexpr int LW_BOARD = 30;           // per game: columns 0..9 | P[k] = AND of columns < k, k = 0..9 | S[k] = AND of columns >= k, k = 1..10
 constexpr int LW_ITEMS = 256;          // deferred (game, slot) placements a warp shares per piece (more than that: their owners evaluate them)
-constexpr int LW_WORDS = LW_BOARD + LW_ITEMS / 32 + 2 * LW_ITEMS / 32;      // + item table (owner | slot << 8) + 64-bit keys of the items
+constexpr int LW_XCH = LW_BOARD + LW_ITEMS / 32 + 2 * LW_ITEMS / 32;        // K2sP: this warp's best (key lo, key hi, slot) per game, double-buffered by piece parity
+constexpr int LW_WORDS = LW_XCH + 6;                                        // board + item table (owner | slot << 8) + 64-bit keys of the items + exchange rows
+
+// K2sP — a group of warps of one block playing the same 32 games (see lockwin_task<.., SPLIT>): they meet once per piece at
+// an mbarrier in shared memory.  The wait is bounded (try_wait + %globaltimer): a warp whose partner never arrives raises the
+// launch's error flag and leaves the kernel instead of hanging the device.
+struct PairLink {
+    uint32_t bar;                  // shared-memory address of the group's mbarrier (arrival count = nparts: lane 0 of every warp)
+    uint32_t phase;                // parity of the phase this warp waits for next
+    int part;                      // this warp's index in the group (0 = the one that writes results); warp-uniform BY CONSTRUCTION (a vote result),
+                                   // so that the slot ranges derived from it keep the descriptor loads on the uniform datapath
+    uint32_t (*peer)[32];          // the partner warp's shared-memory rows
+    uint32_t par;                  // exchange-row parity
+};
+constexpr int PAIR_PARTS = 2;
+// Everything this warp wrote to shared memory before the call is visible to the partner after its matching call returns
+// (__syncwarp orders the lanes' writes before lane 0's arrive.release; lane 0's try_wait.acquire + the shuffle order the partner's
+// writes before every lane's later reads).  The result is a shuffle from lane 0: uniform, also in the compiler's eyes.
+TB_D bool pair_sync(uint32_t bar, uint32_t& phase)
+{
+    __syncwarp(FULLMASK);
+    uint32_t ok = 0;
+    if ((threadIdx.x & 31) == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+        unsigned long long t0 = 0ull;
+        for (;;) {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(phase) : "memory");
+            if (ok) break;
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0ull) t0 = now; else if (now - t0 > 4000000000ull) break;      // 4 s: longer than every other bounded wait of the kernel
+        }
+    }
+    ok = __shfl_sync(FULLMASK, ok, 0);
+    phase ^= 1u;
+    return ok != 0u;
+}
 
 TB_D void lw_store_board(uint32_t (*sb)[32], int lane, const uint32_t c[COLS])
 {
@@ -437,21 +473,31 @@ TB_D void lw_store_board(uint32_t (*sb)[32], int lane, const uint32_t c[COLS])
 
 // Best placement of piece p_cur (warp-uniform) for the game of this lane, window-local evaluation + deferred row-completing
 // placements; key = 0: no legal placement.  cnt counts the legal placements of active lanes (= scorer calls).
-template <bool PRESS>
+// SPLIT: the slots of the piece are shared out between the `nparts` (1 or 2) warps that play these 32 games together (K2sP, see
+// lockwin_task): this warp takes half (part + rotation / 2) mod 2 of every rotation's columns, so the parts stay balanced.
+template <bool PRESS, bool SPLIT = false>
 TB_D void lw_search(const Tables& s_tab, uint32_t (*sb)[32], int lane, const WinCache& wc, const double* w, int p_cur, bool active,
-                    const Pressure& press, int level, uint32_t& cnt, uint64_t& key, uint32_t& tag)
+                    const Pressure& press, int level, uint32_t& cnt, uint64_t& key, uint32_t& tag, const int nparts = 1, const int part = 0)
 {
     uint32_t c[COLS];
     const int p_u = (int)__reduce_max_sync(FULLMASK, (unsigned)p_cur);      // provably uniform: descriptors from constant memory, fields on the uniform datapath
     const int ns = c_tables.nslots[p_u];
     uint32_t dlo = 0u, dhi = 0u;                                 // slots deferred to the general evaluation (they complete a row)
     // slots are enumerated rotation-major, column-minor: per rotation the windows start at column 0 and slide
-    for (int s2 = 0; s2 < ns;) {
+    for (int s2 = 0, rot = 0; s2 < ns; ++rot) {
         WinSlide ws;
         win_reset(wc, ws);
         const int ncol = COLS + 1 - (int)((c_tables.slot[p_u][s2].w[0] >> 6) & 7u);      // columns of this rotation (uniform)
+        int cc = 0, ce = ncol;
+        const int s2_end = s2 + ncol;
+        if (SPLIT) {
+            const int q = (part + (rot >> 1)) & (nparts - 1);      // nparts is 1 (the whole rotation) or 2; all warp-uniform
+            cc = (q * ncol) >> (nparts - 1); ce = ((q + 1) * ncol) >> (nparts - 1);
+            win_skip(ws, cc);
+            s2 += cc;
+        }
 #pragma unroll 1
-        for (int cc = 0; cc < ncol; ++cc, ++s2) {
+        for (; cc < ce; ++cc, ++s2) {
             const SlotDesc d = c_tables.slot[p_u][s2];
             const WinDesc wdsc = c_win[p_u][s2];
             const int c0 = (int)(d.w[0] & 15u), wdt = (int)((d.w[0] >> 6) & 7u);
@@ -464,6 +510,7 @@ TB_D void lw_search(const Tables& s_tab, uint32_t (*sb)[32], int lane, const Win
             if (legal && full != 0u) { k = 0ull; if (s2 < 32) dlo |= 1u << s2; else dhi |= 1u << (s2 - 32); }
             if (k > key) { key = k; tag = (uint32_t)s2; }
         }
+        s2 = s2_end;
     }
     // ---- deferred placements: rows completed, every column moves -> general w6 evaluation.  The lanes of a warp hold very
     //      different numbers of them (0 .. 10 per piece), so they are SHARED: every lane lists its (game, slot) items in shared
@@ -569,9 +616,21 @@ TB_D void lw_commit(const Tables& s_tab, uint32_t (*sb)[32], int lane, WinCache&
 }
 
 // The window-local task: 32 games of sequence sq, one lane per game; sb = this warp's board words in shared memory.
-template <bool PRESS = false>
-TB_D void lockwin_task(const PlayParams& prm, const Tables& s_tab, uint32_t (*sb)[32], uint32_t st, uint32_t sq, uint32_t slot, uint32_t n_in, uint32_t* ctl)
+// SPLIT (K2sP, round 2): TWO warps play the task together.  Both hold the complete state of the 32 games (own board rows, own
+// window cache) and do everything identically, except that each searches only its share of the piece's slots (lw_search);
+// per piece they swap their best (key, slot) per game through shared memory — one mbarrier phase — and then both commit the
+// same winner (higher key, then lower slot: first of max).  Only part 0 writes results / traces / hand-over state; the
+// scorer-call count is additive, so each part adds its own.  For shards that fill less than the machine with one warp per 32
+// games (a rank's 1 250 x 30 slice: 1 200 tasks on 2 368 resident warps) this halves the per-piece latency of the search, which
+// is all that matters there.  Returns false only when the partner never arrived (bounded wait, error flag raised).
+// (SPLIT = the kernel has the pair task at all; `split` = this task is one, warp-uniform.  ONE instantiation serves both: a second
+//  inlined copy of this function pushes the kernel past the size up to which ptxas keeps the slot loop on the uniform datapath —
+//  measured: the plain one-lane path lost 40 %.)
+template <bool PRESS = false, bool SPLIT = false>
+TB_D bool lockwin_task(const PlayParams& prm, const Tables& s_tab, uint32_t (*sb)[32], uint32_t st, uint32_t sq, uint32_t slot, uint32_t n_in, uint32_t* ctl,
+                       bool split = false, PairLink* pl = nullptr)
 {
+    const bool lead = !SPLIT || !split || pl->part == 0;
     constexpr uint32_t GPW = 32;
     const int lane = threadIdx.x & 31;
     const uint32_t T = prm.T, C = prm.lk_C, K = prm.lk_K, S = prm.lk_S;
@@ -599,7 +658,7 @@ TB_D void lockwin_task(const PlayParams& prm, const Tables& s_tab, uint32_t (*sb
             const uint4 a0 = __ldcg(sv), a1 = __ldcg(sv + 1), a2 = __ldcg(sv + 2), a3 = __ldcg(sv + 3), a4 = __ldcg(sv + 4);
             c[0] = a0.x; c[1] = a0.y; c[2] = a0.z; c[3] = a0.w; c[4] = a1.x; c[5] = a1.y; c[6] = a1.z; c[7] = a1.w; c[8] = a2.x; c[9] = a2.y;
             lines = a2.w; h1 = a3.x; h2 = a3.y; h3 = a3.z; h4 = a3.w;
-            cnt = a4.x;
+            cnt = lead ? a4.x : 0u;
             gscore = ((uint64_t)a4.w << 32) | a4.z;
         } else {
             if (prm.init_rows) {
@@ -623,7 +682,7 @@ TB_D void lockwin_task(const PlayParams& prm, const Tables& s_tab, uint32_t (*sb
     const uint32_t t_end = (st + 1 == S || t_next > stop) ? stop : t_next;
     int p_cur = fetch_piece(t), p_next = fetch_piece(t + 1u);
     if (t >= stop || p_cur >= 7) {                                   // nothing to play (stop == 0 or the sequence ends here)
-        if (active) {
+        if (active && lead) {
             tb200_game_result* r = prm.results + game;
             r->pieces = t; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4; r->score = gscore;
             if (cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&r->placements), (unsigned long long)cnt);
@@ -634,7 +693,23 @@ TB_D void lockwin_task(const PlayParams& prm, const Tables& s_tab, uint32_t (*sb
     while (t < t_end && p_cur < 7 && __any_sync(FULLMASK, active)) {
         const int p_after = fetch_piece(t + 2u);
         uint64_t key = 0; uint32_t tag = 0;
-        lw_search<PRESS>(s_tab, sb, lane, wc, w, p_cur, active, prm.press, (int)(lines / 10u), cnt, key, tag);
+        if constexpr (SPLIT) {
+            lw_search<PRESS, true>(s_tab, sb, lane, wc, w, p_cur, active, prm.press, (int)(lines / 10u), cnt, key, tag, split ? PAIR_PARTS : 1, pl->part);
+          if (split) {
+            const uint32_t xr = (uint32_t)LW_XCH + 3u * pl->par;
+            sb[xr][lane] = (uint32_t)key; sb[xr + 1][lane] = (uint32_t)(key >> 32); sb[xr + 2][lane] = tag;
+            if (!pair_sync(pl->bar, pl->phase)) {
+                if (lane == 0) atomicExch(prm.lk_ctl + (size_t)S * G * 4 + 3, 1u);
+                return false;
+            }
+            const uint64_t okey = ((uint64_t)pl->peer[xr + 1][lane] << 32) | pl->peer[xr][lane];
+            const uint32_t otag = pl->peer[xr + 2][lane];
+            if (okey > key || (okey == key && otag < tag)) { key = okey; tag = otag; }      // first of max: the lower slot keeps a tie
+            pl->par ^= 1u;
+          }
+        } else {
+            lw_search<PRESS>(s_tab, sb, lane, wc, w, p_cur, active, prm.press, (int)(lines / 10u), cnt, key, tag);
+        }
         bool finish = false;
         if (active) {
             if (key == 0) {
@@ -649,11 +724,11 @@ TB_D void lockwin_task(const PlayParams& prm, const Tables& s_tab, uint32_t (*sb
                     const uint32_t pts = prm.pts[wk];
                     gscore += (uint64_t)pts * (uint64_t)(lines / 10u + 1u);
                 } else if (prm.pts[0] != 0u) gscore += (uint64_t)prm.pts[0] * (uint64_t)(lines / 10u + 1u);      // State.score(points) with points[0] != 0
-                if (prm.trace) {
+                if (prm.trace && lead) {
                     const uint32_t row = (uint32_t)(ROWS - A.P.y - A.P.ph);
                     reinterpret_cast<uint32_t*>(prm.trace)[(size_t)game * T + t] = (uint32_t)A.P.rot | row << 8 | (uint32_t)A.P.c0 << 16 | wk << 24;
                 }
-                if (prm.score_trace) {
+                if (prm.score_trace && lead) {
                     const uint64_t b = (key & 0x8000000000000000ull) ? (key & 0x7FFFFFFFFFFFFFFFull) : ~key;
                     prm.score_trace[(size_t)game * T + t] = __longlong_as_double((long long)b);
                 }
@@ -664,8 +739,8 @@ TB_D void lockwin_task(const PlayParams& prm, const Tables& s_tab, uint32_t (*sb
         if (finish) {
             const uint32_t played = key == 0 ? t : tn;
             tb200_game_result* r = prm.results + game;
-            r->pieces = played; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4; r->score = gscore;
-            if (prm.final_rows) {
+            if (lead) { r->pieces = played; r->lines = lines; r->hist[0] = h1; r->hist[1] = h2; r->hist[2] = h3; r->hist[3] = h4; r->score = gscore; }
+            if (prm.final_rows && lead) {
                 uint16_t rows[ROWS];
 #pragma unroll
                 for (int k = 0; k < COLS; ++k) c[k] = sb[k][lane];
@@ -681,7 +756,9 @@ TB_D void lockwin_task(const PlayParams& prm, const Tables& s_tab, uint32_t (*sb
     // ---- survivors (alive at move t_end < stop) go to the sequence's list of the next stage ----
     {
         const uint32_t live = __ballot_sync(FULLMASK, active);
-        if (live != 0u) {
+        if (!lead) {                                   // the other part hands the games over; this part's scorer calls are added where they end up
+            if (active && cnt) atomicAdd(reinterpret_cast<unsigned long long*>(&prm.results[game].placements), (unsigned long long)cnt);
+        } else if (live != 0u) {
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(prm.lk_ctl + ((size_t)(st + 1) * G + sq) * 4 + 2, (uint32_t)__popc(live));
             base = __shfl_sync(FULLMASK, base, 0);
@@ -699,9 +776,10 @@ TB_D void lockwin_task(const PlayParams& prm, const Tables& s_tab, uint32_t (*sb
             }
         }
         __syncwarp(FULLMASK);
-        if (lane == 0) { __threadfence(); atomicAdd(ctl + 1, 1u); }
+        if (lane == 0 && lead) { __threadfence(); atomicAdd(ctl + 1, 1u); }
     }
     }
+    return true;
 }
 
 __global__ void __launch_bounds__(BLOCK, 4) play_games_w6lockwin_kernel(const PlayParams prm)
@@ -760,67 +838,122 @@ __global__ void __launch_bounds__(BLOCK, 4) play_games_w6lockwin_kernel(const Pl
 // (prm.lk_thr; measured, tools/auto_probe.py: with many games per warp the lane utilisation decides, with few the per-piece latency)
 // Tasks of different widths are the same device functions the fixed-width kernels run; results do not depend on the width.
 // ---------------------------------------------------------------------------------------------
-TB_D uint32_t lock_auto_lanes(const PlayParams& prm, uint32_t n_in, uint32_t G, uint32_t warps)
+// width code of a bucket: 1 = one lane per game (K2sW task), 2 = one lane per game in each of TWO warps that share the slots
+// (K2sP task), 4 / 8 / 32 = lanes per game of the all-columns task
+// n_prev = games that entered the PREVIOUS stage of the same sequence (0: unknown, first stage).  A population that loses almost nobody
+// per stage is STEADY: its games will still be there hundreds of pieces later, so the cheapest evaluation per placement (one lane per
+// game, window-local) wins down to far fewer games per warp (lk_thr[4]) than for a population that is still thinning out, where the few
+// long-lived games are better served by wide tasks (measured on one rank's 1 250 x 30 slice, tools/pair_probe.py: converged 11.3 ms with one
+// lane per game against 12.6 with four; fresh 11.0 against 6.0).
+TB_D uint32_t lock_auto_lanes(const PlayParams& prm, uint32_t n_in, uint32_t n_prev, uint32_t G, uint32_t warps)
 {
     const uint64_t alive = (uint64_t)n_in * G;                            // estimate: the other sequences thin out alike
-    return alive >= (uint64_t)prm.lk_thr[0] * warps ? 1u : (alive >= (uint64_t)prm.lk_thr[1] * warps ? 4u : (alive >= (uint64_t)prm.lk_thr[2] * warps ? 8u : 32u));
+    const bool steady = n_prev != 0u && (uint64_t)n_in * 16u >= (uint64_t)n_prev * 15u;
+    const uint32_t thr1 = steady && prm.lk_thr[4] < prm.lk_thr[0] ? prm.lk_thr[4] : prm.lk_thr[0];
+    return alive >= (uint64_t)thr1 * warps ? 1u : (alive >= (uint64_t)prm.lk_thr[3] * warps ? 2u :
+           (alive >= (uint64_t)prm.lk_thr[1] * warps ? 4u : (alive >= (uint64_t)prm.lk_thr[2] * warps ? 8u : 32u)));
 }
+TB_D uint32_t lock_auto_tasks(uint32_t n_in, uint32_t lanes) { return lanes == 2u ? (n_in + 31u) / 32u : (n_in * lanes + 31u) / 32u; }
 
-template <int MINB, bool PRESS = false>
+template <int MINB, bool PRESS = false, bool PAIR = false>      // PAIR: with the K2sP task (host: lk_thr[3] < lk_thr[0] only for this instantiation)
 __global__ void __launch_bounds__(BLOCK, MINB) play_games_w6lockauto_kernel(const PlayParams prm)
 {
     __shared__ Tables s_tab;
     __shared__ alignas(16) uint32_t s_board[BLOCK / 32][LW_WORDS][32];
     load_tables<BLOCK>(s_tab);
     __syncthreads();
+    __shared__ alignas(8) unsigned long long s_bar[BLOCK / 64];      // K2sP: one mbarrier per pair of warps
+    __shared__ uint32_t s_slot[BLOCK / 64][2];                        // K2sP: the pair's ticket, double-buffered
     const int lane = threadIdx.x & 31;
-    uint32_t (*sb)[32] = s_board[threadIdx.x >> 5];
+    const uint32_t wib = threadIdx.x >> 5;
+    uint32_t (*sb)[32] = s_board[wib];
     const uint32_t C = prm.lk_C, S = prm.lk_S, G = (uint32_t)prm.G;
     const uint32_t warps = gridDim.x * (BLOCK / 32);
+    PairLink pl;
+    pl.bar = (uint32_t)__cvta_generic_to_shared(&s_bar[wib >> 1]); pl.phase = 0u; pl.part = (int)__reduce_max_sync(FULLMASK, wib & 1u); pl.peer = s_board[wib ^ 1u]; pl.par = 0u;
+    if (PAIR && threadIdx.x < BLOCK / 64) asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" :: "r"((uint32_t)__cvta_generic_to_shared(&s_bar[threadIdx.x])) : "memory");
+    __syncthreads();
+    uint32_t sbuf = 0u;
 
-    // A stage has ntasks x G tasks.  When that is less than the resident warps, only as many warps as there are tasks
-    // take tickets, and they are chosen so that they spread evenly over the SMs (rank = warp-in-block major, block minor:
-    // consecutive ranks sit on different SMs) — otherwise the first warps to arrive pile the tasks onto a few SMs while the
-    // others idle (measured: 20.5 ms against 11.6 ms for a 37 500-game shard with one lane per game).
-    // (the blocks b, b + SMs, b + 2 SMs, ... normally share an SM and warp w of a block runs on scheduler w % 4: rotating the warp
-    //  index by the block's round keeps the chosen warps spread over the four schedulers of every SM as well)
-    const uint32_t sms = gridDim.x / (uint32_t)MINB;
-    const uint32_t rank = (((threadIdx.x >> 5) + blockIdx.x / (sms ? sms : 1u)) & 3u) * gridDim.x + blockIdx.x;
+    // A stage has ntasks x G tasks.  When that is less than the resident warps, only about as many warps as there are tasks take
+    // tickets, and they are chosen so that they spread evenly over the SMs AND over the four warp schedulers of every SM — otherwise
+    // the first warps to arrive pile the tasks onto a few SMs / schedulers while the others idle.  Block placement is not something
+    // a kernel may assume (round 2 first ranked warps by blockIdx, taking blocks b, b + SMs, ... to share an SM: a 1 250 x 30 slice
+    // played with one lane per game then took 20.4 ms against 11.3 ms for the exact-grid kernel), so every warp finds out where it
+    // runs: k = its arrival ordinal on (its SM, its scheduler = %warpid mod 4), from per-launch counters behind the bucket table;
+    // j = 4 k + scheduler orders the warp slots of an SM scheduler-minor, and a bucket is served by the slots j < floor(tasks / SMs).
+    uint32_t slot_j;
+    {
+        uint32_t smid, wid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+        const uint32_t sch = wid & 3u;
+        uint32_t k = 0;
+        if (lane == 0) k = atomicAdd(prm.lk_ctl + (size_t)(S + 1) * G * 4 + (size_t)(smid & 255u) * 4 + sch, 1u);
+        k = __shfl_sync(FULLMASK, k, 0);
+        slot_j = k * 4u + sch;
+    }
+    const uint32_t sms = gridDim.x / (uint32_t)MINB ? gridDim.x / (uint32_t)MINB : 1u;
+    // floor, not ceil: one warp too many on an SM puts three warps on a scheduler that should hold two, and every sequence then waits for
+    // such a warp at every stage boundary; one too few only makes the last tasks of a stage start a little late
+    auto takes = [&](uint32_t tasks_in_stage) -> bool { return tasks_in_stage >= sms ? (uint64_t)(slot_j + 1u) * sms <= (uint64_t)tasks_in_stage : slot_j == 0u; };
+    const uint32_t prank = (((wib >> 1) + blockIdx.x / sms) & 1u) * gridDim.x + blockIdx.x;      // K2sP (experiment): pairs of warps ranked by block index
     uint32_t st = 0, sq = 0;                       // current bucket
     uint32_t n_in = C;
-    uint32_t lanes = lock_auto_lanes(prm, n_in, G, warps);
-    uint32_t ntasks = (n_in * lanes + 31u) / 32u;
-    bool take = (uint64_t)rank < (uint64_t)ntasks * G;
+    const uint32_t lanes0 = lock_auto_lanes(prm, C, 0u, G, warps);      // every bucket of the first stage
+    uint32_t lanes = lanes0;
+    uint32_t ntasks = lock_auto_tasks(n_in, lanes);
+    bool take = lanes == 2u ? (uint64_t)prank < (uint64_t)ntasks * G : takes(ntasks * G);
     for (;;) {
         uint32_t* ctl = prm.lk_ctl + ((size_t)st * G + sq) * 4;
         uint32_t slot = 0xffffffffu;
-        if (take) {
+        if (PAIR && lanes == 2u) {                 // a pair bucket: part 0 takes the ticket for both (both warps walk the same buckets and
+            if (pl.part == 0) {                    // read the same final n_in, so both know this is a pair bucket)
+                if (take && lane == 0) slot = atomicAdd(ctl, 1u);
+                if (lane == 0) s_slot[wib >> 1][sbuf] = slot;
+            }
+            if (!pair_sync(pl.bar, pl.phase)) { if (lane == 0) atomicExch(prm.lk_ctl + (size_t)S * G * 4 + 3, 1u); return; }
+            if (lane == 0) slot = s_slot[wib >> 1][sbuf];
+            slot = __shfl_sync(FULLMASK, slot, 0);      // uniform in the compiler's eyes too (the tasks rely on the uniform datapath)
+            sbuf ^= 1u;
+        } else if (take) {
             if (lane == 0) slot = atomicAdd(ctl, 1u);
             slot = __shfl_sync(FULLMASK, slot, 0);
         }
         if (slot >= ntasks) {                      // bucket handed out (or not mine): open the next one
             if (++sq == G) { sq = 0; if (++st == S) break; }
+            uint32_t n_prev = 0u;
             if (st > 0) {
                 if (lane == 0) {
                     const uint32_t* prev = prm.lk_ctl + ((size_t)(st - 1) * G + sq) * 4;
-                    const uint32_t n_prev = st == 1 ? C : __ldcg(prev + 2);
-                    const uint32_t need = (n_prev * lock_auto_lanes(prm, n_prev, G, warps) + 31u) / 32u;      // tasks of the previous bucket of this sequence
-                    uint32_t spins = 0;
+                    n_prev = st == 1 ? C : __ldcg(prev + 2);
+                    // width the previous bucket of this sequence was played with: a function of its own count and of the count one stage earlier
+                    // (both final since this warp passed there; the two loads are independent)
+                    const uint32_t n_pp = st == 1 ? 0u : (st == 2 ? C : __ldcg(prev - (size_t)G * 4 + 2));
+                    const uint32_t need = lock_auto_tasks(n_prev, lock_auto_lanes(prm, n_prev, n_pp, G, warps));      // tasks of the previous bucket of this sequence
+                    // Warps that take no tickets at the moment (fewer tasks than warps) all wait at the first bucket that is not open yet: a thousand
+                    // warps polling one L2 line every 200 ns starve the counters on that line that the finishing tasks must bump (measured: a
+                    // 1 250 x 30 slice with one lane per game took 20.6 ms inside this kernel against 11.3 ms with an exact grid).  They poll 32 x slower.
+                    const uint32_t nap = take ? 200u : 6400u;
+                    uint64_t waited = 0;
                     while (*reinterpret_cast<volatile const uint32_t*>(prev + 1) < need) {
-                        __nanosleep(200);
-                        if (++spins > (1u << 23)) { atomicExch(prm.lk_ctl + (size_t)S * G * 4 + 3, 1u); break; }   // safety valve (> 1.5 s): never hang the device
+                        __nanosleep(nap);
+                        waited += nap;
+                        if (waited > (1ull << 31)) { atomicExch(prm.lk_ctl + (size_t)S * G * 4 + 3, 1u); break; }   // safety valve (> 2 s of naps): never hang the device
                     }
                     __threadfence();
-                    n_in = spins > (1u << 23) ? 0u : __ldcg(prm.lk_ctl + ((size_t)st * G + sq) * 4 + 2);
+                    n_in = waited > (1ull << 31) ? 0u : __ldcg(prm.lk_ctl + ((size_t)st * G + sq) * 4 + 2);
                 }
                 n_in = __shfl_sync(FULLMASK, n_in, 0);
+                n_prev = __shfl_sync(FULLMASK, n_prev, 0);
             }
-            lanes = lock_auto_lanes(prm, n_in, G, warps);
-            ntasks = (n_in * lanes + 31u) / 32u;
-            take = (uint64_t)rank < (uint64_t)ntasks * G;
+            lanes = lock_auto_lanes(prm, n_in, n_prev, G, warps);
+
+            ntasks = lock_auto_tasks(n_in, lanes);
+            take = lanes == 2u ? (uint64_t)prank < (uint64_t)ntasks * G : takes(ntasks * G);
             continue;
         }
-        if (lanes == 1u) lockwin_task<PRESS>(prm, s_tab, sb, st, sq, slot, n_in, ctl);
+        if (lanes <= 2u) { if (!lockwin_task<PRESS, PAIR>(prm, s_tab, sb, st, sq, slot, n_in, ctl, PAIR && lanes == 2u, &pl)) return; }
         else if (lanes == 4u) lock_task<4, MODE_W6, PRESS>(prm, s_tab, st, sq, slot, n_in, ctl);
         else if (lanes == 8u) lock_task<8, MODE_W6, PRESS>(prm, s_tab, st, sq, slot, n_in, ctl);
         else lock_task<32, MODE_W6, PRESS>(prm, s_tab, st, sq, slot, n_in, ctl);

@@ -226,7 +226,11 @@ struct tb200_ctx {
     bool win_enabled = true;             // K2sW: window-local evaluation in the one-lane-per-game lockstep kernel (TB200_NO_WIN: the all-columns K2s)
     int lock_lanes = 0, lock_K = 64;     // tuning aids: TB200_LOCK_LANES, TB200_LOCK_K
     int lock_thr[3] = {24, 8, 2};        // K2sA width thresholds (games alive per resident warp): TB200_LOCK_THR=a,b,c
-    int lock_minb = 4;                   // K2sA resident blocks per SM (4: 119 registers — the 4- and 8-lane tasks lose 20 % at 96; 5: 96): TB200_LOCK_MINB
+    int lock_steady = 10;                // K2sA: one-lane threshold of a steady bucket (games alive per resident warp; 0: same as lock_thr[0]): TB200_LOCK_STEADY
+    int lock_pair = 0;                   // K2sP (opt-in, measured and not adopted — DESIGN.md §4): games alive per resident warp from which a bucket is played by
+                                         // pairs of warps (0: never): TB200_LOCK_PAIR
+    int lock_minb = 4;                   // K2sA resident blocks per SM (4: 128 registers — the 4- and 8-lane tasks lose 20 % at 96; 5: 96 registers, 25 % more
+                                         // resident warps): TB200_LOCK_MINB
     bool bin_enabled = true;             // K2b; TB200_NO_BINS, TB200_BIN_LANES, TB200_BIN_MIN_GAMES
     int bin_lanes = 0; long long bin_min_games = 32768;
     const uint32_t* lock_flag = nullptr; // device word set by K2s if a bucket wait ever timed out (checked after host-mode calls)
@@ -373,6 +377,8 @@ int tb200_create(int device, tb200_ctx** out)
     if (const char* e6 = getenv("TB200_BIN_MIN_GAMES")) { const long long v = atoll(e6); if (v >= 1024) ctx->bin_min_games = v; }
     if (const char* e3 = getenv("TB200_LOCK_LANES")) ctx->lock_lanes = atoi(e3);
     if (const char* e7 = getenv("TB200_LOCK_THR")) { int a = 0, b = 0, c2 = 0; if (sscanf(e7, "%d,%d,%d", &a, &b, &c2) == 3 && a >= b && b >= c2 && c2 >= 0) { ctx->lock_thr[0] = a; ctx->lock_thr[1] = b; ctx->lock_thr[2] = c2; } }
+    if (const char* e10 = getenv("TB200_LOCK_STEADY")) { const int v = atoi(e10); if (v >= 0) ctx->lock_steady = v; }
+    if (const char* e9 = getenv("TB200_LOCK_PAIR")) { const int v = atoi(e9); if (v >= 0) ctx->lock_pair = v; }
     if (const char* e8 = getenv("TB200_LOCK_MINB")) { const int v = atoi(e8); if (v == 4 || v == 5) ctx->lock_minb = v; }
     if (const char* e4 = getenv("TB200_LOCK_K")) { const int k = atoi(e4); if (k >= 8) ctx->lock_K = k; }
     ctx->stage_cut1 = 4 * ctx->sms; ctx->stage_cut2 = 2 * ctx->sms; ctx->stage_cut3 = ctx->sms;
@@ -497,7 +503,7 @@ static LockPlan lock_plan(const tb200_ctx* ctx, const tb200_play_args& a, int pe
     lp.K = (uint32_t)ctx->lock_K; lp.S = (stop_moves + lp.K - 1) / lp.K + 2;      // see lock_stage_begin
     lp.b_save = align_up(sizeof(tb::GameSave) * (size_t)n_games);
     lp.b_list = align_up(2 * sizeof(uint32_t) * (size_t)n_games);
-    lp.b_ctl = align_up(16 * (size_t)(lp.S + 1) * (size_t)a.games_per_candidate);
+    lp.b_ctl = align_up(16 * (size_t)(lp.S + 1) * (size_t)a.games_per_candidate + 256 * 4 * sizeof(uint32_t));      // + K2sA: warps seen per (SM, scheduler)
     return lp;
 }
 static int ensure_lock_ws(tb200_ctx* ctx, const tb200_play_args& a)
@@ -657,6 +663,19 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
         p.lk_ctl = reinterpret_cast<uint32_t*>(ctx->d_lock + b_save + b_list);
         p.lk_C = (uint32_t)a.n_candidates; p.lk_K = K; p.lk_S = S;
         p.lk_thr[0] = (uint32_t)ctx->lock_thr[0]; p.lk_thr[1] = (uint32_t)ctx->lock_thr[1]; p.lk_thr[2] = (uint32_t)ctx->lock_thr[2];
+        {   // pairs of warps take the range [lock_pair, lock_thr[0]) of games alive per resident warp, when that range is not empty
+            int pr = ctx->lock_pair > 0 ? ctx->lock_pair : ctx->lock_thr[0];
+            if (pr > ctx->lock_thr[0]) pr = ctx->lock_thr[0];
+            if (pr < ctx->lock_thr[1]) pr = ctx->lock_thr[1];
+            p.lk_thr[3] = (uint32_t)pr;
+        }
+        // The pair task can only matter for plays that do not fill the machine with one warp per 32 games from the start (a rank's slice of a
+        // sharded population); only they get the kernel variant that has it (it costs the plain one-lane path 4 %).
+        const unsigned long long warps4 = (unsigned long long)ctx->sms * 4ull * (tb::BLOCK / 32);
+        p.lk_thr[4] = ctx->lock_steady > 0 && ctx->lock_steady < ctx->lock_thr[0] ? (uint32_t)ctx->lock_steady : p.lk_thr[0];
+        const bool pair_on = p.lk_thr[3] < p.lk_thr[0] && (unsigned long long)n_games_ll < (unsigned long long)p.lk_thr[0] * warps4;
+        if (!pair_on) p.lk_thr[3] = p.lk_thr[0];
+        const int minb = ctx->lock_minb;
         ctx->lock_flag = p.lk_ctl + (size_t)S * (size_t)a.games_per_candidate * 4 + 3;
         int ll = ctx->lock_lanes;
         if (ll != 1 && ll != 2 && ll != 4 && ll != 8) {
@@ -666,7 +685,9 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
         tb::play_fn lf;
         const bool lock_auto = ctx->mode == tb::MODE_W6 && ctx->win_enabled && !(ctx->lock_lanes == 1 || ctx->lock_lanes == 2 || ctx->lock_lanes == 4 || ctx->lock_lanes == 8);
         if (lock_auto)
-            lf = move_set == TB200_MOVES_PRESSURE ? tb::play_games_w6lockauto_kernel<4, true> : (ctx->lock_minb == 4 ? tb::play_games_w6lockauto_kernel<4> : tb::play_games_w6lockauto_kernel<5>);      // lanes per game chosen per (stage, sequence) bucket from the live count
+            lf = move_set == TB200_MOVES_PRESSURE ? (pair_on ? tb::play_games_w6lockauto_kernel<4, true, true> : tb::play_games_w6lockauto_kernel<4, true>) :
+                 (pair_on ? (minb == 4 ? tb::play_games_w6lockauto_kernel<4, false, true> : tb::play_games_w6lockauto_kernel<5, false, true>) :
+                            (minb == 4 ? tb::play_games_w6lockauto_kernel<4> : tb::play_games_w6lockauto_kernel<5>));      // lanes per game chosen per (stage, sequence) bucket from the live count
         else if (ctx->mode == tb::MODE_W6 && ll == 1 && ctx->win_enabled)
             lf = tb::play_games_w6lockwin_kernel;
         else if (ctx->mode == tb::MODE_W6)
@@ -691,7 +712,7 @@ static int launch_play(tb200_ctx* ctx, const tb200_play_args& a, cudaStream_t st
         if (lblocks > (long long)ctx->sms * locc || lock_auto) lblocks = (long long)ctx->sms * locc;
         if (lock_auto) {                                        // reported width = the one the first stage plays with (tb::lock_auto_lanes)
             const unsigned long long alive = (unsigned long long)n_games_ll, warps = (unsigned long long)lblocks * (tb::BLOCK / 32);
-            ll = alive >= (unsigned long long)ctx->lock_thr[0] * warps ? 1 : (alive >= (unsigned long long)ctx->lock_thr[1] * warps ? 4 : (alive >= (unsigned long long)ctx->lock_thr[2] * warps ? 8 : 32));
+            ll = alive >= (unsigned long long)p.lk_thr[0] * warps ? 1 : (alive >= (unsigned long long)p.lk_thr[3] * warps ? 2 : (alive >= (unsigned long long)p.lk_thr[1] * warps ? 4 : (alive >= (unsigned long long)p.lk_thr[2] * warps ? 8 : 32)));
         }
         TB_CUDA(ctx, cudaMemsetAsync(p.lk_ctl, 0, b_ctl, st));
         if (record_events) TB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));

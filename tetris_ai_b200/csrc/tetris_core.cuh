@@ -1013,6 +1013,17 @@ TB_HD void win_advance(WinSlide& ws)
     ws.t[0] = funnel_r(ws.t[0], ws.t[1], 8u); ws.t[1] = funnel_r(ws.t[1], ws.t[2], 8u); ws.t[2] >>= 8;
     ws.d[0] = funnel_r(ws.d[0], ws.d[1], 8u); ws.d[1] = funnel_r(ws.d[1], ws.d[2], 8u); ws.d[2] >>= 8;
 }
+// start the windows at first column c0 (0 .. 9, warp-uniform on the device) instead of 0: whole words move, the rest slides
+TB_HD void win_skip(WinSlide& ws, int c0)
+{
+    for (int i = c0 >> 2; i > 0; --i) {
+        ws.x[0] = ws.x[1]; ws.x[1] = ws.x[2]; ws.x[2] = ws.x[3]; ws.x[3] = 0u;
+        ws.r[0] = ws.r[1]; ws.r[1] = ws.r[2]; ws.r[2] = 0u;
+        ws.t[0] = ws.t[1]; ws.t[1] = ws.t[2]; ws.t[2] = 0u;
+        ws.d[0] = ws.d[1]; ws.d[1] = ws.d[2]; ws.d[2] = 0u;
+    }
+    for (int i = c0 & 3; i > 0; --i) win_advance(ws);
+}
 // per-slot constants that do not depend on the board (uniform on the device): piece cells / tops of the piece's own four
 // columns, cut out of the slot descriptor
 struct WinDesc {
