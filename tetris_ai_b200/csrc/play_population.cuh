@@ -903,7 +903,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) play_games_w6lockauto_kernel(cons
     const uint32_t lanes0 = lock_auto_lanes(prm, C, 0u, G, warps);      // every bucket of the first stage
     uint32_t lanes = lanes0;
     uint32_t ntasks = lock_auto_tasks(n_in, lanes);
-    bool take = lanes == 2u ? (uint64_t)prank < (uint64_t)ntasks * G : takes(ntasks * G);
+    bool mine = takes(ntasks * G);                 // this warp's slot serves the current bucket
+    bool take = lanes == 2u ? (uint64_t)prank < (uint64_t)ntasks * G : mine;
     for (;;) {
         uint32_t* ctl = prm.lk_ctl + ((size_t)st * G + sq) * 4;
         uint32_t slot = 0xffffffffu;
@@ -922,11 +923,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) play_games_w6lockauto_kernel(cons
         }
         if (slot >= ntasks) {                      // bucket handed out (or not mine): open the next one
             if (++sq == G) { sq = 0; if (++st == S) break; }
-            uint32_t n_prev = 0u;
-            if (st > 0) {
+            // One bucket = one 16-byte record {ticket, done, games in, -}: it is read with ONE 128-bit load, and the ticket word of the snapshot
+            // tells a warp whether there is anything left to take before it spends an atomic on it.  (When a shard fills the machine only
+            // once, every warp passes every bucket and most find it handed out: ncu of a 2 500 x 30 slice had 13.5 % of the warp time
+            // waiting on these L2 round trips — 2 368 atomics queueing on one word per bucket — and 10.5 % asleep.)
+            uint32_t n_prev = 0u, tk = 0u;
+            if (st == 0) {
+                if (lane == 0) tk = __ldcg(prm.lk_ctl + ((size_t)st * G + sq) * 4);
+                tk = __shfl_sync(FULLMASK, tk, 0);
+            } else {
                 if (lane == 0) {
                     const uint32_t* prev = prm.lk_ctl + ((size_t)(st - 1) * G + sq) * 4;
-                    n_prev = st == 1 ? C : __ldcg(prev + 2);
+                    const uint4 pr = __ldcg(reinterpret_cast<const uint4*>(prev));
+                    n_prev = st == 1 ? C : pr.z;
                     // width the previous bucket of this sequence was played with: a function of its own count and of the count one stage earlier
                     // (both final since this warp passed there; the two loads are independent)
                     const uint32_t n_pp = st == 1 ? 0u : (st == 2 ? C : __ldcg(prev - (size_t)G * 4 + 2));
@@ -934,23 +943,28 @@ __global__ void __launch_bounds__(BLOCK, MINB) play_games_w6lockauto_kernel(cons
                     // Warps that take no tickets at the moment (fewer tasks than warps) all wait at the first bucket that is not open yet: a thousand
                     // warps polling one L2 line every 200 ns starve the counters on that line that the finishing tasks must bump (measured: a
                     // 1 250 x 30 slice with one lane per game took 20.6 ms inside this kernel against 11.3 ms with an exact grid).  They poll 32 x slower.
-                    const uint32_t nap = take ? 200u : 6400u;
+                    const uint32_t nap = mine ? 200u : 6400u;
                     uint64_t waited = 0;
-                    while (*reinterpret_cast<volatile const uint32_t*>(prev + 1) < need) {
+                    uint32_t done = pr.y;
+                    while (done < need) {
                         __nanosleep(nap);
                         waited += nap;
                         if (waited > (1ull << 31)) { atomicExch(prm.lk_ctl + (size_t)S * G * 4 + 3, 1u); break; }   // safety valve (> 2 s of naps): never hang the device
+                        done = *reinterpret_cast<volatile const uint32_t*>(prev + 1);
                     }
                     __threadfence();
-                    n_in = waited > (1ull << 31) ? 0u : __ldcg(prm.lk_ctl + ((size_t)st * G + sq) * 4 + 2);
+                    const uint4 cu = __ldcg(reinterpret_cast<const uint4*>(prm.lk_ctl + ((size_t)st * G + sq) * 4));      // after the fence: `games in` is final
+                    n_in = waited > (1ull << 31) ? 0u : cu.z;
+                    tk = cu.x;
                 }
                 n_in = __shfl_sync(FULLMASK, n_in, 0);
                 n_prev = __shfl_sync(FULLMASK, n_prev, 0);
+                tk = __shfl_sync(FULLMASK, tk, 0);
             }
             lanes = lock_auto_lanes(prm, n_in, n_prev, G, warps);
-
             ntasks = lock_auto_tasks(n_in, lanes);
-            take = lanes == 2u ? (uint64_t)prank < (uint64_t)ntasks * G : takes(ntasks * G);
+            mine = takes(ntasks * G);
+            take = lanes == 2u ? (uint64_t)prank < (uint64_t)ntasks * G : (mine && tk < ntasks);      // tickets only grow: a snapshot >= ntasks = handed out
             continue;
         }
         if (lanes <= 2u) { if (!lockwin_task<PRESS, PAIR>(prm, s_tab, sb, st, sq, slot, n_in, ctl, PAIR && lanes == 2u, &pl)) return; }
