@@ -473,6 +473,27 @@ TB_D void lw_store_board(uint32_t (*sb)[32], int lane, const uint32_t c[COLS])
 
 // Best placement of piece p_cur (warp-uniform) for the game of this lane, window-local evaluation + deferred row-completing
 // placements; key = 0: no legal placement.  cnt counts the legal placements of active lanes (= scorer calls).
+// The slots cc .. ce - 1 of one rotation (piece width WDT, warp-uniform), windows sliding one column per slot.
+template <int WDT, bool PRESS>
+TB_D void lw_slots(uint32_t (*sb)[32], int lane, const WinCache& wc, WinSlide& ws, const double* w, int p_u, int& s2, int cc, int ce, bool active,
+                   const Pressure& press, int level, uint32_t& cnt, uint64_t& key, uint32_t& tag, uint32_t& dlo, uint32_t& dhi)
+{
+#pragma unroll 1
+    for (; cc < ce; ++cc, ++s2) {
+        const SlotDesc d = c_tables.slot[p_u][s2];
+        const WinDesc wdsc = c_win[p_u][s2];
+        const int c0 = (int)(d.w[0] & 15u);
+        const uint32_t and_out = sb[10 + c0][lane] & sb[20 + c0 + WDT - 1][lane];
+        uint32_t full; bool legal; int y;
+        uint64_t k = win_eval_w<WDT>(wc, ws, d, wdsc, w, [&](int kk) -> uint32_t { return sb[kk][lane]; }, and_out, &full, &legal, &y);
+        win_advance(ws);
+        if (PRESS && legal && !is_time(d, y, press, level)) { legal = false; k = 0ull; }      // move_with_pressure: filtered before it is scored
+        cnt += (uint32_t)(legal && active);
+        if (legal && full != 0u) { k = 0ull; if (s2 < 32) dlo |= 1u << s2; else dhi |= 1u << (s2 - 32); }
+        if (k > key) { key = k; tag = (uint32_t)s2; }
+    }
+}
+
 // SPLIT: the slots of the piece are shared out between the `nparts` (1 or 2) warps that play these 32 games together (K2sP, see
 // lockwin_task): this warp takes half (part + rotation / 2) mod 2 of every rotation's columns, so the parts stay balanced.
 template <bool PRESS, bool SPLIT = false>
@@ -496,19 +517,11 @@ TB_D void lw_search(const Tables& s_tab, uint32_t (*sb)[32], int lane, const Win
             win_skip(ws, cc);
             s2 += cc;
         }
-#pragma unroll 1
-        for (; cc < ce; ++cc, ++s2) {
-            const SlotDesc d = c_tables.slot[p_u][s2];
-            const WinDesc wdsc = c_win[p_u][s2];
-            const int c0 = (int)(d.w[0] & 15u), wdt = (int)((d.w[0] >> 6) & 7u);
-            const uint32_t and_out = sb[10 + c0][lane] & sb[20 + c0 + wdt - 1][lane];
-            uint32_t full; bool legal; int y;
-            uint64_t k = win_eval_at(wc, ws, d, wdsc, w, [&](int kk) -> uint32_t { return sb[kk][lane]; }, and_out, &full, &legal, &y);
-            win_advance(ws);
-            if (PRESS && legal && !is_time(d, y, press, level)) { legal = false; k = 0ull; }      // move_with_pressure: filtered before it is scored
-            cnt += (uint32_t)(legal && active);
-            if (legal && full != 0u) { k = 0ull; if (s2 < 32) dlo |= 1u << s2; else dhi |= 1u << (s2 - 32); }
-            if (k > key) { key = k; tag = (uint32_t)s2; }
+        switch (COLS + 1 - ncol) {                 // the rotation's piece width: uniform, so one jump per rotation buys a slot loop without width tests
+        case 1: lw_slots<1, PRESS>(sb, lane, wc, ws, w, p_u, s2, cc, ce, active, press, level, cnt, key, tag, dlo, dhi); break;
+        case 2: lw_slots<2, PRESS>(sb, lane, wc, ws, w, p_u, s2, cc, ce, active, press, level, cnt, key, tag, dlo, dhi); break;
+        case 3: lw_slots<3, PRESS>(sb, lane, wc, ws, w, p_u, s2, cc, ce, active, press, level, cnt, key, tag, dlo, dhi); break;
+        default: lw_slots<4, PRESS>(sb, lane, wc, ws, w, p_u, s2, cc, ce, active, press, level, cnt, key, tag, dlo, dhi); break;
         }
         s2 = s2_end;
     }

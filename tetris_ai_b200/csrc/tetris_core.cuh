@@ -1049,11 +1049,16 @@ TB_HD WinDesc win_desc(const SlotDesc& d)
 // the piece's columns (for the full-row test).  Returns the comparison key (0 = illegal); *full = rows the placement
 // completes: when it is not 0 the returned key is meaningless and the caller must evaluate the placement with
 // w6_pre / w6_clear / w6_post.
-template <class ColFn>
-TB_HD uint64_t win_eval_at(const WinCache& wc, const WinSlide& ws, const SlotDesc& d, const WinDesc& wdsc, const double* w, ColFn col,
-                           uint32_t and_out, uint32_t* full, bool* legal_out, int* y_out = nullptr)
+// WDT = the piece's width in this rotation (1..4), a compile-time constant: the lockstep kernel switches on it once per
+// rotation (it is warp-uniform), so that the slot loop carries no width tests, only the WDT piece columns, WDT height updates,
+// WDT + 2 wells and the byte selectors of exactly that width as immediates (about a tenth fewer instructions per slot than the
+// run-time-width body, and straight-line code between the two neighbour tests).
+template <int WDT, class ColFn>
+TB_HD uint64_t win_eval_w(const WinCache& wc, const WinSlide& ws, const SlotDesc& d, const WinDesc& wdsc, const double* w, ColFn col,
+                          uint32_t and_out, uint32_t* full, bool* legal_out, int* y_out = nullptr)
 {
-    const int c0 = (int)(d.w[0] & 15u), wdt = (int)((d.w[0] >> 6) & 7u);
+    static_assert(WDT >= 1 && WDT <= 4, "piece width");
+    const int c0 = (int)(d.w[0] & 15u);
     const uint32_t W0 = ws.x[0], W1 = ws.x[1];                            // heights of columns c0-2 .. c0+5
     const uint32_t hw = funnel_r(W0, W1, 16u);                            // columns c0 .. c0+3
     const bool legal = ((hw + d.w[2]) & 0x80808080u) == 0u;
@@ -1065,22 +1070,24 @@ TB_HD uint64_t win_eval_at(const WinCache& wc, const WinSlide& ws, const SlotDes
     if (y_out) *y_out = y;
     const uint32_t pbw = wdsc.pbw, tpw = wdsc.tpw;
     const uint32_t one_y = 1u << (y & 31);
-    // imprint + transitions of the window (the piece is 1..4 columns wide)
+    // imprint + transitions of the window
     const uint32_t n0 = byte_of(pbw, 0) * one_y + col(c0);
     uint32_t nl = n0;                                                     // last (right-most) piece column
     uint32_t f = and_out & n0;
     int rtn = 0, ctn = popc((n0 ^ (n0 * 2u)) & 0xFFFFEu);
     if (c0 > 0) rtn += popc(col(c0 - 1) ^ n0);
-    if (wdt > 1) { const uint32_t n1 = byte_of(pbw, 1) * one_y + col(c0 + 1); f &= n1; rtn += popc(nl ^ n1); ctn += popc((n1 ^ (n1 * 2u)) & 0xFFFFEu); nl = n1; }
-    if (wdt > 2) { const uint32_t n2 = byte_of(pbw, 2) * one_y + col(c0 + 2); f &= n2; rtn += popc(nl ^ n2); ctn += popc((n2 ^ (n2 * 2u)) & 0xFFFFEu); nl = n2; }
-    if (wdt > 3) { const uint32_t n3 = (pbw >> 24) * one_y + col(c0 + 3); f &= n3; rtn += popc(nl ^ n3); ctn += popc((n3 ^ (n3 * 2u)) & 0xFFFFEu); nl = n3; }
-    if (c0 + wdt < COLS) rtn += popc(nl ^ col(c0 + wdt));
+    if constexpr (WDT > 1) { const uint32_t n1 = byte_of(pbw, 1) * one_y + col(c0 + 1); f &= n1; rtn += popc(nl ^ n1); ctn += popc((n1 ^ (n1 * 2u)) & 0xFFFFEu); nl = n1; }
+    if constexpr (WDT > 2) { const uint32_t n2 = byte_of(pbw, 2) * one_y + col(c0 + 2); f &= n2; rtn += popc(nl ^ n2); ctn += popc((n2 ^ (n2 * 2u)) & 0xFFFFEu); nl = n2; }
+    if constexpr (WDT > 3) { const uint32_t n3 = (pbw >> 24) * one_y + col(c0 + 3); f &= n3; rtn += popc(nl ^ n3); ctn += popc((n3 ^ (n3 * 2u)) & 0xFFFFEu); nl = n3; }
+    if (c0 + WDT < COLS) rtn += popc(nl ^ col(c0 + WDT));
     *full = f;
-    // old contributions of the same pairs / columns: the first wdt + 1 pairs, wdt columns, wdt + 2 wells of the windows
+    // old contributions of the same pairs / columns: the first WDT + 1 pairs, WDT columns, WDT + 2 wells of the windows
     // (entries outside the board are 0 in the arrays, so the edges need no special case)
-    const int rto = bytesum_sel(ws.r[0], wdsc.mr0) + bytesum_sel(ws.r[1], wdsc.mr1);
-    const int cto = bytesum_sel(ws.t[0], wdsc.mt);
-    const int cwo = bytesq_sel(ws.d[0], wdsc.md0) + bytesq_sel(ws.d[1], wdsc.md1);
+    int rto = bytesum_sel(ws.r[0], low_bytes01(WDT + 1));
+    if constexpr (WDT > 3) rto += bytesum_sel(ws.r[1], low_bytes01(WDT - 3));
+    const int cto = bytesum_sel(ws.t[0], low_bytes01(WDT));
+    int cwo = bytesq_sel(ws.d[0], low_bytes01(WDT + 2) * 255u);
+    if constexpr (WDT > 2) cwo += bytesq_sel(ws.d[1], low_bytes01(WDT - 2) * 255u);
     // heights under the piece
     const int yb = y - 32;
     int q[8];
@@ -1088,16 +1095,16 @@ TB_HD uint64_t win_eval_at(const WinCache& wc, const WinSlide& ws, const SlotDes
     q[4] = (int)byte_of(W1, 0); q[5] = (int)byte_of(W1, 1); q[6] = (int)byte_of(W1, 2); q[7] = (int)(W1 >> 24);
     int dsh = 0;
     { const int t = (int)byte_of(tpw, 0) + yb; const int hn = t > q[2] ? t : q[2]; dsh += hn - q[2]; q[2] = hn; }
-    { const int t = (int)byte_of(tpw, 1) + yb; const int hn = t > q[3] ? t : q[3]; dsh += hn - q[3]; q[3] = hn; }      // top byte 0 beyond the width: t < 0 <= q
-    { const int t = (int)byte_of(tpw, 2) + yb; const int hn = t > q[4] ? t : q[4]; dsh += hn - q[4]; q[4] = hn; }
-    { const int t = (int)(tpw >> 24) + yb;     const int hn = t > q[5] ? t : q[5]; dsh += hn - q[5]; q[5] = hn; }
-    // wells of columns c0-1 .. c0+wdt (window positions 1 .. wdt+2); positions outside the board are walls, not wells
+    if constexpr (WDT > 1) { const int t = (int)byte_of(tpw, 1) + yb; const int hn = t > q[3] ? t : q[3]; dsh += hn - q[3]; q[3] = hn; }
+    if constexpr (WDT > 2) { const int t = (int)byte_of(tpw, 2) + yb; const int hn = t > q[4] ? t : q[4]; dsh += hn - q[4]; q[4] = hn; }
+    if constexpr (WDT > 3) { const int t = (int)(tpw >> 24) + yb;     const int hn = t > q[5] ? t : q[5]; dsh += hn - q[5]; q[5] = hn; }
+    // wells of columns c0-1 .. c0+WDT (window positions 1 .. WDT+2); positions outside the board are walls of height ROWS in the
+    // window, so their "depth" is 0 by itself
     int cwn = 0;
 #pragma unroll
-    for (int p = 1; p <= 6; ++p) {
+    for (int p = 1; p <= WDT + 2; ++p) {
         int dd = (q[p - 1] < q[p + 1] ? q[p - 1] : q[p + 1]) - q[p]; dd = dd > 0 ? dd : 0;
-        // positions outside the board are walls of height ROWS in the window, so their "depth" is 0 by itself
-        cwn += p <= wdt + 2 ? dd * dd + dd : 0;
+        cwn += dd * dd + dd;
     }
     const int rt = wc.RT - rto + rtn, ct = wc.CT - cto + ctn;
     const int pits = wc.SH + dsh - (wc.cells + 4);
@@ -1112,6 +1119,19 @@ TB_HD uint64_t win_eval_at(const WinCache& wc, const WinSlide& ws, const SlotDes
     acc = dadd(acc, dmul(u2d(cw), w[5]));
     const uint64_t key = score_key(acc);
     return legal ? key : 0ull;
+}
+
+// the same with the width read from the descriptor (host tests, and callers outside the per-rotation switch)
+template <class ColFn>
+TB_HD uint64_t win_eval_at(const WinCache& wc, const WinSlide& ws, const SlotDesc& d, const WinDesc& wdsc, const double* w, ColFn col,
+                           uint32_t and_out, uint32_t* full, bool* legal_out, int* y_out = nullptr)
+{
+    switch ((int)((d.w[0] >> 6) & 7u)) {
+    case 1: return win_eval_w<1>(wc, ws, d, wdsc, w, col, and_out, full, legal_out, y_out);
+    case 2: return win_eval_w<2>(wc, ws, d, wdsc, w, col, and_out, full, legal_out, y_out);
+    case 3: return win_eval_w<3>(wc, ws, d, wdsc, w, col, and_out, full, legal_out, y_out);
+    default: return win_eval_w<4>(wc, ws, d, wdsc, w, col, and_out, full, legal_out, y_out);
+    }
 }
 
 // the same for a stand-alone slot (host tests): windows cut out by byte index
