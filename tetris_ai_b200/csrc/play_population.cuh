@@ -476,7 +476,7 @@ TB_D void lw_store_board(uint32_t (*sb)[32], int lane, const uint32_t c[COLS])
 // The slots cc .. ce - 1 of one rotation (piece width WDT, warp-uniform), windows sliding one column per slot.
 template <int WDT, bool PRESS>
 TB_D void lw_slots(uint32_t (*sb)[32], int lane, const WinCache& wc, WinSlide& ws, const double* w, int p_u, int& s2, int cc, int ce, bool active,
-                   const Pressure& press, int level, uint32_t& cnt, uint64_t& key, uint32_t& tag, uint32_t& dlo, uint32_t& dhi)
+                   const Pressure& press, int speed, uint32_t& cnt, uint64_t& key, uint32_t& tag, uint32_t& dlo, uint32_t& dhi)
 {
 #pragma unroll 1
     for (; cc < ce; ++cc, ++s2) {
@@ -487,7 +487,7 @@ TB_D void lw_slots(uint32_t (*sb)[32], int lane, const WinCache& wc, WinSlide& w
         uint32_t full; bool legal; int y;
         uint64_t k = win_eval_w<WDT>(wc, ws, d, wdsc, w, [&](int kk) -> uint32_t { return sb[kk][lane]; }, and_out, &full, &legal, &y);
         win_advance(ws);
-        if (PRESS && legal && !is_time(d, y, press, level)) { legal = false; k = 0ull; }      // move_with_pressure: filtered before it is scored
+        if (PRESS && legal && !is_time_at_speed(d, y, press, speed)) { legal = false; k = 0ull; }      // move_with_pressure: filtered before it is scored
         cnt += (uint32_t)(legal && active);
         if (legal && full != 0u) { k = 0ull; if (s2 < 32) dlo |= 1u << s2; else dhi |= 1u << (s2 - 32); }
         if (k > key) { key = k; tag = (uint32_t)s2; }
@@ -504,6 +504,7 @@ TB_D void lw_search(const Tables& s_tab, uint32_t (*sb)[32], int lane, const Win
     const int p_u = (int)__reduce_max_sync(FULLMASK, (unsigned)p_cur);      // provably uniform: descriptors from constant memory, fields on the uniform datapath
     const int ns = c_tables.nslots[p_u];
     uint32_t dlo = 0u, dhi = 0u;                                 // slots deferred to the general evaluation (they complete a row)
+    const int speed = PRESS ? speed_of_level(level) : 0;         // the level bracket of simulator.py:110-114, once per piece
     // slots are enumerated rotation-major, column-minor: per rotation the windows start at column 0 and slide
     for (int s2 = 0, rot = 0; s2 < ns; ++rot) {
         WinSlide ws;
@@ -518,10 +519,10 @@ TB_D void lw_search(const Tables& s_tab, uint32_t (*sb)[32], int lane, const Win
             s2 += cc;
         }
         switch (COLS + 1 - ncol) {                 // the rotation's piece width: uniform, so one jump per rotation buys a slot loop without width tests
-        case 1: lw_slots<1, PRESS>(sb, lane, wc, ws, w, p_u, s2, cc, ce, active, press, level, cnt, key, tag, dlo, dhi); break;
-        case 2: lw_slots<2, PRESS>(sb, lane, wc, ws, w, p_u, s2, cc, ce, active, press, level, cnt, key, tag, dlo, dhi); break;
-        case 3: lw_slots<3, PRESS>(sb, lane, wc, ws, w, p_u, s2, cc, ce, active, press, level, cnt, key, tag, dlo, dhi); break;
-        default: lw_slots<4, PRESS>(sb, lane, wc, ws, w, p_u, s2, cc, ce, active, press, level, cnt, key, tag, dlo, dhi); break;
+        case 1: lw_slots<1, PRESS>(sb, lane, wc, ws, w, p_u, s2, cc, ce, active, press, speed, cnt, key, tag, dlo, dhi); break;
+        case 2: lw_slots<2, PRESS>(sb, lane, wc, ws, w, p_u, s2, cc, ce, active, press, speed, cnt, key, tag, dlo, dhi); break;
+        case 3: lw_slots<3, PRESS>(sb, lane, wc, ws, w, p_u, s2, cc, ce, active, press, speed, cnt, key, tag, dlo, dhi); break;
+        default: lw_slots<4, PRESS>(sb, lane, wc, ws, w, p_u, s2, cc, ce, active, press, speed, cnt, key, tag, dlo, dhi); break;
         }
         s2 = s2_end;
     }

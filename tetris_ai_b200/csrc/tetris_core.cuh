@@ -396,15 +396,17 @@ TB_HD int speed_of_level(int level)                           // the descending 
            level == 4 ? 470 : level == 3 ? 550 : level == 2 ? 630 : level == 1 ? 720 : 800;
 }
 
-// d = descriptor of the placement's slot, y = height of its bbox bottom, level = level of the state it is generated from
-TB_HD bool is_time(const SlotDesc& d, int y, const Pressure& pr, int level)
+// d = descriptor of the placement's slot, y = height of its bbox bottom, speed = speed_of_level(level of the state it is generated from)
+// (the level is the same for every move of a piece: callers that loop over the slots look the bracket up once)
+TB_HD bool is_time_at_speed(const SlotDesc& d, int y, const Pressure& pr, int speed)
 {
     const int rot = (int)((d.w[0] >> 4) & 3u), ph = (int)((d.w[0] >> 9) & 7u);
     const int clicks = (int)d.w[11] - ((pr.two_but_rot && rot == 3) ? 2 : 0);            // rot 3 costs 1 press instead of 3
     const double t = dadd(pr.resp_time, dmul(dmul(i2d(clicks), pr.move_eff), pr.avg_lat));   // :107, left to right
-    const int limit = (y + ph) * speed_of_level(level);                                  // (rows - row) * speed, :116
+    const int limit = (y + ph) * speed;                                                  // (rows - row) * speed, :116
     return t <= i2d(limit);
 }
+TB_HD bool is_time(const SlotDesc& d, int y, const Pressure& pr, int level) { return is_time_at_speed(d, y, pr, speed_of_level(level)); }
 
 // ---------------------------------------------------------------------------------------------
 // SURVEY.md §8f rank 4 — move_with_wiggle / move_wiggle (simulator.py:49-85): depth-first flood fill of the
