@@ -271,7 +271,6 @@ __global__ void __launch_bounds__(BLOCK) play_games_w32_kernel(const PlayParams 
             return seq ? (int)__ldg(seq + tt) : hashed_piece(prm.seed, stream, tt);
         };
         uint32_t t = 0, lines = prm.init_lines ? prm.init_lines[game] : 0u, h1 = 0, h2 = 0, h3 = 0, h4 = 0, cnt = 0;
-        const uint32_t lines0 = lines;
         uint64_t gscore = 0;
         int p_cur = fetch_piece(0), p_next = fetch_piece(1);
         const uint32_t max_moves = prm.max_moves;

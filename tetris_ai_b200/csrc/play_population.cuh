@@ -367,16 +367,13 @@ TB_D void lock_task(const PlayParams& prm, const Tables& s_tab, uint32_t st, uin
 template <int LANES, int MODE = MODE_W6>
 __global__ void __launch_bounds__(BLOCK) play_games_w6lock_kernel(const PlayParams prm)
 {
-    constexpr bool W6 = MODE == MODE_W6;
     constexpr uint32_t GPW = 32 / LANES;           // games per warp
     __shared__ Tables s_tab;
     load_tables<BLOCK>(s_tab);
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int gl = lane & (LANES - 1);
-    const uint32_t T = prm.T, C = prm.lk_C, K = prm.lk_K, S = prm.lk_S;
+    const uint32_t C = prm.lk_C, S = prm.lk_S;
     const uint32_t G = (uint32_t)prm.G;
-    const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
 
     uint32_t st = 0, sq = 0;                       // current bucket
     uint32_t n_in = C, ntasks = (C + GPW - 1) / GPW;
@@ -805,9 +802,8 @@ __global__ void __launch_bounds__(BLOCK, 4) play_games_w6lockwin_kernel(const Pl
     __syncthreads();
     const int lane = threadIdx.x & 31;
     uint32_t (*sb)[32] = s_board[threadIdx.x >> 5];
-    const uint32_t T = prm.T, C = prm.lk_C, K = prm.lk_K, S = prm.lk_S;
+    const uint32_t C = prm.lk_C, S = prm.lk_S;
     const uint32_t G = (uint32_t)prm.G;
-    const uint32_t stop = T < prm.max_moves ? T : prm.max_moves;
 
     uint32_t st = 0, sq = 0;                       // current bucket
     uint32_t n_in = C, ntasks = (C + GPW - 1) / GPW;
